@@ -1,0 +1,116 @@
+/*
+ * pn2.h -- C ABI of libpn2_sm100.so, the B200 (sm_100a) implementation of the PointNet++
+ * set-abstraction path of Regen2001/PointNet-Like-Pose-Estimation (model/pointnet2_utils.py).
+ *
+ * The reference has no native code and therefore no FFI of its own: its "operator interface" for this
+ * path is the Python surface of model/pointnet2_utils.py.  Each entry point below names the reference
+ * function (file:line) whose arithmetic it replaces; the Python binding that the reference side adds is
+ * shown in INTEGRATION.md and shipped as pointnet-like-pose-estimation_b200/_pn2_native.py.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch); the library never allocates,
+ *     frees or synchronises; all launches go to `stream` (a cudaStream_t passed as void*).
+ *   - coordinates ("points" in this fork) are addressed with int64 ELEMENT strides so that both
+ *     layouts the models produce ([B,C,N] permuted, and contiguous [B,N,C]) are read in place; the
+ *     stride of the last dim also selects the fp32 summation order that ATen would use.
+ *   - return value: 0 ok; <0 argument error found on the host (pn2_last_error_string() explains);
+ *     >0 a cudaError_t from the launch.
+ *   - re-entrant and thread-safe: no global mutable state besides one-time function attributes and a
+ *     thread-local error string.
+ */
+#ifndef PN2_H_
+#define PN2_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PN2_ABI_VERSION 3
+#define PN2_MAX_COORD 16 /* exact summation-order rules are verified against ATen for C <= 16 */
+#define PN2_MAX_LAYERS 8
+
+/* channel order of a grouped row */
+#define PN2_ORDER_SSG 0 /* [xyz - centre, feat]   pointnet2_utils.py:113-114 */
+#define PN2_ORDER_MSG 1 /* [feat, xyz - centre]   pointnet2_utils.py:208-209 */
+#define PN2_ORDER_ALL 2 /* [xyz (raw), feat]      pointnet2_utils.py:134-138 */
+
+/* arithmetic of the shared MLP */
+#define PN2_PREC_F32 0  /* fp32 FFMA, fp32 accumulate           (<= 1e-5 of the reference) */
+#define PN2_PREC_BF16 1 /* bf16 tcgen05.mma, fp32 accumulate in TMEM (<= 2e-2)             */
+
+int pn2_version(void);
+const char *pn2_last_error_string(void);
+
+/* farthest_point_sample -- pointnet2_utils.py:47-68.
+ * points [B,N,C] with element strides (sb,sn,sc); start[B] = the torch.randint draw of :59 (int64, device).
+ * Outputs (any may be NULL): idx64 [B,S] (the function's return value), idx32 [B,S], new_points [B,S,C]
+ * contiguous (= index_points(points, idx), :107 / :201, fused because the cloud is already on chip). */
+int pn2_fps_f32(const float *points, int64_t sb, int64_t sn, int64_t sc, int B, int N, int C,
+                const int64_t *start, int S, int64_t *idx64, int32_t *idx32, float *new_points, void *stream);
+
+/* index_points -- pointnet2_utils.py:28-45.  src [B,N,C] strided; idx [B,M] int64 (M = prod of idx dims 1..);
+ * out [B,M,C] contiguous.  err_flag (int32, device, may be NULL) is set to 1 on an out-of-range index. */
+int pn2_index_points_f32(const float *src, int64_t sb, int64_t sn, int64_t sc, int B, int N, int C,
+                         const int64_t *idx, int64_t M, float *out, int32_t *err_flag, void *stream);
+
+/* square_distance -- pointnet2_utils.py:5-26, the expanded form with the reference's operation order.
+ * src [B,S,C] strided, dst [B,N,C] strided, out [B,S,N] contiguous. */
+int pn2_square_distance_f32(const float *src, int64_t ssb, int64_t ssn, int64_t ssc,
+                            const float *dst, int64_t dsb, int64_t dsn, int64_t dsc,
+                            int B, int S, int N, int C, float *out, void *stream);
+
+/* query_ball_point -- pointnet2_utils.py:70-90.  centres [B,S,C] strided (the reference always passes a
+ * contiguous tensor), points [B,N,C] strided; r2 = (float)(radius**2) computed by the caller in double.
+ * Outputs (either may be NULL): idx64 [B,S,K], idx32 [B,S,K].  empty_flag (int32, device, may be NULL) is
+ * set to 1 if some centre has no neighbour (the reference then fails inside index_points); those rows are
+ * filled with N. */
+int pn2_ball_query_f32(const float *centres, int64_t csb, int64_t csn, int64_t csc,
+                       const float *points, int64_t sb, int64_t sn, int64_t sc,
+                       int B, int S, int N, int C, float r2, int K,
+                       int64_t *idx64, int32_t *idx32, int32_t *empty_flag, void *stream);
+
+/* Materialised grouping -- sample_and_group / sample_and_group_all, pointnet2_utils.py:109-116, :134-140,
+ * :205-211.  Only used by the stand-alone functions and by training mode: the fused kernels never write
+ * this tensor.  feat may be NULL (D = 0).  idx32 [B,S,K] (ignored for PN2_ORDER_ALL, where S=1, K=N).
+ * out [B,S,K,C+D] contiguous. */
+int pn2_group_f32(const float *points, int64_t sb, int64_t sn, int64_t sc,
+                  const float *feat, int64_t fb, int64_t fn, int64_t fc,
+                  const int32_t *idx32, const float *centres,
+                  int B, int N, int S, int K, int C, int D, int order, float *out, void *stream);
+
+/* Fold eval-mode BatchNorm into the 1x1 convolutions and lay the weights out for the fused kernels
+ * (pointnet2_utils.py:154-155, :168-170).  L layers; dims[L+1] = {Cin, C1..CL}.  For layer l the six
+ * device pointers ptrs[6*l + {0..5}] = conv.weight [Cout,Cin], conv.bias, bn.weight, bn.bias,
+ * bn.running_mean, bn.running_var.  pn2_packed_bytes gives the size of `packed` for `prec`.  C (coordinate
+ * channels inside dims[0]) and `order` (PN2_ORDER_*) describe the reference's input-channel order of the
+ * first layer; the tensor-core layout stores features first so that gathered rows are 16-byte aligned. */
+int64_t pn2_packed_bytes(int L, const int *dims, int prec);
+int pn2_pack_weights(int L, const int *dims, const void *const *ptrs, float eps, int prec, int C, int order,
+                     void *packed, void *stream);
+
+/* Fused set abstraction: gather -> shared MLP (folded BN, ReLU) -> max over the K neighbours, the
+ * [B,S,K,Cin] tensor staying on chip -- PointNetSetAbstraction.forward :166-172 and one radius branch of
+ * PointNetSetAbstractionMsg.forward :204-218.
+ *   points [B,N,C] strided, feat [B,N,D] strided or NULL, centres [B,S,C] contiguous (unused for ALL),
+ *   idx32 [B,S,K] (unused for ALL: S=1, K=N).
+ *   out: pooled features, element (b,s,co) at out[b*ob + s*os + co_off + co]  (channels-last; co_off places
+ *   an MSG branch inside the concatenated tensor of :222).  When K rows span several tiles the kernel
+ *   combines with atomicMax and the caller must have zero-filled `out` (see pn2_sa_needs_zero_init). */
+int pn2_sa_needs_zero_init(int S, int K, int L, const int *dims, int prec);
+int pn2_sa_fused(const float *points, int64_t sb, int64_t sn, int64_t sc,
+                 const float *feat, int64_t fb, int64_t fn, int64_t fc,
+                 const float *centres, const int32_t *idx32,
+                 int B, int N, int S, int K, int C, int D, int order,
+                 int L, const int *dims, const void *packed, int prec,
+                 float *out, int64_t ob, int64_t os, int co_off, void *stream);
+
+/* Device self-test of the tcgen05 building blocks (one 128xN tile against a scalar loop in the same
+ * launch).  Returns 0 and writes max|err| to *max_err (device float). */
+int pn2_selftest_umma(int n_cols, int k_dim, int variant, float *max_err, float *dump, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PN2_H_ */

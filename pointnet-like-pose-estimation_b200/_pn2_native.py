@@ -1,0 +1,256 @@
+"""ctypes binding of libpn2_sm100.so (include/pn2.h) at tensor level.
+
+This is the only module that touches the C ABI.  Every method takes CUDA fp32 / int64 / int32 tensors,
+allocates the outputs with torch (the library never allocates), launches on the calling thread's current
+CUDA stream and maps a non-zero return code to RuntimeError(pn2_last_error_string()).  There is no CPU
+path: a CPU tensor, or a missing shared library, is an error.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_NAME = "libpn2_sm100.so"
+LIB_PATH = os.path.join(_HERE, LIB_NAME)
+
+ORDER_SSG, ORDER_MSG, ORDER_ALL = 0, 1, 2
+PREC_F32, PREC_BF16 = 0, 1
+MAX_COORD = 16
+ABI_VERSION = 3
+
+_i64, _i32, _f32, _vp = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+
+_SIGNATURES = {
+    "pn2_version": ([], _i32),
+    "pn2_last_error_string": ([], ctypes.c_char_p),
+    "pn2_fps_f32": ([_vp, _i64, _i64, _i64, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp], _i32),
+    "pn2_index_points_f32": ([_vp, _i64, _i64, _i64, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp], _i32),
+    "pn2_square_distance_f32": ([_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp], _i32),
+    "pn2_ball_query_f32": ([_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _i32,
+                            _vp, _vp, _vp, _vp], _i32),
+    "pn2_group_f32": ([_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _vp,
+                       _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp], _i32),
+    "pn2_packed_bytes": ([_i32, _vp, _i32], _i64),
+    "pn2_pack_weights": ([_i32, _vp, _vp, _f32, _i32, _i32, _i32, _vp, _vp], _i32),
+    "pn2_sa_needs_zero_init": ([_i32, _i32, _i32, _vp, _i32], _i32),
+    "pn2_sa_fused": ([_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _vp,
+                      _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32,
+                      _vp, _i64, _i64, _i32, _vp], _i32),
+    "pn2_selftest_umma": ([_i32, _i32, _i32, _vp, _vp, _vp], _i32),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library(path: str = LIB_PATH):
+    """dlopen the shared library and attach signatures.  Raises if it has not been built."""
+    global _lib
+    with _lib_lock:
+        if _lib is None:
+            if not os.path.exists(path):
+                raise ImportError(
+                    f"{path} is missing: build it with `python __graft_entry__.py build` "
+                    f"(nvcc -gencode arch=compute_100a,code=sm_100a); there is no fallback implementation")
+            lib = ctypes.CDLL(path)
+            for name, (argtypes, restype) in _SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.argtypes = argtypes
+                fn.restype = restype
+            if lib.pn2_version() != ABI_VERSION:
+                raise ImportError(f"{path}: ABI version {lib.pn2_version()} != {ABI_VERSION}; rebuild")
+            _lib = lib
+    return _lib
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _need_cuda(name: str, t: torch.Tensor, dtype) -> None:
+    if not isinstance(t, torch.Tensor) or t.device.type != "cuda":
+        dev = getattr(t, "device", type(t))
+        raise RuntimeError(f"pn2: `{name}` must be a CUDA tensor (got {dev}); this build has no CPU path")
+    if t.dtype != dtype:
+        raise RuntimeError(f"pn2: `{name}` must be {dtype} (got {t.dtype})")
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        msg = load_library().pn2_last_error_string().decode("utf-8", "replace")
+        raise RuntimeError(f"pn2 (rc={rc}): {msg}")
+
+
+def _dims_array(dims) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(dims, dtype=np.int32))
+
+
+class Native:
+    """Tensor-level façade over the C ABI; stateless apart from the loaded library."""
+
+    name = "sm_100a"
+
+    def __init__(self):
+        self.lib = load_library()
+
+    # -- sampling ------------------------------------------------------------------------------------------
+    def fps(self, points, start, number, want_idx64=True, want_idx32=False, want_new_points=False):
+        """points [B,N,C] (any strides), start [B] int64 -> (idx64 [B,S] | None, idx32 | None, new_points [B,S,C] | None)."""
+        _need_cuda("points", points, torch.float32)
+        _need_cuda("start", start, torch.int64)
+        B, N, C = points.shape
+        S = int(number)
+        dev = points.device
+        i64 = torch.empty(B, S, dtype=torch.int64, device=dev) if want_idx64 else None
+        i32 = torch.empty(B, S, dtype=torch.int32, device=dev) if want_idx32 else None
+        npts = torch.empty(B, S, C, dtype=torch.float32, device=dev) if want_new_points else None
+        start = start.contiguous()
+        with torch.cuda.device(dev):
+            _check(self.lib.pn2_fps_f32(points.data_ptr(), *points.stride(), B, N, C, start.data_ptr(), S,
+                                        i64.data_ptr() if want_idx64 else None,
+                                        i32.data_ptr() if want_idx32 else None,
+                                        npts.data_ptr() if want_new_points else None, _stream(points)))
+        return i64, i32, npts
+
+    def index_points(self, src, idx, check=True):
+        """src [B,N,C] strided, idx [B,...] int64 -> [B,...,C] contiguous."""
+        _need_cuda("points", src, torch.float32)
+        _need_cuda("idx", idx, torch.int64)
+        B, N, C = src.shape
+        idx_c = idx.contiguous()
+        M = idx_c.numel() // max(B, 1)
+        out = torch.empty(*idx.shape, C, dtype=torch.float32, device=src.device)
+        flag = torch.zeros(1, dtype=torch.int32, device=src.device) if check else None
+        with torch.cuda.device(src.device):
+            _check(self.lib.pn2_index_points_f32(src.data_ptr(), *src.stride(), B, N, C, idx_c.data_ptr(), M,
+                                                 out.data_ptr(), flag.data_ptr() if check else None, _stream(src)))
+        if check and int(flag.item()) != 0:
+            raise IndexError(f"index out of range in index_points (valid range [-{N}, {N}))")
+        return out
+
+    def square_distance(self, src, dst):
+        _need_cuda("src", src, torch.float32)
+        _need_cuda("dst", dst, torch.float32)
+        B, S, C = src.shape
+        N = dst.shape[1]
+        out = torch.empty(B, S, N, dtype=torch.float32, device=src.device)
+        with torch.cuda.device(src.device):
+            _check(self.lib.pn2_square_distance_f32(src.data_ptr(), *src.stride(), dst.data_ptr(), *dst.stride(),
+                                                    B, S, N, C, out.data_ptr(), _stream(src)))
+        return out
+
+    def ball_query(self, centres, points, r2, number, want_idx64=True, want_idx32=False):
+        """centres [B,S,C], points [B,N,C] (any strides), r2 = fp32(radius**2) -> (idx64 | None, idx32 | None) [B,S,K]."""
+        _need_cuda("new_points", centres, torch.float32)
+        _need_cuda("points", points, torch.float32)
+        B, N, C = points.shape
+        S = centres.shape[1]
+        K = int(number)
+        dev = points.device
+        i64 = torch.empty(B, S, K, dtype=torch.int64, device=dev) if want_idx64 else None
+        i32 = torch.empty(B, S, K, dtype=torch.int32, device=dev) if want_idx32 else None
+        with torch.cuda.device(dev):
+            _check(self.lib.pn2_ball_query_f32(centres.data_ptr(), *centres.stride(), points.data_ptr(), *points.stride(),
+                                               B, S, N, C, float(r2), K,
+                                               i64.data_ptr() if want_idx64 else None,
+                                               i32.data_ptr() if want_idx32 else None, None, _stream(points)))
+        return i64, i32
+
+    # -- grouping ------------------------------------------------------------------------------------------
+    def group(self, points, feature, idx32, centres, order):
+        """Materialised grouped rows [B,S,K,C+D] (SSG / MSG / group_all channel order)."""
+        _need_cuda("points", points, torch.float32)
+        B, N, C = points.shape
+        D = 0
+        fptr, fstr = None, (0, 0, 0)
+        if feature is not None:
+            _need_cuda("feature", feature, torch.float32)
+            D = feature.shape[-1]
+            fptr, fstr = feature.data_ptr(), feature.stride()
+        if order == ORDER_ALL:
+            S, K = 1, N
+            iptr = cptr = None
+        else:
+            _need_cuda("idx", idx32, torch.int32)
+            _need_cuda("new_points", centres, torch.float32)
+            idx32 = idx32.contiguous()
+            centres = centres.contiguous()
+            _, S, K = idx32.shape
+            iptr, cptr = idx32.data_ptr(), centres.data_ptr()
+        out = torch.empty(B, S, K, C + D, dtype=torch.float32, device=points.device)
+        with torch.cuda.device(points.device):
+            _check(self.lib.pn2_group_f32(points.data_ptr(), *points.stride(), fptr, *fstr, iptr, cptr,
+                                          B, N, S, K, C, D, order, out.data_ptr(), _stream(points)))
+        return out
+
+    # -- shared MLP ------------------------------------------------------------------------------------------
+    def pack(self, layers, eps, prec, C, order):
+        """layers: [(W [Cout,Cin(,1,1)], b, gamma, beta, mean, var)] CUDA fp32 -> (packed uint8 tensor, dims)."""
+        dims = [int(layers[0][0].shape[1])] + [int(l[0].shape[0]) for l in layers]
+        dev = layers[0][0].device
+        keep, ptrs = [], []
+        for tup in layers:
+            for t in tup:
+                _need_cuda("layer parameter", t, torch.float32)
+                t = t.detach().contiguous()
+                keep.append(t)
+                ptrs.append(t.data_ptr())
+        d = _dims_array(dims)
+        nbytes = self.lib.pn2_packed_bytes(len(layers), d.ctypes.data, prec)
+        if nbytes < 0:
+            _check(-1)
+        packed = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        parr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+        with torch.cuda.device(dev):
+            _check(self.lib.pn2_pack_weights(len(layers), d.ctypes.data, ctypes.cast(parr, _vp), float(eps), prec,
+                                             int(C), int(order), packed.data_ptr(), _stream(packed)))
+        return packed, dims
+
+    def sa_needs_zero(self, S, K, dims, prec) -> bool:
+        d = _dims_array(dims)
+        rc = self.lib.pn2_sa_needs_zero_init(int(S), int(K), len(dims) - 1, d.ctypes.data, prec)
+        if rc < 0:
+            _check(rc)
+        return bool(rc)
+
+    def sa_fused(self, points, feature, centres, idx32, order, dims, packed, prec, out, co_off=0):
+        """Fused gather -> MLP -> max.  out [B,S,Ctot] (channels-last) receives channels [co_off, co_off+dims[-1])."""
+        _need_cuda("points", points, torch.float32)
+        _need_cuda("out", out, torch.float32)
+        B, N, C = points.shape
+        D = 0
+        fptr, fstr = None, (0, 0, 0)
+        if feature is not None:
+            _need_cuda("feature", feature, torch.float32)
+            D = feature.shape[-1]
+            fptr, fstr = feature.data_ptr(), feature.stride()
+        if order == ORDER_ALL:
+            S, K = 1, N
+            iptr = cptr = None
+        else:
+            _need_cuda("idx", idx32, torch.int32)
+            _need_cuda("new_points", centres, torch.float32)
+            assert idx32.is_contiguous() and centres.is_contiguous()
+            _, S, K = idx32.shape
+            iptr, cptr = idx32.data_ptr(), centres.data_ptr()
+        assert out.shape[0] == B and out.shape[1] == S and out.stride(2) == 1
+        d = _dims_array(dims)
+        with torch.cuda.device(points.device):
+            _check(self.lib.pn2_sa_fused(points.data_ptr(), *points.stride(), fptr, *fstr, cptr, iptr,
+                                         B, N, S, K, C, D, order, len(dims) - 1, d.ctypes.data, packed.data_ptr(), prec,
+                                         out.data_ptr(), out.stride(0), out.stride(1), int(co_off), _stream(points)))
+        return out
+
+    def selftest_umma(self, n_cols, k_dim, variant, device="cuda:0", dump=False):
+        err = torch.full((1,), -1.0, dtype=torch.float32, device=device)
+        d = torch.zeros(128, n_cols, dtype=torch.float32, device=device) if dump else None
+        with torch.cuda.device(err.device):
+            _check(self.lib.pn2_selftest_umma(n_cols, k_dim, variant, err.data_ptr(),
+                                              d.data_ptr() if dump else None, _stream(err)))
+        return err, d

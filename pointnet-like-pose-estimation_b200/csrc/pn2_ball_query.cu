@@ -1,0 +1,273 @@
+// K2 -- ball query (reference: model/pointnet2_utils.py:70-90 on top of square_distance :5-26), plus the
+// stand-alone square_distance kernel.
+//
+// One CTA handles one cloud x a tile of centres.  The cloud (SoA coordinates + |p|^2, computed once per CTA
+// in the layout-dependent summation order) is staged in shared memory; one warp owns one centre at a time
+// and scans the points in index order, 32 per step: ballot + popc give each in-radius lane its output slot,
+// so the "first K in ascending index order" semantics of the reference's sort (:86) falls out without any
+// sort, and the scan stops as soon as K neighbours are found.  The [B,S,N] distance matrix and the
+// [B,S,N] int64 index tensor of the reference never exist.
+//
+// Exactness contract: dot = fl(s0*p0), dot = fma(s_k, p_k, dot) ascending k (MKL sgemm, :23);
+// d = fl(fl(-2*dot + |s|^2) + |p|^2); in radius <=> !(d > r2).
+#include "pn2_common.cuh"
+
+namespace pn2 {
+
+constexpr int BQ_WARPS = 8;
+constexpr int BQ_THREADS = BQ_WARPS * 32;
+
+template <int C>
+__device__ __forceinline__ float sqnorm(const float (&v)[C], bool contig)
+{
+    float t[C];
+#pragma unroll
+    for (int k = 0; k < C; ++k) t[k] = __fmul_rn(v[k], v[k]);
+    return contig ? sum_order<C, true>(t) : sum_order<C, false>(t);
+}
+
+template <int C>
+__device__ __forceinline__ float pair_dist(const float (&s)[C], const float *sp, int stride, int n, float s2, float p2)
+{
+    float dot = __fmul_rn(s[0], sp[n]);
+#pragma unroll
+    for (int k = 1; k < C; ++k) dot = __fmaf_rn(s[k], sp[k * stride + n], dot);
+    float d = __fmul_rn(-2.0f, dot);
+    d = __fadd_rn(d, s2);
+    return __fadd_rn(d, p2);
+}
+
+// smem: [C+1][NCH] floats (coords SoA then |p|^2), then per-warp staging rows [BQ_WARPS][K] int
+template <int C>
+__global__ void __launch_bounds__(BQ_THREADS)
+ball_query_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, int64_t csc,
+                  const float *__restrict__ points, int64_t sb, int64_t sn, int64_t sc,
+                  int S, int N, int NCH, int cpw /*centres per warp*/, float r2, int K,
+                  int64_t *__restrict__ idx64, int32_t *__restrict__ idx32, int32_t *__restrict__ empty_flag)
+{
+    extern __shared__ float smem[];
+    float *sp = smem;                       // [C][NCH]
+    float *sp2 = smem + (size_t)C * NCH;    // [NCH]
+    int *stage = (int *)(sp2 + NCH) + (threadIdx.x >> 5) * K;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    const int s_begin = (blockIdx.x * BQ_WARPS + warp) * cpw;
+    const float *P = points + (int64_t)b * sb;
+    const bool pcontig = (sc == 1);
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    const bool single_chunk = (NCH >= N);
+    // per-warp state for the multi-chunk path lives in registers for cpw == 1 only; otherwise the host
+    // guarantees single_chunk (see launcher).
+    int cnt = 0, first = N;
+    float s[C];
+    float s2 = 0.f;
+    const bool have = s_begin < S;
+    if (!single_chunk && have) {
+#pragma unroll
+        for (int k = 0; k < C; ++k) s[k] = __ldg(centres + (int64_t)b * csb + (int64_t)s_begin * csn + (int64_t)k * csc);
+        s2 = sqnorm<C>(s, csc == 1);
+    }
+
+    for (int n_base = 0; n_base < N; n_base += NCH) {
+        const int nc = min(NCH, N - n_base);
+        if (n_base) __syncthreads();
+        for (int n = tid; n < nc; n += BQ_THREADS) {
+            float v[C];
+#pragma unroll
+            for (int k = 0; k < C; ++k) {
+                v[k] = __ldg(P + (int64_t)(n_base + n) * sn + (int64_t)k * sc);
+                sp[k * NCH + n] = v[k];
+            }
+            sp2[n] = sqnorm<C>(v, pcontig);
+        }
+        __syncthreads();
+
+        if (single_chunk) {
+            for (int ci = 0; ci < cpw; ++ci) {
+                const int sidx = s_begin + ci;
+                if (sidx >= S) break;
+#pragma unroll
+                for (int k = 0; k < C; ++k) s[k] = __ldg(centres + (int64_t)b * csb + (int64_t)sidx * csn + (int64_t)k * csc);
+                s2 = sqnorm<C>(s, csc == 1);
+                cnt = 0; first = N;
+                for (int n0 = 0; n0 < nc && cnt < K; n0 += 64) {
+                    // two independent 32-point steps per trip for ILP
+                    const int na = n0 + lane, nb = n0 + 32 + lane;
+                    const float da = (na < nc) ? pair_dist<C>(s, sp, NCH, na, s2, sp2[na]) : 0.f;
+                    const float db = (nb < nc) ? pair_dist<C>(s, sp, NCH, nb, s2, sp2[nb]) : 0.f;
+                    const bool ina = (na < nc) && !(da > r2);
+                    const bool inb = (nb < nc) && !(db > r2);
+                    const unsigned ma = __ballot_sync(0xffffffffu, ina);
+                    const unsigned mb = __ballot_sync(0xffffffffu, inb);
+                    if (first == N) {
+                        if (ma) first = n0 + __ffs(ma) - 1;
+                        else if (mb) first = n0 + 32 + __ffs(mb) - 1;
+                    }
+                    const int pa = cnt + __popc(ma & lt_mask);
+                    if (ina && pa < K) stage[pa] = na;
+                    cnt += __popc(ma);
+                    const int pb = cnt + __popc(mb & lt_mask);
+                    if (inb && pb < K) stage[pb] = nb;
+                    cnt += __popc(mb);
+                }
+                if (cnt > K) cnt = K;
+                if (cnt == 0 && lane == 0 && empty_flag) atomicOr(empty_flag, 1);
+                __syncwarp();
+                const int64_t o = ((int64_t)b * S + sidx) * K;
+                for (int j = lane; j < K; j += 32) {
+                    const int v = (j < cnt) ? stage[j] : first;
+                    if (idx64) idx64[o + j] = v;
+                    if (idx32) idx32[o + j] = v;
+                }
+                __syncwarp();
+            }
+        } else if (have) {
+            for (int n0 = 0; n0 < nc && cnt < K; n0 += 32) {
+                const int na = n0 + lane;
+                const float da = (na < nc) ? pair_dist<C>(s, sp, NCH, na, s2, sp2[na]) : 0.f;
+                const bool ina = (na < nc) && !(da > r2);
+                const unsigned ma = __ballot_sync(0xffffffffu, ina);
+                if (first == N && ma) first = n_base + n0 + __ffs(ma) - 1;
+                const int pa = cnt + __popc(ma & lt_mask);
+                if (ina && pa < K) stage[pa] = n_base + na;
+                cnt += __popc(ma);
+            }
+        }
+    }
+    if (!single_chunk && have) {
+        if (cnt > K) cnt = K;
+        if (cnt == 0 && lane == 0 && empty_flag) atomicOr(empty_flag, 1);
+        __syncwarp();
+        const int64_t o = ((int64_t)b * S + s_begin) * K;
+        for (int j = lane; j < K; j += 32) {
+            const int v = (j < cnt) ? stage[j] : first;
+            if (idx64) idx64[o + j] = v;
+            if (idx32) idx32[o + j] = v;
+        }
+    }
+}
+
+// Run-time-C fallback (C <= PN2_MAX_COORD): one thread per centre, points streamed from global memory.
+__global__ void ball_query_generic_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, int64_t csc,
+                                          const float *__restrict__ points, int64_t sb, int64_t sn, int64_t sc,
+                                          int B, int S, int N, int C, float r2, int K,
+                                          int64_t *__restrict__ idx64, int32_t *__restrict__ idx32, int32_t *__restrict__ empty_flag)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (int64_t)B * S) return;
+    const int b = (int)(g / S);
+    const float *P = points + (int64_t)b * sb;
+    const float *cp = centres + (int64_t)b * csb + (g % S) * csn;
+    float s[PN2_MAX_COORD], t[PN2_MAX_COORD];
+    for (int k = 0; k < C; ++k) { s[k] = cp[k * csc]; t[k] = __fmul_rn(s[k], s[k]); }
+    const float s2 = sum_order_rt(t, C, csc == 1);
+    const bool pcontig = (sc == 1);
+    int cnt = 0, first = N;
+    for (int n = 0; n < N && cnt < K; ++n) {
+        float dot = 0.f;
+        for (int k = 0; k < C; ++k) {
+            const float x = __ldg(P + (int64_t)n * sn + (int64_t)k * sc);
+            t[k] = __fmul_rn(x, x);
+            dot = (k == 0) ? __fmul_rn(s[0], x) : __fmaf_rn(s[k], x, dot);
+        }
+        const float p2 = sum_order_rt(t, C, pcontig);
+        float d = __fmul_rn(-2.0f, dot);
+        d = __fadd_rn(d, s2);
+        d = __fadd_rn(d, p2);
+        if (!(d > r2)) {
+            if (cnt == 0) first = n;
+            if (idx64) idx64[g * K + cnt] = n;
+            if (idx32) idx32[g * K + cnt] = n;
+            ++cnt;
+        }
+    }
+    if (cnt == 0 && empty_flag) atomicOr(empty_flag, 1);
+    for (int j = cnt; j < K; ++j) {
+        if (idx64) idx64[g * K + j] = first;
+        if (idx32) idx32[g * K + j] = first;
+    }
+}
+
+template <int C>
+static int launch_bq_c(const float *centres, int64_t csb, int64_t csn, int64_t csc,
+                       const float *points, int64_t sb, int64_t sn, int64_t sc,
+                       int B, int S, int N, float r2, int K,
+                       int64_t *idx64, int32_t *idx32, int32_t *empty_flag, cudaStream_t st)
+{
+    const size_t stage_bytes = sizeof(int) * (size_t)BQ_WARPS * K;
+    const size_t budget = 200 * 1024 - stage_bytes;
+    int NCH = N, cpw;
+    if ((size_t)(C + 1) * N * sizeof(float) > budget) {
+        NCH = (int)(budget / ((C + 1) * sizeof(float))) & ~31;
+        cpw = 1;  // multi-chunk path keeps one centre per warp in registers
+    } else {
+        // enough CTAs for ~4 waves of 148 SMs, but amortise the staging of the cloud over >= 8 centres/warp
+        cpw = 8;
+        while (cpw > 1 && (int64_t)B * ((S + BQ_WARPS * cpw - 1) / (BQ_WARPS * cpw)) < 592) cpw >>= 1;
+    }
+    const size_t smem = (size_t)(C + 1) * NCH * sizeof(float) + stage_bytes;
+    auto kern = ball_query_kernel<C>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("ball_query: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    dim3 grid((S + BQ_WARPS * cpw - 1) / (BQ_WARPS * cpw), B);
+    kern<<<grid, BQ_THREADS, smem, st>>>(centres, csb, csn, csc, points, sb, sn, sc, S, N, NCH, cpw, r2, K,
+                                         idx64, idx32, empty_flag);
+    return launch_status("pn2_ball_query_f32");
+}
+
+int launch_ball_query(const float *centres, int64_t csb, int64_t csn, int64_t csc,
+                      const float *points, int64_t sb, int64_t sn, int64_t sc,
+                      int B, int S, int N, int C, float r2, int K,
+                      int64_t *idx64, int32_t *idx32, int32_t *empty_flag, cudaStream_t st)
+{
+    if (B == 0 || S == 0) return 0;
+    PN2_REQUIRE(B <= 65535, "pn2_ball_query_f32: B=%d exceeds gridDim.y", B);
+    if (C == 3) return launch_bq_c<3>(centres, csb, csn, csc, points, sb, sn, sc, B, S, N, r2, K, idx64, idx32, empty_flag, st);
+    if (C == 10) return launch_bq_c<10>(centres, csb, csn, csc, points, sb, sn, sc, B, S, N, r2, K, idx64, idx32, empty_flag, st);
+    const int64_t G = (int64_t)B * S;
+    ball_query_generic_kernel<<<(unsigned)((G + 127) / 128), 128, 0, st>>>(centres, csb, csn, csc, points, sb, sn, sc,
+                                                                            B, S, N, C, r2, K, idx64, idx32, empty_flag);
+    return launch_status("pn2_ball_query_f32(generic)");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// square_distance (pointnet2_utils.py:5-26): materialises [B,S,N]; only the stand-alone function uses it.
+__global__ void square_distance_kernel(const float *__restrict__ src, int64_t ssb, int64_t ssn, int64_t ssc,
+                                       const float *__restrict__ dst, int64_t dsb, int64_t dsn, int64_t dsc,
+                                       int S, int N, int C, float *__restrict__ out)
+{
+    const int b = blockIdx.z, s = blockIdx.y;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float sv[PN2_MAX_COORD], t[PN2_MAX_COORD], u[PN2_MAX_COORD];
+    const float *sp = src + (int64_t)b * ssb + (int64_t)s * ssn;
+    const float *dp = dst + (int64_t)b * dsb + (int64_t)n * dsn;
+    float dot = 0.f;
+    for (int k = 0; k < C; ++k) {
+        sv[k] = __ldg(sp + (int64_t)k * ssc);
+        const float x = __ldg(dp + (int64_t)k * dsc);
+        t[k] = __fmul_rn(sv[k], sv[k]);
+        u[k] = __fmul_rn(x, x);
+        dot = (k == 0) ? __fmul_rn(sv[0], x) : __fmaf_rn(sv[k], x, dot);
+    }
+    float d = __fmul_rn(-2.0f, dot);
+    d = __fadd_rn(d, sum_order_rt(t, C, ssc == 1));
+    d = __fadd_rn(d, sum_order_rt(u, C, dsc == 1));
+    out[((int64_t)b * S + s) * N + n] = d;
+}
+
+int launch_square_distance(const float *src, int64_t ssb, int64_t ssn, int64_t ssc,
+                           const float *dst, int64_t dsb, int64_t dsn, int64_t dsc,
+                           int B, int S, int N, int C, float *out, cudaStream_t st)
+{
+    if (B == 0 || S == 0 || N == 0) return 0;
+    PN2_REQUIRE(B <= 65535 && S <= 65535, "pn2_square_distance_f32: B=%d / S=%d exceed the grid limits", B, S);
+    dim3 grid((N + 255) / 256, S, B);
+    square_distance_kernel<<<grid, 256, 0, st>>>(src, ssb, ssn, ssc, dst, dsb, dsn, dsc, S, N, C, out);
+    return launch_status("pn2_square_distance_f32");
+}
+
+}  // namespace pn2

@@ -1,0 +1,131 @@
+// Internal helpers shared by the translation units of libpn2_sm100.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "pn2.h"
+
+namespace pn2 {
+
+void set_error(const char *fmt, ...);  // thread-local message behind pn2_last_error_string()
+
+#define PN2_REQUIRE(cond, ...)                 \
+    do {                                       \
+        if (!(cond)) {                         \
+            ::pn2::set_error(__VA_ARGS__);     \
+            return -1;                         \
+        }                                      \
+    } while (0)
+
+inline int launch_status(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+// Order in which ATen's CPU sum reduces the C squared terms of one point ("summation
+// order"): strided operand -> one accumulator; contiguous operand -> 4 interleaved partial sums
+// (C < 8) or 8 vector lanes + tail first (C >= 8).  Each add is rounded (no FMA, no reassociation).
+template <int C, bool CONTIG>
+__device__ __forceinline__ float sum_order(const float (&t)[C])
+{
+    if constexpr (!CONTIG) {
+        float a = t[0];
+#pragma unroll
+        for (int k = 1; k < C; ++k) a = __fadd_rn(a, t[k]);
+        return a;
+    } else if constexpr (C < 8) {
+        float p[4] = {0.f, 0.f, 0.f, 0.f};
+        constexpr int n4 = C / 4;
+#pragma unroll
+        for (int i = 0; i < n4; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) p[k] = (i == 0) ? t[k] : __fadd_rn(p[k], t[4 * i + k]);
+#pragma unroll
+        for (int k = 4 * n4; k < C; ++k) p[0] = (n4 == 0 && k == 0) ? t[0] : __fadd_rn(p[0], t[k]);
+        return __fadd_rn(__fadd_rn(__fadd_rn(p[0], p[1]), p[2]), p[3]);
+    } else {
+        float lane[8];
+        constexpr int n8 = C / 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) lane[j] = t[j];
+#pragma unroll
+        for (int i = 1; i < n8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) lane[j] = __fadd_rn(lane[j], t[8 * i + j]);
+        float a = 0.f;
+#pragma unroll
+        for (int k = 8 * n8; k < C; ++k) a = __fadd_rn(a, t[k]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a = __fadd_rn(a, lane[j]);
+        return a;
+    }
+}
+
+// Same rule for a run-time C (generic fallback kernels).
+__device__ __forceinline__ float sum_order_rt(const float *t, int C, bool contig)
+{
+    if (!contig) {
+        float a = t[0];
+        for (int k = 1; k < C; ++k) a = __fadd_rn(a, t[k]);
+        return a;
+    }
+    if (C < 8) {
+        float p[4] = {0.f, 0.f, 0.f, 0.f};
+        int n4 = C / 4;
+        for (int i = 0; i < n4; ++i)
+            for (int k = 0; k < 4; ++k) p[k] = __fadd_rn(p[k], t[4 * i + k]);
+        for (int k = 4 * n4; k < C; ++k) p[0] = __fadd_rn(p[0], t[k]);
+        return __fadd_rn(__fadd_rn(__fadd_rn(p[0], p[1]), p[2]), p[3]);
+    }
+    float lane[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int n8 = C / 8;
+    for (int i = 0; i < n8; ++i)
+        for (int j = 0; j < 8; ++j) lane[j] = __fadd_rn(lane[j], t[8 * i + j]);
+    float a = 0.f;
+    for (int k = 8 * n8; k < C; ++k) a = __fadd_rn(a, t[k]);
+    for (int j = 0; j < 8; ++j) a = __fadd_rn(a, lane[j]);
+    return a;
+}
+
+// per-translation-unit launchers (defined in the .cu files, called from pn2_api.cu)
+int launch_fps(const float *points, int64_t sb, int64_t sn, int64_t sc, int B, int N, int C,
+               const int64_t *start, int S, int64_t *idx64, int32_t *idx32, float *new_points, cudaStream_t st);
+int launch_index_points(const float *src, int64_t sb, int64_t sn, int64_t sc, int B, int N, int C,
+                        const int64_t *idx, int64_t M, float *out, int32_t *err_flag, cudaStream_t st);
+int launch_square_distance(const float *src, int64_t ssb, int64_t ssn, int64_t ssc,
+                           const float *dst, int64_t dsb, int64_t dsn, int64_t dsc,
+                           int B, int S, int N, int C, float *out, cudaStream_t st);
+int launch_ball_query(const float *centres, int64_t csb, int64_t csn, int64_t csc,
+                      const float *points, int64_t sb, int64_t sn, int64_t sc,
+                      int B, int S, int N, int C, float r2, int K,
+                      int64_t *idx64, int32_t *idx32, int32_t *empty_flag, cudaStream_t st);
+int launch_group(const float *points, int64_t sb, int64_t sn, int64_t sc,
+                 const float *feat, int64_t fb, int64_t fn, int64_t fc,
+                 const int32_t *idx32, const float *centres,
+                 int B, int N, int S, int K, int C, int D, int order, float *out, cudaStream_t st);
+
+struct SaArgs {
+    const float *points; int64_t sb, sn, sc;
+    const float *feat;   int64_t fb, fn, fc;
+    const float *centres; const int32_t *idx32;
+    int B, N, S, K, C, D, order;
+    int L; int dims[PN2_MAX_LAYERS + 1];
+    const void *packed;
+    float *out; int64_t ob, os; int co_off;
+};
+int64_t packed_bytes_f32(int L, const int *dims);
+int64_t packed_bytes_bf16(int L, const int *dims);
+int launch_pack_f32(int L, const int *dims, const void *const *ptrs, float eps, void *packed, cudaStream_t st);
+int launch_pack_bf16(int L, const int *dims, const void *const *ptrs, float eps, int C, int order, void *packed, cudaStream_t st);
+int sa_f32_needs_zero(int S, int K, int L, const int *dims);
+int sa_bf16_needs_zero(int S, int K, int L, const int *dims);
+int launch_sa_f32(const SaArgs &a, cudaStream_t st);
+int launch_sa_bf16(const SaArgs &a, cudaStream_t st);
+int launch_selftest_umma(int n_cols, int k_dim, int variant, float *max_err, float *dump, cudaStream_t st);
+
+}  // namespace pn2

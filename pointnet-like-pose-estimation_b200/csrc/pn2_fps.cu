@@ -1,0 +1,191 @@
+// K1 -- farthest point sampling, one CTA per cloud (reference: model/pointnet2_utils.py:47-68).
+//
+// The whole cloud lives on chip for the duration of the S sequential iterations: every thread keeps its
+// PPT points and their running min-distances in registers, a structure-of-arrays copy of the cloud in
+// shared memory serves the (broadcast) read of the newly chosen centroid, and the per-iteration argmax is
+// two REDUX instructions per warp + one 8-byte shared-memory slot per warp + ONE __syncthreads (slots are
+// double-buffered by iteration parity).  No global-memory round trip inside the loop; the only global
+// traffic per iteration is the fire-and-forget store of the chosen index / centroid row.
+//
+// Exactness contract: d = sum_order_k( fl( fl(p_k - c_k)^2 ) ) with separately rounded sub, mul
+// and adds; dist = d if d < dist (NaN never replaces -> fminf); argmax with lowest index on ties.
+#include "pn2_common.cuh"
+
+namespace pn2 {
+
+__device__ __forceinline__ unsigned redux_max(unsigned v) { return __reduce_max_sync(0xffffffffu, v); }
+__device__ __forceinline__ unsigned redux_min(unsigned v) { return __reduce_min_sync(0xffffffffu, v); }
+
+template <int C, int PPT, bool CONTIG, int TMAX>
+__global__ void __launch_bounds__(TMAX) fps_kernel(const float *__restrict__ points, int64_t sb, int64_t sn, int64_t sc, int N,
+                           const int64_t *__restrict__ start, int S,
+                           int64_t *__restrict__ idx64, int32_t *__restrict__ idx32, float *__restrict__ new_points)
+{
+    extern __shared__ float s_pts[];            // [C][Npad]  (Npad = PPT * blockDim.x)
+    __shared__ uint2 s_slot[2][32];             // per-warp (dist bits, index), double-buffered
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+    const int Npad = PPT * T;
+    const int b = blockIdx.x;
+    const float *P = points + (int64_t)b * sb;
+
+    float p[PPT][C];
+    float dist[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        const int n = tid + j * T;
+        const bool ok = n < N;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            float v = ok ? __ldg(P + (int64_t)n * sn + (int64_t)k * sc) : 0.f;
+            p[j][k] = v;
+            s_pts[k * Npad + n] = v;
+        }
+        dist[j] = ok ? 1e10f : 0.f;             // padding can never win: dist 0 and index >= N
+    }
+    int far = (int)start[b];
+    __syncthreads();
+
+    for (int i = 0; i < S; ++i) {
+        float c[C];
+#pragma unroll
+        for (int k = 0; k < C; ++k) c[k] = s_pts[k * Npad + far];
+        if (tid == 0) {
+            if (idx64) idx64[(int64_t)b * S + i] = far;
+            if (idx32) idx32[(int64_t)b * S + i] = far;
+        }
+        if (new_points && tid < C) new_points[((int64_t)b * S + i) * C + tid] = s_pts[tid * Npad + far];
+
+        float best = -1.f;
+        unsigned besti = 0xffffffffu;
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            float t[C];
+#pragma unroll
+            for (int k = 0; k < C; ++k) {
+                const float df = __fsub_rn(p[j][k], c[k]);
+                t[k] = __fmul_rn(df, df);
+            }
+            const float d = sum_order<C, CONTIG>(t);
+            dist[j] = fminf(dist[j], d);        // d < dist ? d : dist, NaN never replaces
+            if (dist[j] > best) { best = dist[j]; besti = (unsigned)(tid + j * T); }
+        }
+        // warp argmax: dist >= +0 so the bit pattern orders like the value; lowest index among equals
+        const unsigned bits = __float_as_uint(best);
+        const unsigned wmax = redux_max(bits);
+        const unsigned widx = redux_min(bits == wmax ? besti : 0xffffffffu);
+        if (lane == 0) s_slot[i & 1][warp] = make_uint2(wmax, widx);
+        __syncthreads();
+        const uint2 sl = (lane < nwarps) ? s_slot[i & 1][lane] : make_uint2(0u, 0xffffffffu);
+        const unsigned gmax = redux_max(sl.x);
+        far = (int)redux_min(sl.x == gmax ? sl.y : 0xffffffffu);
+    }
+}
+
+// Generic fallback: any C <= PN2_MAX_COORD, any N whose distance array fits in shared memory; points are
+// re-read from global memory (L1/L2) every iteration.
+__global__ void fps_generic_kernel(const float *__restrict__ points, int64_t sb, int64_t sn, int64_t sc, int N, int C,
+                                   const int64_t *__restrict__ start, int S,
+                                   int64_t *__restrict__ idx64, int32_t *__restrict__ idx32, float *__restrict__ new_points)
+{
+    extern __shared__ float s_dist[];           // [N]
+    __shared__ uint2 s_slot[2][32];
+    __shared__ float s_c[PN2_MAX_COORD];
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+    const int b = blockIdx.x;
+    const bool contig = (sc == 1);
+    const float *P = points + (int64_t)b * sb;
+    for (int n = tid; n < N; n += T) s_dist[n] = 1e10f;
+    int far = (int)start[b];
+    __syncthreads();
+    for (int i = 0; i < S; ++i) {
+        if (tid < C) {
+            const float v = __ldg(P + (int64_t)far * sn + (int64_t)tid * sc);
+            s_c[tid] = v;
+            if (new_points) new_points[((int64_t)b * S + i) * C + tid] = v;
+        }
+        if (tid == 0) {
+            if (idx64) idx64[(int64_t)b * S + i] = far;
+            if (idx32) idx32[(int64_t)b * S + i] = far;
+        }
+        __syncthreads();
+        float best = -1.f;
+        unsigned besti = 0xffffffffu;
+        for (int n = tid; n < N; n += T) {
+            float t[PN2_MAX_COORD];
+            for (int k = 0; k < C; ++k) {
+                const float df = __fsub_rn(__ldg(P + (int64_t)n * sn + (int64_t)k * sc), s_c[k]);
+                t[k] = __fmul_rn(df, df);
+            }
+            const float d = sum_order_rt(t, C, contig);
+            const float nd = fminf(s_dist[n], d);
+            s_dist[n] = nd;
+            if (nd > best) { best = nd; besti = (unsigned)n; }
+        }
+        const unsigned bits = (besti == 0xffffffffu) ? 0u : __float_as_uint(best);
+        const unsigned wmax = redux_max(bits);
+        const unsigned widx = redux_min(bits == wmax ? besti : 0xffffffffu);
+        if (lane == 0) s_slot[i & 1][warp] = make_uint2(wmax, widx);
+        __syncthreads();
+        const uint2 sl = (lane < nwarps) ? s_slot[i & 1][lane] : make_uint2(0u, 0xffffffffu);
+        const unsigned gmax = redux_max(sl.x);
+        far = (int)redux_min(sl.x == gmax ? sl.y : 0xffffffffu);
+    }
+}
+
+template <int C, int PPT, int TMAX>
+static int launch_fps_t(const float *points, int64_t sb, int64_t sn, int64_t sc, int B, int N, int threads,
+                        const int64_t *start, int S, int64_t *idx64, int32_t *idx32, float *new_points, cudaStream_t st)
+{
+    const size_t smem = sizeof(float) * (size_t)C * PPT * threads;
+    auto run = [&](auto kern) -> int {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { set_error("fps: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+        }
+        kern<<<B, threads, smem, st>>>(points, sb, sn, sc, N, start, S, idx64, idx32, new_points);
+        return launch_status("pn2_fps_f32");
+    };
+    return (sc == 1) ? run(fps_kernel<C, PPT, true, TMAX>) : run(fps_kernel<C, PPT, false, TMAX>);
+}
+
+// threads and points-per-thread: keep the per-thread serial work small (the loop is latency-bound) but do
+// not pay for more warps in the barrier than the cloud needs.  Returns -100 when the cloud is not covered
+// by the register-resident kernel (register budget: 64K / threads).
+template <int C>
+static int launch_fps_c(const float *points, int64_t sb, int64_t sn, int64_t sc, int B, int N,
+                        const int64_t *start, int S, int64_t *idx64, int32_t *idx32, float *new_points, cudaStream_t st)
+{
+#define PN2_FPS_GO(P, TM, T) return launch_fps_t<C, P, TM>(points, sb, sn, sc, B, N, T, start, S, idx64, idx32, new_points, st)
+    if (N <= 128)  PN2_FPS_GO(2, 128, 64);
+    if (N <= 256)  PN2_FPS_GO(2, 128, 128);
+    if (N <= 512)  PN2_FPS_GO(4, 512, 128);
+    if (N <= 1024) PN2_FPS_GO(4, 512, 256);
+    if (N <= 2048) PN2_FPS_GO(4, 512, 512);
+    if constexpr (C <= 4) {
+        if (N <= 4096) PN2_FPS_GO(4, 1024, 1024);
+        if (N <= 8192) PN2_FPS_GO(8, 1024, 1024);
+    }
+#undef PN2_FPS_GO
+    return -100;
+}
+
+int launch_fps(const float *points, int64_t sb, int64_t sn, int64_t sc, int B, int N, int C,
+               const int64_t *start, int S, int64_t *idx64, int32_t *idx32, float *new_points, cudaStream_t st)
+{
+    if (B == 0 || S == 0) return 0;
+    int rc = -100;
+    if (C == 3) rc = launch_fps_c<3>(points, sb, sn, sc, B, N, start, S, idx64, idx32, new_points, st);
+    else if (C == 10) rc = launch_fps_c<10>(points, sb, sn, sc, B, N, start, S, idx64, idx32, new_points, st);
+    if (rc != -100) return rc;
+    const size_t smem = sizeof(float) * (size_t)N;
+    PN2_REQUIRE(smem <= 200 * 1024, "pn2_fps_f32: N=%d too large for the generic kernel (C=%d)", N, C);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(fps_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("fps: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    const int threads = N <= 256 ? 128 : (N <= 2048 ? 256 : 1024);
+    fps_generic_kernel<<<B, threads, smem, st>>>(points, sb, sn, sc, N, C, start, S, idx64, idx32, new_points);
+    return launch_status("pn2_fps_f32(generic)");
+}
+
+}  // namespace pn2

@@ -1,0 +1,730 @@
+// K3 (bf16 mode) -- fused set abstraction on the 5th-generation tensor cores:
+//   gather -> [tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) -> +bias -> ReLU -> bf16 back to smem] x L -> max over K
+// (reference: model/pointnet2_utils.py:166-172 and :204-218; BatchNorm folded by pn2_pack_weights).
+//
+// Shape of the computation.  A tile is 128 grouped rows (= the 128 TMEM lanes = UMMA_M of a cta_group::1
+// MMA): 128/K whole groups, or a 128-row slice of one large group.  Activations never leave the SM: the
+// gathered rows are written as bf16 into a shared-memory A operand, every layer's accumulator lives in
+// TMEM, the epilogue reads it back with tcgen05.ld (one row per thread), applies bias + ReLU and writes
+// the next layer's A operand; after the last layer the K rows of a group are max-reduced with a
+// warp-shuffle reduce-scatter (rows of a group are adjacent TMEM lanes) and only [groups x Cout] floats
+// reach HBM.  Weights are pre-packed by pn2_pack_weights into exactly the shared-memory image the MMA wants
+// and arrive through the TMA bulk-copy engine (cp.async.bulk + mbarrier), either once per CTA (all layers
+// fit next to the activations) or through an mbarrier ring fed by a dedicated producer warp.
+//
+// Operand layout (both A and B): canonical K-major, no swizzle -- 8x8 bf16 "core matrices" of 128 contiguous
+// bytes; rows at 16 B pitch inside a column of core matrices (SBO = 128 B), consecutive k-groups of 8 at
+// LBO bytes.  For A, LBO = 128*16 + 16: the 16 B of padding spreads the gather's stores over all banks.
+#include <cuda_bf16.h>
+#include "pn2_common.cuh"
+
+namespace pn2 {
+
+constexpr int TC_ROWS = 128;
+constexpr int TC_CWARPS = 8;                       // compute warps (gather, MMA issue, epilogue)
+constexpr int TC_CTHREADS = TC_CWARPS * 32;        // 256
+constexpr int TC_THREADS = TC_CTHREADS + 32;       // + 1 producer warp for the weight ring
+constexpr int A_LBO = TC_ROWS * 16 + 16;           // bytes between k-groups of the A operand
+constexpr int KBLK = 64;                           // k extent of one weight chunk
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_SMEM_LIMIT = 227 * 1024;
+
+static inline int rup(int x, int a) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------------
+// Packed layout shared by host (pack + launch) and device.
+// ------------------------------------------------------------------------------------------------------
+struct TcLayer {
+    int K;        // padded input channels (multiple of 16)
+    int Cout;     // real output channels
+    int Npad;     // output channels padded to 32 (= next layer's K)
+    int NS;       // columns per MMA slab (<= 256, divides Npad)
+    int nslab;
+    int nkb;      // number of 64-wide k blocks
+    int w_off;    // byte offset of this layer's first chunk inside the packed buffer
+    int b_off;    // float offset of this layer's bias inside the bias block
+};
+struct TcLayout {
+    int L;
+    TcLayer ly[PN2_MAX_LAYERS];
+    int w_bytes;       // all weight chunks
+    int bias_floats;   // sum of Npad
+    int max_chunk;     // bytes of the largest chunk
+    int n_chunks;
+};
+
+static __host__ __device__ inline int tc_chunk_bytes(const TcLayer &ly, int kb)
+{
+    const int kw = (ly.K - kb * KBLK) < KBLK ? (ly.K - kb * KBLK) : KBLK;
+    return ly.NS * kw * 2;
+}
+
+static TcLayout tc_layout(int L, const int *dims)
+{
+    TcLayout t;
+    t.L = L; t.w_bytes = 0; t.bias_floats = 0; t.max_chunk = 0; t.n_chunks = 0;
+    int K = rup(dims[0], 16);
+    for (int l = 0; l < L; ++l) {
+        TcLayer &y = t.ly[l];
+        y.K = K; y.Cout = dims[l + 1]; y.Npad = rup(dims[l + 1], 32);
+        y.NS = 32;
+        for (int ns = 256; ns >= 32; ns >>= 1) if (y.Npad % ns == 0) { y.NS = ns; break; }
+        y.nslab = y.Npad / y.NS;
+        y.nkb = (K + KBLK - 1) / KBLK;
+        y.w_off = t.w_bytes; y.b_off = t.bias_floats;
+        t.w_bytes += y.Npad * K * 2;
+        t.bias_floats += y.Npad;
+        for (int kb = 0; kb < y.nkb; ++kb) { const int c = tc_chunk_bytes(y, kb); if (c > t.max_chunk) t.max_chunk = c; }
+        t.n_chunks += y.nslab * y.nkb;
+        K = y.Npad;
+    }
+    return t;
+}
+
+int64_t packed_bytes_bf16(int L, const int *dims)
+{
+    const TcLayout t = tc_layout(L, dims);
+    return (int64_t)t.w_bytes + (int64_t)t.bias_floats * 4;
+}
+
+struct TcPackArgs {
+    TcLayout lay;
+    int dims[PN2_MAX_LAYERS + 1];
+    const float *w[PN2_MAX_LAYERS], *b[PN2_MAX_LAYERS], *g[PN2_MAX_LAYERS], *be[PN2_MAX_LAYERS],
+        *mu[PN2_MAX_LAYERS], *var[PN2_MAX_LAYERS];
+    float eps;
+    int C, D, order;   // layer-0 column permutation: internal order is [feat(D), xyz(C), 0-pad]
+};
+
+__global__ void pack_bf16_kernel(TcPackArgs a, unsigned char *__restrict__ packed)
+{
+    float *bias_out = reinterpret_cast<float *>(packed + a.lay.w_bytes);
+    for (int l = 0; l < a.lay.L; ++l) {
+        const TcLayer y = a.lay.ly[l];
+        const int cin = a.dims[l];
+        const int64_t nW = (int64_t)y.Npad * y.K;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nW + y.Npad; i += (int64_t)gridDim.x * blockDim.x) {
+            const bool is_bias = i >= nW;
+            const int n = is_bias ? (int)(i - nW) : (int)(i / y.K);
+            const int k = is_bias ? 0 : (int)(i % y.K);
+            float s = 0.f;
+            if (n < y.Cout) s = __fdiv_rn(a.g[l][n], __fsqrt_rn(__fadd_rn(a.var[l][n], a.eps)));
+            if (is_bias) {
+                float v = 0.f;
+                if (n < y.Cout) v = __fadd_rn(__fmul_rn(__fsub_rn(a.b[l][n], a.mu[l][n]), s), a.be[l][n]);
+                bias_out[y.b_off + n] = v;
+                continue;
+            }
+            int src = k;                       // column of the reference's weight matrix
+            if (l == 0) {
+                const int xo = (a.order == PN2_ORDER_MSG) ? a.D : 0;
+                const int fo = (a.order == PN2_ORDER_MSG) ? 0 : a.C;
+                if (k < a.D) src = fo + k;
+                else if (k < a.D + a.C) src = xo + (k - a.D);
+                else src = -1;
+            } else if (k >= cin) src = -1;
+            float v = 0.f;
+            if (n < y.Cout && src >= 0) v = __fmul_rn(a.w[l][(int64_t)n * cin + src], s);
+            // chunk (slab, kb) then canonical no-swizzle K-major inside the chunk
+            const int slab = n / y.NS, nl = n % y.NS, kb = k / KBLK, kl = k % KBLK;
+            int64_t off = y.w_off + (int64_t)slab * y.NS * y.K * 2 + (int64_t)kb * y.NS * KBLK * 2;
+            off += (int64_t)(kl / 8) * (y.NS * 16) + nl * 16 + (kl % 8) * 2;
+            *reinterpret_cast<__nv_bfloat16 *>(packed + off) = __float2bfloat16_rn(v);
+        }
+    }
+}
+
+int launch_pack_bf16(int L, const int *dims, const void *const *ptrs, float eps, int C, int order, void *packed, cudaStream_t st)
+{
+    TcPackArgs a;
+    a.lay = tc_layout(L, dims);
+    a.eps = eps; a.C = C; a.D = dims[0] - C; a.order = order;
+    for (int l = 0; l <= L; ++l) a.dims[l] = dims[l];
+    for (int l = 0; l < L; ++l) {
+        a.w[l] = (const float *)ptrs[6 * l + 0]; a.b[l] = (const float *)ptrs[6 * l + 1];
+        a.g[l] = (const float *)ptrs[6 * l + 2]; a.be[l] = (const float *)ptrs[6 * l + 3];
+        a.mu[l] = (const float *)ptrs[6 * l + 4]; a.var[l] = (const float *)ptrs[6 * l + 5];
+    }
+    pack_bf16_kernel<<<148, 256, 0, st>>>(a, (unsigned char *)packed);
+    return launch_status("pn2_pack_weights(bf16)");
+}
+
+// ------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate, M = 128, N from idesc, K = 16
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1 = Blackwell)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = bf16, both K-major, M = 128
+__device__ __forceinline__ uint32_t instr_desc_bf16(int n)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
+{
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void cbar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_CTHREADS) : "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
+{
+    const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits)
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+
+// one reduce-scatter step of the max over rows: N live columns -> N/2; partner = lane ^ o
+template <int N>
+__device__ __forceinline__ void rs_step(float (&v)[32], int o, bool upper)
+{
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) {
+        const float a = v[j], b = v[j + N / 2];
+        const float keep = upper ? b : a, send = upper ? a : b;
+        v[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, o));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Kernel
+// ------------------------------------------------------------------------------------------------------
+struct TcParams {
+    const float *points; int64_t sb, sn, sc;
+    const float *feat;   int64_t fb, fn, fc;
+    const float *centres; const int32_t *idx32;
+    int N, S, K, C, D, order;
+    TcLayout lay;
+    const unsigned char *packed;
+    float *out; int64_t ob, os; int co_off;
+    int64_t G;
+    int gpt;           // groups per tile (1, 2 or 128/K)
+    int cpg;           // 128-row chunks per group (K > 128) else 1
+    int64_t tiles;
+    int Kl;            // lanes of a warp that hold rows of the same group (min(K,32) for power-of-two K <= 32, else 32)
+    int direct;        // K <= 32: pooled rows are stored straight from the warp
+    int use_atomic;    // K > 128: combine tiles of a group with atomicMax
+    int feat_fast;     // features can be gathered as 32-byte row segments
+    int tmem_cols;
+    int resident;      // all weight chunks stay in shared memory for the life of the CTA
+    int nstage, stage_bytes;
+    int a_bytes[2];    // activation buffers
+    int pool_cols;     // columns of the cross-warp pooling scratch (0 if direct)
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    // carve-up (all offsets multiples of 16)
+    unsigned char *A[2] = {smem, smem + p.a_bytes[0]};
+    unsigned char *Wsm = A[1] + p.a_bytes[1];
+    const int w_region = p.resident ? p.lay.w_bytes : p.nstage * p.stage_bytes;
+    float *bias_s = reinterpret_cast<float *>(Wsm + w_region);
+    float *pool_s = bias_s + p.lay.bias_floats;                 // [4][pool_cols]
+    int *s_n = reinterpret_cast<int *>(pool_s + 4 * p.pool_cols);
+    int *s_g = s_n + TC_ROWS;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(s_g + TC_ROWS);
+    uint64_t *empty_bar = full_bar + TC_MAX_STAGES;
+    uint64_t *acc_bar = empty_bar + TC_MAX_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_bar + 1);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const TcLayout &lay = p.lay;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+        mbar_init(acc_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    {
+        const float *bsrc = reinterpret_cast<const float *>(p.packed + lay.w_bytes);
+        for (int i = tid; i < lay.bias_floats; i += TC_THREADS) bias_s[i] = __ldg(bsrc + i);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // =====================================================================================================
+    // producer warp: weights -> shared memory through the bulk-copy engine
+    // =====================================================================================================
+    if (warp == TC_CWARPS) {
+        if (lane == 0) {
+            if (p.resident) {
+                mbar_expect_tx(full_bar, (uint32_t)lay.w_bytes);
+                int off = 0;
+                for (int l = 0; l < lay.L; ++l)
+                    for (int sl = 0; sl < lay.ly[l].nslab; ++sl)
+                        for (int kb = 0; kb < lay.ly[l].nkb; ++kb) {
+                            const int cb = tc_chunk_bytes(lay.ly[l], kb);
+                            bulk_g2s(Wsm + off, p.packed + off, (uint32_t)cb, full_bar);
+                            off += cb;
+                        }
+            } else {
+                uint32_t q = 0;
+                for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+                    int off = 0;
+                    for (int l = 0; l < lay.L; ++l)
+                        for (int sl = 0; sl < lay.ly[l].nslab; ++sl)
+                            for (int kb = 0; kb < lay.ly[l].nkb; ++kb, ++q) {
+                                const int cb = tc_chunk_bytes(lay.ly[l], kb);
+                                const int s = q % p.nstage;
+                                const uint32_t ph = (q / p.nstage) & 1u;
+                                mbar_wait(empty_bar + s, ph ^ 1u);
+                                mbar_expect_tx(full_bar + s, (uint32_t)cb);
+                                bulk_g2s(Wsm + (size_t)s * p.stage_bytes, p.packed + off, (uint32_t)cb, full_bar + s);
+                                off += cb;
+                            }
+                }
+            }
+        }
+        // the producer warp takes no further part (it must not fall through to the TMEM dealloc barrier
+        // before its copies are consumed: the compute warps wait on every full barrier they were promised)
+    } else {
+        // =================================================================================================
+        // compute warps
+        // =================================================================================================
+        const int q4 = warp & 3;            // TMEM lane quarter of this warp
+        const int half = warp >> 2;         // which 32-column blocks of a round this warp drains
+        const int row = q4 * 32 + lane;     // the tile row (= TMEM lane) this thread owns in the epilogue
+        const int K = p.K, C = p.C, D = p.D;
+        uint32_t acc_phase = 0, wq = 0;
+        if (p.resident && tid == 0) mbar_wait(full_bar, 0);
+
+        for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+            cbar_sync();
+            // ---- row bookkeeping ------------------------------------------------------------------------
+            if (tid < TC_ROWS) {
+                const int r = tid;
+                int64_t g; int j;
+                if (p.cpg == 1) { g = tile * p.gpt + r / K; j = r % K; if (r >= p.gpt * K) g = p.G; }
+                else            { g = tile / p.cpg; j = (int)(tile % p.cpg) * TC_ROWS + r; }
+                int n = -1;
+                if (g < p.G && j < K) n = (p.order == PN2_ORDER_ALL) ? j : __ldg(p.idx32 + g * K + j);
+                if (n >= p.N) n = -1;            // 'no neighbour' marker of an empty ball (pointnet2_utils.py:85)
+                s_n[r] = n; s_g[r] = (int)g;
+            }
+            cbar_sync();
+            // ---- gather: layer-0 A operand, internal channel order [feat(D), xyz(C), zero pad] ------------
+            {
+                unsigned char *A0 = A[0];
+                const int K0 = lay.ly[0].K;
+                if (p.feat_fast) {
+                    const int cpr = D / 8;                               // 16-byte chunks per row
+                    for (int it = tid; it < TC_ROWS * cpr; it += TC_CTHREADS) {
+                        const int r = it / cpr, kg = it % cpr;
+                        const int n = s_n[r];
+                        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                        if (n >= 0) {
+                            const float *f = p.feat + (int64_t)(s_g[r] / p.S) * p.fb + (int64_t)n * p.fn + kg * 8;
+                            const float4 x = __ldg(reinterpret_cast<const float4 *>(f));
+                            const float4 y = __ldg(reinterpret_cast<const float4 *>(f) + 1);
+                            o = make_uint4(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w), pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+                        }
+                        *reinterpret_cast<uint4 *>(A0 + (size_t)kg * A_LBO + r * 16) = o;
+                    }
+                    if (tid < TC_ROWS) {                                  // xyz + zero padding: k in [D, K0)
+                        const int r = tid, n = s_n[r];
+                        const int64_t g = s_g[r];
+                        for (int kg = D / 8; kg < K0 / 8; ++kg) {
+                            float v[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int c = kg * 8 + i - D;
+                                float x = 0.f;
+                                if (n >= 0 && c < C) {
+                                    x = __ldg(p.points + (g / p.S) * p.sb + (int64_t)n * p.sn + (int64_t)c * p.sc);
+                                    if (p.order != PN2_ORDER_ALL) x = __fsub_rn(x, __ldg(p.centres + g * C + c));
+                                }
+                                v[i] = x;
+                            }
+                            *reinterpret_cast<uint4 *>(A0 + (size_t)kg * A_LBO + r * 16) =
+                                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                        }
+                    }
+                } else {
+                    // generic strides / D not a multiple of 8: one element at a time
+                    for (int it = tid; it < TC_ROWS * K0; it += TC_CTHREADS) {
+                        const int r = it % TC_ROWS, k = it / TC_ROWS;
+                        const int n = s_n[r];
+                        float x = 0.f;
+                        if (n >= 0) {
+                            const int64_t g = s_g[r];
+                            const int64_t b = g / p.S;
+                            if (k < D) x = __ldg(p.feat + b * p.fb + (int64_t)n * p.fn + (int64_t)k * p.fc);
+                            else if (k < D + C) {
+                                const int c = k - D;
+                                x = __ldg(p.points + b * p.sb + (int64_t)n * p.sn + (int64_t)c * p.sc);
+                                if (p.order != PN2_ORDER_ALL) x = __fsub_rn(x, __ldg(p.centres + g * C + c));
+                            }
+                        }
+                        *reinterpret_cast<__nv_bfloat16 *>(A0 + (size_t)(k / 8) * A_LBO + r * 16 + (k % 8) * 2) = __float2bfloat16_rn(x);
+                    }
+                }
+            }
+            fence_proxy_async();     // generic-proxy stores -> visible to the tensor core's async proxy
+
+            const bool row_valid = s_n[row] >= 0;   // written before the last cbar_sync
+            // ---- layers ---------------------------------------------------------------------------------------
+            for (int l = 0; l < lay.L; ++l) {
+                const TcLayer ly = lay.ly[l];
+                const bool last = (l == lay.L - 1);
+                const uint32_t a_in = smem_u32(A[l & 1]);
+                unsigned char *a_out = A[(l + 1) & 1];
+                const int slabs_per_round = p.tmem_cols / ly.NS;
+                const uint32_t idesc = instr_desc_bf16(ly.NS);
+                for (int sl0 = 0; sl0 < ly.nslab; sl0 += slabs_per_round) {
+                    const int sl1 = min(ly.nslab, sl0 + slabs_per_round);
+                    tc_fence_before();
+                    cbar_sync();       // A operand complete / previous round's TMEM reads and pool scratch drained
+                    if (tid == 0) {
+                        tc_fence_after();
+                        for (int sl = sl0; sl < sl1; ++sl) {
+                            const uint32_t d_tmem = tmem_base + (uint32_t)((sl - sl0) * ly.NS);
+                            for (int kb = 0; kb < ly.nkb; ++kb) {
+                                uint32_t w_addr;
+                                int s = 0;
+                                if (p.resident) {
+                                    w_addr = smem_u32(Wsm) + (uint32_t)(ly.w_off + sl * ly.NS * ly.K * 2 + kb * ly.NS * KBLK * 2);
+                                } else {
+                                    s = wq % p.nstage;
+                                    mbar_wait(full_bar + s, (wq / p.nstage) & 1u);
+                                    tc_fence_after();
+                                    w_addr = smem_u32(Wsm) + (uint32_t)(s * p.stage_bytes);
+                                    ++wq;
+                                }
+                                const int kw = min(KBLK, ly.K - kb * KBLK);
+                                for (int j = 0; j < kw / 16; ++j) {
+                                    const uint64_t ad = smem_desc(a_in + (uint32_t)((kb * 8 + j * 2) * A_LBO), A_LBO, 128);
+                                    const uint64_t bd = smem_desc(w_addr + (uint32_t)(j * 2 * ly.NS * 16), (uint32_t)(ly.NS * 16), 128);
+                                    umma_bf16(d_tmem, ad, bd, idesc, (kb | j) ? 1u : 0u);
+                                }
+                                if (!p.resident) umma_commit(empty_bar + s);   // frees the ring slot when these MMAs retire
+                            }
+                        }
+                        umma_commit(acc_bar);
+                    }
+                    __syncwarp();
+                    mbar_wait(acc_bar, acc_phase);
+                    acc_phase ^= 1u;
+                    tc_fence_after();
+
+                    // ---- epilogue of this round: columns [sl0*NS, sl1*NS) -----------------------------------------
+                    const int ncols = (sl1 - sl0) * ly.NS;
+                    const int col_base = sl0 * ly.NS;               // column inside the layer
+                    for (int blk = half; blk < ncols / 32; blk += 2) {
+                        float v[32];
+                        tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(blk * 32), v);
+                        const int c0 = col_base + blk * 32;
+                        if (!last) {
+                            const float *bs = bias_s + ly.b_off + c0;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bs[i], 0.f);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                *reinterpret_cast<uint4 *>(a_out + (size_t)(c0 / 8 + i) * A_LBO + row * 16) =
+                                    make_uint4(pack_bf16x2(v[8 * i + 0], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                               pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+                        } else {
+                            // max over the rows of each group; bias + ReLU commute with the max and are applied after
+                            if (!row_valid) {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) v[i] = -INFINITY;
+                            }
+                            int o = p.Kl >> 1;
+                            if (o) { rs_step<32>(v, o, (lane & o) != 0); o >>= 1; }
+                            if (o) { rs_step<16>(v, o, (lane & o) != 0); o >>= 1; }
+                            if (o) { rs_step<8>(v, o, (lane & o) != 0); o >>= 1; }
+                            if (o) { rs_step<4>(v, o, (lane & o) != 0); o >>= 1; }
+                            if (o) { rs_step<2>(v, o, (lane & o) != 0); }
+                            const int nf = 32 / p.Kl;               // columns left in this lane
+                            const int cl = (lane & (p.Kl - 1)) * nf;
+                            if (p.direct) {
+                                const int64_t g = s_g[row];
+                                if (g < p.G && row_valid) {
+                                    float *o_ptr = p.out + (g / p.S) * p.ob + (g % p.S) * p.os + p.co_off + c0 + cl;
+                                    const float *bs = bias_s + ly.b_off + c0 + cl;
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j)
+                                        if (j < nf && c0 + cl + j < ly.Cout) o_ptr[j] = fmaxf(v[j] + bs[j], 0.f);
+                                }
+                            } else {
+                                pool_s[q4 * p.pool_cols + blk * 32 + lane] = v[0];
+                            }
+                        }
+                    }
+                    if (last && !p.direct) {
+                        cbar_sync();
+                        // combine the 4 lane quarters: one group per tile (gpt == 1) or two (K == 64)
+                        for (int it = tid; it < ncols * p.gpt; it += TC_CTHREADS) {
+                            const int c = it % ncols, gl = it / ncols;
+                            float m;
+                            if (p.gpt == 2) m = fmaxf(pool_s[(2 * gl) * p.pool_cols + c], pool_s[(2 * gl + 1) * p.pool_cols + c]);
+                            else m = fmaxf(fmaxf(pool_s[c], pool_s[p.pool_cols + c]), fmaxf(pool_s[2 * p.pool_cols + c], pool_s[3 * p.pool_cols + c]));
+                            const int r0 = gl * (TC_ROWS / p.gpt);
+                            const int64_t g = s_g[r0];
+                            if (g >= p.G || s_n[r0] < 0 || col_base + c >= ly.Cout) continue;
+                            m = fmaxf(m + bias_s[ly.b_off + col_base + c], 0.f);
+                            float *o_ptr = p.out + (g / p.S) * p.ob + (g % p.S) * p.os + p.co_off + col_base + c;
+                            if (p.use_atomic) atomicMax(reinterpret_cast<int *>(o_ptr), __float_as_int(m));
+                            else *o_ptr = m;
+                        }
+                    }
+                    if (!last) fence_proxy_async();
+                }
+            }
+        }
+        tc_fence_before();
+        cbar_sync();
+        if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------------
+struct TcPlan {
+    TcLayout lay;
+    int a_bytes[2], pool_cols, tmem_cols, resident, nstage, stage_bytes, ctas_per_sm;
+    size_t smem;
+    int gpt, cpg, Kl, direct, use_atomic;
+};
+
+static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+static bool tc_plan(int K, int L, const int *dims, TcPlan *pl)
+{
+    pl->lay = tc_layout(L, dims);
+    const TcLayout &t = pl->lay;
+    pl->a_bytes[0] = pl->a_bytes[1] = 0;
+    int max_ns = 32;
+    for (int l = 0; l < L; ++l) {
+        const int ab = t.ly[l].K / 8 * A_LBO;
+        if (ab > pl->a_bytes[l & 1]) pl->a_bytes[l & 1] = ab;
+        if (t.ly[l].NS > max_ns) max_ns = t.ly[l].NS;
+    }
+    if (pl->a_bytes[1] == 0) pl->a_bytes[1] = 16;
+    // grouping mode
+    if (K <= 32 && is_pow2(K)) { pl->gpt = TC_ROWS / K; pl->cpg = 1; pl->Kl = K; pl->direct = 1; pl->use_atomic = 0; }
+    else if (K == 64)          { pl->gpt = 2; pl->cpg = 1; pl->Kl = 32; pl->direct = 0; pl->use_atomic = 0; }
+    else if (K <= TC_ROWS)     { pl->gpt = 1; pl->cpg = 1; pl->Kl = 32; pl->direct = 0; pl->use_atomic = 0; }
+    else                       { pl->gpt = 1; pl->cpg = (K + TC_ROWS - 1) / TC_ROWS; pl->Kl = 32; pl->direct = 0; pl->use_atomic = 1; }
+    const int last_npad = t.ly[L - 1].Npad;
+    const size_t fixed = (size_t)pl->a_bytes[0] + pl->a_bytes[1] + (size_t)t.bias_floats * 4 + 2 * TC_ROWS * 4 +
+                         (2 * TC_MAX_STAGES + 1) * 8 + 16;
+    // Candidates: two CTAs per SM with 256 TMEM columns each (one CTA's epilogue overlaps the other's MMAs),
+    // or one CTA per SM with all 512 columns.  Weights stay resident in shared memory when they fit, else
+    // they stream through an mbarrier ring.  Preference: resident x2, resident x1, ring x2, ring x1.
+    auto eval = [&](int tmem_cols, int ctas, bool want_resident, TcPlan *o) -> bool {
+        *o = *pl;
+        o->tmem_cols = tmem_cols; o->ctas_per_sm = ctas;
+        o->pool_cols = o->direct ? 0 : (last_npad < tmem_cols ? last_npad : tmem_cols);
+        const size_t base = fixed + (size_t)4 * o->pool_cols * 4;
+        const size_t budget = (size_t)TC_SMEM_LIMIT / ctas - (ctas > 1 ? 1024 : 0);
+        if (want_resident) {
+            if (base + t.w_bytes > budget) return false;
+            o->resident = 1; o->nstage = 1; o->stage_bytes = 0; o->smem = base + t.w_bytes;
+            return true;
+        }
+        if (base + 2 * (size_t)t.max_chunk > budget) return false;
+        int ns = (int)((budget - base) / t.max_chunk);
+        if (ns > TC_MAX_STAGES) ns = TC_MAX_STAGES;
+        o->resident = 0; o->nstage = ns; o->stage_bytes = t.max_chunk; o->smem = base + (size_t)ns * t.max_chunk;
+        return true;
+    };
+    TcPlan c;
+    const bool two_ok = max_ns <= 256;
+    if (two_ok && eval(256, 2, true, &c)) { *pl = c; return true; }
+    if (eval(512, 1, true, &c)) { *pl = c; return true; }
+    if (two_ok && eval(256, 2, false, &c)) { *pl = c; return true; }
+    if (eval(512, 1, false, &c)) { *pl = c; return true; }
+    return false;
+}
+
+int sa_bf16_needs_zero(int S, int K, int L, const int *dims)
+{
+    (void)S; (void)L; (void)dims;
+    return K > TC_ROWS;
+}
+
+int launch_sa_bf16(const SaArgs &a, cudaStream_t st)
+{
+    TcPlan pl;
+    PN2_REQUIRE(tc_plan(a.K, a.L, a.dims, &pl), "pn2_sa_fused(bf16): layer widths do not fit shared memory");
+    TcParams p;
+    p.points = a.points; p.sb = a.sb; p.sn = a.sn; p.sc = a.sc;
+    p.feat = a.feat; p.fb = a.fb; p.fn = a.fn; p.fc = a.fc;
+    p.centres = a.centres; p.idx32 = a.idx32;
+    p.N = a.N; p.S = a.S; p.K = a.K; p.C = a.C; p.D = a.D; p.order = a.order;
+    p.lay = pl.lay;
+    p.packed = (const unsigned char *)a.packed;
+    p.out = a.out; p.ob = a.ob; p.os = a.os; p.co_off = a.co_off;
+    p.G = (int64_t)a.B * a.S;
+    PN2_REQUIRE(p.G < (1ll << 31), "pn2_sa_fused(bf16): too many groups");
+    p.gpt = pl.gpt; p.cpg = pl.cpg; p.Kl = pl.Kl; p.direct = pl.direct; p.use_atomic = pl.use_atomic;
+    p.tiles = pl.cpg > 1 ? p.G * pl.cpg : (p.G + pl.gpt - 1) / pl.gpt;
+    p.feat_fast = (a.D == 0) || (a.fc == 1 && a.D % 8 == 0 && a.fn % 4 == 0 && a.fb % 4 == 0 && ((uintptr_t)a.feat & 15) == 0);
+    p.tmem_cols = pl.tmem_cols; p.resident = pl.resident; p.nstage = pl.nstage; p.stage_bytes = pl.stage_bytes;
+    p.a_bytes[0] = pl.a_bytes[0]; p.a_bytes[1] = pl.a_bytes[1]; p.pool_cols = pl.pool_cols;
+    if (p.tiles == 0) return 0;
+    cudaError_t e = cudaFuncSetAttribute(sa_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    if (e != cudaSuccess) { set_error("sa_tc: smem attribute (%zu B): %s", pl.smem, cudaGetErrorString(e)); return (int)e; }
+    int64_t grid = p.tiles;
+    const int64_t cap = (int64_t)148 * pl.ctas_per_sm;
+    if (grid > cap) grid = cap;
+    sa_tc_kernel<<<(unsigned)grid, TC_THREADS, pl.smem, st>>>(p);
+    return launch_status("pn2_sa_fused(bf16)");
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Self-test: one 128 x n_cols x k_dim product through exactly the descriptor / MMA / TMEM-load helpers
+// above, operands made of small integers (exact in bf16), compared with a scalar loop in the same kernel.
+// variant 0 = the descriptor convention used by the product kernel; 1 = LBO and SBO swapped (diagnostic).
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) umma_selftest_kernel(int n_cols, int k_dim, int variant, float *max_err, float *dump)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float s_err[4];
+    unsigned char *As = smem;                               // [k_dim/8][A_LBO]
+    unsigned char *Bs = smem + (size_t)(k_dim / 8) * A_LBO; // [k_dim/8][n_cols*16]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    auto a_val = [](int r, int k) { return (float)(((r * 7 + k * 3) % 13) - 6); };
+    auto b_val = [](int n, int k) { return (float)(((n * 5 + k * 11) % 9) - 4); };
+    for (int i = tid; i < TC_ROWS * k_dim; i += 128) {
+        const int r = i % TC_ROWS, k = i / TC_ROWS;
+        *reinterpret_cast<__nv_bfloat16 *>(As + (size_t)(k / 8) * A_LBO + r * 16 + (k % 8) * 2) = __float2bfloat16_rn(a_val(r, k));
+    }
+    for (int i = tid; i < n_cols * k_dim; i += 128) {
+        const int n = i % n_cols, k = i / n_cols;
+        *reinterpret_cast<__nv_bfloat16 *>(Bs + (size_t)(k / 8) * (n_cols * 16) + n * 16 + (k % 8) * 2) = __float2bfloat16_rn(b_val(n, k));
+    }
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc(&tmem_slot, 256);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    if (tid == 0) {
+        const uint32_t idesc = instr_desc_bf16(n_cols);
+        for (int j = 0; j < k_dim / 16; ++j) {
+            uint64_t ad, bd;
+            if (variant == 0) {
+                ad = smem_desc(smem_u32(As) + (uint32_t)(j * 2 * A_LBO), A_LBO, 128);
+                bd = smem_desc(smem_u32(Bs) + (uint32_t)(j * 2 * n_cols * 16), (uint32_t)(n_cols * 16), 128);
+            } else {
+                ad = smem_desc(smem_u32(As) + (uint32_t)(j * 2 * A_LBO), 128, A_LBO);
+                bd = smem_desc(smem_u32(Bs) + (uint32_t)(j * 2 * n_cols * 16), 128, (uint32_t)(n_cols * 16));
+            }
+            umma_bf16(tmem_base, ad, bd, idesc, j ? 1u : 0u);
+        }
+        umma_commit(&bar);
+    }
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    float err = 0.f;
+    const int row = warp * 32 + lane;
+    for (int blk = 0; blk < n_cols / 32; ++blk) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(blk * 32), v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int n = blk * 32 + i;
+            float ref = 0.f;
+            for (int k = 0; k < k_dim; ++k) ref += a_val(row, k) * b_val(n, k);
+            err = fmaxf(err, fabsf(ref - v[i]));
+            if (dump) dump[(size_t)row * n_cols + n] = v[i];
+        }
+    }
+    for (int o = 16; o; o >>= 1) err = fmaxf(err, __shfl_xor_sync(0xffffffffu, err, o));
+    if (lane == 0) s_err[warp] = err;
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) *max_err = fmaxf(fmaxf(s_err[0], s_err[1]), fmaxf(s_err[2], s_err[3]));
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+int launch_selftest_umma(int n_cols, int k_dim, int variant, float *max_err, float *dump, cudaStream_t st)
+{
+    PN2_REQUIRE(n_cols >= 32 && n_cols <= 256 && n_cols % 32 == 0, "pn2_selftest_umma: n_cols must be a multiple of 32 in [32,256]");
+    PN2_REQUIRE(k_dim >= 16 && k_dim <= 256 && k_dim % 16 == 0, "pn2_selftest_umma: k_dim must be a multiple of 16 in [16,256]");
+    const size_t smem = (size_t)(k_dim / 8) * A_LBO + (size_t)(k_dim / 8) * n_cols * 16;
+    cudaError_t e = cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("selftest: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+    umma_selftest_kernel<<<1, 128, smem, st>>>(n_cols, k_dim, variant, max_err, dump);
+    return launch_status("pn2_selftest_umma");
+}
+
+}  // namespace pn2

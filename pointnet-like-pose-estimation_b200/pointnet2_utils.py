@@ -1,0 +1,317 @@
+"""Drop-in replacement for the reference's ``model/pointnet2_utils.py`` on B200 (sm_100a).
+
+Put this directory first on ``sys.path`` (the reference's scripts do ``sys.path.append(<root>/model)`` and
+``importlib.import_module(args.model)``, train_rotation.py:16-18,32) and the unchanged model files
+``pointnet2_cls_{ssg,msg}.py``, ``{rotation,translation,sign}_{ssg,msg}.py`` pick up these definitions through
+``from pointnet2_utils import PointNetSetAbstraction, PointNetSetAbstractionMsg``.
+
+Same public names, argument names (this fork: ``points`` = coordinates, ``feature`` = per-point features),
+shapes and dtypes as the reference; the arithmetic runs in hand-written CUDA kernels behind the C ABI of
+``include/pn2.h`` (see ``_pn2_native.py``).  There is no CPU implementation here.
+
+What is deliberately different from the reference (all documented in DESIGN.md):
+  * pooled features are stored channels-last ([B,S,Cout]) and returned as the [B,Cout,S] *view* of that
+    buffer (same shape, dtype and values; strides (S*Cout, 1, Cout) instead of contiguous) so that the next
+    layer gathers whole rows; ``set_reference_strides(True)`` returns contiguous tensors instead.
+  * ``set_precision('bf16')`` runs the shared MLP on the tensor cores (bf16 in, fp32 accumulate);
+    default is 'fp32'.
+"""
+from __future__ import annotations
+
+import contextlib
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+import _pn2_native as _nat
+from _pn2_native import ORDER_ALL, ORDER_MSG, ORDER_SSG, PREC_BF16, PREC_F32
+
+__all__ = ["square_distance", "index_points", "farthest_point_sample", "query_ball_point", "sample_and_group",
+           "sample_and_group_all", "PointNetSetAbstraction", "PointNetSetAbstractionMsg",
+           "set_precision", "get_precision", "set_reference_strides", "fps_start_source"]
+
+_native = None              # created on first use; tests may monkeypatch this attribute
+_precision = os.environ.get("PN2_PRECISION", "fp32")
+_reference_strides = False
+_start_source = None        # optional callable (B, N) -> int64 CPU tensor [B]; default = torch.randint
+
+
+def _backend():
+    global _native
+    if _native is None:
+        _native = _nat.Native()
+    return _native
+
+
+def set_precision(mode: str) -> None:
+    """'fp32' (FFMA, <= 1e-5 of the reference) or 'bf16' (tcgen05 tensor cores, <= 2e-2)."""
+    global _precision
+    if mode not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    _precision = mode
+
+
+def get_precision() -> str:
+    return _precision
+
+
+def set_reference_strides(flag: bool) -> None:
+    """When True the modules return contiguous [B,Cout,S] features exactly like the reference."""
+    global _reference_strides
+    _reference_strides = bool(flag)
+
+
+@contextlib.contextmanager
+def fps_start_source(fn):
+    """Route the FPS start-index draw (pointnet2_utils.py:59) through ``fn(B, N) -> int64 CPU tensor [B]``.
+
+    Used by the batch-sharded runner so that every rank slices ONE global draw (bit-identical to a
+    single-GPU run of the whole batch)."""
+    global _start_source
+    prev, _start_source = _start_source, fn
+    try:
+        yield
+    finally:
+        _start_source = prev
+
+
+def _draw_start(B: int, N: int, device) -> torch.Tensor:
+    # The reference draws on the CPU default generator even when the model is on the GPU (:59); keep that,
+    # one draw per farthest_point_sample call, so seeded runs choose the same centroids.
+    if _start_source is not None:
+        start = _start_source(B, N)
+    else:
+        start = torch.randint(0, N, (B,), dtype=torch.long)
+    return start.to(device)
+
+
+def _radius_sq(radius) -> float:
+    # Python squares in double (0.2**2 = 0.04000000000000001), ATen then compares in fp32 (:85)
+    return float(np.float32(float(radius) ** 2))
+
+
+# ------------------------------------------------------------------------------------------------------
+# functions (reference: pointnet2_utils.py:5-141)
+# ------------------------------------------------------------------------------------------------------
+def square_distance(src, dst):
+    """[B,N,C], [B,M,C] -> [B,N,M] squared distances in the reference's expanded form (:5-26)."""
+    return _backend().square_distance(src, dst)
+
+
+def index_points(points, idx):
+    """points [B,N,C], idx [B,S] or [B,S,K] (int64) -> points[b, idx[b,...], :] (:28-45)."""
+    return _backend().index_points(points, idx)
+
+
+def farthest_point_sample(points, number):
+    """points [B,N,C] -> sampled indices [B,number] int64 (:47-68)."""
+    B, N, _ = points.shape
+    start = _draw_start(B, N, points.device)
+    return _backend().fps(points, start, number, want_idx64=True)[0]
+
+
+def query_ball_point(radius, number, points, new_points):
+    """First `number` in-radius indices in ascending order, padded with the first one (:70-90)."""
+    if number > points.shape[1]:
+        raise RuntimeError(f"query_ball_point: number={number} > N={points.shape[1]} (the reference fails at :89)")
+    return _backend().ball_query(new_points, points, _radius_sq(radius), number, want_idx64=True)[0]
+
+
+def sample_and_group(points, feature, point_number, sample_number, radius, returnfps=False):
+    """(:92-120) -> new_points [B,S,C], new_feature [B,S,K,C+D] = cat([xyz - centre, feat])."""
+    be = _backend()
+    B, N, C = points.shape
+    start = _draw_start(B, N, points.device)
+    fps_idx, _, new_points = be.fps(points, start, point_number, want_idx64=True, want_new_points=True)
+    _, idx32 = be.ball_query(new_points, points, _radius_sq(radius), sample_number, want_idx64=False, want_idx32=True)
+    new_feature = be.group(points, feature, idx32, new_points, ORDER_SSG)
+    if returnfps:
+        grouped = be.index_points(feature if feature is not None else points, idx32.long(), check=False)
+        return new_points, new_feature, grouped, fps_idx
+    return new_points, new_feature
+
+
+def sample_and_group_all(points, feature):
+    """(:122-141) -> zeros [B,1,C], cat([xyz, feat]) viewed [B,1,N,C+D]."""
+    B, N, C = points.shape
+    new_points = torch.zeros(B, 1, C, device=points.device)
+    return new_points, _backend().group(points, feature, None, None, ORDER_ALL)
+
+
+# ------------------------------------------------------------------------------------------------------
+# modules (reference: pointnet2_utils.py:143-223)
+# ------------------------------------------------------------------------------------------------------
+def _prec_code() -> int:
+    return PREC_BF16 if _precision == "bf16" else PREC_F32
+
+
+class _FoldedMLP:
+    """Derived cache: BN-folded, kernel-layout weights of one (Conv2d, BatchNorm2d) stack.
+
+    Never part of state_dict; rebuilt whenever a parameter / buffer changes (tensor ._version), moves, or
+    the precision mode changes."""
+
+    def __init__(self):
+        self.key = None
+        self.packed = None
+        self.dims = None
+
+    def get(self, convs, bns, C, order):
+        tensors = []
+        for conv, bn in zip(convs, bns):
+            tensors += [conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        prec = _prec_code()
+        key = (prec, C, order, tuple((t.data_ptr(), t._version) for t in tensors))
+        if key != self.key:
+            layers = [(conv.weight.detach().reshape(conv.out_channels, conv.in_channels), conv.bias.detach(),
+                       bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var)
+                      for conv, bn in zip(convs, bns)]
+            eps = bns[0].eps
+            assert all(bn.eps == eps for bn in bns)
+            self.packed, self.dims = _backend().pack(layers, eps, prec, C, order)
+            self.key = key
+        return self.packed, self.dims, prec
+
+
+def _finish(new_points_bsc, pooled_bsc):
+    new_points = new_points_bsc.permute(0, 2, 1)       # view of contiguous [B,S,C], like the reference (:173)
+    new_feature = pooled_bsc.permute(0, 2, 1)
+    if _reference_strides:
+        new_feature = new_feature.contiguous()
+    return new_points, new_feature
+
+
+def _shared_mlp_train(x, convs, bns):
+    for conv, bn in zip(convs, bns):
+        x = F.relu(bn(conv(x)))
+    return torch.max(x, 2)[0]
+
+
+class PointNetSetAbstraction(nn.Module):
+    def __init__(self, point_number, sample_number, radius, in_channel, mlp, group_all=False):
+        super().__init__()
+        self.point_number = point_number
+        self.radius = radius
+        self.sample_number = sample_number
+        self.group_all = group_all
+        self.mlp_convs = nn.ModuleList()
+        self.mlp_bns = nn.ModuleList()
+        width = in_channel
+        for out_channel in mlp:
+            self.mlp_convs.append(nn.Conv2d(width, out_channel, 1))
+            self.mlp_bns.append(nn.BatchNorm2d(out_channel))
+            width = out_channel
+        self._folded = _FoldedMLP()
+
+    def forward(self, points, feature):
+        """points [B,C,N], feature [B,D,N] or None -> new_points [B,C,S], new_feature [B,Cout,S]."""
+        be = _backend()
+        pts = points.permute(0, 2, 1)
+        feat = feature.permute(0, 2, 1) if feature is not None else None
+        B, N, C = pts.shape
+        if self.training:
+            return self._forward_train(pts, feat)
+        order = ORDER_ALL if self.group_all else ORDER_SSG
+        packed, dims, prec = self._folded.get(self.mlp_convs, self.mlp_bns, C, order)
+        if self.group_all:
+            new_points = torch.zeros(B, 1, C, device=pts.device)
+            S, K, idx32 = 1, N, None
+        else:
+            S, K = self.point_number, self.sample_number
+            start = _draw_start(B, N, pts.device)
+            _, _, new_points = be.fps(pts, start, S, want_idx64=False, want_new_points=True)
+            _, idx32 = be.ball_query(new_points, pts, _radius_sq(self.radius), K, want_idx64=False, want_idx32=True)
+        alloc = torch.zeros if be.sa_needs_zero(S, K, dims, prec) else torch.empty
+        pooled = alloc(B, S, dims[-1], dtype=torch.float32, device=pts.device)
+        be.sa_fused(pts, feat, new_points if not self.group_all else None, idx32, order, dims, packed, prec, pooled, 0)
+        return _finish(new_points, pooled)
+
+    def _forward_train(self, pts, feat):
+        # Training mode (batch-statistics BatchNorm + autograd): sampling and grouping run on our kernels,
+        # the MLP on cuDNN/ATen so that gradients flow.  Fused training kernels are the next scope row.
+        be = _backend()
+        B, N, C = pts.shape
+        if self.group_all:
+            new_points = torch.zeros(B, 1, C, device=pts.device)
+            rows = pts.reshape(B, 1, N, C) if pts.is_contiguous() else pts.contiguous().view(B, 1, N, C)
+            if feat is not None:
+                rows = torch.cat([rows, feat.reshape(B, 1, N, -1)], dim=-1)
+        else:
+            S, K = self.point_number, self.sample_number
+            start = _draw_start(B, N, pts.device)
+            _, _, new_points = be.fps(pts.detach(), start, S, want_idx64=False, want_new_points=True)
+            _, idx32 = be.ball_query(new_points, pts.detach(), _radius_sq(self.radius), K, want_idx64=False, want_idx32=True)
+            rows = be.group(pts.detach(), None, idx32, new_points, ORDER_SSG)
+            if feat is not None:
+                rows = torch.cat([rows, _gather_rows(feat, idx32)], dim=-1)
+        pooled = _shared_mlp_train(rows.permute(0, 3, 2, 1), self.mlp_convs, self.mlp_bns)
+        return new_points.permute(0, 2, 1), pooled
+
+
+def _gather_rows(feat, idx32):
+    """Differentiable feature gather [B,N,D], [B,S,K] -> [B,S,K,D] (autograd scatter-add in backward)."""
+    B, S, K = idx32.shape
+    D = feat.shape[-1]
+    flat = idx32.reshape(B, S * K, 1).long().expand(-1, -1, D)
+    return torch.gather(feat, 1, flat).view(B, S, K, D)
+
+
+class PointNetSetAbstractionMsg(nn.Module):
+    def __init__(self, point_number, sample_number_list, radius_list, in_channel, mlp_list, num_category=0):
+        super().__init__()
+        self.point_number = point_number
+        self.radius_list = radius_list
+        self.sample_number_list = sample_number_list
+        self.conv_blocks = nn.ModuleList()
+        self.bn_blocks = nn.ModuleList()
+        for widths in mlp_list:
+            convs, bns = nn.ModuleList(), nn.ModuleList()
+            width = in_channel + 3 + num_category
+            for out_channel in widths:
+                convs.append(nn.Conv2d(width, out_channel, 1))
+                bns.append(nn.BatchNorm2d(out_channel))
+                width = out_channel
+            self.conv_blocks.append(convs)
+            self.bn_blocks.append(bns)
+        self._folded = [_FoldedMLP() for _ in mlp_list]
+
+    def forward(self, points, feature):
+        be = _backend()
+        pts = points.permute(0, 2, 1)
+        feat = feature.permute(0, 2, 1) if feature is not None else None
+        B, N, C = pts.shape
+        S = self.point_number
+        start = _draw_start(B, N, pts.device)            # ONE draw per layer, shared by all radii (:201)
+        if self.training:
+            return self._forward_train(pts, feat, start)
+        _, _, new_points = be.fps(pts, start, S, want_idx64=False, want_new_points=True)
+        plans = []
+        for i in range(len(self.radius_list)):
+            packed, dims, prec = self._folded[i].get(self.conv_blocks[i], self.bn_blocks[i], C, ORDER_MSG)
+            plans.append((packed, dims, prec))
+        total = sum(d[-1] for _, d, _ in plans)
+        zero = any(be.sa_needs_zero(S, K, d, prec) for K, (_, d, prec) in zip(self.sample_number_list, plans))
+        pooled = (torch.zeros if zero else torch.empty)(B, S, total, dtype=torch.float32, device=pts.device)
+        co = 0
+        for radius, K, (packed, dims, prec) in zip(self.radius_list, self.sample_number_list, plans):
+            _, idx32 = be.ball_query(new_points, pts, _radius_sq(radius), K, want_idx64=False, want_idx32=True)
+            be.sa_fused(pts, feat, new_points, idx32, ORDER_MSG, dims, packed, prec, pooled, co)   # branch concat (:222) is the channel offset
+            co += dims[-1]
+        return _finish(new_points, pooled)
+
+    def _forward_train(self, pts, feat, start):
+        be = _backend()
+        S = self.point_number
+        _, _, new_points = be.fps(pts.detach(), start, S, want_idx64=False, want_new_points=True)
+        outs = []
+        for i, radius in enumerate(self.radius_list):
+            K = self.sample_number_list[i]
+            _, idx32 = be.ball_query(new_points, pts.detach(), _radius_sq(radius), K, want_idx64=False, want_idx32=True)
+            rows = be.group(pts.detach(), None, idx32, new_points, ORDER_MSG)
+            if feat is not None:
+                rows = torch.cat([_gather_rows(feat, idx32), rows], dim=-1)
+            outs.append(_shared_mlp_train(rows.permute(0, 3, 2, 1), self.conv_blocks[i], self.bn_blocks[i]))
+        return new_points.permute(0, 2, 1), torch.cat(outs, dim=1)

@@ -1,0 +1,66 @@
+"""TEST-ONLY stand-in for _pn2_native.Native backed by the CPU oracle.
+
+Lets the `not gpu` suite exercise the host logic of pointnet2_utils.py (RNG call order, argument plumbing,
+channel orders, branch concatenation, views / strides, weight-cache invalidation) and run the reference's
+unchanged model files on top of it.  Nothing under pointnet-like-pose-estimation_b200/ imports this file.
+"""
+import torch
+
+import pn2_oracle as orc
+from _pn2_native import ORDER_ALL, ORDER_MSG, ORDER_SSG
+
+
+class OracleNative:
+    name = "oracle-fake"
+
+    def __init__(self):
+        self.calls = []
+
+    def fps(self, points, start, number, want_idx64=True, want_idx32=False, want_new_points=False):
+        self.calls.append("fps")
+        idx = orc.farthest_point_sample(points, number, start)
+        return (idx if want_idx64 else None, idx.int() if want_idx32 else None,
+                orc.index_points(points, idx).contiguous() if want_new_points else None)
+
+    def index_points(self, src, idx, check=True):
+        self.calls.append("index_points")
+        N = src.shape[1]
+        if check and ((idx < -N) | (idx >= N)).any():
+            raise IndexError("index out of range in index_points")
+        return orc.index_points(src, idx % N)
+
+    def square_distance(self, src, dst):
+        self.calls.append("square_distance")
+        return orc.square_distance(src, dst)
+
+    def ball_query(self, centres, points, r2, number, want_idx64=True, want_idx32=False):
+        self.calls.append("ball_query")
+        B, N, C = points.shape
+        S = centres.shape[1]
+        out = torch.empty(B, S, number, dtype=torch.int64)
+        sb, sn, sc = points.stride()
+        cen = centres.contiguous()
+        rc = orc.lib().pn2o_ball_query(cen.data_ptr(), points.data_ptr(), sb, sn, sc, B, S, N, C, r2, number, out.data_ptr())
+        assert rc >= 0
+        return (out if want_idx64 else None, out.int() if want_idx32 else None)
+
+    def group(self, points, feature, idx32, centres, order):
+        self.calls.append("group")
+        return orc.group(points, feature, None if idx32 is None else idx32.long(), centres, order)
+
+    def pack(self, layers, eps, prec, C, order):
+        self.calls.append("pack")
+        dims = [int(layers[0][0].shape[1])] + [int(l[0].shape[0]) for l in layers]
+        return ([tuple(t.detach().clone() for t in tup) for tup in layers], eps), dims
+
+    def sa_needs_zero(self, S, K, dims, prec):
+        return False
+
+    def sa_fused(self, points, feature, centres, idx32, order, dims, packed, prec, out, co_off=0):
+        self.calls.append("sa_fused")
+        layers, eps = packed
+        rows = orc.group(points, feature, None if idx32 is None else idx32.long(), centres, order)
+        B, S, K, W = rows.shape
+        pooled = orc.mlp_max(rows.reshape(B * S, K, W), layers, eps).reshape(B, S, -1)
+        out[:, :, co_off:co_off + pooled.shape[-1]] = pooled
+        return out
