@@ -138,7 +138,7 @@ static int launch_fps_t(const float *points, int64_t sb, int64_t sn, int64_t sc,
 {
     const size_t smem = sizeof(float) * (size_t)C * PPT * threads;
     auto run = [&](auto kern) -> int {
-        if (smem > 48 * 1024) {
+        if (smem > 40 * 1024) {   // static shared memory counts against the 48 KB default as well
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) { set_error("fps: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
         }
@@ -179,7 +179,7 @@ int launch_fps(const float *points, int64_t sb, int64_t sn, int64_t sc, int B, i
     if (rc != -100) return rc;
     const size_t smem = sizeof(float) * (size_t)N;
     PN2_REQUIRE(smem <= 200 * 1024, "pn2_fps_f32: N=%d too large for the generic kernel (C=%d)", N, C);
-    if (smem > 48 * 1024) {
+    if (smem > 40 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(fps_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("fps: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
     }

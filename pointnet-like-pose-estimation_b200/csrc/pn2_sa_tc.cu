@@ -14,7 +14,8 @@
 //
 // Operand layout (both A and B): canonical K-major, no swizzle -- 8x8 bf16 "core matrices" of 128 contiguous
 // bytes; rows at 16 B pitch inside a column of core matrices (SBO = 128 B), consecutive k-groups of 8 at
-// LBO bytes.  For A, LBO = 128*16 + 16: the 16 B of padding spreads the gather's stores over all banks.
+// LBO bytes.  For A, LBO = 128*16: a k-group column holds the 128 rows back to back, so a warp that writes
+// 32 consecutive rows of one k-group (gather and epilogue both do) stores 512 contiguous bytes.
 #include <cuda_bf16.h>
 #include "pn2_common.cuh"
 
@@ -24,7 +25,7 @@ constexpr int TC_ROWS = 128;
 constexpr int TC_CWARPS = 8;                       // compute warps (gather, MMA issue, epilogue)
 constexpr int TC_CTHREADS = TC_CWARPS * 32;        // 256
 constexpr int TC_THREADS = TC_CTHREADS + 32;       // + 1 producer warp for the weight ring
-constexpr int A_LBO = TC_ROWS * 16 + 16;           // bytes between k-groups of the A operand
+constexpr int A_LBO = TC_ROWS * 16;                // bytes between k-groups of the A operand
 constexpr int KBLK = 64;                           // k extent of one weight chunk
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
@@ -64,11 +65,15 @@ static TcLayout tc_layout(int L, const int *dims)
     TcLayout t;
     t.L = L; t.w_bytes = 0; t.bias_floats = 0; t.max_chunk = 0; t.n_chunks = 0;
     int K = rup(dims[0], 16);
+    // wide stacks (group_all heads) stream their weights through a small ring next to a large activation
+    // buffer: keep the chunks at 16 KB there
+    int ns_cap = 256;
+    for (int l = 0; l < L; ++l) if (rup(dims[l], 16) > 256) ns_cap = 128;
     for (int l = 0; l < L; ++l) {
         TcLayer &y = t.ly[l];
         y.K = K; y.Cout = dims[l + 1]; y.Npad = rup(dims[l + 1], 32);
         y.NS = 32;
-        for (int ns = 256; ns >= 32; ns >>= 1) if (y.Npad % ns == 0) { y.NS = ns; break; }
+        for (int ns = ns_cap; ns >= 32; ns >>= 1) if (y.Npad % ns == 0) { y.NS = ns; break; }
         y.nslab = y.Npad / y.NS;
         y.nkb = (K + KBLK - 1) / KBLK;
         y.w_off = t.w_bytes; y.b_off = t.bias_floats;
@@ -276,7 +281,7 @@ struct TcParams {
     int tmem_cols;
     int resident;      // all weight chunks stay in shared memory for the life of the CTA
     int nstage, stage_bytes;
-    int a_bytes[2];    // activation buffers
+    int a_bytes[2];    // activation buffers (a_bytes[1] == 0: one buffer, each layer's epilogue overwrites its own input)
     int pool_cols;     // columns of the cross-warp pooling scratch (0 if direct)
 };
 
@@ -284,8 +289,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     // carve-up (all offsets multiples of 16)
-    unsigned char *A[2] = {smem, smem + p.a_bytes[0]};
-    unsigned char *Wsm = A[1] + p.a_bytes[1];
+    unsigned char *A[2] = {smem, p.a_bytes[1] ? smem + p.a_bytes[0] : smem};
+    unsigned char *Wsm = smem + p.a_bytes[0] + p.a_bytes[1];
     const int w_region = p.resident ? p.lay.w_bytes : p.nstage * p.stage_bytes;
     float *bias_s = reinterpret_cast<float *>(Wsm + w_region);
     float *pool_s = bias_s + p.lay.bias_floats;                 // [4][pool_cols]
@@ -381,7 +386,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
                 if (p.feat_fast) {
                     const int cpr = D / 8;                               // 16-byte chunks per row
                     for (int it = tid; it < TC_ROWS * cpr; it += TC_CTHREADS) {
-                        const int r = it / cpr, kg = it % cpr;
+                        const int r = it % TC_ROWS, kg = it / TC_ROWS;
                         const int n = s_n[r];
                         uint4 o = make_uint4(0u, 0u, 0u, 0u);
                         if (n >= 0) {
@@ -565,27 +570,33 @@ static bool tc_plan(int K, int L, const int *dims, TcPlan *pl)
 {
     pl->lay = tc_layout(L, dims);
     const TcLayout &t = pl->lay;
-    pl->a_bytes[0] = pl->a_bytes[1] = 0;
-    int max_ns = 32;
+    int pp[2] = {0, 0}, max_ns = 32, max_mid = 0;
     for (int l = 0; l < L; ++l) {
         const int ab = t.ly[l].K / 8 * A_LBO;
-        if (ab > pl->a_bytes[l & 1]) pl->a_bytes[l & 1] = ab;
+        if (ab > pp[l & 1]) pp[l & 1] = ab;
         if (t.ly[l].NS > max_ns) max_ns = t.ly[l].NS;
+        if (l < L - 1 && t.ly[l].Npad > max_mid) max_mid = t.ly[l].Npad;
     }
-    if (pl->a_bytes[1] == 0) pl->a_bytes[1] = 16;
+    if (pp[1] == 0) pp[1] = 16;
     // grouping mode
     if (K <= 32 && is_pow2(K)) { pl->gpt = TC_ROWS / K; pl->cpg = 1; pl->Kl = K; pl->direct = 1; pl->use_atomic = 0; }
     else if (K == 64)          { pl->gpt = 2; pl->cpg = 1; pl->Kl = 32; pl->direct = 0; pl->use_atomic = 0; }
     else if (K <= TC_ROWS)     { pl->gpt = 1; pl->cpg = 1; pl->Kl = 32; pl->direct = 0; pl->use_atomic = 0; }
     else                       { pl->gpt = 1; pl->cpg = (K + TC_ROWS - 1) / TC_ROWS; pl->Kl = 32; pl->direct = 0; pl->use_atomic = 1; }
     const int last_npad = t.ly[L - 1].Npad;
-    const size_t fixed = (size_t)pl->a_bytes[0] + pl->a_bytes[1] + (size_t)t.bias_floats * 4 + 2 * TC_ROWS * 4 +
-                         (2 * TC_MAX_STAGES + 1) * 8 + 16;
+    const size_t misc = (size_t)t.bias_floats * 4 + 2 * TC_ROWS * 4 + (2 * TC_MAX_STAGES + 1) * 8 + 16;
     // Candidates: two CTAs per SM with 256 TMEM columns each (one CTA's epilogue overlaps the other's MMAs),
     // or one CTA per SM with all 512 columns.  Weights stay resident in shared memory when they fit, else
     // they stream through an mbarrier ring.  Preference: resident x2, resident x1, ring x2, ring x1.
-    auto eval = [&](int tmem_cols, int ctas, bool want_resident, TcPlan *o) -> bool {
+    // Activations ping-pong between two buffers, or -- when that does not fit -- live in ONE buffer that each
+    // layer's epilogue overwrites in place.  In place is legal when every non-last layer finishes all its MMAs
+    // before its epilogue starts, i.e. when its whole output fits the TMEM allocation (one round).
+    auto eval = [&](int tmem_cols, int ctas, bool want_resident, bool inplace, TcPlan *o) -> bool {
         *o = *pl;
+        if (inplace && max_mid > tmem_cols) return false;
+        o->a_bytes[0] = inplace ? (pp[0] > pp[1] ? pp[0] : pp[1]) : pp[0];
+        o->a_bytes[1] = inplace ? 0 : pp[1];
+        const size_t fixed = (size_t)o->a_bytes[0] + o->a_bytes[1] + misc;
         o->tmem_cols = tmem_cols; o->ctas_per_sm = ctas;
         o->pool_cols = o->direct ? 0 : (last_npad < tmem_cols ? last_npad : tmem_cols);
         const size_t base = fixed + (size_t)4 * o->pool_cols * 4;
@@ -603,10 +614,12 @@ static bool tc_plan(int K, int L, const int *dims, TcPlan *pl)
     };
     TcPlan c;
     const bool two_ok = max_ns <= 256;
-    if (two_ok && eval(256, 2, true, &c)) { *pl = c; return true; }
-    if (eval(512, 1, true, &c)) { *pl = c; return true; }
-    if (two_ok && eval(256, 2, false, &c)) { *pl = c; return true; }
-    if (eval(512, 1, false, &c)) { *pl = c; return true; }
+    if (two_ok && eval(256, 2, true, false, &c)) { *pl = c; return true; }
+    if (eval(512, 1, true, false, &c)) { *pl = c; return true; }
+    if (two_ok && eval(256, 2, false, false, &c)) { *pl = c; return true; }
+    if (eval(512, 1, false, false, &c)) { *pl = c; return true; }
+    if (eval(512, 1, true, true, &c)) { *pl = c; return true; }
+    if (eval(512, 1, false, true, &c)) { *pl = c; return true; }
     return false;
 }
 

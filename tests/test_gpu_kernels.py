@@ -1,0 +1,226 @@
+"""-m gpu: the CUDA kernels, called through the C ABI (include/pn2.h via _pn2_native), against the CPU oracle
+and the golden vectors recorded from the live reference.  Indices are compared bit-exactly; features within
+the stated tolerance (fp32 mode 1e-5, bf16 mode 2e-2, both as max|a-b| / max|b|)."""
+import numpy as np
+import pytest
+import torch
+
+import cloudgen
+import golden_io
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32 = 1e-5
+TOL_BF16 = 2e-2
+
+
+@pytest.fixture(scope="module")
+def nat():
+    import _pn2_native
+    return _pn2_native.Native()
+
+
+def rel_err(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+def dev(x):
+    return x.to("cuda:0")
+
+
+# ---- tcgen05 building blocks -------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_cols,k_dim", [(32, 16), (64, 64), (128, 144), (256, 256)])
+def test_umma_selftest(nat, n_cols, k_dim):
+    err, _ = nat.selftest_umma(n_cols, k_dim, 0)
+    torch.cuda.synchronize()
+    assert float(err.item()) == 0.0
+
+
+# ---- golden vectors (reference outputs) ----------------------------------------------------------------------
+@pytest.mark.parametrize("case", sorted(golden_io.index_cases()))
+def test_golden_fps_ball_sqdist(nat, case):
+    d = golden_io.index_cases()[case]
+    pts = golden_io.as_layout(d["points"], d["layout"], "cuda:0")
+    start = dev(torch.from_numpy(d["start"]))
+    i64, i32, new_pts = nat.fps(pts, start, d["S"], want_idx64=True, want_idx32=True, want_new_points=True)
+    ref = torch.from_numpy(d["fps"]).long()
+    assert torch.equal(i64.cpu(), ref)
+    assert torch.equal(i32.cpu().long(), ref)
+    cpu_pts = golden_io.as_layout(d["points"], d["layout"])
+    exp_new = torch.stack([cpu_pts[b][ref[b]] for b in range(ref.shape[0])])
+    assert torch.equal(new_pts.cpu(), exp_new)
+    import pointnet2_utils as pu
+    b64, b32 = nat.ball_query(new_pts, pts, pu._radius_sq(d["r"]), d["K"], want_idx64=True, want_idx32=True)
+    assert torch.equal(b64.cpu(), torch.from_numpy(d["ball"]).long())
+    assert torch.equal(b32.cpu().long(), b64.cpu())
+    sd = nat.square_distance(new_pts, pts)
+    assert torch.equal(sd[:, :4].cpu(), torch.from_numpy(d["sqdist_sample"]))
+
+
+# ---- oracle comparisons on seeded inputs ----------------------------------------------------------------------
+FPS_CASES = [  # (B, N, C, S, layout, kind)
+    (4, 1024, 3, 512, "strided", "uni"), (4, 512, 3, 128, "contig", "uni"), (3, 1024, 10, 512, "strided", "uni"),
+    (3, 512, 10, 128, "contig", "surf"), (2, 2048, 10, 512, "strided", "surf"), (2, 2048, 3, 512, "contig", "dup"),
+    (2, 4096, 3, 1024, "contig", "uni"), (2, 8192, 3, 2048, "contig", "uni"), (2, 8192, 3, 64, "strided", "surf"),
+    (2, 100, 3, 512, "strided", "uni"), (2, 1000, 3, 100, "contig", "dup"), (2, 777, 10, 99, "contig", "dup"),
+    (2, 3000, 10, 64, "strided", "uni"), (2, 300, 5, 64, "contig", "uni"), (2, 300, 16, 64, "strided", "uni"),
+    (1, 2, 3, 4, "contig", "uni"), (2, 33, 8, 40, "contig", "uni"),
+]
+
+
+def make_cloud(B, N, C, kind, seed):
+    base = {"uni": cloudgen.uniform_cloud, "surf": cloudgen.surface_cloud}.get(kind, cloudgen.uniform_cloud)(B, N, seed)
+    if kind == "dup":
+        base = cloudgen.duplicate_heavy(base, 0.6, seed + 1)
+    if C == 3:
+        return base
+    if C == 10:
+        return cloudgen.with_category(base)
+    g = torch.Generator().manual_seed(seed + 2)
+    extra = torch.rand(B, N, C - 3, generator=g) if C > 3 else None
+    return torch.cat([base, extra], -1) if C > 3 else base[..., :C].contiguous()
+
+
+def lay(x, layout):
+    return x.permute(0, 2, 1).contiguous().permute(0, 2, 1) if layout == "strided" else x.contiguous()
+
+
+@pytest.mark.parametrize("B,N,C,S,layout,kind", FPS_CASES)
+def test_fps_vs_oracle(nat, oracle, B, N, C, S, layout, kind):
+    x = lay(make_cloud(B, N, C, kind, 1000 + N + C), layout)
+    g = torch.Generator().manual_seed(7)
+    start = torch.randint(0, N, (B,), generator=g, dtype=torch.long)
+    exp = oracle.farthest_point_sample(x, S, start)
+    i64, _, new_pts = nat.fps(dev(x), dev(start), S, want_idx64=True, want_new_points=True)
+    assert torch.equal(i64.cpu(), exp)
+    assert torch.equal(new_pts.cpu(), oracle.index_points(x, exp))
+
+
+BQ_CASES = [  # (B, N, C, S, K, r, layout, kind)
+    (4, 1024, 3, 512, 32, 0.2, "strided", "uni"), (4, 512, 3, 128, 64, 0.4, "contig", "uni"),
+    (3, 1024, 10, 512, 16, 0.1, "strided", "surf"), (3, 1024, 10, 512, 128, 0.4, "strided", "uni"),
+    (3, 512, 10, 128, 128, 0.8, "contig", "surf"), (2, 2048, 10, 512, 32, 0.2, "strided", "dup"),
+    (2, 8192, 3, 2048, 32, 0.2, "contig", "uni"), (2, 8192, 3, 256, 32, 0.2, "strided", "surf"),
+    (1, 20000, 3, 64, 48, 0.1, "contig", "uni"), (1, 6000, 10, 70, 20, 0.3, "contig", "uni"),
+    (2, 300, 5, 64, 7, 0.5, "contig", "uni"), (2, 300, 16, 64, 300, 5.0, "strided", "uni"),
+    (2, 64, 3, 64, 64, 10.0, "contig", "uni"), (2, 500, 3, 37, 1, 0.05, "contig", "dup"),
+]
+
+
+@pytest.mark.parametrize("B,N,C,S,K,r,layout,kind", BQ_CASES)
+def test_ball_query_vs_oracle(nat, oracle, B, N, C, S, K, r, layout, kind):
+    x = lay(make_cloud(B, N, C, kind, 2000 + N + C + K), layout)
+    g = torch.Generator().manual_seed(8)
+    start = torch.randint(0, N, (B,), generator=g, dtype=torch.long)
+    fps = oracle.farthest_point_sample(x, S, start)
+    cen = oracle.index_points(x, fps).contiguous()
+    exp = oracle.query_ball_point(r, K, x, cen)
+    i64, i32 = nat.ball_query(dev(cen), dev(x), oracle.radius_sq_f32(r), K, want_idx64=True, want_idx32=True)
+    assert torch.equal(i64.cpu(), exp)
+    assert torch.equal(i32.cpu().long(), exp)
+    sd = nat.square_distance(dev(cen[:, :8]), dev(x))
+    assert torch.equal(sd.cpu(), oracle.square_distance(cen[:, :8], x))
+
+
+def test_ball_query_empty_rows_are_flagged_not_oob(nat, oracle):
+    """No point in radius: the reference writes N and fails in index_points; we fill N and never read OOB."""
+    x = cloudgen.uniform_cloud(1, 256, 5)
+    cen = torch.full((1, 4, 3), 50.0)
+    i64, _ = nat.ball_query(dev(cen), dev(x), oracle.radius_sq_f32(0.1), 8)
+    assert (i64.cpu() == 256).all()
+
+
+def test_index_points_and_group_vs_oracle(nat, oracle):
+    x = make_cloud(3, 400, 10, "surf", 31)
+    f = torch.randn(3, 400, 20, generator=torch.Generator().manual_seed(3))
+    for layout in ("strided", "contig"):
+        xs, fs = lay(x, layout), lay(f, layout)
+        g = torch.Generator().manual_seed(9)
+        idx = torch.randint(0, 400, (3, 50, 12), generator=g)
+        assert torch.equal(nat.index_points(dev(xs), dev(idx)).cpu(), oracle.index_points(xs, idx))
+        assert torch.equal(nat.index_points(dev(fs), dev(idx[:, :, 0])).cpu(), oracle.index_points(fs, idx[:, :, 0]))
+        cen = oracle.index_points(xs, idx[:, :, 0]).contiguous()
+        for order in (0, 1):
+            for feat in (None, fs):
+                exp = oracle.group(xs, feat, idx, cen, order)
+                got = nat.group(dev(xs), None if feat is None else dev(feat), dev(idx.int()), dev(cen), order)
+                assert torch.equal(got.cpu(), exp)
+        exp = oracle.group(xs, fs, None, None, 2)
+        assert torch.equal(nat.group(dev(xs), dev(fs), None, None, 2).cpu(), exp)
+    with pytest.raises(IndexError):
+        nat.index_points(dev(x), dev(torch.full((3, 4), 400, dtype=torch.long)))
+
+
+# ---- fused set abstraction --------------------------------------------------------------------------------------
+def rand_layers(dims, seed):
+    g = torch.Generator().manual_seed(seed)
+    layers = []
+    for ci, co in zip(dims[:-1], dims[1:]):
+        W = (torch.rand(co, ci, generator=g) * 2 - 1) / ci ** 0.5
+        b = (torch.rand(co, generator=g) * 2 - 1) / ci ** 0.5
+        gam = torch.rand(co, generator=g) + 0.5
+        bet = torch.randn(co, generator=g) * 0.2
+        mu = torch.randn(co, generator=g) * 0.5
+        var = torch.rand(co, generator=g) * 1.5 + 0.5
+        layers.append((W, b, gam, bet, mu, var))
+    return layers
+
+
+SA_CASES = [  # (name, B, N, C, D, S, K, r, order, mlp)
+    ("ssg_sa1", 3, 1024, 3, 0, 512, 32, 0.2, 0, [64, 64, 128]),
+    ("ssg_sa2", 3, 512, 3, 128, 128, 64, 0.4, 0, [128, 128, 256]),
+    ("ssg_sa3", 5, 128, 3, 256, 1, 128, None, 2, [256, 512, 1024]),
+    ("pose_sa1", 2, 1024, 10, 0, 512, 32, 0.2, 0, [64, 64, 128]),
+    ("pose_sa2", 2, 512, 10, 128, 128, 64, 0.4, 0, [128, 128, 256]),
+    ("trans_sa2", 3, 512, 10, 128, 1, 512, None, 2, [256, 512, 1024]),
+    ("msg_sa1_k16", 2, 1024, 3, 0, 512, 16, 0.1, 1, [32, 32, 64]),
+    ("msg_sa1_k128", 2, 1024, 3, 0, 512, 128, 0.4, 1, [64, 96, 128]),
+    ("msg_sa2_k32", 2, 512, 3, 320, 128, 32, 0.2, 1, [64, 64, 128]),
+    ("msg_sa2_k128", 2, 512, 10, 320, 128, 128, 0.8, 1, [128, 128, 256]),
+    ("msg_all", 2, 128, 3, 640, 1, 128, None, 2, [256, 512, 1024]),
+    ("odd", 2, 300, 5, 7, 50, 12, 0.5, 0, [20, 33]),
+    ("odd_msg", 2, 300, 3, 9, 41, 24, 0.5, 1, [17]),
+    ("odd_all", 3, 77, 3, 5, 1, 77, None, 2, [24, 40]),
+    ("bigk", 1, 700, 3, 8, 9, 300, 2.0, 0, [32, 64]),
+]
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("name,B,N,C,D,S,K,r,order,mlp", SA_CASES, ids=[c[0] for c in SA_CASES])
+def test_sa_fused_vs_oracle(nat, oracle, prec, name, B, N, C, D, S, K, r, order, mlp):
+    x = make_cloud(B, N, C, "uni", 3000 + N)
+    f = torch.randn(B, N, D, generator=torch.Generator().manual_seed(5)) if D else None
+    dims = [C + D] + mlp
+    layers = rand_layers(dims, 11)
+    if order == 2:
+        idx = cen = None
+        rows = oracle.group(x, f, None, None, 2)
+    else:
+        g = torch.Generator().manual_seed(8)
+        start = torch.randint(0, N, (B,), generator=g, dtype=torch.long)
+        fps = oracle.farthest_point_sample(x, S, start)
+        cen = oracle.index_points(x, fps).contiguous()
+        idx = oracle.query_ball_point(r, K, x, cen)
+        rows = oracle.group(x, f, idx, cen, order)
+    exp = oracle.mlp_max(rows.reshape(B * S, K, C + D), layers).reshape(B, S, -1)
+    code = 0 if prec == "fp32" else 1
+    packed, pdims = nat.pack([tuple(dev(t) for t in l) for l in layers], 1e-5, code, C, order)
+    assert pdims == dims
+    co_off, total = 3, mlp[-1] + 8
+    alloc = torch.zeros if nat.sa_needs_zero(S, K, dims, code) else (lambda *a, **k: torch.full(*a, fill_value=-7.0, **k))
+    out = alloc((B, S, total), dtype=torch.float32, device="cuda:0")
+    before = out.clone()
+    nat.sa_fused(dev(x), None if f is None else dev(f), None if cen is None else dev(cen),
+                 None if idx is None else dev(idx.int()), order, dims, packed, code, out, co_off)
+    torch.cuda.synchronize()
+    got = out[:, :, co_off:co_off + mlp[-1]].cpu()
+    err = rel_err(got, exp)
+    assert err <= (TOL_F32 if prec == "fp32" else TOL_BF16), err
+    # channels outside the branch's slice are untouched (MSG concat by offset, pointnet2_utils.py:222)
+    assert torch.equal(out[:, :, :co_off], before[:, :, :co_off])
+    assert torch.equal(out[:, :, co_off + mlp[-1]:], before[:, :, co_off + mlp[-1]:])
+
+
+def test_cpu_tensor_is_an_error(nat):
+    with pytest.raises(RuntimeError):
+        nat.fps(torch.zeros(1, 8, 3), torch.zeros(1, dtype=torch.long), 2)

@@ -1,0 +1,178 @@
+"""-m gpu: whole set-abstraction modules and the eight PointNet++ models on the CUDA path, against the golden
+outputs recorded from the live reference (oracle/make_golden.py) and against the oracle at larger sizes."""
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+import cloudgen
+import golden_io
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-5, "bf16": 2e-2}
+DEV = "cuda:0"
+
+
+def rel_err(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+@pytest.fixture()
+def pu():
+    import pointnet2_utils
+    prev = pointnet2_utils.get_precision()
+    yield pointnet2_utils
+    pointnet2_utils.set_precision(prev)
+    pointnet2_utils.set_reference_strides(False)
+
+
+MODULE_CTORS = {
+    "ssg3": lambda pu: pu.PointNetSetAbstraction(32, 16, 0.4, 3, [16, 24, 40], False),
+    "ssg3f": lambda pu: pu.PointNetSetAbstraction(32, 8, 0.3, 12 + 3, [32, 20], False),
+    "ssg10": lambda pu: pu.PointNetSetAbstraction(24, 32, 0.5, 10, [16, 16, 32], False),
+    "all3f": lambda pu: pu.PointNetSetAbstraction(None, None, None, 12 + 3, [32, 64], True),
+    "msg3": lambda pu: pu.PointNetSetAbstractionMsg(32, [8, 16, 64], [0.2, 0.4, 0.8], 0, [[8, 16], [16, 24], [16, 32]]),
+    "msg3f": lambda pu: pu.PointNetSetAbstractionMsg(16, [16, 32], [0.3, 0.6], 12, [[16, 16, 32], [24, 40]]),
+    "msg10": lambda pu: pu.PointNetSetAbstractionMsg(32, [16, 32], [0.3, 0.6], 0, [[16, 32], [32, 48]], num_category=7),
+}
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", sorted(MODULE_CTORS))
+def test_module_vs_golden(pu, name, prec):
+    d = golden_io.module_cases()[name]
+    pu.set_precision(prec)
+    m = MODULE_CTORS[name](pu)
+    m.load_state_dict(d["sd"])                      # the reference's state_dict loads unchanged
+    m = m.to(DEV).eval()
+    pts = cloudgen.channels_first(torch.from_numpy(d["points"])).to(DEV)
+    feat = torch.from_numpy(d["feature"]).to(DEV) if "feature" in d else None
+    with torch.no_grad():
+        torch.manual_seed(42)
+        new_pts, new_feat = m(pts, feat)
+    assert torch.equal(new_pts.cpu(), torch.from_numpy(d["new_points"]))      # same FPS choices, bit-exact rows
+    assert new_feat.shape == tuple(d["new_feature"].shape)
+    assert rel_err(new_feat.cpu(), torch.from_numpy(d["new_feature"])) <= TOL[prec]
+    if not getattr(m, "group_all", False):
+        S, C = new_pts.shape[2], new_pts.shape[1]
+        assert new_pts.stride() == (S * C, 1, C)   # permuted view of contiguous [B,S,C] (pointnet2_utils.py:173)
+
+
+def build_model(name, pu):
+    import pn2_models
+    torch.manual_seed(0)
+    model = pn2_models.get_model(name, 7)
+    pn2_models.randomize_bn_(model, 7)
+    return model.eval()
+
+
+def model_inputs(name, d):
+    xyz = torch.from_numpy(d["xyz"])
+    pose = not name.startswith("pointnet2_cls")
+    x = cloudgen.channels_first(cloudgen.with_category(xyz) if pose else xyz).to(DEV)
+    if name.startswith("translation"):
+        return (x, torch.from_numpy(d["mean"]).to(DEV))
+    return (x,)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", sorted(golden_io.model_cases()))
+def test_model_vs_golden(pu, name, prec):
+    d = golden_io.model_cases()[name]
+    pu.set_precision(prec)
+    model = build_model(name, pu)
+    sd = model.state_dict()
+    assert list(sd.keys()) == [str(k) for k in d["sd_keys"]]
+    checksum = float(sum(v.double().abs().sum() for v in sd.values()))
+    if abs(checksum - float(d["sd_checksum"][0])) > 1e-6 * checksum:
+        pytest.skip("seeded initialisation differs from the build container's torch; weights not reproducible")
+    model = model.to(DEV)
+    with torch.no_grad():
+        torch.manual_seed(42)
+        out = model(*model_inputs(name, d))
+    outs = out if isinstance(out, tuple) else (out,)
+    tol = TOL[prec]
+    if name.startswith("pointnet2_cls"):
+        assert rel_err(outs[1].cpu(), torch.from_numpy(d["out1"])) <= tol       # l3 feature [B,1024,1]
+        assert rel_err(outs[0].cpu(), torch.from_numpy(d["out0"])) <= 5 * tol   # log-probs after the FC head
+        if prec == "fp32":
+            assert torch.equal(outs[2].cpu(), torch.from_numpy(d["out2"]))
+    elif name.startswith("sign"):
+        assert rel_err(outs[0].cpu(), torch.from_numpy(d["out0"])) <= 5 * tol
+        if prec == "fp32":
+            assert torch.equal(outs[1].cpu(), torch.from_numpy(d["out1"]))
+    else:
+        assert rel_err(outs[0].cpu(), torch.from_numpy(d["out0"])) <= 5 * tol
+
+
+def test_reference_strides_switch(pu):
+    d = golden_io.module_cases()["ssg3"]
+    m = MODULE_CTORS["ssg3"](pu)
+    m.load_state_dict(d["sd"])
+    m = m.to(DEV).eval()
+    pts = cloudgen.channels_first(torch.from_numpy(d["points"])).to(DEV)
+    pu.set_reference_strides(True)
+    with torch.no_grad():
+        torch.manual_seed(42)
+        _, feat = m(pts, None)
+    assert feat.is_contiguous()
+
+
+def test_weight_cache_follows_parameter_updates(pu):
+    d = golden_io.module_cases()["ssg3"]
+    m = MODULE_CTORS["ssg3"](pu)
+    m.load_state_dict(d["sd"])
+    m = m.to(DEV).eval()
+    pts = cloudgen.channels_first(torch.from_numpy(d["points"])).to(DEV)
+    with torch.no_grad():
+        torch.manual_seed(42)
+        _, a = m(pts, None)
+        m.mlp_convs[0].weight.mul_(0.5)
+        torch.manual_seed(42)
+        _, b = m(pts, None)
+        m.mlp_convs[0].weight.mul_(2.0)
+        torch.manual_seed(42)
+        _, c = m(pts, None)
+    assert not torch.equal(a, b)
+    assert torch.equal(a, c)
+
+
+def test_four_threads_share_the_library(pu):
+    """The reference's only concurrency pattern: several heads on Python threads (mutilthreading/predict_test.py:44-62)."""
+    names = ["rotation_ssg", "translation_ssg", "sign_ssg", "pointnet2_cls_ssg"]
+    cases = golden_io.model_cases()
+    models = {n: build_model(n, pu).to(DEV) for n in names}
+    start = torch.randint(0, 1024, (2,), generator=torch.Generator().manual_seed(1), dtype=torch.long)
+    outs, errs = {}, []
+
+    def run(n, slot):
+        try:
+            with torch.no_grad(), torch.cuda.stream(torch.cuda.Stream()):
+                o = models[n](*model_inputs(n, cases[n]))
+                torch.cuda.current_stream().synchronize()
+            outs[slot] = o if not isinstance(o, tuple) else o[0]
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    with pu.fps_start_source(lambda B, N: start):
+        for n in names:
+            run(n, ("serial", n))
+        ts = [threading.Thread(target=run, args=(n, ("thread", n))) for n in names]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+    assert not errs, errs
+    for n in names:
+        assert torch.equal(outs[("serial", n)], outs[("thread", n)])
+
+
+def test_training_mode_runs_and_backpropagates(pu):
+    torch.manual_seed(0)
+    import pn2_models
+    model = pn2_models.get_model("rotation_msg", 7).to(DEV).train()
+    x = cloudgen.channels_first(cloudgen.with_category(cloudgen.uniform_cloud(4, 1024, 77))).to(DEV)
+    out = model(x)
+    out.square().sum().backward()
+    g = model.sa1.conv_blocks[0][0].weight.grad
+    assert g is not None and torch.isfinite(g).all() and g.abs().sum() > 0
