@@ -44,7 +44,8 @@ int pn2_version(void);
 const char *pn2_last_error_string(void);
 
 /* farthest_point_sample -- pointnet2_utils.py:47-68.
- * points [B,N,C] with element strides (sb,sn,sc); start[B] = the torch.randint draw of :59 (int64, device).
+ * points [B,N,C] with element strides (sb,sn,sc); start[B] = the torch.randint draw of :59 (int64, device,
+ * values in [0,N); anything else is clamped into the cloud rather than read out of bounds).
  * Outputs (any may be NULL): idx64 [B,S] (the function's return value), idx32 [B,S], new_points [B,S,C]
  * contiguous (= index_points(points, idx), :107 / :201, fused because the cloud is already on chip). */
 int pn2_fps_f32(const float *points, int64_t sb, int64_t sn, int64_t sc, int B, int N, int C,

@@ -7,6 +7,7 @@ path: a CPU tensor, or a missing shared library, is an error.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import os
 import threading
@@ -98,6 +99,22 @@ class Native:
 
     def __init__(self):
         self.lib = load_library()
+        self.launches = 0      # kernels launched through the C ABI (bench.py reports it as gpu_launches)
+        self.trace = None      # set to a list to record (name, meta, start_event, end_event) per launch
+
+    @contextlib.contextmanager
+    def _span(self, name, **meta):
+        """Count the launch; when tracing, bracket it with CUDA events on the launching (current) stream."""
+        self.launches += 1
+        tr = self.trace
+        if tr is None:
+            yield
+            return
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        yield
+        e.record()
+        tr.append((name, meta, s, e))
 
     # -- sampling ------------------------------------------------------------------------------------------
     def fps(self, points, start, number, want_idx64=True, want_idx32=False, want_new_points=False):
@@ -111,7 +128,7 @@ class Native:
         i32 = torch.empty(B, S, dtype=torch.int32, device=dev) if want_idx32 else None
         npts = torch.empty(B, S, C, dtype=torch.float32, device=dev) if want_new_points else None
         start = start.contiguous()
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), self._span("fps", B=B, N=N, C=C, S=S):
             _check(self.lib.pn2_fps_f32(points.data_ptr(), *points.stride(), B, N, C, start.data_ptr(), S,
                                         i64.data_ptr() if want_idx64 else None,
                                         i32.data_ptr() if want_idx32 else None,
@@ -127,7 +144,7 @@ class Native:
         M = idx_c.numel() // max(B, 1)
         out = torch.empty(*idx.shape, C, dtype=torch.float32, device=src.device)
         flag = torch.zeros(1, dtype=torch.int32, device=src.device) if check else None
-        with torch.cuda.device(src.device):
+        with torch.cuda.device(src.device), self._span("index_points", B=B, N=N, C=C, M=M):
             _check(self.lib.pn2_index_points_f32(src.data_ptr(), *src.stride(), B, N, C, idx_c.data_ptr(), M,
                                                  out.data_ptr(), flag.data_ptr() if check else None, _stream(src)))
         if check and int(flag.item()) != 0:
@@ -140,7 +157,7 @@ class Native:
         B, S, C = src.shape
         N = dst.shape[1]
         out = torch.empty(B, S, N, dtype=torch.float32, device=src.device)
-        with torch.cuda.device(src.device):
+        with torch.cuda.device(src.device), self._span("square_distance", B=B, S=S, N=N, C=C):
             _check(self.lib.pn2_square_distance_f32(src.data_ptr(), *src.stride(), dst.data_ptr(), *dst.stride(),
                                                     B, S, N, C, out.data_ptr(), _stream(src)))
         return out
@@ -155,7 +172,7 @@ class Native:
         dev = points.device
         i64 = torch.empty(B, S, K, dtype=torch.int64, device=dev) if want_idx64 else None
         i32 = torch.empty(B, S, K, dtype=torch.int32, device=dev) if want_idx32 else None
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), self._span("ball_query", B=B, N=N, C=C, S=S, K=K, i64=bool(want_idx64)):
             _check(self.lib.pn2_ball_query_f32(centres.data_ptr(), *centres.stride(), points.data_ptr(), *points.stride(),
                                                B, S, N, C, float(r2), K,
                                                i64.data_ptr() if want_idx64 else None,
@@ -184,7 +201,7 @@ class Native:
             _, S, K = idx32.shape
             iptr, cptr = idx32.data_ptr(), centres.data_ptr()
         out = torch.empty(B, S, K, C + D, dtype=torch.float32, device=points.device)
-        with torch.cuda.device(points.device):
+        with torch.cuda.device(points.device), self._span("group", B=B, N=N, S=S, K=K, C=C, D=D):
             _check(self.lib.pn2_group_f32(points.data_ptr(), *points.stride(), fptr, *fstr, iptr, cptr,
                                           B, N, S, K, C, D, order, out.data_ptr(), _stream(points)))
         return out
@@ -207,7 +224,7 @@ class Native:
             _check(-1)
         packed = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
         parr = (ctypes.c_void_p * len(ptrs))(*ptrs)
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), self._span("pack", dims=tuple(dims)):
             _check(self.lib.pn2_pack_weights(len(layers), d.ctypes.data, ctypes.cast(parr, _vp), float(eps), prec,
                                              int(C), int(order), packed.data_ptr(), _stream(packed)))
         return packed, dims
@@ -241,7 +258,7 @@ class Native:
             iptr, cptr = idx32.data_ptr(), centres.data_ptr()
         assert out.shape[0] == B and out.shape[1] == S and out.stride(2) == 1
         d = _dims_array(dims)
-        with torch.cuda.device(points.device):
+        with torch.cuda.device(points.device), self._span("sa_fused", B=B, N=N, S=S, K=K, C=C, D=D, dims=tuple(dims), prec=prec):
             _check(self.lib.pn2_sa_fused(points.data_ptr(), *points.stride(), fptr, *fstr, cptr, iptr,
                                          B, N, S, K, C, D, order, len(dims) - 1, d.ctypes.data, packed.data_ptr(), prec,
                                          out.data_ptr(), out.stride(0), out.stride(1), int(co_off), _stream(points)))

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(TMAX) fps_kernel(const float *__restrict__ poi
         }
         dist[j] = ok ? 1e10f : 0.f;             // padding can never win: dist 0 and index >= N
     }
-    int far = (int)start[b];
+    int far = (int)min(max(start[b], (int64_t)0), (int64_t)N - 1);   // contract: start in [0,N); never index out of the cloud
     __syncthreads();
 
     for (int i = 0; i < S; ++i) {
@@ -95,7 +95,7 @@ __global__ void fps_generic_kernel(const float *__restrict__ points, int64_t sb,
     const bool contig = (sc == 1);
     const float *P = points + (int64_t)b * sb;
     for (int n = tid; n < N; n += T) s_dist[n] = 1e10f;
-    int far = (int)start[b];
+    int far = (int)min(max(start[b], (int64_t)0), (int64_t)N - 1);
     __syncthreads();
     for (int i = 0; i < S; ++i) {
         if (tid < C) {

@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from pointnet2_utils import PointNetSetAbstraction, PointNetSetAbstractionMsg
+import pointnet2_utils as _default_sa
 
 # (kind, args) per set-abstraction level; `c` = coordinate channels (3, or 3 + num_category for pose heads)
 _SSG_SA = lambda c: [  # pointnet2_cls_ssg.py:9-11, rotation_ssg.py:11-13
@@ -54,8 +54,11 @@ ARCH = {
 class PointNet2Head(nn.Module):
     """One of the eight PointNet++ models of the reference, selected by name (see ARCH)."""
 
-    def __init__(self, name: str, num_category: int = 7, mean_mlp: str = "True"):
+    def __init__(self, name: str, num_category: int = 7, mean_mlp: str = "True", sa_impl=None):
+        """sa_impl: module providing PointNetSetAbstraction / PointNetSetAbstractionMsg (default: this package's
+        CUDA-backed pointnet2_utils; the CPU baseline legs of bench.py and the tests pass other providers)."""
         super().__init__()
+        sa_impl = sa_impl or _default_sa
         backbone, pose, out_width, self.kind = ARCH[name]
         self.arch = name
         c = 3 + num_category if pose else 3
@@ -63,7 +66,7 @@ class PointNet2Head(nn.Module):
         spec = {"ssg3": lambda: _SSG_SA(c), "msg3": lambda: _MSG_SA(c, k),
                 "ssg2": lambda: _SSG2_SA(c), "msg2": lambda: _MSG2_SA(c, k)}[backbone]()
         for i, (kind, kw) in enumerate(spec, 1):
-            cls = PointNetSetAbstraction if kind == "ssg" else PointNetSetAbstractionMsg
+            cls = sa_impl.PointNetSetAbstraction if kind == "ssg" else sa_impl.PointNetSetAbstractionMsg
             setattr(self, f"sa{i}", cls(**kw))
         self.n_sa = len(spec)
         self.fc1 = nn.Linear(1024, 512)
