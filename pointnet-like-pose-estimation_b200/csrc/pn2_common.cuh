@@ -126,6 +126,7 @@ int sa_f32_needs_zero(int S, int K, int L, const int *dims);
 int sa_bf16_needs_zero(int S, int K, int L, const int *dims);
 int launch_sa_f32(const SaArgs &a, cudaStream_t st);
 int launch_sa_bf16(const SaArgs &a, cudaStream_t st);
+int launch_sa_bf16_pipelined(const SaArgs &a, cudaStream_t st);   // -100: configuration not covered
 int launch_selftest_umma(int n_cols, int k_dim, int variant, float *max_err, float *dump, cudaStream_t st);
 
 }  // namespace pn2

@@ -1,0 +1,389 @@
+// K3 (bf16 mode), pipelined variant -- the fused set-abstraction kernel for stacks whose weights fit in
+// shared memory next to the activations (every sa1 / sa2 configuration of the reference's SSG models and most
+// MSG branches).  Reference: model/pointnet2_utils.py:166-172 (SSG) and :204-218 (one MSG branch).
+//
+// One persistent CTA per SM runs U independent "units".  A unit is a warpgroup of 4 warps (128 threads, one
+// thread per row of a 128-row tile = one TMEM lane) that walks its tiles through the chain
+//     gather -> [MMA l -> epilogue l] x (L-1) -> MMA L-1 -> max-pool -> store
+// and owns one activation buffer in shared memory (each layer's epilogue overwrites its own, fully consumed,
+// input) and one accumulator region in TMEM.  A single extra warp issues every tcgen05.mma of the CTA: it
+// serves the units round-robin, waiting on a unit's "operand ready" mbarrier and committing to its
+// "accumulator ready" mbarrier, so while one unit drains TMEM / gathers, the tensor core works for the others.
+// All weights (BN folded, bf16, canonical K-major core-matrix layout, written by pn2_pack_weights) are
+// bulk-copied (cp.async.bulk + mbarrier) into shared memory once per CTA.
+//
+//   epilogue (hidden layer): tcgen05.ld 32x32b.x32 -> +bias (FADD2) -> cvt.rn.relu.bf16x2 -> st.shared.v4
+//   pooling  (last layer)  : tcgen05.ld -> per column CREDUX.MAX.F32 over the 32 rows a warp owns (masked per
+//                            group when K < 32; combined through shared memory when K is 64 or 128) -> +bias,
+//                            ReLU (both commute with the max) -> 128-byte coalesced stores of [group][channel]
+#include "pn2_tc.cuh"
+
+namespace pn2 {
+
+constexpr int T2_MAX_UNITS = 4;
+constexpr int T2_MAX_THREADS = (4 * T2_MAX_UNITS + 1) * 32;   // 544
+constexpr int T2_SMEM_LIMIT = 227 * 1024;
+
+struct Tc2Params {
+    const float *points; int64_t sb, sn, sc;
+    const float *feat;   int64_t fb, fn, fc;
+    const float *centres; const int32_t *idx32;
+    int N, S, K, C, D, order;
+    TcLayout lay;
+    const unsigned char *packed;
+    float *out; int64_t ob, os; int co_off;
+    int64_t G, rows, tiles;
+    int U, cols_per_unit, tmem_cols, a_unit_bytes, pool_cols, feat_fast;
+};
+
+__device__ __forceinline__ void unit_bar_sync(int u) { asm volatile("bar.sync %0, 128;" ::"r"(u + 1) : "memory"); }
+
+__device__ __forceinline__ float2 add2(float2 a, float2 b)
+{
+    unsigned long long x, y, z;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(b.x), "f"(b.y));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(z) : "l"(x), "l"(y));
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(z));
+    return r;
+}
+
+// hidden-layer epilogue of 32 accumulator columns [c0, c0+32) of this thread's row
+__device__ __forceinline__ void epi_block(const uint32_t (&r)[32], const float *bs, unsigned char *A, int c0, int row)
+{
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 b0 = *reinterpret_cast<const float4 *>(bs + c0 + 8 * i);
+        const float4 b1 = *reinterpret_cast<const float4 *>(bs + c0 + 8 * i + 4);
+        const float2 v0 = add2(make_float2(__uint_as_float(r[8 * i + 0]), __uint_as_float(r[8 * i + 1])), make_float2(b0.x, b0.y));
+        const float2 v1 = add2(make_float2(__uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3])), make_float2(b0.z, b0.w));
+        const float2 v2 = add2(make_float2(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5])), make_float2(b1.x, b1.y));
+        const float2 v3 = add2(make_float2(__uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7])), make_float2(b1.z, b1.w));
+        *reinterpret_cast<uint4 *>(A + (size_t)(c0 / 8 + i) * A_LBO + row * 16) =
+            make_uint4(relu_pack_bf16x2(v0.x, v0.y), relu_pack_bf16x2(v1.x, v1.y), relu_pack_bf16x2(v2.x, v2.y), relu_pack_bf16x2(v3.x, v3.y));
+    }
+}
+
+// column maxima of one 32-column block over the rows of this warp, NG groups of 32/NG rows each:
+// afterwards lane j holds, for every group gi, the maximum of column j in m[gi]
+template <int NG>
+__device__ __forceinline__ void pool_block(const uint32_t (&r)[32], bool valid, int lane, float (&m)[NG])
+{
+    constexpr int KL = 32 / NG;
+    const int my = lane / KL;
+#pragma unroll
+    for (int gi = 0; gi < NG; ++gi) m[gi] = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const float x = valid ? __uint_as_float(r[j]) : -INFINITY;
+#pragma unroll
+        for (int gi = 0; gi < NG; ++gi) {
+            const float red = warp_max_f32((NG == 1 || my == gi) ? x : -INFINITY);
+            if (lane == j) m[gi] = red;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Params p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const TcLayout &lay = p.lay;
+    const int U = p.U;
+    unsigned char *Wsm = smem;
+    float *bias_s = reinterpret_cast<float *>(Wsm + lay.w_bytes);
+    unsigned char *A_base = reinterpret_cast<unsigned char *>(bias_s + lay.bias_floats);
+    float *pool_base = reinterpret_cast<float *>(A_base + (size_t)U * p.a_unit_bytes);      // [U][4][pool_cols]
+    uint64_t *a_ready = reinterpret_cast<uint64_t *>(pool_base + (size_t)U * 4 * p.pool_cols);
+    uint64_t *acc_ready = a_ready + T2_MAX_UNITS;
+    uint64_t *w_bar = acc_ready + T2_MAX_UNITS;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w_bar + 1);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int mma_warp = 4 * U;
+    const int L = lay.L;
+
+    if (tid == 0) {
+        for (int u = 0; u < T2_MAX_UNITS; ++u) { mbar_init(a_ready + u, 4); mbar_init(acc_ready + u, 1); }
+        mbar_init(w_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == mma_warp) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    {
+        const float *bsrc = reinterpret_cast<const float *>(p.packed + lay.w_bytes);
+        for (int i = tid; i < lay.bias_floats; i += blockDim.x) bias_s[i] = __ldg(bsrc + i);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int64_t stride = (int64_t)gridDim.x * U;
+
+    if (warp == mma_warp) {
+        // =================================================================================================
+        // MMA warp: weights in once, then every tcgen05.mma of the CTA, units served round-robin
+        // =================================================================================================
+        if (lane == 0) {
+            mbar_expect_tx(w_bar, (uint32_t)lay.w_bytes);
+            for (int off = 0; off < lay.w_bytes; off += 32768) {
+                const int nb = min(32768, lay.w_bytes - off);
+                bulk_g2s(Wsm + off, p.packed + off, (uint32_t)nb, w_bar);
+            }
+            int64_t n_max = 0;
+            for (int u = 0; u < U; ++u) {
+                const int64_t gu = (int64_t)blockIdx.x * U + u;
+                const int64_t n_u = gu < p.tiles ? (p.tiles - gu + stride - 1) / stride : 0;
+                if (n_u > n_max) n_max = n_u;
+            }
+            mbar_wait(w_bar, 0);
+            uint32_t phases = 0;
+            for (int64_t it = 0; it < n_max; ++it) {
+                for (int l = 0; l < L; ++l) {
+                    const TcLayer ly = lay.ly[l];
+                    const uint32_t idesc = instr_desc_bf16(ly.NS);
+                    const uint32_t w_addr = smem_u32(Wsm) + (uint32_t)ly.w_off;
+                    const uint32_t w_lbo = (uint32_t)ly.NS * 16u;
+                    const int nks = ly.K / 16;
+                    for (int u = 0; u < U; ++u) {
+                        const int64_t tile = (int64_t)blockIdx.x * U + u + it * stride;
+                        if (tile >= p.tiles) continue;
+                        mbar_wait(a_ready + u, (phases >> u) & 1u);
+                        phases ^= 1u << u;
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(A_base) + (uint32_t)(u * p.a_unit_bytes);
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(u * p.cols_per_unit);
+                        for (int ks = 0; ks < nks; ++ks) {
+                            const uint64_t ad = smem_desc(a_addr + (uint32_t)(ks * 2 * A_LBO), A_LBO, 128);
+                            const uint64_t bd = smem_desc(w_addr + (uint32_t)ks * 2u * w_lbo, w_lbo, 128);
+                            umma_bf16(d_tmem, ad, bd, idesc, ks ? 1u : 0u);
+                        }
+                        umma_commit(acc_ready + u);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp < mma_warp) {
+        // =================================================================================================
+        // unit warpgroups: gather, epilogues, pooling
+        // =================================================================================================
+        const int u = warp >> 2, q = warp & 3, row = q * 32 + lane;
+        unsigned char *A = A_base + (size_t)u * p.a_unit_bytes;
+        float *pool_s = pool_base + (size_t)u * 4 * p.pool_cols;
+        const uint32_t tmem_row = tmem_base + (uint32_t)(u * p.cols_per_unit) + ((uint32_t)(q * 32) << 16);
+        const int K = p.K, C = p.C, D = p.D, K0 = lay.ly[0].K;
+        const bool grouped = (p.order != PN2_ORDER_ALL);
+        uint32_t acc_phase = 0;
+        const int64_t gu = (int64_t)blockIdx.x * U + u;
+
+        auto load_index = [&](int64_t tile) -> int {
+            const int64_t r = tile * TC_ROWS + row;
+            if (tile >= p.tiles || r >= p.rows) return -1;
+            int n = grouped ? __ldg(p.idx32 + r) : (int)(r % K);
+            return (n >= 0 && n < p.N) ? n : -1;       // n == N: 'no neighbour' marker of an empty ball (:85)
+        };
+        int n_next = load_index(gu);
+
+        for (int64_t tile = gu; tile < p.tiles; tile += stride) {
+            const int n = n_next;
+            n_next = load_index(tile + stride);
+            const bool valid = n >= 0;
+            const int64_t g = (tile * TC_ROWS + row) / K;      // group of this row
+            const int64_t b = g / p.S;
+
+            // ---- gather: this thread's row, internal channel order [feat(D), xyz(C), zero pad] ----------------
+            if (p.feat_fast) {
+                const float *f = valid && D ? p.feat + b * p.fb + (int64_t)n * p.fn : nullptr;
+                for (int kg0 = 0; kg0 < D / 8; kg0 += 4) {
+                    float4 v[8];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        v[2 * i] = v[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (f && kg0 + i < D / 8) {
+                            v[2 * i] = __ldg(reinterpret_cast<const float4 *>(f + (kg0 + i) * 8));
+                            v[2 * i + 1] = __ldg(reinterpret_cast<const float4 *>(f + (kg0 + i) * 8 + 4));
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (kg0 + i < D / 8)
+                            *reinterpret_cast<uint4 *>(A + (size_t)(kg0 + i) * A_LBO + row * 16) =
+                                make_uint4(pack_bf16x2(v[2 * i].x, v[2 * i].y), pack_bf16x2(v[2 * i].z, v[2 * i].w),
+                                           pack_bf16x2(v[2 * i + 1].x, v[2 * i + 1].y), pack_bf16x2(v[2 * i + 1].z, v[2 * i + 1].w));
+                }
+                const float *pp = p.points + b * p.sb + (int64_t)n * p.sn;
+                const float *cc = p.centres + g * C;
+                for (int kg = D / 8; kg < K0 / 8; ++kg) {
+                    float x[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int c = kg * 8 + i - D;
+                        float t = 0.f;
+                        if (valid && c < C) {
+                            t = __ldg(pp + (int64_t)c * p.sc);
+                            if (grouped) t = __fsub_rn(t, __ldg(cc + c));
+                        }
+                        x[i] = t;
+                    }
+                    *reinterpret_cast<uint4 *>(A + (size_t)kg * A_LBO + row * 16) =
+                        make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+                }
+            } else {
+                for (int k = 0; k < K0; ++k) {
+                    float t = 0.f;
+                    if (valid) {
+                        if (k < D) t = __ldg(p.feat + b * p.fb + (int64_t)n * p.fn + (int64_t)k * p.fc);
+                        else if (k < D + C) {
+                            t = __ldg(p.points + b * p.sb + (int64_t)n * p.sn + (int64_t)(k - D) * p.sc);
+                            if (grouped) t = __fsub_rn(t, __ldg(p.centres + g * C + (k - D)));
+                        }
+                    }
+                    *reinterpret_cast<__nv_bfloat16 *>(A + (size_t)(k / 8) * A_LBO + row * 16 + (k % 8) * 2) = __float2bfloat16_rn(t);
+                }
+            }
+            fence_proxy_async();                 // generic-proxy stores -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_ready + u);
+
+            for (int l = 0; l < L; ++l) {
+                const TcLayer ly = lay.ly[l];
+                mbar_wait(acc_ready + u, acc_phase);
+                acc_phase ^= 1u;
+                tc_fence_after();
+                const float *bs = bias_s + ly.b_off;
+                if (l < L - 1) {
+                    // ---- hidden layer: accumulator -> +bias -> ReLU -> bf16 -> the next layer's A operand (in place) --
+                    for (int c0 = 0; c0 < ly.Npad; c0 += 64) {
+                        uint32_t r0[32], r1[32];
+                        const bool two = c0 + 32 < ly.Npad;
+                        tmem_ld32_nowait(tmem_row + (uint32_t)c0, r0);
+                        if (two) tmem_ld32_nowait(tmem_row + (uint32_t)(c0 + 32), r1);
+                        tmem_ld_wait();
+                        epi_block(r0, bs, A, c0, row);
+                        if (two) epi_block(r1, bs, A, c0 + 32, row);
+                    }
+                    tc_fence_before();           // TMEM reads ordered before the MMA warp's next write to this region
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(a_ready + u);
+                } else {
+                    // ---- last layer: max over the K rows of each group, then bias + ReLU, then store ---------------
+                    if (K <= 32) {
+                        const int ng = 32 / K;                          // groups inside this warp
+                        const int64_t g0 = (tile * TC_ROWS + q * 32) / K;
+                        // a group is stored when its first row is a real neighbour (padding rows repeat it)
+                        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+                        for (int c0 = 0; c0 < ly.Npad; c0 += 32) {
+                            uint32_t r[32];
+                            tmem_ld32_nowait(tmem_row + (uint32_t)c0, r);
+                            tmem_ld_wait();
+                            float m[4];
+                            if (ng == 1) { float t[1]; pool_block<1>(r, valid, lane, t); m[0] = t[0]; }
+                            else if (ng == 2) { float t[2]; pool_block<2>(r, valid, lane, t); m[0] = t[0]; m[1] = t[1]; }
+                            else { pool_block<4>(r, valid, lane, m); }
+                            const int c = c0 + lane;
+                            if (c < ly.Cout) {
+                                const float bv = bs[c];
+#pragma unroll
+                                for (int gi = 0; gi < 4; ++gi) {
+                                    if (gi < ng && g0 + gi < p.G && ((vmask >> (gi * K)) & ((K == 32) ? 0xffffffffu : ((1u << K) - 1u)))) {
+                                        const int64_t gg = g0 + gi;
+                                        p.out[(gg / p.S) * p.ob + (gg % p.S) * p.os + p.co_off + c] = fmaxf(m[gi] + bv, 0.f);
+                                    }
+                                }
+                            }
+                        }
+                        tc_fence_before();
+                    } else {
+                        // K = 64 or 128: per-warp column maxima -> shared scratch -> combine the quarters of a group
+                        for (int c0 = 0; c0 < ly.Npad; c0 += 32) {
+                            uint32_t r[32];
+                            tmem_ld32_nowait(tmem_row + (uint32_t)c0, r);
+                            tmem_ld_wait();
+                            float t[1];
+                            pool_block<1>(r, valid, lane, t);
+                            pool_s[q * p.pool_cols + c0 + lane] = t[0];
+                        }
+                        tc_fence_before();
+                        unit_bar_sync(u);
+                        const int qpg = K / 32;                         // quarters per group (2 or 4)
+                        const int gpt = TC_ROWS / K;
+                        for (int it = q * 32 + lane; it < gpt * ly.Npad; it += 128) {
+                            const int gi = it / ly.Npad, c = it % ly.Npad;
+                            float m = -INFINITY;
+                            for (int qq = 0; qq < qpg; ++qq) m = fmaxf(m, pool_s[(gi * qpg + qq) * p.pool_cols + c]);
+                            const int64_t gg = tile * gpt + gi;
+                            if (gg < p.G && c < ly.Cout && m > -INFINITY)
+                                p.out[(gg / p.S) * p.ob + (gg % p.S) * p.os + p.co_off + c] = fmaxf(m + bs[c], 0.f);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == mma_warp) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------------
+static int pow2_at_least(int x) { int p = 32; while (p < x) p <<= 1; return p; }
+
+struct Tc2Plan { int U, cols_per_unit, tmem_cols, a_unit_bytes, pool_cols; size_t smem; };
+
+static bool tc2_plan(int K, int order, const TcLayout &t, Tc2Plan *pl)
+{
+    if (order == PN2_ORDER_ALL) return false;                       // group_all stacks are wide: pn2_sa_tc.cu
+    if (K < 8 || K > TC_ROWS || (K & (K - 1))) return false;
+    int kmax = 0, nmax = 0;
+    for (int l = 0; l < t.L; ++l) {
+        if (t.ly[l].nslab != 1 || t.ly[l].NS > 256) return false;
+        if (t.ly[l].K > kmax) kmax = t.ly[l].K;
+        if (t.ly[l].Npad > nmax) nmax = t.ly[l].Npad;
+    }
+    pl->cols_per_unit = pow2_at_least(nmax);
+    pl->a_unit_bytes = kmax / 8 * A_LBO;
+    pl->pool_cols = K > 32 ? t.ly[t.L - 1].Npad : 0;
+    for (int U = T2_MAX_UNITS; U >= 1; U >>= 1) {
+        if (U * pl->cols_per_unit > 512) continue;
+        const size_t smem = (size_t)t.w_bytes + (size_t)t.bias_floats * 4 + (size_t)U * pl->a_unit_bytes +
+                            (size_t)U * 4 * pl->pool_cols * 4 + (2 * T2_MAX_UNITS + 1) * 8 + 16;
+        if (smem > (size_t)T2_SMEM_LIMIT) continue;
+        pl->U = U; pl->smem = smem; pl->tmem_cols = pow2_at_least(U * pl->cols_per_unit);
+        return true;
+    }
+    return false;
+}
+
+// returns -100 when this variant does not cover the configuration (the caller falls back to pn2_sa_tc.cu)
+int launch_sa_bf16_pipelined(const SaArgs &a, cudaStream_t st)
+{
+    const TcLayout lay = tc_layout(a.L, a.dims);
+    Tc2Plan pl;
+    if (!tc2_plan(a.K, a.order, lay, &pl)) return -100;
+    Tc2Params p;
+    p.points = a.points; p.sb = a.sb; p.sn = a.sn; p.sc = a.sc;
+    p.feat = a.feat; p.fb = a.fb; p.fn = a.fn; p.fc = a.fc;
+    p.centres = a.centres; p.idx32 = a.idx32;
+    p.N = a.N; p.S = a.S; p.K = a.K; p.C = a.C; p.D = a.D; p.order = a.order;
+    p.lay = lay;
+    p.packed = (const unsigned char *)a.packed;
+    p.out = a.out; p.ob = a.ob; p.os = a.os; p.co_off = a.co_off;
+    p.G = (int64_t)a.B * a.S;
+    p.rows = p.G * a.K;
+    p.tiles = (p.rows + TC_ROWS - 1) / TC_ROWS;
+    p.U = pl.U; p.cols_per_unit = pl.cols_per_unit; p.tmem_cols = pl.tmem_cols;
+    p.a_unit_bytes = pl.a_unit_bytes; p.pool_cols = pl.pool_cols;
+    p.feat_fast = (a.D == 0) || (a.fc == 1 && a.D % 8 == 0 && a.fn % 4 == 0 && a.fb % 4 == 0 && ((uintptr_t)a.feat & 15) == 0);
+    if (p.tiles == 0) return 0;
+    cudaError_t e = cudaFuncSetAttribute(sa_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    if (e != cudaSuccess) { set_error("sa_tc2: smem attribute (%zu B): %s", pl.smem, cudaGetErrorString(e)); return (int)e; }
+    int64_t grid = (p.tiles + pl.U - 1) / pl.U;
+    if (grid > 148) grid = 148;
+    sa_tc2_kernel<<<(unsigned)grid, (4 * pl.U + 1) * 32, pl.smem, st>>>(p);
+    return launch_status("pn2_sa_fused(bf16, pipelined)");
+}
+
+}  // namespace pn2

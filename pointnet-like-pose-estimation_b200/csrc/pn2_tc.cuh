@@ -1,0 +1,215 @@
+// Shared by the tensor-core translation units (pn2_sa_tc.cu, pn2_sa_tc2.cu): packed-weight layout and the
+// tcgen05 / mbarrier / bulk-copy PTX wrappers.  Not part of the ABI.
+#pragma once
+#include <cuda_bf16.h>
+#include "pn2_common.cuh"
+
+namespace pn2 {
+
+constexpr int TC_ROWS = 128;
+constexpr int TC_CWARPS = 8;                       // compute warps (gather, MMA issue, epilogue)
+constexpr int TC_CTHREADS = TC_CWARPS * 32;        // 256
+constexpr int TC_THREADS = TC_CTHREADS + 32;       // + 1 producer warp for the weight ring
+constexpr int A_LBO = TC_ROWS * 16;                // bytes between k-groups of the A operand
+constexpr int KBLK = 64;                           // k extent of one weight chunk
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_SMEM_LIMIT = 227 * 1024;
+
+static inline int rup(int x, int a) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------------
+// Packed layout shared by host (pack + launch) and device.
+// ------------------------------------------------------------------------------------------------------
+struct TcLayer {
+    int K;        // padded input channels (multiple of 16)
+    int Cout;     // real output channels
+    int Npad;     // output channels padded to 32 (= next layer's K)
+    int NS;       // columns per MMA slab (<= 256, divides Npad)
+    int nslab;
+    int nkb;      // number of 64-wide k blocks
+    int w_off;    // byte offset of this layer's first chunk inside the packed buffer
+    int b_off;    // float offset of this layer's bias inside the bias block
+};
+struct TcLayout {
+    int L;
+    TcLayer ly[PN2_MAX_LAYERS];
+    int w_bytes;       // all weight chunks
+    int bias_floats;   // sum of Npad
+    int max_chunk;     // bytes of the largest chunk
+    int n_chunks;
+};
+
+static __host__ __device__ inline int tc_chunk_bytes(const TcLayer &ly, int kb)
+{
+    const int kw = (ly.K - kb * KBLK) < KBLK ? (ly.K - kb * KBLK) : KBLK;
+    return ly.NS * kw * 2;
+}
+
+static inline TcLayout tc_layout(int L, const int *dims)
+{
+    TcLayout t;
+    t.L = L; t.w_bytes = 0; t.bias_floats = 0; t.max_chunk = 0; t.n_chunks = 0;
+    int K = rup(dims[0], 16);
+    // wide stacks (group_all heads) stream their weights through a small ring next to a large activation
+    // buffer: keep the chunks at 16 KB there
+    int ns_cap = 256;
+    for (int l = 0; l < L; ++l) if (rup(dims[l], 16) > 256) ns_cap = 128;
+    for (int l = 0; l < L; ++l) {
+        TcLayer &y = t.ly[l];
+        y.K = K; y.Cout = dims[l + 1]; y.Npad = rup(dims[l + 1], 32);
+        // one MMA slab per layer when the layer fits an instruction (N <= 256, any multiple of 16 is legal at
+        // M = 128); otherwise the largest power-of-two slab that divides the width
+        y.NS = 32;
+        if (y.Npad <= ns_cap) y.NS = y.Npad;
+        else for (int ns = ns_cap; ns >= 32; ns >>= 1) if (y.Npad % ns == 0) { y.NS = ns; break; }
+        y.nslab = y.Npad / y.NS;
+        y.nkb = (K + KBLK - 1) / KBLK;
+        y.w_off = t.w_bytes; y.b_off = t.bias_floats;
+        t.w_bytes += y.Npad * K * 2;
+        t.bias_floats += y.Npad;
+        for (int kb = 0; kb < y.nkb; ++kb) { const int c = tc_chunk_bytes(y, kb); if (c > t.max_chunk) t.max_chunk = c; }
+        t.n_chunks += y.nslab * y.nkb;
+        K = y.Npad;
+    }
+    return t;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate, M = 128, N from idesc, K = 16
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1 = Blackwell)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = bf16, both K-major, M = 128
+__device__ __forceinline__ uint32_t instr_desc_bf16(int n)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
+{
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void cbar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_CTHREADS) : "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
+{
+    const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits)
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+
+// one reduce-scatter step of the max over rows: N live columns -> N/2; partner = lane ^ o
+template <int N>
+__device__ __forceinline__ void rs_step(float (&v)[32], int o, bool upper)
+{
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) {
+        const float a = v[j], b = v[j + N / 2];
+        const float keep = upper ? b : a, send = upper ? a : b;
+        v[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, o));
+    }
+}
+
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// max over the 32 lanes of a warp, result uniform (CREDUX.MAX.F32 on sm_100a)
+__device__ __forceinline__ float warp_max_f32(float x)
+{
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(x));
+    return r;
+}
+// relu(lo), relu(hi) -> packed bf16x2 (lo in the low half); one F2FP.RELU.BF16.F32.PACK_AB
+__device__ __forceinline__ uint32_t relu_pack_bf16x2(float lo, float hi)
+{
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+}  // namespace pn2
