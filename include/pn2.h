@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PN2_ABI_VERSION 3
+#define PN2_ABI_VERSION 4
 #define PN2_MAX_COORD 16 /* exact summation-order rules are verified against ATen for C <= 16 */
 #define PN2_MAX_LAYERS 8
 
@@ -100,12 +100,19 @@ int pn2_pack_weights(int L, const int *dims, const void *const *ptrs, float eps,
  *   an MSG branch inside the concatenated tensor of :222).  When K rows span several tiles the kernel
  *   combines with atomicMax and the caller must have zero-filled `out` (see pn2_sa_needs_zero_init). */
 int pn2_sa_needs_zero_init(int S, int K, int L, const int *dims, int prec);
+/* bf16 side tensors (PN2_PREC_BF16 only): in bf16 mode consecutive set-abstraction layers can hand the pooled
+ * features over in bf16 as well -- out_bf16 (same addressing as out, element type bf16) is written next to the
+ * fp32 result and a later launch may pass it as feat_bf16 ([B,N,D] contiguous, D % 8 == 0), which the gather
+ * then copies straight into the MMA operand with cp.async.  Both may be NULL.  pn2_sa_bf16_side_io tells the
+ * caller whether the kernel that serves this configuration reads / writes them (1) or ignores them (0). */
+int pn2_sa_bf16_side_io(int K, int order, int L, const int *dims, int prec);
 int pn2_sa_fused(const float *points, int64_t sb, int64_t sn, int64_t sc,
                  const float *feat, int64_t fb, int64_t fn, int64_t fc,
                  const float *centres, const int32_t *idx32,
                  int B, int N, int S, int K, int C, int D, int order,
                  int L, const int *dims, const void *packed, int prec,
-                 float *out, int64_t ob, int64_t os, int co_off, void *stream);
+                 float *out, int64_t ob, int64_t os, int co_off,
+                 const void *feat_bf16, void *out_bf16, void *stream);
 
 /* Device self-test of the tcgen05 building blocks (one 128xN tile against a scalar loop in the same
  * launch).  Returns 0 and writes max|err| to *max_err (device float). */

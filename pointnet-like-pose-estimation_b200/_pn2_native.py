@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(_HERE, LIB_NAME)
 ORDER_SSG, ORDER_MSG, ORDER_ALL = 0, 1, 2
 PREC_F32, PREC_BF16 = 0, 1
 MAX_COORD = 16
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _i64, _i32, _f32, _vp = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p
 
@@ -39,9 +39,10 @@ _SIGNATURES = {
     "pn2_packed_bytes": ([_i32, _vp, _i32], _i64),
     "pn2_pack_weights": ([_i32, _vp, _vp, _f32, _i32, _i32, _i32, _vp, _vp], _i32),
     "pn2_sa_needs_zero_init": ([_i32, _i32, _i32, _vp, _i32], _i32),
+    "pn2_sa_bf16_side_io": ([_i32, _i32, _i32, _vp, _i32], _i32),
     "pn2_sa_fused": ([_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _vp,
                       _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32,
-                      _vp, _i64, _i64, _i32, _vp], _i32),
+                      _vp, _i64, _i64, _i32, _vp, _vp, _vp], _i32),
     "pn2_selftest_umma": ([_i32, _i32, _i32, _vp, _vp, _vp], _i32),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -236,8 +237,18 @@ class Native:
             _check(rc)
         return bool(rc)
 
-    def sa_fused(self, points, feature, centres, idx32, order, dims, packed, prec, out, co_off=0):
-        """Fused gather -> MLP -> max.  out [B,S,Ctot] (channels-last) receives channels [co_off, co_off+dims[-1])."""
+    def sa_bf16_side_io(self, K, order, dims, prec) -> bool:
+        """True when the kernel serving this configuration reads `feature_bf16` / writes `out_bf16`."""
+        d = _dims_array(dims)
+        rc = self.lib.pn2_sa_bf16_side_io(int(K), int(order), len(dims) - 1, d.ctypes.data, prec)
+        if rc < 0:
+            _check(rc)
+        return bool(rc)
+
+    def sa_fused(self, points, feature, centres, idx32, order, dims, packed, prec, out, co_off=0,
+                 feature_bf16=None, out_bf16=None):
+        """Fused gather -> MLP -> max.  out [B,S,Ctot] (channels-last) receives channels [co_off, co_off+dims[-1]).
+        feature_bf16 [B,N,D] / out_bf16 [B,S,Ctot]: optional bf16 side tensors (see include/pn2.h)."""
         _need_cuda("points", points, torch.float32)
         _need_cuda("out", out, torch.float32)
         B, N, C = points.shape
@@ -257,11 +268,19 @@ class Native:
             _, S, K = idx32.shape
             iptr, cptr = idx32.data_ptr(), centres.data_ptr()
         assert out.shape[0] == B and out.shape[1] == S and out.stride(2) == 1
+        if feature_bf16 is not None:
+            _need_cuda("feature_bf16", feature_bf16, torch.bfloat16)
+            assert feature_bf16.shape == (B, N, D) and feature_bf16.is_contiguous()
+        if out_bf16 is not None:
+            _need_cuda("out_bf16", out_bf16, torch.bfloat16)
+            assert out_bf16.shape == out.shape and out_bf16.stride() == out.stride()
         d = _dims_array(dims)
         with torch.cuda.device(points.device), self._span("sa_fused", B=B, N=N, S=S, K=K, C=C, D=D, dims=tuple(dims), prec=prec):
             _check(self.lib.pn2_sa_fused(points.data_ptr(), *points.stride(), fptr, *fstr, cptr, iptr,
                                          B, N, S, K, C, D, order, len(dims) - 1, d.ctypes.data, packed.data_ptr(), prec,
-                                         out.data_ptr(), out.stride(0), out.stride(1), int(co_off), _stream(points)))
+                                         out.data_ptr(), out.stride(0), out.stride(1), int(co_off),
+                                         feature_bf16.data_ptr() if feature_bf16 is not None else None,
+                                         out_bf16.data_ptr() if out_bf16 is not None else None, _stream(points)))
         return out
 
     def selftest_umma(self, n_cols, k_dim, variant, device="cuda:0", dump=False):

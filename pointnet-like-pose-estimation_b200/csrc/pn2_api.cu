@@ -107,12 +107,19 @@ int pn2_sa_needs_zero_init(int S, int K, int L, const int *dims, int prec)
     return prec == PN2_PREC_BF16 ? sa_bf16_needs_zero(S, K, L, dims) : sa_f32_needs_zero(S, K, L, dims);
 }
 
+int pn2_sa_bf16_side_io(int K, int order, int L, const int *dims, int prec)
+{
+    if (!valid_dims(L, dims)) { set_error("pn2_sa_bf16_side_io: bad layer list"); return -1; }
+    return prec == PN2_PREC_BF16 ? sa_bf16_pipelined_covers(K, order, L, dims) : 0;
+}
+
 int pn2_sa_fused(const float *points, int64_t sb, int64_t sn, int64_t sc,
                  const float *feat, int64_t fb, int64_t fn, int64_t fc,
                  const float *centres, const int32_t *idx32,
                  int B, int N, int S, int K, int C, int D, int order,
                  int L, const int *dims, const void *packed, int prec,
-                 float *out, int64_t ob, int64_t os, int co_off, void *stream)
+                 float *out, int64_t ob, int64_t os, int co_off,
+                 const void *feat_bf16, void *out_bf16, void *stream)
 {
     PN2_REQUIRE(points && packed && out, "pn2_sa_fused: null pointer");
     PN2_REQUIRE(valid_dims(L, dims), "pn2_sa_fused: bad layer list");
@@ -130,6 +137,8 @@ int pn2_sa_fused(const float *points, int64_t sb, int64_t sn, int64_t sc,
     a.L = L;
     for (int l = 0; l <= L; ++l) a.dims[l] = dims[l];
     a.packed = packed; a.out = out; a.ob = ob; a.os = os; a.co_off = co_off;
+    a.feat_bf16 = (prec == PN2_PREC_BF16) ? feat_bf16 : nullptr;
+    a.out_bf16 = (prec == PN2_PREC_BF16) ? out_bf16 : nullptr;
     if (prec == PN2_PREC_F32) return launch_sa_f32(a, (cudaStream_t)stream);
     if (prec == PN2_PREC_BF16) return launch_sa_bf16(a, (cudaStream_t)stream);
     PN2_REQUIRE(false, "pn2_sa_fused: unknown precision %d", prec);

@@ -117,6 +117,8 @@ struct SaArgs {
     int L; int dims[PN2_MAX_LAYERS + 1];
     const void *packed;
     float *out; int64_t ob, os; int co_off;
+    const void *feat_bf16;   // optional bf16 copy of feat, [B,N,D] contiguous (produced by a previous launch)
+    void *out_bf16;          // optional bf16 copy of the pooled output, same (ob, os, co_off) addressing as out
 };
 int64_t packed_bytes_f32(int L, const int *dims);
 int64_t packed_bytes_bf16(int L, const int *dims);
@@ -127,6 +129,7 @@ int sa_bf16_needs_zero(int S, int K, int L, const int *dims);
 int launch_sa_f32(const SaArgs &a, cudaStream_t st);
 int launch_sa_bf16(const SaArgs &a, cudaStream_t st);
 int launch_sa_bf16_pipelined(const SaArgs &a, cudaStream_t st);   // -100: configuration not covered
+int sa_bf16_pipelined_covers(int K, int order, int L, const int *dims);
 int launch_selftest_umma(int n_cols, int k_dim, int variant, float *max_err, float *dump, cudaStream_t st);
 
 }  // namespace pn2

@@ -13,9 +13,15 @@
 // bulk-copied (cp.async.bulk + mbarrier) into shared memory once per CTA.
 //
 //   epilogue (hidden layer): tcgen05.ld 32x32b.x32 -> +bias (FADD2) -> cvt.rn.relu.bf16x2 -> st.shared.v4
-//   pooling  (last layer)  : tcgen05.ld -> per column CREDUX.MAX.F32 over the 32 rows a warp owns (masked per
-//                            group when K < 32; combined through shared memory when K is 64 or 128) -> +bias,
-//                            ReLU (both commute with the max) -> 128-byte coalesced stores of [group][channel]
+//   last layer + pooling   : the product is issued TRANSPOSED, D^T[channel][row] = W (M operand) x X^T (N operand;
+//                            both are K-major in shared memory, so swapping roles costs nothing).  A thread then
+//                            owns one output channel (TMEM lane) and the rows of a group are consecutive TMEM
+//                            columns: the max over the K neighbours is a chain of FMNMX3 on the registers that
+//                            tcgen05.ld returns, bias + ReLU (which commute with the max) are applied once per
+//                            group, and a warp stores 32 consecutive channels of a group (128 B coalesced).
+//   gather                 : features of the previous set-abstraction layer arrive in bf16 (side output of this
+//                            kernel) and go global -> shared with cp.async, 16 B = one k-group of one row,
+//                            no registers; fp32 features / raw coordinates go through registers.
 #include "pn2_tc.cuh"
 
 namespace pn2 {
@@ -33,10 +39,9 @@ struct Tc2Params {
     const unsigned char *packed;
     float *out; int64_t ob, os; int co_off;
     int64_t G, rows, tiles;
-    int U, cols_per_unit, tmem_cols, a_unit_bytes, pool_cols, feat_fast;
+    int U, cols_per_unit, tmem_cols, a_unit_bytes, feat_fast;
+    const __nv_bfloat16 *feat_bf16; __nv_bfloat16 *out_bf16;
 };
-
-__device__ __forceinline__ void unit_bar_sync(int u) { asm volatile("bar.sync %0, 128;" ::"r"(u + 1) : "memory"); }
 
 __device__ __forceinline__ float2 add2(float2 a, float2 b)
 {
@@ -65,24 +70,28 @@ __device__ __forceinline__ void epi_block(const uint32_t (&r)[32], const float *
     }
 }
 
-// column maxima of one 32-column block over the rows of this warp, NG groups of 32/NG rows each:
-// afterwards lane j holds, for every group gi, the maximum of column j in m[gi]
-template <int NG>
-__device__ __forceinline__ void pool_block(const uint32_t (&r)[32], bool valid, int lane, float (&m)[NG])
+__device__ __forceinline__ float max3(float a, float b, float c)
 {
-    constexpr int KL = 32 / NG;
-    const int my = lane / KL;
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+// max of r[OFF .. OFF+CNT) (CNT = 8, 16 or 32) as a tree of 3-input maxima
+template <int OFF, int CNT>
+__device__ __forceinline__ float max_range(const uint32_t (&r)[32])
+{
+    float m = __uint_as_float(r[OFF]);
 #pragma unroll
-    for (int gi = 0; gi < NG; ++gi) m[gi] = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const float x = valid ? __uint_as_float(r[j]) : -INFINITY;
-#pragma unroll
-        for (int gi = 0; gi < NG; ++gi) {
-            const float red = warp_max_f32((NG == 1 || my == gi) ? x : -INFINITY);
-            if (lane == j) m[gi] = red;
-        }
-    }
+    for (int j = 1; j + 1 < CNT; j += 2) m = max3(m, __uint_as_float(r[OFF + j]), __uint_as_float(r[OFF + j + 1]));
+    return fmaxf(m, __uint_as_float(r[OFF + CNT - 1]));
+}
+__device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gsrc, bool pred)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(pred ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Params p)
@@ -93,8 +102,8 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
     unsigned char *Wsm = smem;
     float *bias_s = reinterpret_cast<float *>(Wsm + lay.w_bytes);
     unsigned char *A_base = reinterpret_cast<unsigned char *>(bias_s + lay.bias_floats);
-    float *pool_base = reinterpret_cast<float *>(A_base + (size_t)U * p.a_unit_bytes);      // [U][4][pool_cols]
-    uint64_t *a_ready = reinterpret_cast<uint64_t *>(pool_base + (size_t)U * 4 * p.pool_cols);
+    uint32_t *vmask_base = reinterpret_cast<uint32_t *>(A_base + (size_t)U * p.a_unit_bytes);   // [U][2][4] valid-row ballots, by tile parity
+    uint64_t *a_ready = reinterpret_cast<uint64_t *>(vmask_base + 8 * T2_MAX_UNITS);
     uint64_t *acc_ready = a_ready + T2_MAX_UNITS;
     uint64_t *w_bar = acc_ready + T2_MAX_UNITS;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w_bar + 1);
@@ -141,6 +150,7 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
                 for (int l = 0; l < L; ++l) {
                     const TcLayer ly = lay.ly[l];
                     const uint32_t idesc = instr_desc_bf16(ly.NS);
+                    const uint32_t idesc_t = instr_desc_bf16(TC_ROWS);
                     const uint32_t w_addr = smem_u32(Wsm) + (uint32_t)ly.w_off;
                     const uint32_t w_lbo = (uint32_t)ly.NS * 16u;
                     const int nks = ly.K / 16;
@@ -152,10 +162,21 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
                         tc_fence_after();
                         const uint32_t a_addr = smem_u32(A_base) + (uint32_t)(u * p.a_unit_bytes);
                         const uint32_t d_tmem = tmem_base + (uint32_t)(u * p.cols_per_unit);
-                        for (int ks = 0; ks < nks; ++ks) {
-                            const uint64_t ad = smem_desc(a_addr + (uint32_t)(ks * 2 * A_LBO), A_LBO, 128);
-                            const uint64_t bd = smem_desc(w_addr + (uint32_t)ks * 2u * w_lbo, w_lbo, 128);
-                            umma_bf16(d_tmem, ad, bd, idesc, ks ? 1u : 0u);
+                        if (l < L - 1) {
+                            for (int ks = 0; ks < nks; ++ks) {
+                                const uint64_t ad = smem_desc(a_addr + (uint32_t)(ks * 2 * A_LBO), A_LBO, 128);
+                                const uint64_t bd = smem_desc(w_addr + (uint32_t)ks * 2u * w_lbo, w_lbo, 128);
+                                umma_bf16(d_tmem, ad, bd, idesc, ks ? 1u : 0u);
+                            }
+                        } else {
+                            // transposed: 128 output channels (rows of W) per MMA as M, the tile's 128 rows as N
+                            const uint32_t wl = (uint32_t)ly.Npad * 16u;
+                            for (int mh = 0; mh < ly.Npad / TC_ROWS; ++mh)
+                                for (int ks = 0; ks < nks; ++ks) {
+                                    const uint64_t ad = smem_desc(w_addr + (uint32_t)(mh * TC_ROWS * 16) + (uint32_t)ks * 2u * wl, wl, 128);
+                                    const uint64_t bd = smem_desc(a_addr + (uint32_t)(ks * 2 * A_LBO), A_LBO, 128);
+                                    umma_bf16(d_tmem + (uint32_t)(mh * TC_ROWS), ad, bd, idesc_t, ks ? 1u : 0u);
+                                }
                         }
                         umma_commit(acc_ready + u);
                     }
@@ -169,22 +190,25 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
         // =================================================================================================
         const int u = warp >> 2, q = warp & 3, row = q * 32 + lane;
         unsigned char *A = A_base + (size_t)u * p.a_unit_bytes;
-        float *pool_s = pool_base + (size_t)u * 4 * p.pool_cols;
+        uint32_t *vmask_u = vmask_base + 8 * u;
+        uint32_t parity = 0;
         const uint32_t tmem_row = tmem_base + (uint32_t)(u * p.cols_per_unit) + ((uint32_t)(q * 32) << 16);
         const int K = p.K, C = p.C, D = p.D, K0 = lay.ly[0].K;
-        const bool grouped = (p.order != PN2_ORDER_ALL);
+        const int gpt = TC_ROWS / K;
         uint32_t acc_phase = 0;
         const int64_t gu = (int64_t)blockIdx.x * U + u;
 
         auto load_index = [&](int64_t tile) -> int {
             const int64_t r = tile * TC_ROWS + row;
             if (tile >= p.tiles || r >= p.rows) return -1;
-            int n = grouped ? __ldg(p.idx32 + r) : (int)(r % K);
+            const int n = __ldg(p.idx32 + r);
             return (n >= 0 && n < p.N) ? n : -1;       // n == N: 'no neighbour' marker of an empty ball (:85)
         };
         int n_next = load_index(gu);
 
         for (int64_t tile = gu; tile < p.tiles; tile += stride) {
+            uint32_t *vmask_s = vmask_u + 4 * parity;    // a warp can run at most one tile ahead of its unit
+            parity ^= 1u;
             const int n = n_next;
             n_next = load_index(tile + stride);
             const bool valid = n >= 0;
@@ -193,23 +217,28 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
 
             // ---- gather: this thread's row, internal channel order [feat(D), xyz(C), zero pad] ----------------
             if (p.feat_fast) {
-                const float *f = valid && D ? p.feat + b * p.fb + (int64_t)n * p.fn : nullptr;
-                for (int kg0 = 0; kg0 < D / 8; kg0 += 4) {
-                    float4 v[8];
+                if (p.feat_bf16) {
+                    const __nv_bfloat16 *f = p.feat_bf16 + (valid ? (b * p.N + n) * (int64_t)D : 0);
+                    for (int kg = 0; kg < D / 8; ++kg) cp_async16_zfill(A + (size_t)kg * A_LBO + row * 16, f + kg * 8, valid);
+                } else {
+                    const float *f = valid && D ? p.feat + b * p.fb + (int64_t)n * p.fn : nullptr;
+                    for (int kg0 = 0; kg0 < D / 8; kg0 += 4) {
+                        float4 v[8];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        v[2 * i] = v[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (f && kg0 + i < D / 8) {
-                            v[2 * i] = __ldg(reinterpret_cast<const float4 *>(f + (kg0 + i) * 8));
-                            v[2 * i + 1] = __ldg(reinterpret_cast<const float4 *>(f + (kg0 + i) * 8 + 4));
+                        for (int i = 0; i < 4; ++i) {
+                            v[2 * i] = v[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (f && kg0 + i < D / 8) {
+                                v[2 * i] = __ldg(reinterpret_cast<const float4 *>(f + (kg0 + i) * 8));
+                                v[2 * i + 1] = __ldg(reinterpret_cast<const float4 *>(f + (kg0 + i) * 8 + 4));
+                            }
                         }
-                    }
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (kg0 + i < D / 8)
-                            *reinterpret_cast<uint4 *>(A + (size_t)(kg0 + i) * A_LBO + row * 16) =
-                                make_uint4(pack_bf16x2(v[2 * i].x, v[2 * i].y), pack_bf16x2(v[2 * i].z, v[2 * i].w),
-                                           pack_bf16x2(v[2 * i + 1].x, v[2 * i + 1].y), pack_bf16x2(v[2 * i + 1].z, v[2 * i + 1].w));
+                        for (int i = 0; i < 4; ++i)
+                            if (kg0 + i < D / 8)
+                                *reinterpret_cast<uint4 *>(A + (size_t)(kg0 + i) * A_LBO + row * 16) =
+                                    make_uint4(pack_bf16x2(v[2 * i].x, v[2 * i].y), pack_bf16x2(v[2 * i].z, v[2 * i].w),
+                                               pack_bf16x2(v[2 * i + 1].x, v[2 * i + 1].y), pack_bf16x2(v[2 * i + 1].z, v[2 * i + 1].w));
+                    }
                 }
                 const float *pp = p.points + b * p.sb + (int64_t)n * p.sn;
                 const float *cc = p.centres + g * C;
@@ -219,28 +248,26 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
                     for (int i = 0; i < 8; ++i) {
                         const int c = kg * 8 + i - D;
                         float t = 0.f;
-                        if (valid && c < C) {
-                            t = __ldg(pp + (int64_t)c * p.sc);
-                            if (grouped) t = __fsub_rn(t, __ldg(cc + c));
-                        }
+                        if (valid && c < C) t = __fsub_rn(__ldg(pp + (int64_t)c * p.sc), __ldg(cc + c));
                         x[i] = t;
                     }
                     *reinterpret_cast<uint4 *>(A + (size_t)kg * A_LBO + row * 16) =
                         make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
                 }
+                if (p.feat_bf16) cp_async_commit_wait_all();
             } else {
                 for (int k = 0; k < K0; ++k) {
                     float t = 0.f;
                     if (valid) {
                         if (k < D) t = __ldg(p.feat + b * p.fb + (int64_t)n * p.fn + (int64_t)k * p.fc);
-                        else if (k < D + C) {
-                            t = __ldg(p.points + b * p.sb + (int64_t)n * p.sn + (int64_t)(k - D) * p.sc);
-                            if (grouped) t = __fsub_rn(t, __ldg(p.centres + g * C + (k - D)));
-                        }
+                        else if (k < D + C)
+                            t = __fsub_rn(__ldg(p.points + b * p.sb + (int64_t)n * p.sn + (int64_t)(k - D) * p.sc), __ldg(p.centres + g * C + (k - D)));
                     }
                     *reinterpret_cast<__nv_bfloat16 *>(A + (size_t)(k / 8) * A_LBO + row * 16 + (k % 8) * 2) = __float2bfloat16_rn(t);
                 }
             }
+            const unsigned vm = __ballot_sync(0xffffffffu, valid);
+            if (lane == 0) vmask_s[q] = vm;      // read by the whole unit in the pooling step (ordered by the mbarriers)
             fence_proxy_async();                 // generic-proxy stores -> visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(a_ready + u);
@@ -267,56 +294,52 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
                     __syncwarp();
                     if (lane == 0) mbar_arrive(a_ready + u);
                 } else {
-                    // ---- last layer: max over the K rows of each group, then bias + ReLU, then store ---------------
-                    if (K <= 32) {
-                        const int ng = 32 / K;                          // groups inside this warp
-                        const int64_t g0 = (tile * TC_ROWS + q * 32) / K;
-                        // a group is stored when its first row is a real neighbour (padding rows repeat it)
-                        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-                        for (int c0 = 0; c0 < ly.Npad; c0 += 32) {
+                    // ---- last layer (transposed): this thread = channel mh*128 + row; columns = the tile's rows ------
+                    const uint32_t m0 = vmask_s[0], m1 = vmask_s[1], m2 = vmask_s[2], m3 = vmask_s[3];
+                    const bool all_valid = (m0 & m1 & m2 & m3) == 0xffffffffu;
+                    const int64_t g0 = tile * gpt;
+                    const int64_t b0 = g0 / p.S;
+                    const int s0 = (int)(g0 % p.S);
+                    auto emit = [&](int gi, float m, int c, float bv) {
+                        // group gi of this tile, channel c: max over its rows -> + bias -> ReLU -> [B,S,Ctot]
+                        int64_t bb = b0; int ss = s0 + gi;
+                        while (ss >= p.S) { ss -= p.S; ++bb; }
+                        if (g0 + gi < p.G && c < ly.Cout && m > -INFINITY) {
+                            const int64_t o = bb * p.ob + (int64_t)ss * p.os + p.co_off + c;
+                            const float y = fmaxf(m + bv, 0.f);
+                            p.out[o] = y;
+                            if (p.out_bf16) p.out_bf16[o] = __float2bfloat16_rn(y);
+                        }
+                    };
+                    for (int mh = 0; mh < ly.Npad / TC_ROWS; ++mh) {
+                        const int c = mh * TC_ROWS + row;
+                        const float bv = bs[c];
+                        float run = -INFINITY;
+#pragma unroll 1
+                        for (int blk = 0; blk < 4; ++blk) {
                             uint32_t r[32];
-                            tmem_ld32_nowait(tmem_row + (uint32_t)c0, r);
+                            tmem_ld32_nowait(tmem_row + (uint32_t)(mh * TC_ROWS + blk * 32), r);
                             tmem_ld_wait();
-                            float m[4];
-                            if (ng == 1) { float t[1]; pool_block<1>(r, valid, lane, t); m[0] = t[0]; }
-                            else if (ng == 2) { float t[2]; pool_block<2>(r, valid, lane, t); m[0] = t[0]; m[1] = t[1]; }
-                            else { pool_block<4>(r, valid, lane, m); }
-                            const int c = c0 + lane;
-                            if (c < ly.Cout) {
-                                const float bv = bs[c];
+                            if (!all_valid) {        // padding rows / empty balls (never on the reference's configurations)
+                                const uint32_t mk = blk == 0 ? m0 : blk == 1 ? m1 : blk == 2 ? m2 : m3;
 #pragma unroll
-                                for (int gi = 0; gi < 4; ++gi) {
-                                    if (gi < ng && g0 + gi < p.G && ((vmask >> (gi * K)) & ((K == 32) ? 0xffffffffu : ((1u << K) - 1u)))) {
-                                        const int64_t gg = g0 + gi;
-                                        p.out[(gg / p.S) * p.ob + (gg % p.S) * p.os + p.co_off + c] = fmaxf(m[gi] + bv, 0.f);
-                                    }
-                                }
+                                for (int j = 0; j < 32; ++j) if (!((mk >> j) & 1u)) r[j] = 0xff800000u;   // -inf
+                            }
+                            if (K >= 32) {
+                                run = fmaxf(run, max_range<0, 32>(r));
+                                if (((blk + 1) * 32) % K == 0) { emit(blk * 32 / K, run, c, bv); run = -INFINITY; }
+                            } else if (K == 16) {
+                                emit(2 * blk, max_range<0, 16>(r), c, bv);
+                                emit(2 * blk + 1, max_range<16, 16>(r), c, bv);
+                            } else {
+                                emit(4 * blk, max_range<0, 8>(r), c, bv);
+                                emit(4 * blk + 1, max_range<8, 8>(r), c, bv);
+                                emit(4 * blk + 2, max_range<16, 8>(r), c, bv);
+                                emit(4 * blk + 3, max_range<24, 8>(r), c, bv);
                             }
                         }
-                        tc_fence_before();
-                    } else {
-                        // K = 64 or 128: per-warp column maxima -> shared scratch -> combine the quarters of a group
-                        for (int c0 = 0; c0 < ly.Npad; c0 += 32) {
-                            uint32_t r[32];
-                            tmem_ld32_nowait(tmem_row + (uint32_t)c0, r);
-                            tmem_ld_wait();
-                            float t[1];
-                            pool_block<1>(r, valid, lane, t);
-                            pool_s[q * p.pool_cols + c0 + lane] = t[0];
-                        }
-                        tc_fence_before();
-                        unit_bar_sync(u);
-                        const int qpg = K / 32;                         // quarters per group (2 or 4)
-                        const int gpt = TC_ROWS / K;
-                        for (int it = q * 32 + lane; it < gpt * ly.Npad; it += 128) {
-                            const int gi = it / ly.Npad, c = it % ly.Npad;
-                            float m = -INFINITY;
-                            for (int qq = 0; qq < qpg; ++qq) m = fmaxf(m, pool_s[(gi * qpg + qq) * p.pool_cols + c]);
-                            const int64_t gg = tile * gpt + gi;
-                            if (gg < p.G && c < ly.Cout && m > -INFINITY)
-                                p.out[(gg / p.S) * p.ob + (gg % p.S) * p.os + p.co_off + c] = fmaxf(m + bs[c], 0.f);
-                        }
                     }
+                    tc_fence_before();
                 }
             }
         }
@@ -331,30 +354,37 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
 // ------------------------------------------------------------------------------------------------------
 static int pow2_at_least(int x) { int p = 32; while (p < x) p <<= 1; return p; }
 
-struct Tc2Plan { int U, cols_per_unit, tmem_cols, a_unit_bytes, pool_cols; size_t smem; };
+struct Tc2Plan { int U, cols_per_unit, tmem_cols, a_unit_bytes; size_t smem; };
 
 static bool tc2_plan(int K, int order, const TcLayout &t, Tc2Plan *pl)
 {
     if (order == PN2_ORDER_ALL) return false;                       // group_all stacks are wide: pn2_sa_tc.cu
     if (K < 8 || K > TC_ROWS || (K & (K - 1))) return false;
     int kmax = 0, nmax = 0;
+    if (t.L < 1 || t.ly[t.L - 1].Npad > 512) return false;
     for (int l = 0; l < t.L; ++l) {
-        if (t.ly[l].nslab != 1 || t.ly[l].NS > 256) return false;
+        if (l < t.L - 1 && (t.ly[l].nslab != 1 || t.ly[l].NS > 256)) return false;
         if (t.ly[l].K > kmax) kmax = t.ly[l].K;
         if (t.ly[l].Npad > nmax) nmax = t.ly[l].Npad;
     }
     pl->cols_per_unit = pow2_at_least(nmax);
     pl->a_unit_bytes = kmax / 8 * A_LBO;
-    pl->pool_cols = K > 32 ? t.ly[t.L - 1].Npad : 0;
     for (int U = T2_MAX_UNITS; U >= 1; U >>= 1) {
         if (U * pl->cols_per_unit > 512) continue;
         const size_t smem = (size_t)t.w_bytes + (size_t)t.bias_floats * 4 + (size_t)U * pl->a_unit_bytes +
-                            (size_t)U * 4 * pl->pool_cols * 4 + (2 * T2_MAX_UNITS + 1) * 8 + 16;
+                            8 * T2_MAX_UNITS * 4 + (2 * T2_MAX_UNITS + 1) * 8 + 16;
         if (smem > (size_t)T2_SMEM_LIMIT) continue;
         pl->U = U; pl->smem = smem; pl->tmem_cols = pow2_at_least(U * pl->cols_per_unit);
         return true;
     }
     return false;
+}
+
+int sa_bf16_pipelined_covers(int K, int order, int L, const int *dims)
+{
+    const TcLayout lay = tc_layout(L, dims);
+    Tc2Plan pl;
+    return tc2_plan(K, order, lay, &pl) ? 1 : 0;
 }
 
 // returns -100 when this variant does not cover the configuration (the caller falls back to pn2_sa_tc.cu)
@@ -375,8 +405,11 @@ int launch_sa_bf16_pipelined(const SaArgs &a, cudaStream_t st)
     p.rows = p.G * a.K;
     p.tiles = (p.rows + TC_ROWS - 1) / TC_ROWS;
     p.U = pl.U; p.cols_per_unit = pl.cols_per_unit; p.tmem_cols = pl.tmem_cols;
-    p.a_unit_bytes = pl.a_unit_bytes; p.pool_cols = pl.pool_cols;
+    p.a_unit_bytes = pl.a_unit_bytes;
     p.feat_fast = (a.D == 0) || (a.fc == 1 && a.D % 8 == 0 && a.fn % 4 == 0 && a.fb % 4 == 0 && ((uintptr_t)a.feat & 15) == 0);
+    // bf16 features of the previous layer: [B,N,D] contiguous, 16-byte rows chunks
+    p.feat_bf16 = (a.feat_bf16 && p.feat_fast && a.D > 0 && ((uintptr_t)a.feat_bf16 & 15) == 0) ? (const __nv_bfloat16 *)a.feat_bf16 : nullptr;
+    p.out_bf16 = (__nv_bfloat16 *)a.out_bf16;
     if (p.tiles == 0) return 0;
     cudaError_t e = cudaFuncSetAttribute(sa_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) { set_error("sa_tc2: smem attribute (%zu B): %s", pl.smem, cudaGetErrorString(e)); return (int)e; }

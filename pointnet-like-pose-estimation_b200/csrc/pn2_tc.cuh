@@ -23,7 +23,7 @@ static inline int rup(int x, int a) { return (x + a - 1) / a * a; }
 struct TcLayer {
     int K;        // padded input channels (multiple of 16)
     int Cout;     // real output channels
-    int Npad;     // output channels padded to 32 (= next layer's K)
+    int Npad;     // output channels padded to 32 (hidden: = next layer's K) or 128 (last layer)
     int NS;       // columns per MMA slab (<= 256, divides Npad)
     int nslab;
     int nkb;      // number of 64-wide k blocks
@@ -56,7 +56,9 @@ static inline TcLayout tc_layout(int L, const int *dims)
     for (int l = 0; l < L; ++l) if (rup(dims[l], 16) > 256) ns_cap = 128;
     for (int l = 0; l < L; ++l) {
         TcLayer &y = t.ly[l];
-        y.K = K; y.Cout = dims[l + 1]; y.Npad = rup(dims[l + 1], 32);
+        // hidden layers pad to 32 columns (one tcgen05.ld block); the last layer pads to 128 because the
+        // pipelined kernel uses its weight matrix as the M = 128 operand of a transposed product
+        y.K = K; y.Cout = dims[l + 1]; y.Npad = rup(dims[l + 1], l == L - 1 ? 128 : 32);
         // one MMA slab per layer when the layer fits an instruction (N <= 256, any multiple of 16 is legal at
         // M = 128); otherwise the largest power-of-two slab that divides the width
         y.NS = 32;

@@ -176,12 +176,27 @@ class _FoldedMLP:
         return self.packed, self.dims, prec
 
 
-def _finish(new_points_bsc, pooled_bsc):
+def _finish(new_points_bsc, pooled_bsc, pooled_bf16=None):
     new_points = new_points_bsc.permute(0, 2, 1)       # view of contiguous [B,S,C], like the reference (:173)
     new_feature = pooled_bsc.permute(0, 2, 1)
     if _reference_strides:
         new_feature = new_feature.contiguous()
+    if pooled_bf16 is not None:
+        # bf16 mode: the same values rounded to bf16 ride along for the next set-abstraction layer, which then
+        # gathers them with cp.async instead of converting fp32 rows (derived data, dropped if the tensor changes)
+        new_feature._pn2_bf16 = (pooled_bf16, new_feature._version)
     return new_points, new_feature
+
+
+def _bf16_twin(feature_bdn, B, N, D):
+    """The bf16 [B,N,D] copy attached by _finish to a feature tensor this module returned, if still current."""
+    twin = getattr(feature_bdn, "_pn2_bf16", None)
+    if twin is None or _precision != "bf16":
+        return None
+    t, version = twin
+    if version != feature_bdn._version or t.shape != (B, N, D) or t.device != feature_bdn.device:
+        return None
+    return t
 
 
 def _shared_mlp_train(x, convs, bns):
@@ -226,8 +241,12 @@ class PointNetSetAbstraction(nn.Module):
             _, idx32 = be.ball_query(new_points, pts, _radius_sq(self.radius), K, want_idx64=False, want_idx32=True)
         alloc = torch.zeros if be.sa_needs_zero(S, K, dims, prec) else torch.empty
         pooled = alloc(B, S, dims[-1], dtype=torch.float32, device=pts.device)
-        be.sa_fused(pts, feat, new_points if not self.group_all else None, idx32, order, dims, packed, prec, pooled, 0)
-        return _finish(new_points, pooled)
+        side = be.sa_bf16_side_io(K, order, dims, prec)
+        twin_in = _bf16_twin(feature, B, N, feat.shape[-1]) if (side and feat is not None) else None
+        twin_out = torch.empty(B, S, dims[-1], dtype=torch.bfloat16, device=pts.device) if side else None
+        be.sa_fused(pts, feat, new_points if not self.group_all else None, idx32, order, dims, packed, prec, pooled, 0,
+                    feature_bf16=twin_in, out_bf16=twin_out)
+        return _finish(new_points, pooled, twin_out)
 
     def _forward_train(self, pts, feat):
         # Training mode (batch-statistics BatchNorm + autograd): sampling and grouping run on our kernels,
@@ -295,12 +314,17 @@ class PointNetSetAbstractionMsg(nn.Module):
         total = sum(d[-1] for _, d, _ in plans)
         zero = any(be.sa_needs_zero(S, K, d, prec) for K, (_, d, prec) in zip(self.sample_number_list, plans))
         pooled = (torch.zeros if zero else torch.empty)(B, S, total, dtype=torch.float32, device=pts.device)
+        sides = [be.sa_bf16_side_io(K, ORDER_MSG, d, prec) for K, (_, d, prec) in zip(self.sample_number_list, plans)]
+        twin_in = _bf16_twin(feature, B, N, feat.shape[-1]) if (any(sides) and feat is not None) else None
+        # the bf16 twin of the concatenated output is only complete if every branch's kernel writes its slice
+        twin_out = torch.empty(B, S, total, dtype=torch.bfloat16, device=pts.device) if all(sides) else None
         co = 0
         for radius, K, (packed, dims, prec) in zip(self.radius_list, self.sample_number_list, plans):
             _, idx32 = be.ball_query(new_points, pts, _radius_sq(radius), K, want_idx64=False, want_idx32=True)
-            be.sa_fused(pts, feat, new_points, idx32, ORDER_MSG, dims, packed, prec, pooled, co)   # branch concat (:222) is the channel offset
+            be.sa_fused(pts, feat, new_points, idx32, ORDER_MSG, dims, packed, prec, pooled, co,   # branch concat (:222) is the channel offset
+                        feature_bf16=twin_in, out_bf16=twin_out)
             co += dims[-1]
-        return _finish(new_points, pooled)
+        return _finish(new_points, pooled, twin_out)
 
     def _forward_train(self, pts, feat, start):
         be = _backend()

@@ -56,7 +56,11 @@ class OracleNative:
     def sa_needs_zero(self, S, K, dims, prec):
         return False
 
-    def sa_fused(self, points, feature, centres, idx32, order, dims, packed, prec, out, co_off=0):
+    def sa_bf16_side_io(self, K, order, dims, prec):
+        return False
+
+    def sa_fused(self, points, feature, centres, idx32, order, dims, packed, prec, out, co_off=0,
+                 feature_bf16=None, out_bf16=None):
         self.calls.append("sa_fused")
         layers, eps = packed
         rows = orc.group(points, feature, None if idx32 is None else idx32.long(), centres, order)

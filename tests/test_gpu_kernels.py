@@ -224,3 +224,30 @@ def test_sa_fused_vs_oracle(nat, oracle, prec, name, B, N, C, D, S, K, r, order,
 def test_cpu_tensor_is_an_error(nat):
     with pytest.raises(RuntimeError):
         nat.fps(torch.zeros(1, 8, 3), torch.zeros(1, dtype=torch.long), 2)
+
+
+@pytest.mark.parametrize("K,order", [(64, 0), (32, 1), (16, 1), (128, 1), (8, 0)])
+def test_sa_fused_bf16_side_tensors(nat, oracle, K, order):
+    """bf16 twin of the features in (cp.async gather) and of the pooled output: same values as the fp32 route."""
+    B, N, C, D, S, r, mlp = 2, 512, 3, 64, 96, 0.6, [64, 32, 128]
+    x = make_cloud(B, N, C, "uni", 77)
+    f = torch.randn(B, N, D, generator=torch.Generator().manual_seed(6))
+    dims = [C + D] + mlp
+    layers = rand_layers(dims, 12)
+    start = torch.randint(0, N, (B,), generator=torch.Generator().manual_seed(8), dtype=torch.long)
+    cen = oracle.index_points(x, oracle.farthest_point_sample(x, S, start)).contiguous()
+    idx = oracle.query_ball_point(r, K, x, cen)
+    assert nat.sa_bf16_side_io(K, order, dims, 1)
+    packed, _ = nat.pack([tuple(dev(t) for t in l) for l in layers], 1e-5, 1, C, order)
+    outs = []
+    for twin in (False, True):
+        out = torch.full((B, S, mlp[-1]), -7.0, device="cuda:0")
+        ob = torch.zeros(B, S, mlp[-1], dtype=torch.bfloat16, device="cuda:0")
+        nat.sa_fused(dev(x), dev(f), dev(cen), dev(idx.int()), order, dims, packed, 1, out, 0,
+                     feature_bf16=dev(f).bfloat16().contiguous() if twin else None, out_bf16=ob)
+        outs.append((out.cpu(), ob.cpu()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[0][0].bfloat16())
+    rows = oracle.group(x, f, idx, cen, order)
+    exp = oracle.mlp_max(rows.reshape(B * S, K, C + D), layers).reshape(B, S, -1)
+    assert rel_err(outs[0][0], exp) <= TOL_BF16
