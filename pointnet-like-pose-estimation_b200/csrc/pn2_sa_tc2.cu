@@ -94,6 +94,19 @@ __device__ __forceinline__ void cp_async_commit_wait_all()
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
+constexpr int T2_MAX_L = 4;
+
+__device__ __forceinline__ uint64_t mk_desc(uint32_t lo, uint32_t hi)
+{
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+    return d;
+}
+// low / high words of a K-major no-swizzle descriptor (see smem_desc): stepping the start address by X bytes
+// is `lo += X >> 4`
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16); }
+constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);      // SBO = 128 B, descriptor version 1
+
 __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Params p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -126,11 +139,13 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int64_t stride = (int64_t)gridDim.x * U;
+    const int tiles = (int)p.tiles;
+    const int stride = (int)gridDim.x * U;
 
     if (warp == mma_warp) {
         // =================================================================================================
-        // MMA warp: weights in once, then every tcgen05.mma of the CTA, units served round-robin
+        // MMA warp: weights in once, then every tcgen05.mma of the CTA, units served round-robin.  One thread;
+        // the per-stage path is kept to wait -> fence -> MMAs (descriptor = base + step) -> commit.
         // =================================================================================================
         if (lane == 0) {
             mbar_expect_tx(w_bar, (uint32_t)lay.w_bytes);
@@ -138,47 +153,56 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
                 const int nb = min(32768, lay.w_bytes - off);
                 bulk_g2s(Wsm + off, p.packed + off, (uint32_t)nb, w_bar);
             }
-            int64_t n_max = 0;
-            for (int u = 0; u < U; ++u) {
-                const int64_t gu = (int64_t)blockIdx.x * U + u;
-                const int64_t n_u = gu < p.tiles ? (p.tiles - gu + stride - 1) / stride : 0;
-                if (n_u > n_max) n_max = n_u;
+            int n_u[T2_MAX_UNITS], n_max = 0;
+            uint32_t a_lo[T2_MAX_UNITS], d_tm[T2_MAX_UNITS];
+#pragma unroll
+            for (int u = 0; u < T2_MAX_UNITS; ++u) {
+                const int gu = (int)blockIdx.x * U + u;
+                n_u[u] = (u < U && gu < tiles) ? (tiles - gu + stride - 1) / stride : 0;
+                n_max = max(n_max, n_u[u]);
+                a_lo[u] = desc_lo(smem_u32(A_base) + (uint32_t)(u * p.a_unit_bytes), A_LBO);
+                d_tm[u] = tmem_base + (uint32_t)(u * p.cols_per_unit);
             }
+            uint32_t w_lo[T2_MAX_L], w_step[T2_MAX_L], idesc[T2_MAX_L];
+            int nks[T2_MAX_L];
+#pragma unroll
+            for (int l = 0; l < T2_MAX_L; ++l) {
+                const TcLayer &ly = lay.ly[l < L ? l : 0];
+                const bool last = (l == L - 1);
+                const uint32_t lbo = (uint32_t)(last ? ly.Npad : ly.NS) * 16u;
+                w_lo[l] = desc_lo(smem_u32(Wsm) + (uint32_t)ly.w_off, lbo);
+                w_step[l] = (2u * lbo) >> 4;
+                idesc[l] = instr_desc_bf16(last ? TC_ROWS : ly.NS);
+                nks[l] = ly.K / 16;
+            }
+            const int n_mh = lay.ly[L - 1].Npad / TC_ROWS;
             mbar_wait(w_bar, 0);
             uint32_t phases = 0;
-            for (int64_t it = 0; it < n_max; ++it) {
-                for (int l = 0; l < L; ++l) {
-                    const TcLayer ly = lay.ly[l];
-                    const uint32_t idesc = instr_desc_bf16(ly.NS);
-                    const uint32_t idesc_t = instr_desc_bf16(TC_ROWS);
-                    const uint32_t w_addr = smem_u32(Wsm) + (uint32_t)ly.w_off;
-                    const uint32_t w_lbo = (uint32_t)ly.NS * 16u;
-                    const int nks = ly.K / 16;
-                    for (int u = 0; u < U; ++u) {
-                        const int64_t tile = (int64_t)blockIdx.x * U + u + it * stride;
-                        if (tile >= p.tiles) continue;
-                        mbar_wait(a_ready + u, (phases >> u) & 1u);
-                        phases ^= 1u << u;
-                        tc_fence_after();
-                        const uint32_t a_addr = smem_u32(A_base) + (uint32_t)(u * p.a_unit_bytes);
-                        const uint32_t d_tmem = tmem_base + (uint32_t)(u * p.cols_per_unit);
-                        if (l < L - 1) {
-                            for (int ks = 0; ks < nks; ++ks) {
-                                const uint64_t ad = smem_desc(a_addr + (uint32_t)(ks * 2 * A_LBO), A_LBO, 128);
-                                const uint64_t bd = smem_desc(w_addr + (uint32_t)ks * 2u * w_lbo, w_lbo, 128);
-                                umma_bf16(d_tmem, ad, bd, idesc, ks ? 1u : 0u);
-                            }
-                        } else {
-                            // transposed: 128 output channels (rows of W) per MMA as M, the tile's 128 rows as N
-                            const uint32_t wl = (uint32_t)ly.Npad * 16u;
-                            for (int mh = 0; mh < ly.Npad / TC_ROWS; ++mh)
-                                for (int ks = 0; ks < nks; ++ks) {
-                                    const uint64_t ad = smem_desc(w_addr + (uint32_t)(mh * TC_ROWS * 16) + (uint32_t)ks * 2u * wl, wl, 128);
-                                    const uint64_t bd = smem_desc(a_addr + (uint32_t)(ks * 2 * A_LBO), A_LBO, 128);
-                                    umma_bf16(d_tmem + (uint32_t)(mh * TC_ROWS), ad, bd, idesc_t, ks ? 1u : 0u);
+            for (int it = 0; it < n_max; ++it) {
+#pragma unroll
+                for (int l = 0; l < T2_MAX_L; ++l) {
+                    if (l < L) {
+#pragma unroll
+                        for (int u = 0; u < T2_MAX_UNITS; ++u) {
+                            if (it < n_u[u]) {
+                                mbar_wait(a_ready + u, (phases >> u) & 1u);
+                                phases ^= 1u << u;
+                                tc_fence_after();
+                                if (l < L - 1) {
+                                    for (int ks = 0; ks < nks[l]; ++ks)
+                                        umma_bf16(d_tm[u], mk_desc(a_lo[u] + (uint32_t)ks * (2 * A_LBO / 16), DESC_HI),
+                                                  mk_desc(w_lo[l] + (uint32_t)ks * w_step[l], DESC_HI), idesc[l], ks ? 1u : 0u);
+                                } else {
+                                    // transposed: 128 output channels (rows of W) per MMA as M, the tile's 128 rows as N
+                                    for (int mh = 0; mh < n_mh; ++mh)
+                                        for (int ks = 0; ks < nks[l]; ++ks)
+                                            umma_bf16(d_tm[u] + (uint32_t)(mh * TC_ROWS),
+                                                      mk_desc(w_lo[l] + (uint32_t)(mh * TC_ROWS) + (uint32_t)ks * w_step[l], DESC_HI),
+                                                      mk_desc(a_lo[u] + (uint32_t)ks * (2 * A_LBO / 16), DESC_HI), idesc[l], ks ? 1u : 0u);
                                 }
+                                umma_commit(acc_ready + u);
+                            }
                         }
-                        umma_commit(acc_ready + u);
                     }
                 }
             }
@@ -190,38 +214,42 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
         // =================================================================================================
         const int u = warp >> 2, q = warp & 3, row = q * 32 + lane;
         unsigned char *A = A_base + (size_t)u * p.a_unit_bytes;
+        unsigned char *A_row = A + row * 16;
         uint32_t *vmask_u = vmask_base + 8 * u;
         uint32_t parity = 0;
         const uint32_t tmem_row = tmem_base + (uint32_t)(u * p.cols_per_unit) + ((uint32_t)(q * 32) << 16);
-        const int K = p.K, C = p.C, D = p.D, K0 = lay.ly[0].K;
-        const int gpt = TC_ROWS / K;
+        const int K = p.K, C = p.C, D = p.D, K0 = lay.ly[0].K, S = p.S;
+        const int logK = 31 - __clz(K);
+        const int gpt = TC_ROWS >> logK;
+        const int rows = (int)p.rows, G = (int)p.G;
         uint32_t acc_phase = 0;
-        const int64_t gu = (int64_t)blockIdx.x * U + u;
+        const int gu = (int)blockIdx.x * U + u;
+        uint64_t *my_a_ready = a_ready + u, *my_acc_ready = acc_ready + u;
 
-        auto load_index = [&](int64_t tile) -> int {
-            const int64_t r = tile * TC_ROWS + row;
-            if (tile >= p.tiles || r >= p.rows) return -1;
+        auto load_index = [&](int tile) -> int {
+            const int r = tile * TC_ROWS + row;
+            if (tile >= tiles || r >= rows) return -1;
             const int n = __ldg(p.idx32 + r);
             return (n >= 0 && n < p.N) ? n : -1;       // n == N: 'no neighbour' marker of an empty ball (:85)
         };
         int n_next = load_index(gu);
 
-        for (int64_t tile = gu; tile < p.tiles; tile += stride) {
+        for (int tile = gu; tile < tiles; tile += stride) {
             uint32_t *vmask_s = vmask_u + 4 * parity;    // a warp can run at most one tile ahead of its unit
             parity ^= 1u;
             const int n = n_next;
             n_next = load_index(tile + stride);
             const bool valid = n >= 0;
-            const int64_t g = (tile * TC_ROWS + row) / K;      // group of this row
-            const int64_t b = g / p.S;
+            const int g = (tile * TC_ROWS + row) >> logK;      // group of this row
+            const int b = (int)((unsigned)g / (unsigned)S);
 
             // ---- gather: this thread's row, internal channel order [feat(D), xyz(C), zero pad] ----------------
             if (p.feat_fast) {
                 if (p.feat_bf16) {
-                    const __nv_bfloat16 *f = p.feat_bf16 + (valid ? (b * p.N + n) * (int64_t)D : 0);
-                    for (int kg = 0; kg < D / 8; ++kg) cp_async16_zfill(A + (size_t)kg * A_LBO + row * 16, f + kg * 8, valid);
+                    const __nv_bfloat16 *f = p.feat_bf16 + (valid ? ((int64_t)b * p.N + n) * D : 0);
+                    for (int kg = 0; kg < D / 8; ++kg) cp_async16_zfill(A_row + (size_t)kg * A_LBO, f + kg * 8, valid);
                 } else {
-                    const float *f = valid && D ? p.feat + b * p.fb + (int64_t)n * p.fn : nullptr;
+                    const float *f = valid && D ? p.feat + (int64_t)b * p.fb + (int64_t)n * p.fn : nullptr;
                     for (int kg0 = 0; kg0 < D / 8; kg0 += 4) {
                         float4 v[8];
 #pragma unroll
@@ -235,13 +263,13 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
                             if (kg0 + i < D / 8)
-                                *reinterpret_cast<uint4 *>(A + (size_t)(kg0 + i) * A_LBO + row * 16) =
+                                *reinterpret_cast<uint4 *>(A_row + (size_t)(kg0 + i) * A_LBO) =
                                     make_uint4(pack_bf16x2(v[2 * i].x, v[2 * i].y), pack_bf16x2(v[2 * i].z, v[2 * i].w),
                                                pack_bf16x2(v[2 * i + 1].x, v[2 * i + 1].y), pack_bf16x2(v[2 * i + 1].z, v[2 * i + 1].w));
                     }
                 }
-                const float *pp = p.points + b * p.sb + (int64_t)n * p.sn;
-                const float *cc = p.centres + g * C;
+                const float *pp = p.points + (int64_t)b * p.sb + (int64_t)n * p.sn;
+                const float *cc = p.centres + (int64_t)g * C;
                 for (int kg = D / 8; kg < K0 / 8; ++kg) {
                     float x[8];
 #pragma unroll
@@ -251,7 +279,7 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
                         if (valid && c < C) t = __fsub_rn(__ldg(pp + (int64_t)c * p.sc), __ldg(cc + c));
                         x[i] = t;
                     }
-                    *reinterpret_cast<uint4 *>(A + (size_t)kg * A_LBO + row * 16) =
+                    *reinterpret_cast<uint4 *>(A_row + (size_t)kg * A_LBO) =
                         make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
                 }
                 if (p.feat_bf16) cp_async_commit_wait_all();
@@ -259,53 +287,54 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
                 for (int k = 0; k < K0; ++k) {
                     float t = 0.f;
                     if (valid) {
-                        if (k < D) t = __ldg(p.feat + b * p.fb + (int64_t)n * p.fn + (int64_t)k * p.fc);
+                        if (k < D) t = __ldg(p.feat + (int64_t)b * p.fb + (int64_t)n * p.fn + (int64_t)k * p.fc);
                         else if (k < D + C)
-                            t = __fsub_rn(__ldg(p.points + b * p.sb + (int64_t)n * p.sn + (int64_t)(k - D) * p.sc), __ldg(p.centres + g * C + (k - D)));
+                            t = __fsub_rn(__ldg(p.points + (int64_t)b * p.sb + (int64_t)n * p.sn + (int64_t)(k - D) * p.sc),
+                                          __ldg(p.centres + (int64_t)g * C + (k - D)));
                     }
-                    *reinterpret_cast<__nv_bfloat16 *>(A + (size_t)(k / 8) * A_LBO + row * 16 + (k % 8) * 2) = __float2bfloat16_rn(t);
+                    *reinterpret_cast<__nv_bfloat16 *>(A_row + (size_t)(k / 8) * A_LBO + (k % 8) * 2) = __float2bfloat16_rn(t);
                 }
             }
             const unsigned vm = __ballot_sync(0xffffffffu, valid);
             if (lane == 0) vmask_s[q] = vm;      // read by the whole unit in the pooling step (ordered by the mbarriers)
             fence_proxy_async();                 // generic-proxy stores -> visible to the tensor core (async proxy)
             __syncwarp();
-            if (lane == 0) mbar_arrive(a_ready + u);
+            if (lane == 0) mbar_arrive(my_a_ready);
 
-            for (int l = 0; l < L; ++l) {
-                const TcLayer ly = lay.ly[l];
-                mbar_wait(acc_ready + u, acc_phase);
+#pragma unroll
+            for (int l = 0; l < T2_MAX_L; ++l) {
+                if (l >= L) break;
+                const TcLayer &ly = lay.ly[l];
+                mbar_wait(my_acc_ready, acc_phase);
                 acc_phase ^= 1u;
                 tc_fence_after();
                 const float *bs = bias_s + ly.b_off;
                 if (l < L - 1) {
                     // ---- hidden layer: accumulator -> +bias -> ReLU -> bf16 -> the next layer's A operand (in place) --
-                    for (int c0 = 0; c0 < ly.Npad; c0 += 64) {
-                        uint32_t r0[32], r1[32];
-                        const bool two = c0 + 32 < ly.Npad;
-                        tmem_ld32_nowait(tmem_row + (uint32_t)c0, r0);
-                        if (two) tmem_ld32_nowait(tmem_row + (uint32_t)(c0 + 32), r1);
+#pragma unroll 1
+                    for (int c0 = 0; c0 < ly.Npad; c0 += 32) {
+                        uint32_t r[32];
+                        tmem_ld32_nowait(tmem_row + (uint32_t)c0, r);
                         tmem_ld_wait();
-                        epi_block(r0, bs, A, c0, row);
-                        if (two) epi_block(r1, bs, A, c0 + 32, row);
+                        epi_block(r, bs, A, c0, row);
                     }
                     tc_fence_before();           // TMEM reads ordered before the MMA warp's next write to this region
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(a_ready + u);
+                    if (lane == 0) mbar_arrive(my_a_ready);
                 } else {
                     // ---- last layer (transposed): this thread = channel mh*128 + row; columns = the tile's rows ------
                     const uint32_t m0 = vmask_s[0], m1 = vmask_s[1], m2 = vmask_s[2], m3 = vmask_s[3];
                     const bool all_valid = (m0 & m1 & m2 & m3) == 0xffffffffu;
-                    const int64_t g0 = tile * gpt;
-                    const int64_t b0 = g0 / p.S;
-                    const int s0 = (int)(g0 % p.S);
+                    const int g0 = tile * gpt;
+                    const int b0 = (int)((unsigned)g0 / (unsigned)S);
+                    const int s0 = g0 - b0 * S;
                     auto emit = [&](int gi, float m, int c, float bv) {
                         // group gi of this tile, channel c: max over its rows -> + bias -> ReLU -> [B,S,Ctot]
-                        int64_t bb = b0; int ss = s0 + gi;
-                        while (ss >= p.S) { ss -= p.S; ++bb; }
-                        if (g0 + gi < p.G && c < ly.Cout && m > -INFINITY) {
-                            const int64_t o = bb * p.ob + (int64_t)ss * p.os + p.co_off + c;
+                        int bb = b0, ss = s0 + gi;
+                        while (ss >= S) { ss -= S; ++bb; }
+                        if (g0 + gi < G && c < ly.Cout && m > -INFINITY) {
+                            const int64_t o = (int64_t)bb * p.ob + (int64_t)ss * p.os + p.co_off + c;
                             const float y = fmaxf(m + bv, 0.f);
                             p.out[o] = y;
                             if (p.out_bf16) p.out_bf16[o] = __float2bfloat16_rn(y);
@@ -327,7 +356,7 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
                             }
                             if (K >= 32) {
                                 run = fmaxf(run, max_range<0, 32>(r));
-                                if (((blk + 1) * 32) % K == 0) { emit(blk * 32 / K, run, c, bv); run = -INFINITY; }
+                                if ((((blk + 1) * 32) & (K - 1)) == 0) { emit((blk * 32) >> logK, run, c, bv); run = -INFINITY; }
                             } else if (K == 16) {
                                 emit(2 * blk, max_range<0, 16>(r), c, bv);
                                 emit(2 * blk + 1, max_range<16, 16>(r), c, bv);
@@ -360,6 +389,7 @@ static bool tc2_plan(int K, int order, const TcLayout &t, Tc2Plan *pl)
 {
     if (order == PN2_ORDER_ALL) return false;                       // group_all stacks are wide: pn2_sa_tc.cu
     if (K < 8 || K > TC_ROWS || (K & (K - 1))) return false;
+    if (t.L > 4) return false;
     int kmax = 0, nmax = 0;
     if (t.L < 1 || t.ly[t.L - 1].Npad > 512) return false;
     for (int l = 0; l < t.L; ++l) {
@@ -404,6 +434,7 @@ int launch_sa_bf16_pipelined(const SaArgs &a, cudaStream_t st)
     p.G = (int64_t)a.B * a.S;
     p.rows = p.G * a.K;
     p.tiles = (p.rows + TC_ROWS - 1) / TC_ROWS;
+    if (p.rows >= (1ll << 31) - TC_ROWS) return -100;             // the kernel indexes rows with 32-bit integers
     p.U = pl.U; p.cols_per_unit = pl.cols_per_unit; p.tmem_cols = pl.tmem_cols;
     p.a_unit_bytes = pl.a_unit_bytes;
     p.feat_fast = (a.D == 0) || (a.fc == 1 && a.D % 8 == 0 && a.fn % 4 == 0 && a.fb % 4 == 0 && ((uintptr_t)a.feat & 15) == 0);
