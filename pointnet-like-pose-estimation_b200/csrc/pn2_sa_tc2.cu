@@ -218,37 +218,67 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
         uint32_t *vmask_u = vmask_base + 8 * u;
         uint32_t parity = 0;
         const uint32_t tmem_row = tmem_base + (uint32_t)(u * p.cols_per_unit) + ((uint32_t)(q * 32) << 16);
-        const int K = p.K, C = p.C, D = p.D, K0 = lay.ly[0].K, S = p.S;
+        const int K = p.K, C = p.C, D = p.D, K0 = lay.ly[0].K, S = p.S, N = p.N;
         const int logK = 31 - __clz(K);
         const int gpt = TC_ROWS >> logK;
         const int rows = (int)p.rows, G = (int)p.G;
         uint32_t acc_phase = 0;
         const int gu = (int)blockIdx.x * U + u;
         uint64_t *my_a_ready = a_ready + u, *my_acc_ready = acc_ready + u;
+        const bool twin = p.feat_fast && p.feat_bf16 != nullptr;    // bf16 features: cp.async straight into the operand
+        const bool pre_xyz = p.feat_fast && C <= 4;                 // coordinates prefetched one tile ahead
 
+        // raw neighbour index of this thread's row in `tile` (-1 outside the problem); no use of the value here,
+        // so the load stays in flight
         auto load_index = [&](int tile) -> int {
             const int r = tile * TC_ROWS + row;
-            if (tile >= tiles || r >= rows) return -1;
-            const int n = __ldg(p.idx32 + r);
-            return (n >= 0 && n < p.N) ? n : -1;       // n == N: 'no neighbour' marker of an empty ball (:85)
+            return (tile < tiles && r < rows) ? __ldg(p.idx32 + r) : -1;
         };
-        int n_next = load_index(gu);
+        // n == N is the 'no neighbour' marker of an empty ball (:85)
+        auto is_valid = [&](int n) -> bool { return n >= 0 && n < N; };
+        // coordinates of point n and of the group's centre (first 4 channels), raw
+        auto load_xyz4 = [&](int tile, int n, float (&px)[4], float (&pc)[4]) {
+            const int g = (tile * TC_ROWS + row) >> logK;
+            const int b = (int)((unsigned)g / (unsigned)S);
+            const float *pp = p.points + (int64_t)b * p.sb + (int64_t)n * p.sn;
+            const float *cc = p.centres + (int64_t)g * C;
+            const bool ok = is_valid(n);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                px[i] = pc[i] = 0.f;
+                if (ok && i < C) { px[i] = __ldg(pp); pc[i] = __ldg(cc + i); }
+                pp += p.sc;
+            }
+        };
+        // bf16 feature rows -> operand buffer, asynchronously (the buffer must be free)
+        auto issue_twin = [&](int tile, int n) {
+            const int g = (tile * TC_ROWS + row) >> logK;
+            const int b = (int)((unsigned)g / (unsigned)S);
+            const bool ok = is_valid(n);
+            const __nv_bfloat16 *f = p.feat_bf16 + (ok ? ((int64_t)b * N + n) * D : 0);
+            for (int kg = 0; kg < D / 8; ++kg) cp_async16_zfill(A_row + (size_t)kg * A_LBO, f + kg * 8, ok);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+
+        int n_cur = load_index(gu);
+        float px[4], pc[4];
+        if (gu < tiles) {
+            if (twin) issue_twin(gu, n_cur);
+            if (pre_xyz) load_xyz4(gu, n_cur, px, pc);
+        }
 
         for (int tile = gu; tile < tiles; tile += stride) {
             uint32_t *vmask_s = vmask_u + 4 * parity;    // a warp can run at most one tile ahead of its unit
             parity ^= 1u;
-            const int n = n_next;
-            n_next = load_index(tile + stride);
-            const bool valid = n >= 0;
+            const int n = n_cur;
+            const int n_next = load_index(tile + stride);          // used after the first epilogue at the earliest
+            const bool valid = is_valid(n);
             const int g = (tile * TC_ROWS + row) >> logK;      // group of this row
             const int b = (int)((unsigned)g / (unsigned)S);
 
             // ---- gather: this thread's row, internal channel order [feat(D), xyz(C), zero pad] ----------------
             if (p.feat_fast) {
-                if (p.feat_bf16) {
-                    const __nv_bfloat16 *f = p.feat_bf16 + (valid ? ((int64_t)b * p.N + n) * D : 0);
-                    for (int kg = 0; kg < D / 8; ++kg) cp_async16_zfill(A_row + (size_t)kg * A_LBO, f + kg * 8, valid);
-                } else {
+                if (!twin) {
                     const float *f = valid && D ? p.feat + (int64_t)b * p.fb + (int64_t)n * p.fn : nullptr;
                     for (int kg0 = 0; kg0 < D / 8; kg0 += 4) {
                         float4 v[8];
@@ -268,21 +298,30 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
                                                pack_bf16x2(v[2 * i + 1].x, v[2 * i + 1].y), pack_bf16x2(v[2 * i + 1].z, v[2 * i + 1].w));
                     }
                 }
-                const float *pp = p.points + (int64_t)b * p.sb + (int64_t)n * p.sn;
-                const float *cc = p.centres + (int64_t)g * C;
-                for (int kg = D / 8; kg < K0 / 8; ++kg) {
-                    float x[8];
+                if (pre_xyz) {
+                    // x - centre for the (<= 4) coordinate channels, then zero k-groups up to K0
+                    unsigned char *dst = A_row + (size_t)(D / 8) * A_LBO;
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(pack_bf16x2(__fsub_rn(px[0], pc[0]), __fsub_rn(px[1], pc[1])),
+                                                                 pack_bf16x2(__fsub_rn(px[2], pc[2]), __fsub_rn(px[3], pc[3])), 0u, 0u);
+                    for (int kg = D / 8 + 1; kg < K0 / 8; ++kg) *reinterpret_cast<uint4 *>(A_row + (size_t)kg * A_LBO) = make_uint4(0u, 0u, 0u, 0u);
+                } else {
+                    const float *pp = p.points + (int64_t)b * p.sb + (int64_t)n * p.sn;
+                    const float *cc = p.centres + (int64_t)g * C;
+                    float x[16];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int c = kg * 8 + i - D;
-                        float t = 0.f;
-                        if (valid && c < C) t = __fsub_rn(__ldg(pp + (int64_t)c * p.sc), __ldg(cc + c));
-                        x[i] = t;
+                    for (int i = 0; i < 16; ++i) {
+                        float a0 = 0.f, a1 = 0.f;
+                        if (valid && i < C) { a0 = __ldg(pp); a1 = __ldg(cc + i); }
+                        pp += p.sc;
+                        x[i] = __fsub_rn(a0, a1);
                     }
-                    *reinterpret_cast<uint4 *>(A_row + (size_t)kg * A_LBO) =
-                        make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+                    unsigned char *dst = A_row + (size_t)(D / 8) * A_LBO;
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+                    if (K0 / 8 > D / 8 + 1)
+                        *reinterpret_cast<uint4 *>(dst + A_LBO) = make_uint4(pack_bf16x2(x[8], x[9]), pack_bf16x2(x[10], x[11]), pack_bf16x2(x[12], x[13]), pack_bf16x2(x[14], x[15]));
+                    for (int kg = D / 8 + 2; kg < K0 / 8; ++kg) *reinterpret_cast<uint4 *>(A_row + (size_t)kg * A_LBO) = make_uint4(0u, 0u, 0u, 0u);
                 }
-                if (p.feat_bf16) cp_async_commit_wait_all();
+                if (twin) asm volatile("cp.async.wait_group 0;" ::: "memory");
             } else {
                 for (int k = 0; k < K0; ++k) {
                     float t = 0.f;
@@ -300,6 +339,7 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
             fence_proxy_async();                 // generic-proxy stores -> visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(my_a_ready);
+            const bool more = tile + stride < tiles;
 
 #pragma unroll
             for (int l = 0; l < T2_MAX_L; ++l) {
@@ -322,27 +362,39 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(my_a_ready);
+                    // the next tile's index has arrived by now: start its coordinate loads (they land during the
+                    // remaining layers)
+                    if (l == 0 && L > 1 && more && pre_xyz) load_xyz4(tile + stride, n_next, px, pc);
                 } else {
                     // ---- last layer (transposed): this thread = channel mh*128 + row; columns = the tile's rows ------
+                    // every MMA that reads the operand buffer has completed: the next tile's feature rows can start
+                    // flowing in underneath the pooling
+                    if (more) {
+                        if (twin) issue_twin(tile + stride, n_next);
+                        if (L == 1 && pre_xyz) load_xyz4(tile + stride, n_next, px, pc);
+                    }
                     const uint32_t m0 = vmask_s[0], m1 = vmask_s[1], m2 = vmask_s[2], m3 = vmask_s[3];
                     const bool all_valid = (m0 & m1 & m2 & m3) == 0xffffffffu;
                     const int g0 = tile * gpt;
                     const int b0 = (int)((unsigned)g0 / (unsigned)S);
                     const int s0 = g0 - b0 * S;
-                    auto emit = [&](int gi, float m, int c, float bv) {
-                        // group gi of this tile, channel c: max over its rows -> + bias -> ReLU -> [B,S,Ctot]
-                        int bb = b0, ss = s0 + gi;
-                        while (ss >= S) { ss -= S; ++bb; }
-                        if (g0 + gi < G && c < ly.Cout && m > -INFINITY) {
-                            const int64_t o = (int64_t)bb * p.ob + (int64_t)ss * p.os + p.co_off + c;
-                            const float y = fmaxf(m + bv, 0.f);
-                            p.out[o] = y;
-                            if (p.out_bf16) p.out_bf16[o] = __float2bfloat16_rn(y);
-                        }
-                    };
+                    const int64_t wrap = p.ob - (int64_t)S * p.os;      // offset correction when a group index rolls into the next cloud
                     for (int mh = 0; mh < ly.Npad / TC_ROWS; ++mh) {
                         const int c = mh * TC_ROWS + row;
                         const float bv = bs[c];
+                        const bool c_ok = c < ly.Cout;
+                        int64_t o = (int64_t)b0 * p.ob + (int64_t)s0 * p.os + p.co_off + c;   // output element of (group, channel)
+                        int ss = s0, gg = g0;
+                        // group finished: max over its rows -> + bias -> ReLU -> [B,S,Ctot]; then step to the next group
+                        auto emit = [&](float m) {
+                            if (c_ok && gg < G && (all_valid || m > -INFINITY)) {
+                                const float y = fmaxf(m + bv, 0.f);
+                                p.out[o] = y;
+                                if (p.out_bf16) p.out_bf16[o] = __float2bfloat16_rn(y);
+                            }
+                            ++gg; o += p.os;
+                            if (++ss == S) { ss = 0; o += wrap; }
+                        };
                         float run = -INFINITY;
 #pragma unroll 1
                         for (int blk = 0; blk < 4; ++blk) {
@@ -356,21 +408,22 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
                             }
                             if (K >= 32) {
                                 run = fmaxf(run, max_range<0, 32>(r));
-                                if ((((blk + 1) * 32) & (K - 1)) == 0) { emit((blk * 32) >> logK, run, c, bv); run = -INFINITY; }
+                                if ((((blk + 1) * 32) & (K - 1)) == 0) { emit(run); run = -INFINITY; }
                             } else if (K == 16) {
-                                emit(2 * blk, max_range<0, 16>(r), c, bv);
-                                emit(2 * blk + 1, max_range<16, 16>(r), c, bv);
+                                emit(max_range<0, 16>(r));
+                                emit(max_range<16, 16>(r));
                             } else {
-                                emit(4 * blk, max_range<0, 8>(r), c, bv);
-                                emit(4 * blk + 1, max_range<8, 8>(r), c, bv);
-                                emit(4 * blk + 2, max_range<16, 8>(r), c, bv);
-                                emit(4 * blk + 3, max_range<24, 8>(r), c, bv);
+                                emit(max_range<0, 8>(r));
+                                emit(max_range<8, 8>(r));
+                                emit(max_range<16, 8>(r));
+                                emit(max_range<24, 8>(r));
                             }
                         }
                     }
                     tc_fence_before();
                 }
             }
+            n_cur = n_next;
         }
     }
     tc_fence_before();
