@@ -57,6 +57,9 @@ def gen_indices(ref):
         ("uni10", cloudgen.with_category(cloudgen.uniform_cloud(3, 256, 15)), 64, 0.25, 16),
         ("dup10", cloudgen.with_category(cloudgen.duplicate_heavy(cloudgen.surface_cloud(2, 160, 16), 0.5, 17)), 48, 0.4, 32),
         ("over3", cloudgen.uniform_cloud(2, 40, 18), 64, 0.5, 8),       # S > N (pointnet2_utils.py:240-245)
+        # N % 32 != 0 with dense 10-D / 6-D coordinates: exercises the leftover-point summation order of the strided layout
+        ("rand10", torch.rand(2, 300, 10, generator=torch.Generator().manual_seed(19)), 64, 0.9, 16),
+        ("rand6", torch.rand(3, 77, 6, generator=torch.Generator().manual_seed(20)), 40, 0.6, 12),
     ]
     for name, x, S, r, K in specs:
         for lay, pts in layouts(x).items():

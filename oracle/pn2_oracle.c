@@ -24,26 +24,33 @@
 /* ---------------------------------------------------------------------------------------------
  * Summation order of torch.sum(v, -1) over the C coordinate channels (pointnet2_utils.py:24-25,
  * :64).  ATen picks the order from the memory layout of the [B,.,C] operand:
- *   stride(-1) != 1 : strided outer reduce, one accumulator, ascending k.
- *   stride(-1) == 1, C <  8 : 4 interleaved partial sums, tail into p0, ((p0+p1)+p2)+p3.
+ *   stride(-1) == 1, C <  8 : 4 interleaved partial sums, tail into p0, ((p0+p1)+p2)+p3   ("ILP-4").
  *   stride(-1) == 1, C >= 8 : 8 vector lanes over the first 8*floor(C/8) terms, then
  *                             acc = tail terms in order, then += lane0..lane7.
+ *   stride(-1) != 1 (the [B,C,N].permute(0,2,1) view the first layer receives: unit stride along
+ *   the point index n): ATen vectorises over n, 32 points per step, one accumulator per point in
+ *   ascending k; the points left over, n >= 32*floor(N/32), go through the scalar ILP-4 loop.
+ * `n` / `n_total` locate the point inside its cloud for the strided rule (ignored otherwise).
  * ------------------------------------------------------------------------------------------- */
-static float sum_order(const float *v, int C, int contiguous)
+static float sum_ilp4(const float *v, int C)
+{
+    float p[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    int n4 = C / 4;
+    for (int i = 0; i < n4; ++i)
+        for (int k = 0; k < 4; ++k) p[k] = p[k] + v[4 * i + k];
+    for (int t = 4 * n4; t < C; ++t) p[0] = p[0] + v[t];
+    return ((p[0] + p[1]) + p[2]) + p[3];
+}
+
+static float sum_order(const float *v, int C, int contiguous, int64_t n, int64_t n_total)
 {
     if (!contiguous) {
+        if (n >= (n_total / 32) * 32) return sum_ilp4(v, C);
         float a = 0.0f;
         for (int k = 0; k < C; ++k) a = a + v[k];
         return a;
     }
-    if (C < 8) {
-        float p[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        int n4 = C / 4;
-        for (int i = 0; i < n4; ++i)
-            for (int k = 0; k < 4; ++k) p[k] = p[k] + v[4 * i + k];
-        for (int t = 4 * n4; t < C; ++t) p[0] = p[0] + v[t];
-        return ((p[0] + p[1]) + p[2]) + p[3];
-    }
+    if (C < 8) return sum_ilp4(v, C);
     float lane[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int n8 = C / 8;
     for (int i = 0; i < n8; ++i)
@@ -54,7 +61,8 @@ static float sum_order(const float *v, int C, int contiguous)
     return a;
 }
 
-float pn2o_sum_order(const float *v, int C, int contiguous) { return sum_order(v, C, contiguous); }
+/* mode 0: strided, vectorised body; 1: contiguous; 2: strided, leftover points */
+float pn2o_sum_order(const float *v, int C, int mode) { return sum_order(v, C, mode == 1, mode == 2 ? 1 : 0, mode == 2 ? 1 : 32); }
 
 /* ---------------------------------------------------------------------------------------------
  * farthest_point_sample (pointnet2_utils.py:47-68).
@@ -86,7 +94,7 @@ int pn2o_fps(const float *pts, int64_t sb, int64_t sn, int64_t sc, int B, int N,
                     float df = P[(int64_t)n * sn + k * sc] - c[k];
                     t[k] = df * df;
                 }
-                float d = sum_order(t, C, contiguous);
+                float d = sum_order(t, C, contiguous, n, N);
                 if (d < dist[n]) dist[n] = d;
                 if (dist[n] > best) { best = dist[n]; besti = n; }
             }
@@ -111,7 +119,7 @@ static void sq_norms(const float *P, int64_t sn, int64_t sc, int N, int C, int c
             float x = P[(int64_t)n * sn + k * sc];
             t[k] = x * x;
         }
-        out[n] = sum_order(t, C, contiguous);
+        out[n] = sum_order(t, C, contiguous, n, N);
     }
 }
 
@@ -165,7 +173,7 @@ int pn2o_ball_query(const float *centres, const float *pts, int64_t sb, int64_t 
         for (int s = 0; s < S; ++s) {
             const float *sx = centres + ((int64_t)b * S + s) * C;
             for (int k = 0; k < C; ++k) t[k] = sx[k] * sx[k];
-            float s2 = sum_order(t, C, 1);
+            float s2 = sum_order(t, C, 1, 0, 0);
             int64_t *row = out + ((int64_t)b * S + s) * K;
             int cnt = 0;
             for (int n = 0; n < N && cnt < K; ++n) {

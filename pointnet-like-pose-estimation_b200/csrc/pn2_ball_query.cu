@@ -18,12 +18,12 @@ constexpr int BQ_WARPS = 8;
 constexpr int BQ_THREADS = BQ_WARPS * 32;
 
 template <int C>
-__device__ __forceinline__ float sqnorm(const float (&v)[C], bool contig)
+__device__ __forceinline__ float sqnorm(const float (&v)[C], bool contig, bool tail)
 {
     float t[C];
 #pragma unroll
     for (int k = 0; k < C; ++k) t[k] = __fmul_rn(v[k], v[k]);
-    return contig ? sum_order<C, true>(t) : sum_order<C, false>(t);
+    return contig ? sum_order<C, true>(t) : sum_order<C, false>(t, tail);
 }
 
 template <int C>
@@ -66,7 +66,7 @@ ball_query_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, i
     if (!single_chunk && have) {
 #pragma unroll
         for (int k = 0; k < C; ++k) s[k] = __ldg(centres + (int64_t)b * csb + (int64_t)s_begin * csn + (int64_t)k * csc);
-        s2 = sqnorm<C>(s, csc == 1);
+        s2 = sqnorm<C>(s, csc == 1, s_begin >= (S & ~31));
     }
 
     for (int n_base = 0; n_base < N; n_base += NCH) {
@@ -79,7 +79,7 @@ ball_query_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, i
                 v[k] = __ldg(P + (int64_t)(n_base + n) * sn + (int64_t)k * sc);
                 sp[k * NCH + n] = v[k];
             }
-            sp2[n] = sqnorm<C>(v, pcontig);
+            sp2[n] = sqnorm<C>(v, pcontig, n_base + n >= (N & ~31));
         }
         __syncthreads();
 
@@ -89,7 +89,7 @@ ball_query_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, i
                 if (sidx >= S) break;
 #pragma unroll
                 for (int k = 0; k < C; ++k) s[k] = __ldg(centres + (int64_t)b * csb + (int64_t)sidx * csn + (int64_t)k * csc);
-                s2 = sqnorm<C>(s, csc == 1);
+                s2 = sqnorm<C>(s, csc == 1, sidx >= (S & ~31));
                 cnt = 0; first = N;
                 for (int n0 = 0; n0 < nc && cnt < K; n0 += 64) {
                     // two independent 32-point steps per trip for ILP
@@ -161,7 +161,7 @@ __global__ void ball_query_generic_kernel(const float *__restrict__ centres, int
     const float *cp = centres + (int64_t)b * csb + (g % S) * csn;
     float s[PN2_MAX_COORD], t[PN2_MAX_COORD];
     for (int k = 0; k < C; ++k) { s[k] = cp[k * csc]; t[k] = __fmul_rn(s[k], s[k]); }
-    const float s2 = sum_order_rt(t, C, csc == 1);
+    const float s2 = sum_order_rt(t, C, csc == 1, (int)(g % S) >= (S & ~31));
     const bool pcontig = (sc == 1);
     int cnt = 0, first = N;
     for (int n = 0; n < N && cnt < K; ++n) {
@@ -171,7 +171,7 @@ __global__ void ball_query_generic_kernel(const float *__restrict__ centres, int
             t[k] = __fmul_rn(x, x);
             dot = (k == 0) ? __fmul_rn(s[0], x) : __fmaf_rn(s[k], x, dot);
         }
-        const float p2 = sum_order_rt(t, C, pcontig);
+        const float p2 = sum_order_rt(t, C, pcontig, n >= (N & ~31));
         float d = __fmul_rn(-2.0f, dot);
         d = __fadd_rn(d, s2);
         d = __fadd_rn(d, p2);
@@ -254,8 +254,8 @@ __global__ void square_distance_kernel(const float *__restrict__ src, int64_t ss
         dot = (k == 0) ? __fmul_rn(sv[0], x) : __fmaf_rn(sv[k], x, dot);
     }
     float d = __fmul_rn(-2.0f, dot);
-    d = __fadd_rn(d, sum_order_rt(t, C, ssc == 1));
-    d = __fadd_rn(d, sum_order_rt(u, C, dsc == 1));
+    d = __fadd_rn(d, sum_order_rt(t, C, ssc == 1, s >= (S & ~31)));
+    d = __fadd_rn(d, sum_order_rt(u, C, dsc == 1, n >= (N & ~31)));
     out[((int64_t)b * S + s) * N + n] = d;
 }
 

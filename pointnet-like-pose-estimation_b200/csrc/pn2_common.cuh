@@ -28,26 +28,37 @@ inline int launch_status(const char *what)
 }
 
 // Order in which ATen's CPU sum reduces the C squared terms of one point ("summation
-// order"): strided operand -> one accumulator; contiguous operand -> 4 interleaved partial sums
-// (C < 8) or 8 vector lanes + tail first (C >= 8).  Each add is rounded (no FMA, no reassociation).
+// order").  Each add is rounded (no FMA, no reassociation).
+//   contiguous operand: 4 interleaved partial sums ("ILP-4", C < 8) or 8 vector lanes + tail first (C >= 8);
+//   strided operand (the [B,C,N].permute(0,2,1) view, unit stride along the point index): one accumulator
+//   in ascending k for the points ATen vectorises over (n < 32*floor(N/32)), ILP-4 for the leftover points.
+template <int C>
+__device__ __forceinline__ float sum_ilp4(const float (&t)[C])
+{
+    float p[4] = {0.f, 0.f, 0.f, 0.f};
+    constexpr int n4 = C / 4;
+#pragma unroll
+    for (int i = 0; i < n4; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) p[k] = (i == 0) ? t[k] : __fadd_rn(p[k], t[4 * i + k]);
+#pragma unroll
+    for (int k = 4 * n4; k < C; ++k) p[0] = (n4 == 0 && k == 0) ? t[0] : __fadd_rn(p[0], t[k]);
+    return __fadd_rn(__fadd_rn(__fadd_rn(p[0], p[1]), p[2]), p[3]);
+}
+
+// `tail`: the point is one of the leftover points of a strided operand (ignored for contiguous operands;
+// for C <= 4 both strided orders coincide)
 template <int C, bool CONTIG>
-__device__ __forceinline__ float sum_order(const float (&t)[C])
+__device__ __forceinline__ float sum_order(const float (&t)[C], bool tail = false)
 {
     if constexpr (!CONTIG) {
+        if constexpr (C > 4) { if (tail) return sum_ilp4<C>(t); }
         float a = t[0];
 #pragma unroll
         for (int k = 1; k < C; ++k) a = __fadd_rn(a, t[k]);
         return a;
     } else if constexpr (C < 8) {
-        float p[4] = {0.f, 0.f, 0.f, 0.f};
-        constexpr int n4 = C / 4;
-#pragma unroll
-        for (int i = 0; i < n4; ++i)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) p[k] = (i == 0) ? t[k] : __fadd_rn(p[k], t[4 * i + k]);
-#pragma unroll
-        for (int k = 4 * n4; k < C; ++k) p[0] = (n4 == 0 && k == 0) ? t[0] : __fadd_rn(p[0], t[k]);
-        return __fadd_rn(__fadd_rn(__fadd_rn(p[0], p[1]), p[2]), p[3]);
+        return sum_ilp4<C>(t);
     } else {
         float lane[8];
         constexpr int n8 = C / 8;
@@ -67,14 +78,14 @@ __device__ __forceinline__ float sum_order(const float (&t)[C])
 }
 
 // Same rule for a run-time C (generic fallback kernels).
-__device__ __forceinline__ float sum_order_rt(const float *t, int C, bool contig)
+__device__ __forceinline__ float sum_order_rt(const float *t, int C, bool contig, bool tail = false)
 {
-    if (!contig) {
+    if (!contig && !tail) {
         float a = t[0];
         for (int k = 1; k < C; ++k) a = __fadd_rn(a, t[k]);
         return a;
     }
-    if (C < 8) {
+    if (!contig || C < 8) {
         float p[4] = {0.f, 0.f, 0.f, 0.f};
         int n4 = C / 4;
         for (int i = 0; i < n4; ++i)

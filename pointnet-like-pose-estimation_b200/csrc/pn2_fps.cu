@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(TMAX) fps_kernel(const float *__restrict__ poi
     __shared__ uint2 s_slot[2][32];             // per-warp (dist bits, index), double-buffered
     const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
     const int Npad = PPT * T;
+    const int n_body = N & ~31;                 // strided operand: points >= n_body reduce in the leftover order
     const int b = blockIdx.x;
     const float *P = points + (int64_t)b * sb;
 
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(TMAX) fps_kernel(const float *__restrict__ poi
                 const float df = __fsub_rn(p[j][k], c[k]);
                 t[k] = __fmul_rn(df, df);
             }
-            const float d = sum_order<C, CONTIG>(t);
+            const float d = sum_order<C, CONTIG>(t, tid + j * T >= n_body);
             dist[j] = fminf(dist[j], d);        // d < dist ? d : dist, NaN never replaces
             if (dist[j] > best) { best = dist[j]; besti = (unsigned)(tid + j * T); }
         }
@@ -116,7 +117,7 @@ __global__ void fps_generic_kernel(const float *__restrict__ points, int64_t sb,
                 const float df = __fsub_rn(__ldg(P + (int64_t)n * sn + (int64_t)k * sc), s_c[k]);
                 t[k] = __fmul_rn(df, df);
             }
-            const float d = sum_order_rt(t, C, contig);
+            const float d = sum_order_rt(t, C, contig, n >= (N & ~31));
             const float nd = fminf(s_dist[n], d);
             s_dist[n] = nd;
             if (nd > best) { best = nd; besti = (unsigned)n; }

@@ -80,16 +80,21 @@ def test_oracle_and_port_modules_match_reference(oracle, name):
 @pytest.mark.parametrize("C", [3, 5, 8, 10, 13, 16])
 def test_summation_order_rule_matches_this_hosts_aten(oracle, C):
     """Self-check of the layout-dependent sum order against torch.sum on THIS host: documents an
-    ATen / CPU-capability drift instead of letting index parity fail silently somewhere else."""
+    ATen / CPU-capability drift instead of letting index parity fail silently somewhere else.
+    mode 1 = contiguous operand; strided operand ([B,C,N] permuted): mode 0 for the points ATen vectorises
+    over (n < 32*floor(N/32)), mode 2 for the leftover points."""
     import ctypes
     g = torch.Generator().manual_seed(C)
-    v = torch.rand(4096, C, generator=g) ** 2
-    strided = v.t().contiguous().t()
-    for t, contig in ((v, 1), (strided, 0)):
-        want = t.sum(-1)
-        rows = t.contiguous()
-        got = torch.tensor([oracle.lib().pn2o_sum_order(ctypes.c_void_p(rows[i].data_ptr()), C, contig) for i in range(rows.shape[0])])
-        assert torch.equal(got, want), (C, contig)
+    N = 32 * 5 + 19
+    v = torch.rand(1, N, C, generator=g) ** 2
+    strided = v.permute(0, 2, 1).contiguous().permute(0, 2, 1)
+
+    def rule(rows, modes):
+        return torch.tensor([oracle.lib().pn2o_sum_order(ctypes.c_void_p(rows[i].data_ptr()), C, modes[i]) for i in range(rows.shape[0])])
+
+    rows = v[0].contiguous()
+    assert torch.equal(rule(rows, [1] * N), v.sum(-1)[0]), (C, "contiguous")
+    assert torch.equal(rule(rows, [0 if n < 32 * 5 else 2 for n in range(N)]), strided.sum(-1)[0]), (C, "strided")
 
 
 def test_fps_edge_cases(oracle):
