@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PN2_ABI_VERSION 4
+#define PN2_ABI_VERSION 5
 #define PN2_MAX_COORD 16 /* exact summation-order rules are verified against ATen for C <= 16 */
 #define PN2_MAX_LAYERS 8
 
@@ -105,7 +105,7 @@ int pn2_sa_needs_zero_init(int S, int K, int L, const int *dims, int prec);
  * fp32 result and a later launch may pass it as feat_bf16 ([B,N,D] contiguous, D % 8 == 0), which the gather
  * then copies straight into the MMA operand with cp.async.  Both may be NULL.  pn2_sa_bf16_side_io tells the
  * caller whether the kernel that serves this configuration reads / writes them (1) or ignores them (0). */
-int pn2_sa_bf16_side_io(int K, int order, int L, const int *dims, int prec);
+int pn2_sa_bf16_side_io(int K, int C, int order, int L, const int *dims, int prec);
 int pn2_sa_fused(const float *points, int64_t sb, int64_t sn, int64_t sc,
                  const float *feat, int64_t fb, int64_t fn, int64_t fc,
                  const float *centres, const int32_t *idx32,
@@ -117,6 +117,17 @@ int pn2_sa_fused(const float *points, int64_t sb, int64_t sn, int64_t sc,
 /* Device self-test of the tcgen05 building blocks (one 128xN tile against a scalar loop in the same
  * launch).  Returns 0 and writes max|err| to *max_err (device float). */
 int pn2_selftest_umma(int n_cols, int k_dim, int variant, float *max_err, float *dump, void *stream);
+
+/* Device self-test of the TMA row gather (cp.async.bulk.tensor tile::gather4 with a 128-byte-swizzled tensor map)
+ * used for the bf16 feature gather: src [rows][cols] bf16 contiguous; rows4 (device) holds 4 row indices per
+ * instruction, n_inst <= 32 instructions; out (device) receives n_inst * 512 bytes: the shared-memory image. */
+int pn2_selftest_tma_gather(const void *src_bf16, int64_t rows, int cols, const int32_t *rows4, int n_inst, int col0,
+                            void *out, void *stream);
+
+/* Debug: stage timeline of the pipelined fused kernel.  buf = device buffer of 5 * 1024 uint64 (roles: unit 0..3,
+ * MMA warp), zero-filled by the caller, or NULL to switch tracing off.  CTA 0 appends (event << 48) | clock64 per
+ * pipeline stage (events: tools/tc2_trace.py).  Process-wide, not thread-safe; not for production use. */
+int pn2_debug_trace(void *buf);
 
 #ifdef __cplusplus
 }

@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(_HERE, LIB_NAME)
 ORDER_SSG, ORDER_MSG, ORDER_ALL = 0, 1, 2
 PREC_F32, PREC_BF16 = 0, 1
 MAX_COORD = 16
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _i64, _i32, _f32, _vp = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p
 
@@ -39,11 +39,13 @@ _SIGNATURES = {
     "pn2_packed_bytes": ([_i32, _vp, _i32], _i64),
     "pn2_pack_weights": ([_i32, _vp, _vp, _f32, _i32, _i32, _i32, _vp, _vp], _i32),
     "pn2_sa_needs_zero_init": ([_i32, _i32, _i32, _vp, _i32], _i32),
-    "pn2_sa_bf16_side_io": ([_i32, _i32, _i32, _vp, _i32], _i32),
+    "pn2_sa_bf16_side_io": ([_i32, _i32, _i32, _i32, _vp, _i32], _i32),
     "pn2_sa_fused": ([_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _vp,
                       _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32,
                       _vp, _i64, _i64, _i32, _vp, _vp, _vp], _i32),
     "pn2_selftest_umma": ([_i32, _i32, _i32, _vp, _vp, _vp], _i32),
+    "pn2_debug_trace": ([_vp], _i32),
+    "pn2_selftest_tma_gather": ([_vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp], _i32),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -237,10 +239,10 @@ class Native:
             _check(rc)
         return bool(rc)
 
-    def sa_bf16_side_io(self, K, order, dims, prec) -> bool:
+    def sa_bf16_side_io(self, K, C, order, dims, prec) -> bool:
         """True when the kernel serving this configuration reads `feature_bf16` / writes `out_bf16`."""
         d = _dims_array(dims)
-        rc = self.lib.pn2_sa_bf16_side_io(int(K), int(order), len(dims) - 1, d.ctypes.data, prec)
+        rc = self.lib.pn2_sa_bf16_side_io(int(K), int(C), int(order), len(dims) - 1, d.ctypes.data, prec)
         if rc < 0:
             _check(rc)
         return bool(rc)

@@ -107,10 +107,11 @@ int pn2_sa_needs_zero_init(int S, int K, int L, const int *dims, int prec)
     return prec == PN2_PREC_BF16 ? sa_bf16_needs_zero(S, K, L, dims) : sa_f32_needs_zero(S, K, L, dims);
 }
 
-int pn2_sa_bf16_side_io(int K, int order, int L, const int *dims, int prec)
+int pn2_sa_bf16_side_io(int K, int C, int order, int L, const int *dims, int prec)
 {
     if (!valid_dims(L, dims)) { set_error("pn2_sa_bf16_side_io: bad layer list"); return -1; }
-    return prec == PN2_PREC_BF16 ? sa_bf16_pipelined_covers(K, order, L, dims) : 0;
+    if (C < 1 || C > dims[0]) { set_error("pn2_sa_bf16_side_io: bad C"); return -1; }
+    return prec == PN2_PREC_BF16 ? sa_bf16_pipelined_covers(K, C, dims[0] - C, order, L, dims) : 0;
 }
 
 int pn2_sa_fused(const float *points, int64_t sb, int64_t sn, int64_t sc,
@@ -142,6 +143,17 @@ int pn2_sa_fused(const float *points, int64_t sb, int64_t sn, int64_t sc,
     if (prec == PN2_PREC_F32) return launch_sa_f32(a, (cudaStream_t)stream);
     if (prec == PN2_PREC_BF16) return launch_sa_bf16(a, (cudaStream_t)stream);
     PN2_REQUIRE(false, "pn2_sa_fused: unknown precision %d", prec);
+}
+
+int pn2_selftest_tma_gather(const void *src_bf16, int64_t rows, int cols, const int32_t *rows4, int n_inst, int col0, void *out, void *stream)
+{
+    return launch_selftest_tma_gather(src_bf16, rows, cols, rows4, n_inst, col0, out, (cudaStream_t)stream);
+}
+
+int pn2_debug_trace(void *buf)
+{
+    set_debug_trace(buf);
+    return 0;
 }
 
 int pn2_selftest_umma(int n_cols, int k_dim, int variant, float *max_err, float *dump, void *stream)

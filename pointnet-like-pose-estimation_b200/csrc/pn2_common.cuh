@@ -140,7 +140,10 @@ int sa_bf16_needs_zero(int S, int K, int L, const int *dims);
 int launch_sa_f32(const SaArgs &a, cudaStream_t st);
 int launch_sa_bf16(const SaArgs &a, cudaStream_t st);
 int launch_sa_bf16_pipelined(const SaArgs &a, cudaStream_t st);   // -100: configuration not covered
-int sa_bf16_pipelined_covers(int K, int order, int L, const int *dims);
+int sa_bf16_pipelined_covers(int K, int C, int D, int order, int L, const int *dims);
+void set_debug_trace(void *buf);
+int make_row_gather_map(const void *base, int64_t rows, int cols, void *out_map);
+int launch_selftest_tma_gather(const void *src_bf16, int64_t rows, int cols, const int32_t *rows4, int n_inst, int col0, void *out, cudaStream_t st);
 int launch_selftest_umma(int n_cols, int k_dim, int variant, float *max_err, float *dump, cudaStream_t st);
 
 }  // namespace pn2

@@ -498,7 +498,9 @@ int launch_sa_bf16(const SaArgs &a, cudaStream_t st)
 // ------------------------------------------------------------------------------------------------------
 // Self-test: one 128 x n_cols x k_dim product through exactly the descriptor / MMA / TMEM-load helpers
 // above, operands made of small integers (exact in bf16), compared with a scalar loop in the same kernel.
-// variant 0 = the descriptor convention used by the product kernel; 1 = LBO and SBO swapped (diagnostic).
+// variant 0 = the no-swizzle descriptor convention of the product kernels; 1 = LBO and SBO swapped (diagnostic);
+// 2 = A operand 128-byte swizzled (activations of the pipelined kernel); 3 = B operand 128-byte swizzled (its
+// transposed last layer: weights as A, activations as B).
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(int n_cols, int k_dim, int variant, float *max_err, float *dump)
 {
@@ -506,18 +508,22 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(int n_cols, int k
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
     __shared__ float s_err[4];
-    unsigned char *As = smem;                               // [k_dim/8][A_LBO]
-    unsigned char *Bs = smem + (size_t)(k_dim / 8) * A_LBO; // [k_dim/8][n_cols*16]
+    unsigned char *base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);    // swizzled blocks need 1024-byte alignment
+    const size_t a_bytes = variant == 2 ? (size_t)((k_dim + 63) / 64) * SW128_BLOCK : (size_t)(k_dim / 8) * A_LBO;
+    unsigned char *As = base;                               // [k_dim/8][A_LBO], or swizzled blocks
+    unsigned char *Bs = base + a_bytes;                     // [k_dim/8][n_cols*16], or swizzled blocks (variant 3, n_cols = 128)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     auto a_val = [](int r, int k) { return (float)(((r * 7 + k * 3) % 13) - 6); };
     auto b_val = [](int n, int k) { return (float)(((n * 5 + k * 11) % 9) - 4); };
     for (int i = tid; i < TC_ROWS * k_dim; i += 128) {
         const int r = i % TC_ROWS, k = i / TC_ROWS;
-        *reinterpret_cast<__nv_bfloat16 *>(As + (size_t)(k / 8) * A_LBO + r * 16 + (k % 8) * 2) = __float2bfloat16_rn(a_val(r, k));
+        const size_t off = variant == 2 ? (size_t)sw128_chunk_off(r, k / 8) + (k % 8) * 2 : (size_t)(k / 8) * A_LBO + r * 16 + (k % 8) * 2;
+        *reinterpret_cast<__nv_bfloat16 *>(As + off) = __float2bfloat16_rn(a_val(r, k));
     }
     for (int i = tid; i < n_cols * k_dim; i += 128) {
         const int n = i % n_cols, k = i / n_cols;
-        *reinterpret_cast<__nv_bfloat16 *>(Bs + (size_t)(k / 8) * (n_cols * 16) + n * 16 + (k % 8) * 2) = __float2bfloat16_rn(b_val(n, k));
+        const size_t off = variant == 3 ? (size_t)sw128_chunk_off(n, k / 8) + (k % 8) * 2 : (size_t)(k / 8) * (n_cols * 16) + n * 16 + (k % 8) * 2;
+        *reinterpret_cast<__nv_bfloat16 *>(Bs + off) = __float2bfloat16_rn(b_val(n, k));
     }
     if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc(&tmem_slot, 256);
@@ -530,9 +536,11 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(int n_cols, int k
         const uint32_t idesc = instr_desc_bf16(n_cols);
         for (int j = 0; j < k_dim / 16; ++j) {
             uint64_t ad, bd;
-            if (variant == 0) {
+            if (variant == 0 || variant == 2 || variant == 3) {
                 ad = smem_desc(smem_u32(As) + (uint32_t)(j * 2 * A_LBO), A_LBO, 128);
                 bd = smem_desc(smem_u32(Bs) + (uint32_t)(j * 2 * n_cols * 16), (uint32_t)(n_cols * 16), 128);
+                if (variant == 2) ad = smem_desc_sw128(smem_u32(As) + (uint32_t)((j / 4) * SW128_BLOCK + (j % 4) * 32));
+                if (variant == 3) bd = smem_desc_sw128(smem_u32(Bs) + (uint32_t)((j / 4) * SW128_BLOCK + (j % 4) * 32));
             } else {
                 ad = smem_desc(smem_u32(As) + (uint32_t)(j * 2 * A_LBO), 128, A_LBO);
                 bd = smem_desc(smem_u32(Bs) + (uint32_t)(j * 2 * n_cols * 16), 128, (uint32_t)(n_cols * 16));
@@ -566,11 +574,58 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(int n_cols, int k
     if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
+// TMEM -> register read bandwidth probe (variant >= 10 of pn2_selftest_umma): `warps` warps of one CTA each issue
+// `reps` x tcgen05.ld.32x32b.x32 back to back (wait every `batch` loads); *max_err receives bytes per clock.
+__global__ void __launch_bounds__(512, 1) tmem_bw_probe_kernel(int reps, int batch, float *result)
+{
+    __shared__ uint32_t tmem_slot;
+    __shared__ long long t_begin[16], t_end[16];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t base = tmem_slot + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t acc = 0;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int i = 0; i < reps; i += batch) {
+        for (int j = 0; j < batch; ++j) {
+            uint32_t r[32];
+            tmem_ld32_nowait(base + (uint32_t)(((i + j) * 32) & 511), r);
+            if (j == batch - 1) tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) acc ^= r[k];
+        }
+    }
+    tmem_ld_wait();
+    const long long t1 = clock64();
+    if (lane == 0) { t_begin[warp] = t0; t_end[warp] = t1; }
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+        const int nw = blockDim.x >> 5;
+        long long lo = t_begin[0], hi = t_end[0];
+        for (int w = 1; w < nw; ++w) { lo = min(lo, t_begin[w]); hi = max(hi, t_end[w]); }
+        result[0] = (float)((double)nw * reps * 4096.0 / (double)(hi - lo));
+        result[1] = (float)(hi - lo);
+    }
+    if (acc == 0x12345678u) result[2] = 1.f;
+    if (warp == 0) tmem_dealloc(tmem_slot, 512);
+}
+
 int launch_selftest_umma(int n_cols, int k_dim, int variant, float *max_err, float *dump, cudaStream_t st)
 {
+    if (variant >= 10) {   // TMEM read-bandwidth probe: n_cols = warps, k_dim = loads per warp, variant - 10 = loads per wait
+        PN2_REQUIRE(n_cols >= 1 && n_cols <= 16 && k_dim >= 1 && dump, "pn2_selftest_umma(probe): bad arguments");
+        tmem_bw_probe_kernel<<<1, n_cols * 32, 0, st>>>(k_dim, variant - 10 < 1 ? 1 : variant - 10, dump);
+        return launch_status("pn2_selftest_umma(probe)");
+    }
     PN2_REQUIRE(n_cols >= 32 && n_cols <= 256 && n_cols % 32 == 0, "pn2_selftest_umma: n_cols must be a multiple of 32 in [32,256]");
     PN2_REQUIRE(k_dim >= 16 && k_dim <= 256 && k_dim % 16 == 0, "pn2_selftest_umma: k_dim must be a multiple of 16 in [16,256]");
-    const size_t smem = (size_t)(k_dim / 8) * A_LBO + (size_t)(k_dim / 8) * n_cols * 16;
+    PN2_REQUIRE(variant != 3 || n_cols == TC_ROWS, "pn2_selftest_umma: variant 3 needs n_cols = 128");
+    const size_t sw = (size_t)((k_dim + 63) / 64) * SW128_BLOCK;
+    const size_t smem = 1024 + (variant == 2 ? sw : (size_t)(k_dim / 8) * A_LBO) + (variant == 3 ? sw : (size_t)(k_dim / 8) * n_cols * 16);
     cudaError_t e = cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("selftest: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
     umma_selftest_kernel<<<1, 128, smem, st>>>(n_cols, k_dim, variant, max_err, dump);

@@ -6,9 +6,11 @@
 // thread per row of a 128-row tile = one TMEM lane) that walks its tiles through the chain
 //     gather -> [MMA l -> epilogue l] x (L-1) -> MMA L-1 -> max-pool -> store
 // and owns one activation buffer in shared memory (each layer's epilogue overwrites its own, fully consumed,
-// input) and one accumulator region in TMEM.  A single extra warp issues every tcgen05.mma of the CTA: it
-// serves the units round-robin, waiting on a unit's "operand ready" mbarrier and committing to its
-// "accumulator ready" mbarrier, so while one unit drains TMEM / gathers, the tensor core works for the others.
+// input) and one accumulator region in TMEM.  The unit's first warp issues the unit's own tcgen05.mma (one
+// elected lane, descriptors on the uniform datapath) after a unit-wide named barrier, and commits to the
+// unit's "accumulator ready" mbarrier that all four warps then wait on; the units are otherwise independent,
+// so while one drains TMEM or gathers, the tensor core works for the others (and MMA issue, ~100 cycles per
+// instruction from a single thread, proceeds from U threads in parallel).
 // All weights (BN folded, bf16, canonical K-major core-matrix layout, written by pn2_pack_weights) are
 // bulk-copied (cp.async.bulk + mbarrier) into shared memory once per CTA.
 //
@@ -22,12 +24,14 @@
 //   gather                 : features of the previous set-abstraction layer arrive in bf16 (side output of this
 //                            kernel) and go global -> shared with cp.async, 16 B = one k-group of one row,
 //                            no registers; fp32 features / raw coordinates go through registers.
+#include <cuda.h>
+#include <stdlib.h>
 #include "pn2_tc.cuh"
 
 namespace pn2 {
 
 constexpr int T2_MAX_UNITS = 4;
-constexpr int T2_MAX_THREADS = (4 * T2_MAX_UNITS + 1) * 32;   // 544
+constexpr int T2_MAX_THREADS = 4 * T2_MAX_UNITS * 32;         // 512
 constexpr int T2_SMEM_LIMIT = 227 * 1024;
 
 struct Tc2Params {
@@ -39,8 +43,11 @@ struct Tc2Params {
     const unsigned char *packed;
     float *out; int64_t ob, os; int co_off;
     int64_t G, rows, tiles;
-    int U, cols_per_unit, tmem_cols, a_unit_bytes, feat_fast;
+    int U, cols_per_unit, tmem_cols, a_unit_bytes, xyz_off, feat_fast;   // xyz_off: the no-swizzle coordinate block inside a unit's buffer
     const __nv_bfloat16 *feat_bf16; __nv_bfloat16 *out_bf16;
+    unsigned long long *trace;   // debug timeline (pn2_debug_trace), CTA 0 only; nullptr = off
+    int use_tma, feat_rows;      // bf16 features gathered by TMA (tile::gather4) through `tmap` = [feat_rows = B*N][D]
+    alignas(64) CUtensorMap tmap;
 };
 
 __device__ __forceinline__ float2 add2(float2 a, float2 b)
@@ -65,7 +72,7 @@ __device__ __forceinline__ void epi_block(const uint32_t (&r)[32], const float *
         const float2 v1 = add2(make_float2(__uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3])), make_float2(b0.z, b0.w));
         const float2 v2 = add2(make_float2(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5])), make_float2(b1.x, b1.y));
         const float2 v3 = add2(make_float2(__uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7])), make_float2(b1.z, b1.w));
-        *reinterpret_cast<uint4 *>(A + (size_t)(c0 / 8 + i) * A_LBO + row * 16) =
+        *reinterpret_cast<uint4 *>(A + sw128_chunk_off(row, c0 / 8 + i)) =
             make_uint4(relu_pack_bf16x2(v0.x, v0.y), relu_pack_bf16x2(v1.x, v1.y), relu_pack_bf16x2(v2.x, v2.y), relu_pack_bf16x2(v3.x, v3.y));
     }
 }
@@ -95,6 +102,17 @@ __device__ __forceinline__ void cp_async_commit_wait_all()
 }
 
 constexpr int T2_MAX_L = 4;
+constexpr int T2_TRACE_SLOTS = 1024;     // per role (units 0..3, MMA warp = 4)
+
+// debug timeline: (event << 48) | clock, appended to this role's slice of the trace buffer
+struct Tracer {
+    unsigned long long *buf; int n;
+    __device__ __forceinline__ void init(unsigned long long *base, int role, bool on) { buf = (on && base) ? base + (size_t)role * T2_TRACE_SLOTS : nullptr; n = 0; }
+    __device__ __forceinline__ void mark(int ev)
+    {
+        if (buf && n < T2_TRACE_SLOTS) buf[n++] = ((unsigned long long)ev << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull);
+    }
+};
 
 __device__ __forceinline__ uint64_t mk_desc(uint32_t lo, uint32_t hi)
 {
@@ -107,30 +125,37 @@ __device__ __forceinline__ uint64_t mk_desc(uint32_t lo, uint32_t hi)
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16); }
 constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);      // SBO = 128 B, descriptor version 1
 
-__global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Params p)
+__global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const __grid_constant__ Tc2Params p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const TcLayout &lay = p.lay;
     const int U = p.U;
-    unsigned char *Wsm = smem;
+    // activation buffers first: their 128-byte-swizzled blocks need 1024-byte alignment
+    unsigned char *A_base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+    unsigned char *Wsm = A_base + (size_t)U * p.a_unit_bytes;
     float *bias_s = reinterpret_cast<float *>(Wsm + lay.w_bytes);
-    unsigned char *A_base = reinterpret_cast<unsigned char *>(bias_s + lay.bias_floats);
-    uint32_t *vmask_base = reinterpret_cast<uint32_t *>(A_base + (size_t)U * p.a_unit_bytes);   // [U][2][4] valid-row ballots, by tile parity
-    uint64_t *a_ready = reinterpret_cast<uint64_t *>(vmask_base + 8 * T2_MAX_UNITS);
-    uint64_t *acc_ready = a_ready + T2_MAX_UNITS;
-    uint64_t *w_bar = acc_ready + T2_MAX_UNITS;
+    uint32_t *vmask_base = reinterpret_cast<uint32_t *>(bias_s + lay.bias_floats);   // [U][2][4] valid-row ballots, by tile parity
+    uint64_t *acc_ready = reinterpret_cast<uint64_t *>(vmask_base + 8 * T2_MAX_UNITS);
+    uint64_t *feat_ready = acc_ready + T2_MAX_UNITS;     // per unit: the TMA gather of the next tile's feature rows has landed
+    uint64_t *w_bar = feat_ready + T2_MAX_UNITS;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w_bar + 1);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int mma_warp = 4 * U;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler (uniform datapath)
     const int L = lay.L;
 
     if (tid == 0) {
-        for (int u = 0; u < T2_MAX_UNITS; ++u) { mbar_init(a_ready + u, 4); mbar_init(acc_ready + u, 1); }
+        for (int u = 0; u < T2_MAX_UNITS; ++u) { mbar_init(acc_ready + u, 1); mbar_init(feat_ready + u, 1); }
         mbar_init(w_bar, 1);
         fence_mbar_init();
+        // all weights, once per CTA, through the bulk-copy engine
+        mbar_expect_tx(w_bar, (uint32_t)lay.w_bytes);
+        for (int off = 0; off < lay.w_bytes; off += 32768) {
+            const int nb = min(32768, lay.w_bytes - off);
+            bulk_g2s(Wsm + off, p.packed + off, (uint32_t)nb, w_bar);
+        }
     }
-    if (warp == mma_warp) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     {
         const float *bsrc = reinterpret_cast<const float *>(p.packed + lay.w_bytes);
         for (int i = tid; i < lay.bias_floats; i += blockDim.x) bias_s[i] = __ldg(bsrc + i);
@@ -142,91 +167,22 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
     const int tiles = (int)p.tiles;
     const int stride = (int)gridDim.x * U;
 
-    if (warp == mma_warp) {
-        // =================================================================================================
-        // MMA warp: weights in once, then every tcgen05.mma of the CTA, units served round-robin.  One thread;
-        // the per-stage path is kept to wait -> fence -> MMAs (descriptor = base + step) -> commit.
-        // =================================================================================================
-        if (lane == 0) {
-            mbar_expect_tx(w_bar, (uint32_t)lay.w_bytes);
-            for (int off = 0; off < lay.w_bytes; off += 32768) {
-                const int nb = min(32768, lay.w_bytes - off);
-                bulk_g2s(Wsm + off, p.packed + off, (uint32_t)nb, w_bar);
-            }
-            int n_u[T2_MAX_UNITS], n_max = 0;
-            uint32_t a_lo[T2_MAX_UNITS], d_tm[T2_MAX_UNITS];
-#pragma unroll
-            for (int u = 0; u < T2_MAX_UNITS; ++u) {
-                const int gu = (int)blockIdx.x * U + u;
-                n_u[u] = (u < U && gu < tiles) ? (tiles - gu + stride - 1) / stride : 0;
-                n_max = max(n_max, n_u[u]);
-                a_lo[u] = desc_lo(smem_u32(A_base) + (uint32_t)(u * p.a_unit_bytes), A_LBO);
-                d_tm[u] = tmem_base + (uint32_t)(u * p.cols_per_unit);
-            }
-            uint32_t w_lo[T2_MAX_L], w_step[T2_MAX_L], idesc[T2_MAX_L];
-            int nks[T2_MAX_L];
-#pragma unroll
-            for (int l = 0; l < T2_MAX_L; ++l) {
-                const TcLayer &ly = lay.ly[l < L ? l : 0];
-                const bool last = (l == L - 1);
-                const uint32_t lbo = (uint32_t)(last ? ly.Npad : ly.NS) * 16u;
-                w_lo[l] = desc_lo(smem_u32(Wsm) + (uint32_t)ly.w_off, lbo);
-                w_step[l] = (2u * lbo) >> 4;
-                idesc[l] = instr_desc_bf16(last ? TC_ROWS : ly.NS);
-                nks[l] = ly.K / 16;
-            }
-            const int n_mh = lay.ly[L - 1].Npad / TC_ROWS;
-            mbar_wait(w_bar, 0);
-            uint32_t phases = 0;
-            for (int it = 0; it < n_max; ++it) {
-#pragma unroll
-                for (int l = 0; l < T2_MAX_L; ++l) {
-                    if (l < L) {
-#pragma unroll
-                        for (int u = 0; u < T2_MAX_UNITS; ++u) {
-                            if (it < n_u[u]) {
-                                mbar_wait(a_ready + u, (phases >> u) & 1u);
-                                phases ^= 1u << u;
-                                tc_fence_after();
-                                if (l < L - 1) {
-                                    for (int ks = 0; ks < nks[l]; ++ks)
-                                        umma_bf16(d_tm[u], mk_desc(a_lo[u] + (uint32_t)ks * (2 * A_LBO / 16), DESC_HI),
-                                                  mk_desc(w_lo[l] + (uint32_t)ks * w_step[l], DESC_HI), idesc[l], ks ? 1u : 0u);
-                                } else {
-                                    // transposed: 128 output channels (rows of W) per MMA as M, the tile's 128 rows as N
-                                    for (int mh = 0; mh < n_mh; ++mh)
-                                        for (int ks = 0; ks < nks[l]; ++ks)
-                                            umma_bf16(d_tm[u] + (uint32_t)(mh * TC_ROWS),
-                                                      mk_desc(w_lo[l] + (uint32_t)(mh * TC_ROWS) + (uint32_t)ks * w_step[l], DESC_HI),
-                                                      mk_desc(a_lo[u] + (uint32_t)ks * (2 * A_LBO / 16), DESC_HI), idesc[l], ks ? 1u : 0u);
-                                }
-                                umma_commit(acc_ready + u);
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        __syncwarp();
-    } else if (warp < mma_warp) {
-        // =================================================================================================
-        // unit warpgroups: gather, epilogues, pooling
-        // =================================================================================================
+    {
         const int u = warp >> 2, q = warp & 3, row = q * 32 + lane;
         unsigned char *A = A_base + (size_t)u * p.a_unit_bytes;
-        unsigned char *A_row = A + row * 16;
+        unsigned char *X_row = A + p.xyz_off + row * 16;            // this row in the coordinate block [2][128][16 B]
         uint32_t *vmask_u = vmask_base + 8 * u;
         uint32_t parity = 0;
         const uint32_t tmem_row = tmem_base + (uint32_t)(u * p.cols_per_unit) + ((uint32_t)(q * 32) << 16);
-        const int K = p.K, C = p.C, D = p.D, K0 = lay.ly[0].K, S = p.S, N = p.N;
+        const int K = p.K, C = p.C, D = p.D, S = p.S, N = p.N;
         const int logK = 31 - __clz(K);
         const int gpt = TC_ROWS >> logK;
         const int rows = (int)p.rows, G = (int)p.G;
         uint32_t acc_phase = 0;
         const int gu = (int)blockIdx.x * U + u;
-        uint64_t *my_a_ready = a_ready + u, *my_acc_ready = acc_ready + u;
+        uint64_t *my_acc_ready = acc_ready + u;
         const bool twin = p.feat_fast && p.feat_bf16 != nullptr;    // bf16 features: cp.async straight into the operand
-        const bool pre_xyz = p.feat_fast && C <= 4;                 // coordinates prefetched one tile ahead
+        const bool pre_xyz = C <= 4;                                // coordinates prefetched one tile ahead
 
         // raw neighbour index of this thread's row in `tile` (-1 outside the problem); no use of the value here,
         // so the load stays in flight
@@ -250,16 +206,115 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
                 pp += p.sc;
             }
         };
-        // bf16 feature rows -> operand buffer, asynchronously (the buffer must be free)
-        auto issue_twin = [&](int tile, int n) {
-            const int g = (tile * TC_ROWS + row) >> logK;
-            const int b = (int)((unsigned)g / (unsigned)S);
-            const bool ok = is_valid(n);
-            const __nv_bfloat16 *f = p.feat_bf16 + (ok ? ((int64_t)b * N + n) * D : 0);
-            for (int kg = 0; kg < D / 8; ++kg) cp_async16_zfill(A_row + (size_t)kg * A_LBO, f + kg * 8, ok);
+        // Feature rows -> operand buffer.  Lanes are mapped (4 rows) x (8 chunks of 16 B): eight lanes read 128
+        // contiguous bytes of one source row (bf16) and write one 128-byte swizzled line, so the copy is coalesced
+        // in global memory and conflict free in shared memory.  The row's neighbour index lives in the lane that
+        // owns the row (thread = row everywhere else) and is fetched with a shuffle.
+        // bf16 features: asynchronous (cp.async), the buffer must be free when this is called.
+        uint64_t *my_feat_ready = feat_ready + u;
+        uint32_t feat_phase = 0;
+        auto issue_twin = [&](int tile, int n_mine) {
+            if (p.use_tma) {
+                // TMA gather4: lane l < 8 moves rows 4l..4l+3 of this warp's 32 (one instruction per 64-channel
+                // block); invalid rows use an out-of-range row index and arrive as zeros
+                const int g = (tile * TC_ROWS + row) >> logK;
+                const int b = (int)((unsigned)g / (unsigned)S);
+                const int ri = is_valid(n_mine) ? b * N + n_mine : p.feat_rows;
+                const int l4 = (lane & 7) * 4;
+                const int r0 = __shfl_sync(0xffffffffu, ri, l4), r1 = __shfl_sync(0xffffffffu, ri, l4 + 1);
+                const int r2 = __shfl_sync(0xffffffffu, ri, l4 + 2), r3 = __shfl_sync(0xffffffffu, ri, l4 + 3);
+                if (q == 0 && lane == 0) mbar_expect_tx(my_feat_ready, (uint32_t)(TC_ROWS * D * 2));
+                if (lane < 8)
+                    for (int c0 = 0; c0 < D; c0 += 64)
+                        tma_gather4(A + (c0 >> 6) * SW128_BLOCK + (q * 32 + l4) * 128, &p.tmap, c0, r0, r1, r2, r3, my_feat_ready);
+                return;
+            }
+            const int nv = is_valid(n_mine) ? n_mine : -1;
+            const int ch = lane & 7;
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i) {
+                const int rl = i * 4 + (lane >> 3);
+                const int r = q * 32 + rl;
+                const int nr = __shfl_sync(0xffffffffu, nv, rl);
+                const int g = (tile * TC_ROWS + r) >> logK;
+                const int b = (int)((unsigned)g / (unsigned)S);
+                const __nv_bfloat16 *src = p.feat_bf16 + ((int64_t)b * N + (nr < 0 ? 0 : nr)) * D + ch * 8;
+                unsigned char *dst = A + r * 128 + ((ch ^ (r & 7)) << 4);
+                for (int c0 = 0; c0 < D; c0 += 64)
+                    if (c0 + ch * 8 < D) cp_async16_zfill(dst + (c0 >> 6) * SW128_BLOCK, src + c0, nr >= 0);
+            }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
+        // fp32 features: through registers (convert to bf16), same lane mapping
+        auto gather_f32 = [&](int tile, int n_mine) {
+            const int nv = is_valid(n_mine) ? n_mine : -1;
+            const int ch = lane & 7;
+            for (int c0 = 0; c0 < D; c0 += 64) {
+                float4 v[16];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rl = i * 4 + (lane >> 3);
+                    const int r = q * 32 + rl;
+                    const int nr = __shfl_sync(0xffffffffu, nv, rl);
+                    const int g = (tile * TC_ROWS + r) >> logK;
+                    const int b = (int)((unsigned)g / (unsigned)S);
+                    v[2 * i] = v[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (nr >= 0 && c0 + ch * 8 < D) {
+                        const float *src = p.feat + (int64_t)b * p.fb + (int64_t)nr * p.fn + c0 + ch * 8;
+                        v[2 * i] = __ldg(reinterpret_cast<const float4 *>(src));
+                        v[2 * i + 1] = __ldg(reinterpret_cast<const float4 *>(src) + 1);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = q * 32 + i * 4 + (lane >> 3);
+                    if (c0 + ch * 8 < D)
+                        *reinterpret_cast<uint4 *>(A + (c0 >> 6) * SW128_BLOCK + r * 128 + ((ch ^ (r & 7)) << 4)) =
+                            make_uint4(pack_bf16x2(v[2 * i].x, v[2 * i].y), pack_bf16x2(v[2 * i].z, v[2 * i].w),
+                                       pack_bf16x2(v[2 * i + 1].x, v[2 * i + 1].y), pack_bf16x2(v[2 * i + 1].z, v[2 * i + 1].w));
+                }
+            }
+        };
 
+        Tracer tr; tr.init(p.trace, u, blockIdx.x == 0 && q == 0 && lane == 0);
+        // ---- MMA issue (warp 0 of the unit; warp-uniform operands) ----------------------------------------
+        const uint32_t a_sw = desc_lo_sw128(smem_u32(A));                       // swizzled blocks: + (ks/4)*block + (ks%4)*32 bytes
+        const uint32_t a_xyz = desc_lo(smem_u32(A) + (uint32_t)p.xyz_off, A_LBO);   // coordinate block, no swizzle
+        const uint32_t d_tm = tmem_base + (uint32_t)(u * p.cols_per_unit);
+        const int ks_xyz = D / 16;          // layer 0: K-steps [0, D/16) read features, step D/16 reads the coordinates
+        bool w_ready = false;
+        auto issue_layer = [&](int l) {
+            // all four warps have written (and proxy-fenced) the operand / drained TMEM: unit-wide barrier,
+            // then one elected lane of warp 0 issues the layer and commits to the unit's mbarrier
+            asm volatile("bar.sync %0, 128;" ::"r"(u + 1) : "memory");
+            if (q == 0) {
+                if (!w_ready) { mbar_wait(w_bar, 0); w_ready = true; }
+                tc_fence_after();
+                const TcLayer &ly = lay.ly[l];
+                const bool last = (l == L - 1);
+                const uint32_t lbo = (uint32_t)(last ? ly.Npad : ly.NS) * 16u;
+                const uint32_t w_lo = desc_lo(smem_u32(Wsm) + (uint32_t)ly.w_off, lbo);
+                const uint32_t w_step = (2u * lbo) >> 4;
+                const uint32_t idesc = instr_desc_bf16(last ? TC_ROWS : ly.NS);
+                const int nks = ly.K / 16;
+                if (elect_one()) {
+                    const int n_mh = last ? ly.Npad / TC_ROWS : 1;
+                    for (int mh = 0; mh < n_mh; ++mh)
+                        for (int ks = 0; ks < nks; ++ks) {
+                            const bool xyz = (l == 0 && ks == ks_xyz);
+                            const uint64_t act = xyz ? mk_desc(a_xyz, DESC_HI)
+                                                     : mk_desc(a_sw + (uint32_t)((ks >> 2) * (SW128_BLOCK / 16) + (ks & 3) * 2), DESC_HI_SW128);
+                            const uint64_t wgt = mk_desc(w_lo + (uint32_t)(mh * TC_ROWS) + (uint32_t)ks * w_step, DESC_HI);
+                            // hidden layers: D[row][channel] = X (M operand) x W^T; last layer, transposed:
+                            // D[channel][row] = W (128 output channels as M) x X^T (the tile's 128 rows as N)
+                            if (!last) umma_bf16(d_tm, act, wgt, idesc, ks ? 1u : 0u);
+                            else umma_bf16(d_tm + (uint32_t)(mh * TC_ROWS), wgt, act, idesc, ks ? 1u : 0u);
+                        }
+                    umma_commit(my_acc_ready);
+                }
+                __syncwarp();
+            }
+        };
         int n_cur = load_index(gu);
         float px[4], pc[4];
         if (gu < tiles) {
@@ -276,69 +331,45 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
             const int g = (tile * TC_ROWS + row) >> logK;      // group of this row
             const int b = (int)((unsigned)g / (unsigned)S);
 
-            // ---- gather: this thread's row, internal channel order [feat(D), xyz(C), zero pad] ----------------
-            if (p.feat_fast) {
-                if (!twin) {
-                    const float *f = valid && D ? p.feat + (int64_t)b * p.fb + (int64_t)n * p.fn : nullptr;
-                    for (int kg0 = 0; kg0 < D / 8; kg0 += 4) {
-                        float4 v[8];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            v[2 * i] = v[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (f && kg0 + i < D / 8) {
-                                v[2 * i] = __ldg(reinterpret_cast<const float4 *>(f + (kg0 + i) * 8));
-                                v[2 * i + 1] = __ldg(reinterpret_cast<const float4 *>(f + (kg0 + i) * 8 + 4));
-                            }
-                        }
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            if (kg0 + i < D / 8)
-                                *reinterpret_cast<uint4 *>(A_row + (size_t)(kg0 + i) * A_LBO) =
-                                    make_uint4(pack_bf16x2(v[2 * i].x, v[2 * i].y), pack_bf16x2(v[2 * i].z, v[2 * i].w),
-                                               pack_bf16x2(v[2 * i + 1].x, v[2 * i + 1].y), pack_bf16x2(v[2 * i + 1].z, v[2 * i + 1].w));
+            // ---- gather: features (swizzled blocks) were started earlier (bf16 twin) or are converted here (fp32);
+            //      coordinates minus centre go to the unit's coordinate block: channels [D, D+16) of layer 0 ----------
+            if (D) {
+                if (p.feat_fast) { if (!twin) gather_f32(tile, n); }
+                else {
+                    for (int k = 0; k < D; ++k) {
+                        const float t = valid ? __ldg(p.feat + (int64_t)b * p.fb + (int64_t)n * p.fn + (int64_t)k * p.fc) : 0.f;
+                        *reinterpret_cast<__nv_bfloat16 *>(A + sw128_chunk_off(row, k >> 3) + (k & 7) * 2) = __float2bfloat16_rn(t);
                     }
                 }
-                if (pre_xyz) {
-                    // x - centre for the (<= 4) coordinate channels, then zero k-groups up to K0
-                    unsigned char *dst = A_row + (size_t)(D / 8) * A_LBO;
-                    *reinterpret_cast<uint4 *>(dst) = make_uint4(pack_bf16x2(__fsub_rn(px[0], pc[0]), __fsub_rn(px[1], pc[1])),
-                                                                 pack_bf16x2(__fsub_rn(px[2], pc[2]), __fsub_rn(px[3], pc[3])), 0u, 0u);
-                    for (int kg = D / 8 + 1; kg < K0 / 8; ++kg) *reinterpret_cast<uint4 *>(A_row + (size_t)kg * A_LBO) = make_uint4(0u, 0u, 0u, 0u);
-                } else {
-                    const float *pp = p.points + (int64_t)b * p.sb + (int64_t)n * p.sn;
-                    const float *cc = p.centres + (int64_t)g * C;
-                    float x[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float a0 = 0.f, a1 = 0.f;
-                        if (valid && i < C) { a0 = __ldg(pp); a1 = __ldg(cc + i); }
-                        pp += p.sc;
-                        x[i] = __fsub_rn(a0, a1);
-                    }
-                    unsigned char *dst = A_row + (size_t)(D / 8) * A_LBO;
-                    *reinterpret_cast<uint4 *>(dst) = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
-                    if (K0 / 8 > D / 8 + 1)
-                        *reinterpret_cast<uint4 *>(dst + A_LBO) = make_uint4(pack_bf16x2(x[8], x[9]), pack_bf16x2(x[10], x[11]), pack_bf16x2(x[12], x[13]), pack_bf16x2(x[14], x[15]));
-                    for (int kg = D / 8 + 2; kg < K0 / 8; ++kg) *reinterpret_cast<uint4 *>(A_row + (size_t)kg * A_LBO) = make_uint4(0u, 0u, 0u, 0u);
-                }
-                if (twin) asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            if (pre_xyz) {
+                *reinterpret_cast<uint4 *>(X_row) = make_uint4(pack_bf16x2(__fsub_rn(px[0], pc[0]), __fsub_rn(px[1], pc[1])),
+                                                               pack_bf16x2(__fsub_rn(px[2], pc[2]), __fsub_rn(px[3], pc[3])), 0u, 0u);
+                *reinterpret_cast<uint4 *>(X_row + A_LBO) = make_uint4(0u, 0u, 0u, 0u);
             } else {
-                for (int k = 0; k < K0; ++k) {
-                    float t = 0.f;
-                    if (valid) {
-                        if (k < D) t = __ldg(p.feat + (int64_t)b * p.fb + (int64_t)n * p.fn + (int64_t)k * p.fc);
-                        else if (k < D + C)
-                            t = __fsub_rn(__ldg(p.points + (int64_t)b * p.sb + (int64_t)n * p.sn + (int64_t)(k - D) * p.sc),
-                                          __ldg(p.centres + (int64_t)g * C + (k - D)));
-                    }
-                    *reinterpret_cast<__nv_bfloat16 *>(A_row + (size_t)(k / 8) * A_LBO + (k % 8) * 2) = __float2bfloat16_rn(t);
+                const float *pp = p.points + (int64_t)b * p.sb + (int64_t)n * p.sn;
+                const float *cc = p.centres + (int64_t)g * C;
+                float x[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float a0 = 0.f, a1 = 0.f;
+                    if (valid && i < C) { a0 = __ldg(pp); a1 = __ldg(cc + i); }
+                    pp += p.sc;
+                    x[i] = __fsub_rn(a0, a1);
                 }
+                *reinterpret_cast<uint4 *>(X_row) = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+                *reinterpret_cast<uint4 *>(X_row + A_LBO) = make_uint4(pack_bf16x2(x[8], x[9]), pack_bf16x2(x[10], x[11]), pack_bf16x2(x[12], x[13]), pack_bf16x2(x[14], x[15]));
+            }
+            if (twin) {
+                if (p.use_tma) { mbar_wait(my_feat_ready, feat_phase); feat_phase ^= 1u; }
+                else asm volatile("cp.async.wait_group 0;" ::: "memory");
             }
             const unsigned vm = __ballot_sync(0xffffffffu, valid);
             if (lane == 0) vmask_s[q] = vm;      // read by the whole unit in the pooling step (ordered by the mbarriers)
             fence_proxy_async();                 // generic-proxy stores -> visible to the tensor core (async proxy)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(my_a_ready);
+            tr.mark(0x300);
+            issue_layer(0);
+            tr.mark(0x700);
             const bool more = tile + stride < tiles;
 
 #pragma unroll
@@ -348,6 +379,7 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
                 mbar_wait(my_acc_ready, acc_phase);
                 acc_phase ^= 1u;
                 tc_fence_after();
+                tr.mark(0x400 + l);
                 const float *bs = bias_s + ly.b_off;
                 if (l < L - 1) {
                     // ---- hidden layer: accumulator -> +bias -> ReLU -> bf16 -> the next layer's A operand (in place) --
@@ -358,10 +390,11 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
                         tmem_ld_wait();
                         epi_block(r, bs, A, c0, row);
                     }
-                    tc_fence_before();           // TMEM reads ordered before the MMA warp's next write to this region
+                    tc_fence_before();           // TMEM reads ordered before the next MMA's write to this region
                     fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(my_a_ready);
+                    tr.mark(0x500 + l);
+                    issue_layer(l + 1);
+                    tr.mark(0x700 + l + 1);
                     // the next tile's index has arrived by now: start its coordinate loads (they land during the
                     // remaining layers)
                     if (l == 0 && L > 1 && more && pre_xyz) load_xyz4(tile + stride, n_next, px, pc);
@@ -373,6 +406,7 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
                         if (twin) issue_twin(tile + stride, n_next);
                         if (L == 1 && pre_xyz) load_xyz4(tile + stride, n_next, px, pc);
                     }
+                    tr.mark(0x610);
                     const uint32_t m0 = vmask_s[0], m1 = vmask_s[1], m2 = vmask_s[2], m3 = vmask_s[3];
                     const bool all_valid = (m0 & m1 & m2 & m3) == 0xffffffffu;
                     const int g0 = tile * gpt;
@@ -401,6 +435,7 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
                             uint32_t r[32];
                             tmem_ld32_nowait(tmem_row + (uint32_t)(mh * TC_ROWS + blk * 32), r);
                             tmem_ld_wait();
+                            tr.mark(0x620 + mh * 4 + blk);
                             if (!all_valid) {        // padding rows / empty balls (never on the reference's configurations)
                                 const uint32_t mk = blk == 0 ? m0 : blk == 1 ? m1 : blk == 2 ? m2 : m3;
 #pragma unroll
@@ -418,9 +453,11 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
                                 emit(max_range<16, 8>(r));
                                 emit(max_range<24, 8>(r));
                             }
+                            tr.mark(0x630 + mh * 4 + blk);
                         }
                     }
                     tc_fence_before();
+                    tr.mark(0x600);
                 }
             }
             n_cur = n_next;
@@ -428,34 +465,40 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const Tc2Para
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == mma_warp) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------------
+static unsigned long long *g_trace = nullptr;
+void set_debug_trace(void *buf) { g_trace = (unsigned long long *)buf; }
+
 static int pow2_at_least(int x) { int p = 32; while (p < x) p <<= 1; return p; }
 
-struct Tc2Plan { int U, cols_per_unit, tmem_cols, a_unit_bytes; size_t smem; };
+struct Tc2Plan { int U, cols_per_unit, tmem_cols, a_unit_bytes, xyz_off; size_t smem; };
 
-static bool tc2_plan(int K, int order, const TcLayout &t, Tc2Plan *pl)
+static bool tc2_plan(int K, int C, int D, int order, const TcLayout &t, Tc2Plan *pl)
 {
+    // features fill whole K = 16 slices of the swizzled blocks, the (<= 16) coordinate channels their own slice
+    if (D % 16 != 0 || C < 1 || C > 16 || t.ly[0].K != D + 16) return false;
     if (order == PN2_ORDER_ALL) return false;                       // group_all stacks are wide: pn2_sa_tc.cu
     if (K < 8 || K > TC_ROWS || (K & (K - 1))) return false;
     if (t.L > 4) return false;
-    int kmax = 0, nmax = 0;
     if (t.L < 1 || t.ly[t.L - 1].Npad > 512) return false;
+    int kmax = D, nmax = 0;                                         // widest feature part of any layer's operand
     for (int l = 0; l < t.L; ++l) {
         if (l < t.L - 1 && (t.ly[l].nslab != 1 || t.ly[l].NS > 256)) return false;
-        if (t.ly[l].K > kmax) kmax = t.ly[l].K;
+        if (l > 0 && t.ly[l].K > kmax) kmax = t.ly[l].K;
         if (t.ly[l].Npad > nmax) nmax = t.ly[l].Npad;
     }
     pl->cols_per_unit = pow2_at_least(nmax);
-    pl->a_unit_bytes = kmax / 8 * A_LBO;
+    pl->xyz_off = (kmax + 63) / 64 * SW128_BLOCK;                   // swizzled 64-channel blocks, then [2][128][16 B] coordinates
+    pl->a_unit_bytes = pl->xyz_off + 2 * A_LBO;
     for (int U = T2_MAX_UNITS; U >= 1; U >>= 1) {
         if (U * pl->cols_per_unit > 512) continue;
         const size_t smem = (size_t)t.w_bytes + (size_t)t.bias_floats * 4 + (size_t)U * pl->a_unit_bytes +
-                            8 * T2_MAX_UNITS * 4 + (2 * T2_MAX_UNITS + 1) * 8 + 16;
+                            8 * T2_MAX_UNITS * 4 + (2 * T2_MAX_UNITS + 1) * 8 + 16 + 1024;   // + alignment slack
         if (smem > (size_t)T2_SMEM_LIMIT) continue;
         pl->U = U; pl->smem = smem; pl->tmem_cols = pow2_at_least(U * pl->cols_per_unit);
         return true;
@@ -463,11 +506,11 @@ static bool tc2_plan(int K, int order, const TcLayout &t, Tc2Plan *pl)
     return false;
 }
 
-int sa_bf16_pipelined_covers(int K, int order, int L, const int *dims)
+int sa_bf16_pipelined_covers(int K, int C, int D, int order, int L, const int *dims)
 {
     const TcLayout lay = tc_layout(L, dims);
     Tc2Plan pl;
-    return tc2_plan(K, order, lay, &pl) ? 1 : 0;
+    return tc2_plan(K, C, D, order, lay, &pl) ? 1 : 0;
 }
 
 // returns -100 when this variant does not cover the configuration (the caller falls back to pn2_sa_tc.cu)
@@ -475,7 +518,7 @@ int launch_sa_bf16_pipelined(const SaArgs &a, cudaStream_t st)
 {
     const TcLayout lay = tc_layout(a.L, a.dims);
     Tc2Plan pl;
-    if (!tc2_plan(a.K, a.order, lay, &pl)) return -100;
+    if (!tc2_plan(a.K, a.C, a.D, a.order, lay, &pl)) return -100;
     Tc2Params p;
     p.points = a.points; p.sb = a.sb; p.sn = a.sn; p.sc = a.sc;
     p.feat = a.feat; p.fb = a.fb; p.fn = a.fn; p.fc = a.fc;
@@ -489,17 +532,23 @@ int launch_sa_bf16_pipelined(const SaArgs &a, cudaStream_t st)
     p.tiles = (p.rows + TC_ROWS - 1) / TC_ROWS;
     if (p.rows >= (1ll << 31) - TC_ROWS) return -100;             // the kernel indexes rows with 32-bit integers
     p.U = pl.U; p.cols_per_unit = pl.cols_per_unit; p.tmem_cols = pl.tmem_cols;
-    p.a_unit_bytes = pl.a_unit_bytes;
-    p.feat_fast = (a.D == 0) || (a.fc == 1 && a.D % 8 == 0 && a.fn % 4 == 0 && a.fb % 4 == 0 && ((uintptr_t)a.feat & 15) == 0);
+    p.a_unit_bytes = pl.a_unit_bytes; p.xyz_off = pl.xyz_off;
+    p.feat_fast = (a.D == 0) || (a.fc == 1 && a.fn % 4 == 0 && a.fb % 4 == 0 && ((uintptr_t)a.feat & 15) == 0);
     // bf16 features of the previous layer: [B,N,D] contiguous, 16-byte rows chunks
     p.feat_bf16 = (a.feat_bf16 && p.feat_fast && a.D > 0 && ((uintptr_t)a.feat_bf16 & 15) == 0) ? (const __nv_bfloat16 *)a.feat_bf16 : nullptr;
     p.out_bf16 = (__nv_bfloat16 *)a.out_bf16;
+    p.trace = g_trace;
+    p.use_tma = 0; p.feat_rows = a.B * a.N;
+    static const bool no_tma = getenv("PN2_NO_TMA_GATHER") != nullptr;
+    if (p.feat_bf16 && a.D % 64 == 0 && (int64_t)a.B * a.N < (1ll << 31) - 1 && !no_tma) {
+        if (make_row_gather_map(p.feat_bf16, (int64_t)a.B * a.N, a.D, &p.tmap) == 0) p.use_tma = 1;
+    }
     if (p.tiles == 0) return 0;
     cudaError_t e = cudaFuncSetAttribute(sa_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) { set_error("sa_tc2: smem attribute (%zu B): %s", pl.smem, cudaGetErrorString(e)); return (int)e; }
     int64_t grid = (p.tiles + pl.U - 1) / pl.U;
     if (grid > 148) grid = 148;
-    sa_tc2_kernel<<<(unsigned)grid, (4 * pl.U + 1) * 32, pl.smem, st>>>(p);
+    sa_tc2_kernel<<<(unsigned)grid, 4 * pl.U * 32, pl.smem, st>>>(p);
     return launch_status("pn2_sa_fused(bf16, pipelined)");
 }
 

@@ -110,6 +110,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// TMA gather: rows r0..r3 (any order, out-of-range rows read as zero) x the tensor map's box of columns starting at
+// `col` -> 4 consecutive rows of the box width at `dst` (swizzled as the tensor map says), bytes counted on `bar`
+__device__ __forceinline__ void tma_gather4(void *dst, const void *tmap, int col, int r0, int r1, int r2, int r3, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                 ::"r"(smem_u32(dst)), "l"(tmap), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -141,6 +148,23 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// ---- 128-byte-swizzled K-major operand (UMMA LayoutType::SWIZZLE_128B) ---------------------------------------
+// A block holds 64 bf16 channels of 128 rows: row r is 128 contiguous bytes at r*128, its eight 16-byte chunks
+// stored at chunk position (j ^ (r & 7)).  Whole rows are therefore contiguous (coalesced global copies, one
+// 128-byte line per 8 lanes, bank-conflict free) and a warp writing one chunk of 32 consecutive rows is
+// conflict free as well.  Blocks of 64 channels follow each other at SW128_BLOCK bytes; they must be 1024-byte
+// aligned.  The K = 16 slice number ks of a block is addressed by advancing the start address by 32*ks bytes.
+constexpr int SW128_BLOCK = TC_ROWS * 128;      // 16 KB
+__host__ __device__ __forceinline__ uint32_t sw128_chunk_off(int row, int chunk /* global chunk index = channel / 8 */)
+{
+    return (uint32_t)((chunk >> 3) * SW128_BLOCK + row * 128 + (((chunk & 7) ^ (row & 7)) << 4));
+}
+constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr)
+{
+    return (uint64_t)desc_lo_sw128(saddr) | ((uint64_t)DESC_HI_SW128 << 32);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = bf16, both K-major, M = 128
 __device__ __forceinline__ uint32_t instr_desc_bf16(int n)
@@ -213,6 +237,17 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[3
           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr) : "memory");
+}
+// true in exactly one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 

@@ -241,7 +241,7 @@ class PointNetSetAbstraction(nn.Module):
             _, idx32 = be.ball_query(new_points, pts, _radius_sq(self.radius), K, want_idx64=False, want_idx32=True)
         alloc = torch.zeros if be.sa_needs_zero(S, K, dims, prec) else torch.empty
         pooled = alloc(B, S, dims[-1], dtype=torch.float32, device=pts.device)
-        side = be.sa_bf16_side_io(K, order, dims, prec)
+        side = be.sa_bf16_side_io(K, C, order, dims, prec)
         twin_in = _bf16_twin(feature, B, N, feat.shape[-1]) if (side and feat is not None) else None
         twin_out = torch.empty(B, S, dims[-1], dtype=torch.bfloat16, device=pts.device) if side else None
         be.sa_fused(pts, feat, new_points if not self.group_all else None, idx32, order, dims, packed, prec, pooled, 0,
@@ -314,7 +314,7 @@ class PointNetSetAbstractionMsg(nn.Module):
         total = sum(d[-1] for _, d, _ in plans)
         zero = any(be.sa_needs_zero(S, K, d, prec) for K, (_, d, prec) in zip(self.sample_number_list, plans))
         pooled = (torch.zeros if zero else torch.empty)(B, S, total, dtype=torch.float32, device=pts.device)
-        sides = [be.sa_bf16_side_io(K, ORDER_MSG, d, prec) for K, (_, d, prec) in zip(self.sample_number_list, plans)]
+        sides = [be.sa_bf16_side_io(K, C, ORDER_MSG, d, prec) for K, (_, d, prec) in zip(self.sample_number_list, plans)]
         twin_in = _bf16_twin(feature, B, N, feat.shape[-1]) if (any(sides) and feat is not None) else None
         # the bf16 twin of the concatenated output is only complete if every branch's kernel writes its slice
         twin_out = torch.empty(B, S, total, dtype=torch.bfloat16, device=pts.device) if all(sides) else None

@@ -56,7 +56,7 @@ class OracleNative:
     def sa_needs_zero(self, S, K, dims, prec):
         return False
 
-    def sa_bf16_side_io(self, K, order, dims, prec):
+    def sa_bf16_side_io(self, K, C, order, dims, prec):
         return False
 
     def sa_fused(self, points, feature, centres, idx32, order, dims, packed, prec, out, co_off=0,

@@ -29,9 +29,14 @@ def dev(x):
 
 
 # ---- tcgen05 building blocks -------------------------------------------------------------------------------
-@pytest.mark.parametrize("n_cols,k_dim", [(32, 16), (64, 64), (128, 144), (256, 256)])
-def test_umma_selftest(nat, n_cols, k_dim):
-    err, _ = nat.selftest_umma(n_cols, k_dim, 0)
+@pytest.mark.parametrize("variant", [0, 2, 3])
+@pytest.mark.parametrize("n_cols,k_dim", [(32, 16), (64, 64), (128, 144), (256, 256), (128, 32), (128, 96)])
+def test_umma_selftest(nat, n_cols, k_dim, variant):
+    """Hand-built tcgen05 descriptors (no-swizzle operands; 128-byte-swizzled A; 128-byte-swizzled B) against a
+    scalar loop on the device, integer-valued operands: exact."""
+    if variant == 3 and n_cols != 128:
+        pytest.skip("the swizzled-B form is used with N = 128 only")
+    err, _ = nat.selftest_umma(n_cols, k_dim, variant)
     torch.cuda.synchronize()
     assert float(err.item()) == 0.0
 
@@ -237,7 +242,7 @@ def test_sa_fused_bf16_side_tensors(nat, oracle, K, order):
     start = torch.randint(0, N, (B,), generator=torch.Generator().manual_seed(8), dtype=torch.long)
     cen = oracle.index_points(x, oracle.farthest_point_sample(x, S, start)).contiguous()
     idx = oracle.query_ball_point(r, K, x, cen)
-    assert nat.sa_bf16_side_io(K, order, dims, 1)
+    assert nat.sa_bf16_side_io(K, C, order, dims, 1)
     packed, _ = nat.pack([tuple(dev(t) for t in l) for l in layers], 1e-5, 1, C, order)
     outs = []
     for twin in (False, True):
@@ -251,3 +256,25 @@ def test_sa_fused_bf16_side_tensors(nat, oracle, K, order):
     rows = oracle.group(x, f, idx, cen, order)
     exp = oracle.mlp_max(rows.reshape(B * S, K, C + D), layers).reshape(B, S, -1)
     assert rel_err(outs[0][0], exp) <= TOL_BF16
+
+
+def test_tma_gather4_matches_the_swizzled_operand_layout(nat):
+    """cp.async.bulk.tensor tile::gather4 + 128-byte swizzle: 4 arbitrary rows -> 4 consecutive swizzled smem rows
+    (chunk j of row r at r*128 + ((j ^ (r & 7)) << 4)); rows outside the tensor read as zeros."""
+    R, D, n_inst = 300, 128, 8
+    g = torch.Generator().manual_seed(4)
+    src = torch.randn(R, D, generator=g).bfloat16().cuda()
+    rows = torch.randint(0, R, (n_inst * 4,), generator=g, dtype=torch.int32)
+    rows[5] = R + 7                      # out of range -> zeros
+    out = torch.zeros(n_inst * 512, dtype=torch.uint8, device="cuda:0")
+    for col0 in (0, 64):
+        rc = nat.lib.pn2_selftest_tma_gather(src.data_ptr(), R, D, rows.cuda().data_ptr(), n_inst, col0, out.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, nat.lib.pn2_last_error_string()
+        torch.cuda.synchronize()
+        img = out.cpu().view(n_inst * 4, 8, 16)                      # [smem row][chunk position][16 B]
+        srcb = src.cpu().view(torch.uint8).view(R, D * 2)
+        for r in range(n_inst * 4):
+            want_row = srcb[rows[r], col0 * 2: col0 * 2 + 128].view(8, 16) if rows[r] < R else torch.zeros(8, 16, dtype=torch.uint8)
+            for j in range(8):
+                assert torch.equal(img[r, j ^ (r & 7)], want_row[j]), (col0, r, j)
