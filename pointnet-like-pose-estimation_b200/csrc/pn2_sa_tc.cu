@@ -614,8 +614,74 @@ __global__ void __launch_bounds__(512, 1) tmem_bw_probe_kernel(int reps, int bat
     if (warp == 0) tmem_dealloc(tmem_slot, 512);
 }
 
+// tcgen05.mma throughput probe (variant 100 + 10*a_swizzled + b_swizzled [+ 50: two accumulators interleaved] of
+// pn2_selftest_umma): one thread issues k_dim MMAs (M = 128, N = n_cols, K = 16) back to back into the same
+// accumulator, then commits; dump[0] = cycles per MMA (issue to completion), dump[1] = cycles spent issuing.
+__global__ void __launch_bounds__(128, 1) umma_rate_probe_kernel(int n_cols, int count, int a_sw, int b_sw, int two_acc, float *result)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    unsigned char *base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+    unsigned char *As = base, *Bs = base + 4 * SW128_BLOCK;          // 256 channels of 128 rows each, zero-filled
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 8 * SW128_BLOCK / 16; i += 128) reinterpret_cast<uint4 *>(base)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+        const uint32_t idesc = instr_desc_bf16(n_cols);
+        if (two_acc == 2) {
+            // issue-rate floor: the same two descriptors every time, loop unrolled by 8, nothing else in the loop
+            const uint64_t ad = smem_desc_sw128(smem_u32(As)), bd = smem_desc(smem_u32(Bs), (uint32_t)(n_cols * 16), 128);
+            const long long t0 = clock64();
+            for (int j = 0; j < count; j += 8) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) umma_bf16(tmem_slot, ad, bd, idesc, 1u);
+            }
+            const long long t1 = clock64();
+            umma_commit(&bar);
+            mbar_wait(&bar, 0);
+            const long long t2 = clock64();
+            result[0] = (float)((double)(t2 - t0) / count);
+            result[1] = (float)((double)(t1 - t0) / count);
+        } else {
+        const long long t0 = clock64();
+        for (int j = 0; j < count; ++j) {
+            const int ks = j & 15;                                  // 16 K-steps = 256 channels, then wrap
+            const uint64_t ad = a_sw ? smem_desc_sw128(smem_u32(As) + (uint32_t)((ks >> 2) * SW128_BLOCK + (ks & 3) * 32))
+                                     : smem_desc(smem_u32(As) + (uint32_t)(ks * 2 * A_LBO), A_LBO, 128);
+            const uint64_t bd = b_sw ? smem_desc_sw128(smem_u32(Bs) + (uint32_t)((ks >> 2) * SW128_BLOCK + (ks & 3) * 32))
+                                     : smem_desc(smem_u32(Bs) + (uint32_t)(ks * 2 * n_cols * 16), (uint32_t)(n_cols * 16), 128);
+            umma_bf16(tmem_slot + (two_acc ? (uint32_t)((j & 1) * 256) : 0u), ad, bd, idesc, 1u);
+        }
+        const long long t1 = clock64();
+        umma_commit(&bar);
+        mbar_wait(&bar, 0);
+        const long long t2 = clock64();
+        result[0] = (float)((double)(t2 - t0) / count);
+        result[1] = (float)((double)(t1 - t0) / count);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_slot, 512);
+}
+
 int launch_selftest_umma(int n_cols, int k_dim, int variant, float *max_err, float *dump, cudaStream_t st)
 {
+    if (variant >= 100) {  // MMA rate probe
+        const int v = variant - 100, two = v >= 200 ? 2 : (v >= 50 ? 1 : 0), a_sw = ((v % 50) / 10) != 0, b_sw = (v % 10) != 0;
+        PN2_REQUIRE(dump && n_cols >= 16 && n_cols <= 256 && n_cols % 16 == 0 && (!b_sw || n_cols == TC_ROWS), "pn2_selftest_umma(rate probe): bad arguments");
+        const size_t smem = 1024 + 8 * (size_t)SW128_BLOCK;
+        cudaError_t e = cudaFuncSetAttribute(umma_rate_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("rate probe: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+        umma_rate_probe_kernel<<<1, 128, smem, st>>>(n_cols, k_dim, a_sw, b_sw, two, dump);
+        return launch_status("pn2_selftest_umma(rate probe)");
+    }
     if (variant >= 10) {   // TMEM read-bandwidth probe: n_cols = warps, k_dim = loads per warp, variant - 10 = loads per wait
         PN2_REQUIRE(n_cols >= 1 && n_cols <= 16 && k_dim >= 1 && dump, "pn2_selftest_umma(probe): bad arguments");
         tmem_bw_probe_kernel<<<1, n_cols * 32, 0, st>>>(k_dim, variant - 10 < 1 ? 1 : variant - 10, dump);

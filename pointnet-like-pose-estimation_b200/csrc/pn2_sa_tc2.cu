@@ -6,11 +6,11 @@
 // thread per row of a 128-row tile = one TMEM lane) that walks its tiles through the chain
 //     gather -> [MMA l -> epilogue l] x (L-1) -> MMA L-1 -> max-pool -> store
 // and owns one activation buffer in shared memory (each layer's epilogue overwrites its own, fully consumed,
-// input) and one accumulator region in TMEM.  The unit's first warp issues the unit's own tcgen05.mma (one
-// elected lane, descriptors on the uniform datapath) after a unit-wide named barrier, and commits to the
-// unit's "accumulator ready" mbarrier that all four warps then wait on; the units are otherwise independent,
-// so while one drains TMEM or gathers, the tensor core works for the others (and MMA issue, ~100 cycles per
-// instruction from a single thread, proceeds from U threads in parallel).
+// input) and one accumulator region in TMEM.  One extra warp issues every tcgen05.mma of the CTA (one elected
+// lane, descriptors on the uniform datapath: ~65 cycles per instruction, the tensor-pipe time of an N = 128
+// MMA): it serves the units round-robin, waiting on a unit's "operand ready" mbarrier (4 warp arrivals) and
+// committing to its "accumulator ready" mbarrier, so a unit's MMAs run back to back at pipe speed while the
+// other units drain TMEM or gather.
 // All weights (BN folded, bf16, canonical K-major core-matrix layout, written by pn2_pack_weights) are
 // bulk-copied (cp.async.bulk + mbarrier) into shared memory once per CTA.
 //
@@ -31,7 +31,7 @@
 namespace pn2 {
 
 constexpr int T2_MAX_UNITS = 4;
-constexpr int T2_MAX_THREADS = 4 * T2_MAX_UNITS * 32;         // 512
+constexpr int T2_MAX_THREADS = (4 * T2_MAX_UNITS + 1) * 32;   // 544: unit warps + the MMA-issue warp
 constexpr int T2_SMEM_LIMIT = 227 * 1024;
 
 struct Tc2Params {
@@ -46,6 +46,7 @@ struct Tc2Params {
     int U, cols_per_unit, tmem_cols, a_unit_bytes, xyz_off, feat_fast;   // xyz_off: the no-swizzle coordinate block inside a unit's buffer
     const __nv_bfloat16 *feat_bf16; __nv_bfloat16 *out_bf16;
     unsigned long long *trace;   // debug timeline (pn2_debug_trace), CTA 0 only; nullptr = off
+    int unit_issue;              // 1: each unit's first warp issues its own MMAs (small stacks, U = 4); 0: the MMA warp does
     int use_tma, feat_rows;      // bf16 features gathered by TMA (tile::gather4) through `tmap` = [feat_rows = B*N][D]
     alignas(64) CUtensorMap tmap;
 };
@@ -136,7 +137,8 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const __grid_
     float *bias_s = reinterpret_cast<float *>(Wsm + lay.w_bytes);
     uint32_t *vmask_base = reinterpret_cast<uint32_t *>(bias_s + lay.bias_floats);   // [U][2][4] valid-row ballots, by tile parity
     uint64_t *acc_ready = reinterpret_cast<uint64_t *>(vmask_base + 8 * T2_MAX_UNITS);
-    uint64_t *feat_ready = acc_ready + T2_MAX_UNITS;     // per unit: the TMA gather of the next tile's feature rows has landed
+    uint64_t *a_ready = acc_ready + T2_MAX_UNITS;        // per unit: operand written / TMEM drained (one arrival per warp)
+    uint64_t *feat_ready = a_ready + T2_MAX_UNITS;     // per unit: the TMA gather of the next tile's feature rows has landed
     uint64_t *w_bar = feat_ready + T2_MAX_UNITS;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w_bar + 1);
 
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const __grid_
     const int L = lay.L;
 
     if (tid == 0) {
-        for (int u = 0; u < T2_MAX_UNITS; ++u) { mbar_init(acc_ready + u, 1); mbar_init(feat_ready + u, 1); }
+        for (int u = 0; u < T2_MAX_UNITS; ++u) { mbar_init(acc_ready + u, 1); mbar_init(a_ready + u, 4); mbar_init(feat_ready + u, 1); }
         mbar_init(w_bar, 1);
         fence_mbar_init();
         // all weights, once per CTA, through the bulk-copy engine
@@ -155,7 +157,8 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const __grid_
             bulk_g2s(Wsm + off, p.packed + off, (uint32_t)nb, w_bar);
         }
     }
-    if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    const int mma_warp = 4 * U;
+    if (warp == mma_warp) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     {
         const float *bsrc = reinterpret_cast<const float *>(p.packed + lay.w_bytes);
         for (int i = tid; i < lay.bias_floats; i += blockDim.x) bias_s[i] = __ldg(bsrc + i);
@@ -167,7 +170,61 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const __grid_
     const int tiles = (int)p.tiles;
     const int stride = (int)gridDim.x * U;
 
-    {
+    if (warp == mma_warp) {
+      if (!p.unit_issue) {
+        // =================================================================================================
+        // MMA warp: every tcgen05.mma of the CTA, units served round-robin.  The whole warp runs the loop
+        // (warp-uniform values -> uniform datapath), one elected lane issues.
+        // =================================================================================================
+        int n_max = 0;
+        for (int u = 0; u < U; ++u) {
+            const int gu = (int)blockIdx.x * U + u;
+            n_max = max(n_max, gu < tiles ? (tiles - gu + stride - 1) / stride : 0);
+        }
+        const int ks_xyz = p.D / 16;
+        mbar_wait(w_bar, 0);
+        uint32_t phases = 0;
+        for (int it = 0; it < n_max; ++it) {
+#pragma unroll
+            for (int l = 0; l < T2_MAX_L; ++l) {
+                if (l >= L) break;
+                const TcLayer &ly = lay.ly[l];
+                const bool last = (l == L - 1);
+                const uint32_t lbo = (uint32_t)(last ? ly.Npad : ly.NS) * 16u;
+                const uint32_t w_lo = desc_lo(smem_u32(Wsm) + (uint32_t)ly.w_off, lbo);
+                const uint32_t w_step = (2u * lbo) >> 4;
+                const uint32_t idesc = instr_desc_bf16(last ? TC_ROWS : ly.NS);
+                const int nks = ly.K / 16;
+                const int n_mh = last ? ly.Npad / TC_ROWS : 1;
+                for (int u = 0; u < U; ++u) {
+                    if ((int)blockIdx.x * U + u + it * stride >= tiles) continue;
+                    mbar_wait(a_ready + u, (phases >> u) & 1u);
+                    phases ^= 1u << u;
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(A_base) + (uint32_t)(u * p.a_unit_bytes);
+                    const uint32_t a_sw = desc_lo_sw128(a_addr);
+                    const uint32_t a_xyz = desc_lo(a_addr + (uint32_t)p.xyz_off, A_LBO);
+                    const uint32_t d_tm = tmem_base + (uint32_t)(u * p.cols_per_unit);
+                    if (elect_one()) {
+                        for (int mh = 0; mh < n_mh; ++mh)
+                            for (int ks = 0; ks < nks; ++ks) {
+                                const bool xyz = (l == 0 && ks == ks_xyz);
+                                const uint64_t act = xyz ? mk_desc(a_xyz, DESC_HI)
+                                                         : mk_desc(a_sw + (uint32_t)((ks >> 2) * (SW128_BLOCK / 16) + (ks & 3) * 2), DESC_HI_SW128);
+                                const uint64_t wgt = mk_desc(w_lo + (uint32_t)(mh * TC_ROWS) + (uint32_t)ks * w_step, DESC_HI);
+                                // hidden layers: D[row][channel] = X (M operand) x W^T; last layer, transposed:
+                                // D[channel][row] = W (128 output channels as M) x X^T (the tile's 128 rows as N)
+                                if (!last) umma_bf16(d_tm, act, wgt, idesc, ks ? 1u : 0u);
+                                else umma_bf16(d_tm + (uint32_t)(mh * TC_ROWS), wgt, act, idesc, ks ? 1u : 0u);
+                            }
+                        umma_commit(acc_ready + u);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+      }
+    } else {
         const int u = warp >> 2, q = warp & 3, row = q * 32 + lane;
         unsigned char *A = A_base + (size_t)u * p.a_unit_bytes;
         unsigned char *X_row = A + p.xyz_off + row * 16;            // this row in the coordinate block [2][128][16 B]
@@ -277,15 +334,20 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const __grid_
         };
 
         Tracer tr; tr.init(p.trace, u, blockIdx.x == 0 && q == 0 && lane == 0);
-        // ---- MMA issue (warp 0 of the unit; warp-uniform operands) ----------------------------------------
-        const uint32_t a_sw = desc_lo_sw128(smem_u32(A));                       // swizzled blocks: + (ks/4)*block + (ks%4)*32 bytes
-        const uint32_t a_xyz = desc_lo(smem_u32(A) + (uint32_t)p.xyz_off, A_LBO);   // coordinate block, no swizzle
+        uint64_t *my_a_ready = a_ready + u;
+        const uint32_t a_sw = desc_lo_sw128(smem_u32(A));
+        const uint32_t a_xyz = desc_lo(smem_u32(A) + (uint32_t)p.xyz_off, A_LBO);
         const uint32_t d_tm = tmem_base + (uint32_t)(u * p.cols_per_unit);
-        const int ks_xyz = D / 16;          // layer 0: K-steps [0, D/16) read features, step D/16 reads the coordinates
+        const int ks_xyz = D / 16;
         bool w_ready = false;
+        // operand written (and proxy-fenced) / TMEM drained by this warp.  Either tell the MMA warp, or (small
+        // stacks) meet the unit's other warps at a named barrier and let this unit's first warp issue the layer.
         auto issue_layer = [&](int l) {
-            // all four warps have written (and proxy-fenced) the operand / drained TMEM: unit-wide barrier,
-            // then one elected lane of warp 0 issues the layer and commits to the unit's mbarrier
+            if (!p.unit_issue) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(my_a_ready);
+                return;
+            }
             asm volatile("bar.sync %0, 128;" ::"r"(u + 1) : "memory");
             if (q == 0) {
                 if (!w_ready) { mbar_wait(w_bar, 0); w_ready = true; }
@@ -305,8 +367,6 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const __grid_
                             const uint64_t act = xyz ? mk_desc(a_xyz, DESC_HI)
                                                      : mk_desc(a_sw + (uint32_t)((ks >> 2) * (SW128_BLOCK / 16) + (ks & 3) * 2), DESC_HI_SW128);
                             const uint64_t wgt = mk_desc(w_lo + (uint32_t)(mh * TC_ROWS) + (uint32_t)ks * w_step, DESC_HI);
-                            // hidden layers: D[row][channel] = X (M operand) x W^T; last layer, transposed:
-                            // D[channel][row] = W (128 output channels as M) x X^T (the tile's 128 rows as N)
                             if (!last) umma_bf16(d_tm, act, wgt, idesc, ks ? 1u : 0u);
                             else umma_bf16(d_tm + (uint32_t)(mh * TC_ROWS), wgt, act, idesc, ks ? 1u : 0u);
                         }
@@ -465,7 +525,7 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const __grid_
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (warp == mma_warp) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -498,7 +558,7 @@ static bool tc2_plan(int K, int C, int D, int order, const TcLayout &t, Tc2Plan 
     for (int U = T2_MAX_UNITS; U >= 1; U >>= 1) {
         if (U * pl->cols_per_unit > 512) continue;
         const size_t smem = (size_t)t.w_bytes + (size_t)t.bias_floats * 4 + (size_t)U * pl->a_unit_bytes +
-                            8 * T2_MAX_UNITS * 4 + (2 * T2_MAX_UNITS + 1) * 8 + 16 + 1024;   // + alignment slack
+                            8 * T2_MAX_UNITS * 4 + (3 * T2_MAX_UNITS + 1) * 8 + 16 + 1024;   // + alignment slack
         if (smem > (size_t)T2_SMEM_LIMIT) continue;
         pl->U = U; pl->smem = smem; pl->tmem_cols = pow2_at_least(U * pl->cols_per_unit);
         return true;
@@ -538,6 +598,8 @@ int launch_sa_bf16_pipelined(const SaArgs &a, cudaStream_t st)
     p.feat_bf16 = (a.feat_bf16 && p.feat_fast && a.D > 0 && ((uintptr_t)a.feat_bf16 & 15) == 0) ? (const __nv_bfloat16 *)a.feat_bf16 : nullptr;
     p.out_bf16 = (__nv_bfloat16 *)a.out_bf16;
     p.trace = g_trace;
+    static const int issue_env = getenv("PN2_UNIT_ISSUE") ? atoi(getenv("PN2_UNIT_ISSUE")) : -1;
+    p.unit_issue = issue_env >= 0 ? issue_env : (pl.U == T2_MAX_UNITS);   // measured: profiles/README.md
     p.use_tma = 0; p.feat_rows = a.B * a.N;
     static const bool no_tma = getenv("PN2_NO_TMA_GATHER") != nullptr;
     if (p.feat_bf16 && a.D % 64 == 0 && (int64_t)a.B * a.N < (1ll << 31) - 1 && !no_tma) {
@@ -548,7 +610,7 @@ int launch_sa_bf16_pipelined(const SaArgs &a, cudaStream_t st)
     if (e != cudaSuccess) { set_error("sa_tc2: smem attribute (%zu B): %s", pl.smem, cudaGetErrorString(e)); return (int)e; }
     int64_t grid = (p.tiles + pl.U - 1) / pl.U;
     if (grid > 148) grid = 148;
-    sa_tc2_kernel<<<(unsigned)grid, 4 * pl.U * 32, pl.smem, st>>>(p);
+    sa_tc2_kernel<<<(unsigned)grid, (4 * pl.U + 1) * 32, pl.smem, st>>>(p);
     return launch_status("pn2_sa_fused(bf16, pipelined)");
 }
 

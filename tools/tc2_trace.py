@@ -42,6 +42,8 @@ def name(ev):
     k, l, u = ev & 0xF00, (ev >> 4) & 0xF, ev & 0xF
     if 0x610 <= ev < 0x640: return {0x610: "twin_issued", 0x620: "pool_ld", 0x630: "pool_blk"}[ev & 0xFF0] + (f" {ev & 0xF}" if ev != 0x610 else "")
     if 0x700 <= ev < 0x710: return f"mma_issued l{ev & 0xF}"
+    if 0x710 <= ev < 0x720: return f"unit_barrier l{ev & 0xF}"
+    if 0x520 <= ev < 0x550: return {0x520: "epi_ldwait", 0x530: "epi_blocks", 0x540: "epi_tcfence"}[ev & 0xFF0] + f" l{ev & 0xF}"
     return {0x100: f"mma_wait_done l{l} u{u}", 0x200: f"mma_issued   l{l} u{u}", 0x400: f"acc_ready l{ev & 0xF}", 0x500: f"epi_done  l{ev & 0xF}"}.get(k, hex(ev))
 for r, evs in enumerate(roles):
     if not evs: continue
