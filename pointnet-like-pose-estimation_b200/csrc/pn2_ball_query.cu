@@ -26,6 +26,18 @@ __device__ __forceinline__ float sqnorm(const float (&v)[C], bool contig, bool t
     return contig ? sum_order<C, true>(t) : sum_order<C, false>(t, tail);
 }
 
+// distances of centre s to the two consecutive points n, n+1 (n even)
+template <int C>
+__device__ __forceinline__ float2 pair_dist2(const f32x2 (&s)[C], const float *sp, int stride, int n, f32x2 s2, f32x2 m2)
+{
+    f32x2 dot = mul2(s[0], *reinterpret_cast<const f32x2 *>(sp + n));
+#pragma unroll
+    for (int k = 1; k < C; ++k) dot = fma2(s[k], *reinterpret_cast<const f32x2 *>(sp + k * stride + n), dot);
+    f32x2 d = mul2(m2, dot);
+    d = add2(d, s2);
+    return unpk2(add2(d, *reinterpret_cast<const f32x2 *>(sp + (size_t)C * stride + n)));
+}
+
 template <int C>
 __device__ __forceinline__ float pair_dist(const float (&s)[C], const float *sp, int stride, int n, float s2, float p2)
 {
@@ -91,25 +103,27 @@ ball_query_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, i
                 for (int k = 0; k < C; ++k) s[k] = __ldg(centres + (int64_t)b * csb + (int64_t)sidx * csn + (int64_t)k * csc);
                 s2 = sqnorm<C>(s, csc == 1, sidx >= (S & ~31));
                 cnt = 0; first = N;
+                f32x2 sv[C];
+#pragma unroll
+                for (int k = 0; k < C; ++k) sv[k] = pk2(s[k], s[k]);
+                const f32x2 s2v = pk2(s2, s2), m2v = pk2(-2.0f, -2.0f);
                 for (int n0 = 0; n0 < nc && cnt < K; n0 += 64) {
-                    // two independent 32-point steps per trip for ILP
-                    const int na = n0 + lane, nb = n0 + 32 + lane;
-                    const float da = (na < nc) ? pair_dist<C>(s, sp, NCH, na, s2, sp2[na]) : 0.f;
-                    const float db = (nb < nc) ? pair_dist<C>(s, sp, NCH, nb, s2, sp2[nb]) : 0.f;
-                    const bool ina = (na < nc) && !(da > r2);
-                    const bool inb = (nb < nc) && !(db > r2);
+                    // 64 points per trip, two consecutive ones per lane; the shared-memory rows are padded to an even
+                    // length, so the pair load never leaves the row
+                    const int na = n0 + 2 * lane;
+                    const float2 d = (na < nc) ? pair_dist2<C>(sv, sp, NCH, na, s2v, m2v) : make_float2(0.f, 0.f);
+                    const bool ina = (na < nc) && !(d.x > r2);
+                    const bool inb = (na + 1 < nc) && !(d.y > r2);
                     const unsigned ma = __ballot_sync(0xffffffffu, ina);
                     const unsigned mb = __ballot_sync(0xffffffffu, inb);
-                    if (first == N) {
-                        if (ma) first = n0 + __ffs(ma) - 1;
-                        else if (mb) first = n0 + 32 + __ffs(mb) - 1;
+                    if (first == N && (ma | mb)) {
+                        const int fa = ma ? n0 + 2 * (__ffs(ma) - 1) : N, fb = mb ? n0 + 2 * (__ffs(mb) - 1) + 1 : N;
+                        first = min(fa, fb);
                     }
-                    const int pa = cnt + __popc(ma & lt_mask);
+                    const int pa = cnt + __popc(ma & lt_mask) + __popc(mb & lt_mask);       // hits at lower indices
                     if (ina && pa < K) stage[pa] = na;
-                    cnt += __popc(ma);
-                    const int pb = cnt + __popc(mb & lt_mask);
-                    if (inb && pb < K) stage[pb] = nb;
-                    cnt += __popc(mb);
+                    if (inb && pa + (int)ina < K) stage[pa + (int)ina] = na + 1;
+                    cnt += __popc(ma) + __popc(mb);
                 }
                 if (cnt > K) cnt = K;
                 if (cnt == 0 && lane == 0 && empty_flag) atomicOr(empty_flag, 1);
@@ -197,8 +211,8 @@ static int launch_bq_c(const float *centres, int64_t csb, int64_t csn, int64_t c
 {
     const size_t stage_bytes = sizeof(int) * (size_t)BQ_WARPS * K;
     const size_t budget = 200 * 1024 - stage_bytes;
-    int NCH = N, cpw;
-    if ((size_t)(C + 1) * N * sizeof(float) > budget) {
+    int NCH = (N + 1) & ~1, cpw;            // even row length: the packed inner loop loads two points at a time
+    if ((size_t)(C + 1) * NCH * sizeof(float) > budget) {
         NCH = (int)(budget / ((C + 1) * sizeof(float))) & ~31;
         cpw = 1;  // multi-chunk path keeps one centre per warp in registers
     } else {

@@ -77,6 +77,57 @@ __device__ __forceinline__ float sum_order(const float (&t)[C], bool tail = fals
     }
 }
 
+// ---- two points per instruction (add.rn.f32x2 / mul.rn.f32x2 / fma.rn.f32x2, sm_100): lane-wise IEEE
+// round-to-nearest, so each half is bit-identical to the scalar sequence -------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float2 unpk2(f32x2 v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+// sum_order for a pair of points (neither of them a leftover point of a strided operand)
+template <int C, bool CONTIG>
+__device__ __forceinline__ f32x2 sum_order2(const f32x2 (&t)[C])
+{
+    if constexpr (!CONTIG || C < 8) {
+        if constexpr (!CONTIG) {
+            f32x2 a = t[0];
+#pragma unroll
+            for (int k = 1; k < C; ++k) a = add2(a, t[k]);
+            return a;
+        } else {
+            f32x2 p[4];
+            constexpr int n4 = C / 4;
+            const f32x2 zero = pk2(0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) p[k] = zero;
+#pragma unroll
+            for (int i = 0; i < n4; ++i)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) p[k] = (i == 0) ? t[k] : add2(p[k], t[4 * i + k]);
+#pragma unroll
+            for (int k = 4 * n4; k < C; ++k) p[0] = (n4 == 0 && k == 0) ? t[0] : add2(p[0], t[k]);
+            return add2(add2(add2(p[0], p[1]), p[2]), p[3]);
+        }
+    } else {
+        f32x2 lane[8];
+        constexpr int n8 = C / 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) lane[j] = t[j];
+#pragma unroll
+        for (int i = 1; i < n8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) lane[j] = add2(lane[j], t[8 * i + j]);
+        f32x2 a = pk2(0.f, 0.f);
+#pragma unroll
+        for (int k = 8 * n8; k < C; ++k) a = add2(a, t[k]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a = add2(a, lane[j]);
+        return a;
+    }
+}
+
 // Same rule for a run-time C (generic fallback kernels).
 __device__ __forceinline__ float sum_order_rt(const float *t, int C, bool contig, bool tail = false)
 {

@@ -26,22 +26,27 @@ __global__ void __launch_bounds__(TMAX) fps_kernel(const float *__restrict__ poi
     const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
     const int Npad = PPT * T;
     const int n_body = N & ~31;                 // strided operand: points >= n_body reduce in the leftover order
+    // packed (two points per instruction) unless some point needs the leftover order
+    const bool packed = CONTIG || C <= 4 || n_body == N;
     const int b = blockIdx.x;
     const float *P = points + (int64_t)b * sb;
 
-    float p[PPT][C];
+    static_assert(PPT % 2 == 0, "points are kept as register pairs");
+    f32x2 pp[PPT / 2][C];                       // this thread's points (tid + j*T), two per 64-bit register
     float dist[PPT];
 #pragma unroll
-    for (int j = 0; j < PPT; ++j) {
-        const int n = tid + j * T;
-        const bool ok = n < N;
+    for (int j = 0; j < PPT; j += 2) {
+        const int n0 = tid + j * T, n1 = n0 + T;
 #pragma unroll
         for (int k = 0; k < C; ++k) {
-            float v = ok ? __ldg(P + (int64_t)n * sn + (int64_t)k * sc) : 0.f;
-            p[j][k] = v;
-            s_pts[k * Npad + n] = v;
+            const float v0 = n0 < N ? __ldg(P + (int64_t)n0 * sn + (int64_t)k * sc) : 0.f;
+            const float v1 = n1 < N ? __ldg(P + (int64_t)n1 * sn + (int64_t)k * sc) : 0.f;
+            pp[j / 2][k] = pk2(v0, v1);
+            s_pts[k * Npad + n0] = v0;
+            s_pts[k * Npad + n1] = v1;
         }
-        dist[j] = ok ? 1e10f : 0.f;             // padding can never win: dist 0 and index >= N
+        dist[j] = n0 < N ? 1e10f : 0.f;         // padding can never win: dist 0 and index >= N
+        dist[j + 1] = n1 < N ? 1e10f : 0.f;
     }
     int far = (int)min(max(start[b], (int64_t)0), (int64_t)N - 1);   // contract: start in [0,N); never index out of the cloud
     __syncthreads();
@@ -58,17 +63,39 @@ __global__ void __launch_bounds__(TMAX) fps_kernel(const float *__restrict__ poi
 
         float best = -1.f;
         unsigned besti = 0xffffffffu;
+        if (packed) {
+            // two of this thread's points per instruction (sub as add of the negated centroid: exact)
+            f32x2 nc[C];
+#pragma unroll
+            for (int k = 0; k < C; ++k) nc[k] = pk2(-c[k], -c[k]);
+#pragma unroll
+            for (int j = 0; j < PPT; j += 2) {
+                f32x2 t[C];
+#pragma unroll
+                for (int k = 0; k < C; ++k) {
+                    const f32x2 df = add2(pp[j / 2][k], nc[k]);
+                    t[k] = mul2(df, df);
+                }
+                const float2 d = unpk2(sum_order2<C, CONTIG>(t));
+                dist[j] = fminf(dist[j], d.x);          // d < dist ? d : dist, NaN never replaces
+                dist[j + 1] = fminf(dist[j + 1], d.y);
+                if (dist[j] > best) { best = dist[j]; besti = (unsigned)(tid + j * T); }
+                if (dist[j + 1] > best) { best = dist[j + 1]; besti = (unsigned)(tid + (j + 1) * T); }
+            }
+        } else {
 #pragma unroll
         for (int j = 0; j < PPT; ++j) {
             float t[C];
 #pragma unroll
             for (int k = 0; k < C; ++k) {
-                const float df = __fsub_rn(p[j][k], c[k]);
+                const float2 pv = unpk2(pp[j / 2][k]);
+                const float df = __fsub_rn((j & 1) ? pv.y : pv.x, c[k]);
                 t[k] = __fmul_rn(df, df);
             }
             const float d = sum_order<C, CONTIG>(t, tid + j * T >= n_body);
             dist[j] = fminf(dist[j], d);        // d < dist ? d : dist, NaN never replaces
             if (dist[j] > best) { best = dist[j]; besti = (unsigned)(tid + j * T); }
+        }
         }
         // warp argmax: dist >= +0 so the bit pattern orders like the value; lowest index among equals
         const unsigned bits = __float_as_uint(best);
