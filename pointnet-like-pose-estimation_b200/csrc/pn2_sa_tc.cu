@@ -111,6 +111,8 @@ struct TcParams {
     int tmem_cols;
     int resident;      // all weight chunks stay in shared memory for the life of the CTA
     int nstage, stage_bytes;
+    int cs;            // thread-block cluster size: the CTAs of a cluster share every streamed weight chunk (TMA multicast)
+    int64_t n_iter;    // tile-loop trips, identical for every CTA (a CTA without a tile still takes part in the ring)
     int a_bytes[2];    // activation buffers (a_bytes[1] == 0: one buffer, each layer's epilogue overwrites its own input)
     int pool_cols;     // columns of the cross-warp pooling scratch (0 if direct)
 };
@@ -129,13 +131,15 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(s_g + TC_ROWS);
     uint64_t *empty_bar = full_bar + TC_MAX_STAGES;
     uint64_t *acc_bar = empty_bar + TC_MAX_STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_bar + 1);
+    uint64_t *slot_free = acc_bar + 1;      // in cluster rank 0: every CTA of the cluster has released ring slot s
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(slot_free + TC_MAX_STAGES);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform for the compiler (MMA descriptors on the uniform datapath)
     const TcLayout &lay = p.lay;
 
     if (tid == 0) {
-        for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+        for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); mbar_init(slot_free + s, (uint32_t)p.cs); }
         mbar_init(acc_bar, 1);
         fence_mbar_init();
     }
@@ -148,6 +152,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    uint32_t cta_rank = 0;
+    if (p.cs > 1) {
+        // barriers of every CTA initialised before any remote arrive / multicast copy can reach them
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
 
     // =====================================================================================================
     // producer warp: weights -> shared memory through the bulk-copy engine
@@ -165,8 +175,15 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
                             off += cb;
                         }
             } else {
+                // Ring of weight chunks.  In a cluster every CTA runs this loop in lock step (same chunk sequence); a
+                // CTA frees slot s locally (its MMAs retired), posts the byte count on its own full barrier and
+                // reports to rank 0; rank 0 issues ONE multicast copy per chunk once all CTAs have reported, which
+                // lands in every CTA's slot and completes every CTA's full barrier: L2 -> SM weight traffic / cs.
                 uint32_t q = 0;
-                for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+                uint32_t free_remote = 0;
+                if (p.cs > 1) asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(free_remote) : "r"(smem_u32(slot_free)));
+                const uint16_t mask = (uint16_t)((1u << p.cs) - 1u);
+                for (int64_t it = 0; it < p.n_iter; ++it) {
                     int off = 0;
                     for (int l = 0; l < lay.L; ++l)
                         for (int sl = 0; sl < lay.ly[l].nslab; ++sl)
@@ -176,7 +193,17 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
                                 const uint32_t ph = (q / p.nstage) & 1u;
                                 mbar_wait(empty_bar + s, ph ^ 1u);
                                 mbar_expect_tx(full_bar + s, (uint32_t)cb);
-                                bulk_g2s(Wsm + (size_t)s * p.stage_bytes, p.packed + off, (uint32_t)cb, full_bar + s);
+                                if (p.cs == 1) {
+                                    bulk_g2s(Wsm + (size_t)s * p.stage_bytes, p.packed + off, (uint32_t)cb, full_bar + s);
+                                } else {
+                                    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(free_remote + (uint32_t)(s * 8)) : "memory");
+                                    if (cta_rank == 0) {
+                                        mbar_wait_cluster(slot_free + s, ph);
+                                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                                                     ::"r"(smem_u32(Wsm + (size_t)s * p.stage_bytes)), "l"(p.packed + off), "r"((uint32_t)cb),
+                                                       "r"(smem_u32(full_bar + s)), "h"(mask) : "memory");
+                                    }
+                                }
                                 off += cb;
                             }
                 }
@@ -193,9 +220,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
         const int row = q4 * 32 + lane;     // the tile row (= TMEM lane) this thread owns in the epilogue
         const int K = p.K, C = p.C, D = p.D;
         uint32_t acc_phase = 0, wq = 0;
-        if (p.resident && tid == 0) mbar_wait(full_bar, 0);
+        if (p.resident && warp == 0) mbar_wait(full_bar, 0);
 
-        for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+        for (int64_t it = 0; it < p.n_iter; ++it) {
+            const int64_t tile = it * gridDim.x + blockIdx.x;     // beyond p.tiles: an all-padding tile (keeps the cluster's ring in step)
             cbar_sync();
             // ---- row bookkeeping ------------------------------------------------------------------------
             if (tid < TC_ROWS) {
@@ -203,6 +231,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
                 int64_t g; int j;
                 if (p.cpg == 1) { g = tile * p.gpt + r / K; j = r % K; if (r >= p.gpt * K) g = p.G; }
                 else            { g = tile / p.cpg; j = (int)(tile % p.cpg) * TC_ROWS + r; }
+                if (tile >= p.tiles) g = p.G;
                 int n = -1;
                 if (g < p.G && j < K) n = (p.order == PN2_ORDER_ALL) ? j : __ldg(p.idx32 + g * K + j);
                 if (n >= p.N) n = -1;            // 'no neighbour' marker of an empty ball (pointnet2_utils.py:85)
@@ -281,7 +310,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
                     const int sl1 = min(ly.nslab, sl0 + slabs_per_round);
                     tc_fence_before();
                     cbar_sync();       // A operand complete / previous round's TMEM reads and pool scratch drained
-                    if (tid == 0) {
+                    if (warp == 0) {
+                        // the whole warp walks the chunk sequence (warp-uniform addresses -> uniform datapath), one
+                        // elected lane issues: ~65 cycles per MMA instead of ~120 from a divergent single thread
                         tc_fence_after();
                         for (int sl = sl0; sl < sl1; ++sl) {
                             const uint32_t d_tmem = tmem_base + (uint32_t)((sl - sl0) * ly.NS);
@@ -298,15 +329,18 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
                                     ++wq;
                                 }
                                 const int kw = min(KBLK, ly.K - kb * KBLK);
-                                for (int j = 0; j < kw / 16; ++j) {
-                                    const uint64_t ad = smem_desc(a_in + (uint32_t)((kb * 8 + j * 2) * A_LBO), A_LBO, 128);
-                                    const uint64_t bd = smem_desc(w_addr + (uint32_t)(j * 2 * ly.NS * 16), (uint32_t)(ly.NS * 16), 128);
-                                    umma_bf16(d_tmem, ad, bd, idesc, (kb | j) ? 1u : 0u);
+                                const uint32_t a_lo = desc_lo_ns(a_in + (uint32_t)(kb * 8 * A_LBO), A_LBO);
+                                const uint32_t b_lo = desc_lo_ns(w_addr, (uint32_t)(ly.NS * 16));
+                                if (elect_one()) {
+                                    for (int j = 0; j < kw / 16; ++j)
+                                        umma_bf16(d_tmem, mk_desc64(a_lo + (uint32_t)(j * 2 * A_LBO / 16), DESC_HI_NS),
+                                                  mk_desc64(b_lo + (uint32_t)(j * 2 * ly.NS), DESC_HI_NS), idesc, (kb | j) ? 1u : 0u);
+                                    if (!p.resident) umma_commit(empty_bar + s);   // frees the ring slot when these MMAs retire
                                 }
-                                if (!p.resident) umma_commit(empty_bar + s);   // frees the ring slot when these MMAs retire
+                                __syncwarp();
                             }
                         }
-                        umma_commit(acc_bar);
+                        if (elect_one()) umma_commit(acc_bar);
                     }
                     __syncwarp();
                     mbar_wait(acc_bar, acc_phase);
@@ -382,6 +416,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
         cbar_sync();
         if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }
+    // no CTA of a cluster may exit while a peer can still write its shared memory or signal its barriers
+    if (p.cs > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -414,7 +450,7 @@ static bool tc_plan(int K, int L, const int *dims, TcPlan *pl)
     else if (K <= TC_ROWS)     { pl->gpt = 1; pl->cpg = 1; pl->Kl = 32; pl->direct = 0; pl->use_atomic = 0; }
     else                       { pl->gpt = 1; pl->cpg = (K + TC_ROWS - 1) / TC_ROWS; pl->Kl = 32; pl->direct = 0; pl->use_atomic = 1; }
     const int last_npad = t.ly[L - 1].Npad;
-    const size_t misc = (size_t)t.bias_floats * 4 + 2 * TC_ROWS * 4 + (2 * TC_MAX_STAGES + 1) * 8 + 16;
+    const size_t misc = (size_t)t.bias_floats * 4 + 2 * TC_ROWS * 4 + (3 * TC_MAX_STAGES + 1) * 8 + 16;
     // Candidates: two CTAs per SM with 256 TMEM columns each (one CTA's epilogue overlaps the other's MMAs),
     // or one CTA per SM with all 512 columns.  Weights stay resident in shared memory when they fit, else
     // they stream through an mbarrier ring.  Preference: resident x2, resident x1, ring x2, ring x1.
@@ -491,7 +527,36 @@ int launch_sa_bf16(const SaArgs &a, cudaStream_t st)
     int64_t grid = p.tiles;
     const int64_t cap = (int64_t)148 * pl.ctas_per_sm;
     if (grid > cap) grid = cap;
-    sa_tc_kernel<<<(unsigned)grid, TC_THREADS, pl.smem, st>>>(p);
+    // streamed weights with one CTA per SM: clusters of up to 8 CTAs share each chunk through TMA multicast
+    static const int cs_env = getenv("PN2_TC_CLUSTER") ? atoi(getenv("PN2_TC_CLUSTER")) : 1;   // measured slower so far (profiles/README.md): off by default
+    p.cs = 1;
+    if (!pl.resident && pl.ctas_per_sm == 1) {
+        int cs = cs_env < 1 ? 1 : (cs_env > 8 ? 8 : cs_env);
+        while (cs > 1 && (cs & (cs - 1))) --cs;
+        while (cs > 1 && p.tiles < 2 * cs) cs >>= 1;
+        p.cs = cs;
+        if (cs > 1) { const int64_t ncl = (p.tiles + cs - 1) / cs; grid = (ncl < 148 / cs ? ncl : 148 / cs) * cs; }
+    }
+    if (p.cs == 1) {
+        p.n_iter = (p.tiles + grid - 1) / grid;
+        sa_tc_kernel<<<(unsigned)grid, TC_THREADS, pl.smem, st>>>(p);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)p.cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        // persistent: no more clusters than can be resident at once (a cluster must fit inside one GPC)
+        int max_clusters = 0;
+        e = cudaOccupancyMaxActiveClusters(&max_clusters, sa_tc_kernel, &cfg);
+        if (e != cudaSuccess || max_clusters < 1) { set_error("sa_tc: cluster occupancy (cs=%d): %s", p.cs, cudaGetErrorString(e)); return e ? (int)e : -1; }
+        if (grid / p.cs > max_clusters) grid = (int64_t)max_clusters * p.cs;
+        cfg.gridDim = dim3((unsigned)grid);
+        p.n_iter = (p.tiles + grid - 1) / grid;
+        e = cudaLaunchKernelEx(&cfg, sa_tc_kernel, p);
+        if (e != cudaSuccess) { set_error("sa_tc: cluster launch (cs=%d): %s", p.cs, cudaGetErrorString(e)); return (int)e; }
+    }
     return launch_status("pn2_sa_fused(bf16)");
 }
 

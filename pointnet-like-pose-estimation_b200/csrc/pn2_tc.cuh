@@ -105,6 +105,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     while (!mbar_try_wait(bar, parity)) {}
 }
+// wait on a barrier that CTAs of the cluster arrive on (acquire at cluster scope)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
+    } while (!ok);
+}
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -165,6 +177,15 @@ __device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t saddr) { return ((sad
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr)
 {
     return (uint64_t)desc_lo_sw128(saddr) | ((uint64_t)DESC_HI_SW128 << 32);
+}
+// low / high words of a no-swizzle descriptor (see smem_desc): stepping the start address by X bytes is lo += X >> 4
+__device__ __forceinline__ uint32_t desc_lo_ns(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16); }
+constexpr uint32_t DESC_HI_NS = (128u >> 4) | (1u << 14);      // SBO = 128 B, descriptor version 1
+__device__ __forceinline__ uint64_t mk_desc64(uint32_t lo, uint32_t hi)
+{
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+    return d;
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = bf16, both K-major, M = 128
 __device__ __forceinline__ uint32_t instr_desc_bf16(int n)
