@@ -93,6 +93,15 @@ ball_query_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, i
             }
             sp2[n] = sqnorm<C>(v, pcontig, n_base + n >= (N & ~31));
         }
+        if (single_chunk) {
+            // pad the rows to a multiple of 64 points with zero coordinates and |p|^2 = +inf: d = +inf, never in
+            // radius (a NaN centre finds its K neighbours among the real points first), so the scan needs no bounds
+            for (int n = nc + tid; n < NCH; n += BQ_THREADS) {
+#pragma unroll
+                for (int k = 0; k < C; ++k) sp[k * NCH + n] = 0.f;
+                sp2[n] = INFINITY;
+            }
+        }
         __syncthreads();
 
         if (single_chunk) {
@@ -102,29 +111,27 @@ ball_query_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, i
 #pragma unroll
                 for (int k = 0; k < C; ++k) s[k] = __ldg(centres + (int64_t)b * csb + (int64_t)sidx * csn + (int64_t)k * csc);
                 s2 = sqnorm<C>(s, csc == 1, sidx >= (S & ~31));
-                cnt = 0; first = N;
+                cnt = 0;
                 f32x2 sv[C];
 #pragma unroll
                 for (int k = 0; k < C; ++k) sv[k] = pk2(s[k], s[k]);
                 const f32x2 s2v = pk2(s2, s2), m2v = pk2(-2.0f, -2.0f);
-                for (int n0 = 0; n0 < nc && cnt < K; n0 += 64) {
-                    // 64 points per trip, two consecutive ones per lane; the shared-memory rows are padded to an even
-                    // length, so the pair load never leaves the row
+                for (int n0 = 0; n0 < NCH && cnt < K; n0 += 64) {
+                    // 64 points per trip, two consecutive ones per lane (rows are padded to a multiple of 64)
                     const int na = n0 + 2 * lane;
-                    const float2 d = (na < nc) ? pair_dist2<C>(sv, sp, NCH, na, s2v, m2v) : make_float2(0.f, 0.f);
-                    const bool ina = (na < nc) && !(d.x > r2);
-                    const bool inb = (na + 1 < nc) && !(d.y > r2);
+                    const float2 d = pair_dist2<C>(sv, sp, NCH, na, s2v, m2v);
+                    const bool ina = !(d.x > r2), inb = !(d.y > r2);
                     const unsigned ma = __ballot_sync(0xffffffffu, ina);
                     const unsigned mb = __ballot_sync(0xffffffffu, inb);
-                    if (first == N && (ma | mb)) {
-                        const int fa = ma ? n0 + 2 * (__ffs(ma) - 1) : N, fb = mb ? n0 + 2 * (__ffs(mb) - 1) + 1 : N;
-                        first = min(fa, fb);
+                    if (ma | mb) {                                                              // warp-uniform; most trips have no hit
+                        const int pa = cnt + __popc(ma & lt_mask) + __popc(mb & lt_mask);       // hits at lower indices
+                        if (ina && pa < K) stage[pa] = na;
+                        if (inb && pa + (int)ina < K) stage[pa + (int)ina] = na + 1;
+                        cnt += __popc(ma) + __popc(mb);
                     }
-                    const int pa = cnt + __popc(ma & lt_mask) + __popc(mb & lt_mask);       // hits at lower indices
-                    if (ina && pa < K) stage[pa] = na;
-                    if (inb && pa + (int)ina < K) stage[pa + (int)ina] = na + 1;
-                    cnt += __popc(ma) + __popc(mb);
                 }
+                __syncwarp();
+                first = cnt ? stage[0] : N;                                                     // hits are staged in index order
                 if (cnt > K) cnt = K;
                 if (cnt == 0 && lane == 0 && empty_flag) atomicOr(empty_flag, 1);
                 __syncwarp();
@@ -211,7 +218,7 @@ static int launch_bq_c(const float *centres, int64_t csb, int64_t csn, int64_t c
 {
     const size_t stage_bytes = sizeof(int) * (size_t)BQ_WARPS * K;
     const size_t budget = 200 * 1024 - stage_bytes;
-    int NCH = (N + 1) & ~1, cpw;            // even row length: the packed inner loop loads two points at a time
+    int NCH = (N + 63) & ~63, cpw;          // rows padded to 64 points: the packed inner loop scans 64 per trip, unguarded
     if ((size_t)(C + 1) * NCH * sizeof(float) > budget) {
         NCH = (int)(budget / ((C + 1) * sizeof(float))) & ~31;
         cpw = 1;  // multi-chunk path keeps one centre per warp in registers
