@@ -528,6 +528,315 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const __grid_
     if (warp == mma_warp) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// ======================================================================================================
+// Cooperative variant, for stacks whose weights leave room for only TWO tiles per SM (sa2-sized).
+//
+// With two units of four warps each unit's chain (epilogue, pooling: a few hundred dependent instructions per
+// warp, ~8 cycles each) is far longer than its MMAs, and the two chains tend to run in phase, so the tensor
+// pipe idles.  Here all 16 worker warps serve BOTH tiles: the CTA walks a fixed schedule
+//     for layer l: for unit u: wait acc(u,l) -> epilogue / pooling of (u,l) split 16 ways -> signal MMA warp
+// so every CUDA-core phase is four times shorter and the MMAs of one unit always run underneath the phase of
+// the other.  Warp w covers TMEM lane quarter w & 3 and column share w >> 2; threads of share 0 also own "their"
+// row for the gather bookkeeping (neighbour index, coordinates, valid-row ballot).
+// ======================================================================================================
+constexpr int T3_WORKERS = 16;
+constexpr int T3_THREADS = (T3_WORKERS + 1) * 32;      // + the MMA-issue warp
+
+__global__ void __launch_bounds__(T3_THREADS, 1) sa_tc3_kernel(const __grid_constant__ Tc2Params p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const TcLayout &lay = p.lay;
+    constexpr int U = 2;
+    unsigned char *A_base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+    unsigned char *Wsm = A_base + (size_t)U * p.a_unit_bytes;
+    float *bias_s = reinterpret_cast<float *>(Wsm + lay.w_bytes);
+    uint32_t *vmask_base = reinterpret_cast<uint32_t *>(bias_s + lay.bias_floats);   // [U][2][4] valid-row ballots, by tile parity
+    uint64_t *acc_ready = reinterpret_cast<uint64_t *>(vmask_base + 8 * T2_MAX_UNITS);
+    uint64_t *a_ready = acc_ready + T2_MAX_UNITS;        // per unit: 16 warp arrivals (+ the TMA bytes of a gather)
+    uint64_t *w_bar = a_ready + 2 * T2_MAX_UNITS;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w_bar + 1);
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int L = lay.L;
+
+    if (tid == 0) {
+        for (int u = 0; u < U; ++u) { mbar_init(acc_ready + u, 1); mbar_init(a_ready + u, T3_WORKERS); }
+        mbar_init(w_bar, 1);
+        fence_mbar_init();
+        mbar_expect_tx(w_bar, (uint32_t)lay.w_bytes);
+        for (int off = 0; off < lay.w_bytes; off += 32768) {
+            const int nb = min(32768, lay.w_bytes - off);
+            bulk_g2s(Wsm + off, p.packed + off, (uint32_t)nb, w_bar);
+        }
+    }
+    if (warp == T3_WORKERS) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    {
+        const float *bsrc = reinterpret_cast<const float *>(p.packed + lay.w_bytes);
+        for (int i = tid; i < lay.bias_floats; i += blockDim.x) bias_s[i] = __ldg(bsrc + i);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int tiles = (int)p.tiles;
+    const int stride = (int)gridDim.x * U;
+    const int first_tile = (int)blockIdx.x * U;
+    const int n_iter = first_tile < tiles ? (tiles - first_tile + stride - 1) / stride : 0;   // trips of unit 0 (>= unit 1's)
+
+    if (warp == T3_WORKERS) {
+        // ---- MMA warp: same schedule as the workers, one elected lane issues ---------------------------------
+        const int ks_xyz = p.D / 16;
+        mbar_wait(w_bar, 0);
+        uint32_t phases = 0;
+        for (int it = 0; it < n_iter; ++it) {
+#pragma unroll
+            for (int l = 0; l < T2_MAX_L; ++l) {
+                if (l >= L) break;
+                const TcLayer &ly = lay.ly[l];
+                const bool last = (l == L - 1);
+                const uint32_t lbo = (uint32_t)(last ? ly.Npad : ly.NS) * 16u;
+                const uint32_t w_lo = desc_lo(smem_u32(Wsm) + (uint32_t)ly.w_off, lbo);
+                const uint32_t w_step = (2u * lbo) >> 4;
+                const uint32_t idesc = instr_desc_bf16(last ? TC_ROWS : ly.NS);
+                const int nks = ly.K / 16;
+                const int n_mh = last ? ly.Npad / TC_ROWS : 1;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (first_tile + u + it * stride >= tiles) continue;
+                    mbar_wait(a_ready + u, (phases >> u) & 1u);
+                    phases ^= 1u << u;
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(A_base) + (uint32_t)(u * p.a_unit_bytes);
+                    const uint32_t a_sw = desc_lo_sw128(a_addr);
+                    const uint32_t a_xyz = desc_lo(a_addr + (uint32_t)p.xyz_off, A_LBO);
+                    const uint32_t d_tm = tmem_base + (uint32_t)(u * p.cols_per_unit);
+                    if (elect_one()) {
+                        for (int mh = 0; mh < n_mh; ++mh)
+                            for (int ks = 0; ks < nks; ++ks) {
+                                const bool xyz = (l == 0 && ks == ks_xyz);
+                                const uint64_t act = xyz ? mk_desc(a_xyz, DESC_HI)
+                                                         : mk_desc(a_sw + (uint32_t)((ks >> 2) * (SW128_BLOCK / 16) + (ks & 3) * 2), DESC_HI_SW128);
+                                const uint64_t wgt = mk_desc(w_lo + (uint32_t)(mh * TC_ROWS) + (uint32_t)ks * w_step, DESC_HI);
+                                if (!last) umma_bf16(d_tm, act, wgt, idesc, ks ? 1u : 0u);
+                                else umma_bf16(d_tm + (uint32_t)(mh * TC_ROWS), wgt, act, idesc, ks ? 1u : 0u);
+                            }
+                        umma_commit(acc_ready + u);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ---- worker warps -----------------------------------------------------------------------------------
+        const int q = warp & 3, hb = warp >> 2, row = q * 32 + lane;
+        const int K = p.K, C = p.C, D = p.D, S = p.S, N = p.N;
+        const int logK = 31 - __clz(K);
+        const int gpt = TC_ROWS >> logK;
+        const int rows = (int)p.rows, G = (int)p.G;
+        const bool pre_xyz = C <= 4;
+        const int n_blk_feat = D / 64;                  // the coop variant is only launched with TMA-gathered features (D % 64 == 0) or D == 0
+        uint32_t acc_phase = 0;
+        Tracer tr; tr.init(p.trace, 0, blockIdx.x == 0 && warp == 0 && lane == 0);
+
+        auto load_index = [&](int tile) -> int {
+            const int r = tile * TC_ROWS + row;
+            return (tile < tiles && r < rows) ? __ldg(p.idx32 + r) : -1;
+        };
+        auto is_valid = [&](int n) -> bool { return n >= 0 && n < N; };
+        auto load_xyz4 = [&](int tile, int n, float (&px)[4], float (&pc)[4]) {
+            const int g = (tile * TC_ROWS + row) >> logK;
+            const int b = (int)((unsigned)g / (unsigned)S);
+            const float *pp = p.points + (int64_t)b * p.sb + (int64_t)n * p.sn;
+            const float *cc = p.centres + (int64_t)g * C;
+            const bool ok = is_valid(n);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                px[i] = pc[i] = 0.f;
+                if (ok && i < C) { px[i] = __ldg(pp); pc[i] = __ldg(cc + i); }
+                pp += p.sc;
+            }
+        };
+        // feature rows of `tile` -> unit u's swizzled blocks by TMA gather4: warps of share hb < D/64 move block hb
+        // (lane l < 8: rows 4l..4l+3 of this warp's quarter); one thread posts the byte count on the unit's barrier
+        auto issue_gather = [&](int u, int tile, int n_mine) {
+            if (n_blk_feat == 0) return;
+            unsigned char *A = A_base + (size_t)u * p.a_unit_bytes;
+            const int g = (tile * TC_ROWS + row) >> logK;
+            const int b = (int)((unsigned)g / (unsigned)S);
+            const int ri = is_valid(n_mine) ? b * N + n_mine : p.feat_rows;
+            const int l4 = (lane & 7) * 4;
+            const int r0 = __shfl_sync(0xffffffffu, ri, l4), r1 = __shfl_sync(0xffffffffu, ri, l4 + 1);
+            const int r2 = __shfl_sync(0xffffffffu, ri, l4 + 2), r3 = __shfl_sync(0xffffffffu, ri, l4 + 3);
+            if (warp == 0 && lane == 0) mbar_expect_tx_only(a_ready + u, (uint32_t)(TC_ROWS * D * 2));
+            if (lane < 8)
+                for (int blk = hb; blk < n_blk_feat; blk += 4)
+                    tma_gather4(A + blk * SW128_BLOCK + (q * 32 + l4) * 128, &p.tmap, blk * 64, r0, r1, r2, r3, a_ready + u);
+        };
+        // coordinates minus centre (+ zero padding) of this thread's row -> unit u's coordinate block; valid-row ballot
+        auto finish_gather = [&](int u, int tile, int n, const float (&px)[4], const float (&pc)[4], uint32_t par) {
+            if (hb != 0) return;
+            unsigned char *X_row = A_base + (size_t)u * p.a_unit_bytes + p.xyz_off + row * 16;
+            const bool valid = is_valid(n);
+            if (pre_xyz) {
+                *reinterpret_cast<uint4 *>(X_row) = make_uint4(pack_bf16x2(__fsub_rn(px[0], pc[0]), __fsub_rn(px[1], pc[1])),
+                                                               pack_bf16x2(__fsub_rn(px[2], pc[2]), __fsub_rn(px[3], pc[3])), 0u, 0u);
+                *reinterpret_cast<uint4 *>(X_row + A_LBO) = make_uint4(0u, 0u, 0u, 0u);
+            } else {
+                const int g = (tile * TC_ROWS + row) >> logK;
+                const int b = (int)((unsigned)g / (unsigned)S);
+                const float *pp = p.points + (int64_t)b * p.sb + (int64_t)n * p.sn;
+                const float *cc = p.centres + (int64_t)g * C;
+                float x[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float a0 = 0.f, a1 = 0.f;
+                    if (valid && i < C) { a0 = __ldg(pp); a1 = __ldg(cc + i); }
+                    pp += p.sc;
+                    x[i] = __fsub_rn(a0, a1);
+                }
+                *reinterpret_cast<uint4 *>(X_row) = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+                *reinterpret_cast<uint4 *>(X_row + A_LBO) = make_uint4(pack_bf16x2(x[8], x[9]), pack_bf16x2(x[10], x[11]), pack_bf16x2(x[12], x[13]), pack_bf16x2(x[14], x[15]));
+            }
+            const unsigned vm = __ballot_sync(0xffffffffu, valid);
+            if (lane == 0) vmask_base[8 * u + 4 * par + q] = vm;
+        };
+        auto arrive = [&](int u) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_ready + u);
+        };
+
+        // ---- prologue: first tile of each unit ----------------------------------------------------------------
+        int n_cur[U], n_nxt[U];
+        float px[U][4], pc[U][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int tile = first_tile + u;
+            n_cur[u] = load_index(tile);
+            n_nxt[u] = -1;
+            if (tile < tiles) {
+                issue_gather(u, tile, n_cur[u]);
+                if (pre_xyz && hb == 0) load_xyz4(tile, n_cur[u], px[u], pc[u]);
+                finish_gather(u, tile, n_cur[u], px[u], pc[u], 0u);
+                fence_proxy_async();
+                arrive(u);
+            }
+        }
+
+        for (int it = 0; it < n_iter; ++it) {
+            const uint32_t par = (uint32_t)it & 1u;
+#pragma unroll
+            for (int l = 0; l < T2_MAX_L; ++l) {
+                if (l >= L) break;
+                const TcLayer &ly = lay.ly[l];
+                const float *bs = bias_s + ly.b_off;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int tile = first_tile + u + it * stride;
+                    if (tile >= tiles) continue;
+                    unsigned char *A = A_base + (size_t)u * p.a_unit_bytes;
+                    const uint32_t tmem_row = tmem_base + (uint32_t)(u * p.cols_per_unit) + ((uint32_t)(q * 32) << 16);
+                    const bool more = tile + stride < tiles;
+                    if (l == 0) n_nxt[u] = load_index(tile + stride);      // needed after this tile's first epilogue at the earliest
+                    mbar_wait(acc_ready + u, (acc_phase >> u) & 1u);
+                    acc_phase ^= 1u << u;
+                    tc_fence_after();
+                    tr.mark(0x400 + l * 2 + u);
+                    if (l < L - 1) {
+                        // hidden layer: this warp's 32-column blocks hb, hb+4, ...
+#pragma unroll 1
+                        for (int c0 = 32 * hb; c0 < ly.Npad; c0 += 128) {
+                            uint32_t r[32];
+                            tmem_ld32_nowait(tmem_row + (uint32_t)c0, r);
+                            tmem_ld_wait();
+                            epi_block(r, bs, A, c0, row);
+                        }
+                        tc_fence_before();
+                        fence_proxy_async();
+                        arrive(u);
+                        tr.mark(0x500 + l * 2 + u);
+                        if (l == 0 && more && pre_xyz && hb == 0) load_xyz4(tile + stride, n_nxt[u], px[u], pc[u]);
+                    } else {
+                        // last layer (transposed): the operand buffer is free -> next tile's feature rows start flowing
+                        if (more) {
+                            issue_gather(u, tile + stride, n_nxt[u]);
+                            if (L == 1 && pre_xyz && hb == 0) load_xyz4(tile + stride, n_nxt[u], px[u], pc[u]);
+                        }
+                        const uint32_t *vm = vmask_base + 8 * u + 4 * par;
+                        const bool all_valid = (vm[0] & vm[1] & vm[2] & vm[3]) == 0xffffffffu;
+                        const int g0 = tile * gpt;
+                        const int64_t wrap = p.ob - (int64_t)S * p.os;
+                        // 16-way split of the (128-channel slice, 32-row block) items of this lane quarter: whole groups
+                        // stay in one warp
+                        const int n_mh = ly.Npad / TC_ROWS;
+                        const int bpg = K >= 32 ? K / 32 : 1;                   // 32-row blocks per group
+                        int ipw = (n_mh * 4) / 4; if (ipw < bpg) ipw = bpg;     // items per warp
+                        const int item0 = hb * ipw;
+                        if (item0 < n_mh * 4) {
+                            const int mh = item0 >> 2, blk_lo = item0 & 3, blk_hi = min(4, blk_lo + ipw);
+                            for (int mhh = mh; mhh < n_mh && mhh * 4 < item0 + ipw; ++mhh) {
+                                const int c = mhh * TC_ROWS + row;
+                                const float bv = bs[c];
+                                const bool c_ok = c < ly.Cout;
+                                const int b_lo = (mhh == mh) ? blk_lo : 0;
+                                const int b_hi = (mhh == mh) ? blk_hi : min(4, item0 + ipw - mhh * 4);
+                                int gg = g0 + ((b_lo * 32) >> logK);
+                                const int bb = (int)((unsigned)gg / (unsigned)S);
+                                int ss = gg - bb * S;
+                                int64_t o = (int64_t)bb * p.ob + (int64_t)ss * p.os + p.co_off + c;
+                                auto emit = [&](float m) {
+                                    if (c_ok && gg < G && (all_valid || m > -INFINITY)) {
+                                        const float y = fmaxf(m + bv, 0.f);
+                                        p.out[o] = y;
+                                        if (p.out_bf16) p.out_bf16[o] = __float2bfloat16_rn(y);
+                                    }
+                                    ++gg; o += p.os;
+                                    if (++ss == S) { ss = 0; o += wrap; }
+                                };
+                                float run = -INFINITY;
+#pragma unroll 1
+                                for (int blk = b_lo; blk < b_hi; ++blk) {
+                                    uint32_t r[32];
+                                    tmem_ld32_nowait(tmem_row + (uint32_t)(mhh * TC_ROWS + blk * 32), r);
+                                    tmem_ld_wait();
+                                    if (!all_valid) {
+                                        const uint32_t mk = vm[blk];
+#pragma unroll
+                                        for (int j = 0; j < 32; ++j) if (!((mk >> j) & 1u)) r[j] = 0xff800000u;
+                                    }
+                                    if (K >= 32) {
+                                        run = fmaxf(run, max_range<0, 32>(r));
+                                        if ((((blk + 1) * 32) & (K - 1)) == 0) { emit(run); run = -INFINITY; }
+                                    } else if (K == 16) {
+                                        emit(max_range<0, 16>(r));
+                                        emit(max_range<16, 16>(r));
+                                    } else {
+                                        emit(max_range<0, 8>(r));
+                                        emit(max_range<8, 8>(r));
+                                        emit(max_range<16, 8>(r));
+                                        emit(max_range<24, 8>(r));
+                                    }
+                                }
+                            }
+                        }
+                        tc_fence_before();
+                        if (more) {
+                            finish_gather(u, tile + stride, n_nxt[u], px[u], pc[u], par ^ 1u);
+                            fence_proxy_async();
+                            arrive(u);
+                        }
+                        tr.mark(0x600 + u);
+                        n_cur[u] = n_nxt[u];
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == T3_WORKERS) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
 // ------------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------------
@@ -606,6 +915,15 @@ int launch_sa_bf16_pipelined(const SaArgs &a, cudaStream_t st)
         if (make_row_gather_map(p.feat_bf16, (int64_t)a.B * a.N, a.D, &p.tmap) == 0) p.use_tma = 1;
     }
     if (p.tiles == 0) return 0;
+    static const int coop_env = getenv("PN2_TC_COOP") ? atoi(getenv("PN2_TC_COOP")) : 1;
+    if (coop_env && pl.U == 2 && (a.D == 0 || p.use_tma)) {
+        cudaError_t e3 = cudaFuncSetAttribute(sa_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+        if (e3 != cudaSuccess) { set_error("sa_tc3: smem attribute (%zu B): %s", pl.smem, cudaGetErrorString(e3)); return (int)e3; }
+        int64_t grid3 = (p.tiles + 1) / 2;
+        if (grid3 > 148) grid3 = 148;
+        sa_tc3_kernel<<<(unsigned)grid3, T3_THREADS, pl.smem, st>>>(p);
+        return launch_status("pn2_sa_fused(bf16, cooperative)");
+    }
     cudaError_t e = cudaFuncSetAttribute(sa_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) { set_error("sa_tc2: smem attribute (%zu B): %s", pl.smem, cudaGetErrorString(e)); return (int)e; }
     int64_t grid = (p.tiles + pl.U - 1) / pl.U;
