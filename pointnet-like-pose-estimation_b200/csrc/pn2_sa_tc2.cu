@@ -657,20 +657,21 @@ __global__ void __launch_bounds__(T3_THREADS, 1) sa_tc3_kernel(const __grid_cons
                 pp += p.sc;
             }
         };
-        // feature rows of `tile` -> unit u's swizzled blocks by TMA gather4: warps of share hb < D/64 move block hb
-        // (lane l < 8: rows 4l..4l+3 of this warp's quarter); one thread posts the byte count on the unit's barrier
+        // feature rows of `tile` -> unit u's swizzled blocks by TMA gather4, spread evenly over the 16 warps: warp
+        // (q, hb) moves rows q*32 + hb*8 .. +8 (lanes 0 and 1: 4 rows each), all 64-channel blocks; one thread posts
+        // the byte count on the unit's barrier
         auto issue_gather = [&](int u, int tile, int n_mine) {
             if (n_blk_feat == 0) return;
             unsigned char *A = A_base + (size_t)u * p.a_unit_bytes;
             const int g = (tile * TC_ROWS + row) >> logK;
             const int b = (int)((unsigned)g / (unsigned)S);
             const int ri = is_valid(n_mine) ? b * N + n_mine : p.feat_rows;
-            const int l4 = (lane & 7) * 4;
+            const int l4 = hb * 8 + (lane & 1) * 4;
             const int r0 = __shfl_sync(0xffffffffu, ri, l4), r1 = __shfl_sync(0xffffffffu, ri, l4 + 1);
             const int r2 = __shfl_sync(0xffffffffu, ri, l4 + 2), r3 = __shfl_sync(0xffffffffu, ri, l4 + 3);
             if (warp == 0 && lane == 0) mbar_expect_tx_only(a_ready + u, (uint32_t)(TC_ROWS * D * 2));
-            if (lane < 8)
-                for (int blk = hb; blk < n_blk_feat; blk += 4)
+            if (lane < 2)
+                for (int blk = 0; blk < n_blk_feat; ++blk)
                     tma_gather4(A + blk * SW128_BLOCK + (q * 32 + l4) * 128, &p.tmap, blk * 64, r0, r1, r2, r3, a_ready + u);
         };
         // coordinates minus centre (+ zero padding) of this thread's row -> unit u's coordinate block; valid-row ballot

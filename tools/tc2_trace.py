@@ -8,6 +8,7 @@ for p in ("pointnet-like-pose-estimation_b200", "tests"):
 import torch, cloudgen, pn2_models, pointnet2_utils as pu
 
 which = sys.argv[1] if len(sys.argv) > 1 else "sa2"
+COOP = which == "sa2" and os.environ.get("PN2_TC_COOP", "1") != "0"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 dev = "cuda:0"
 pu.set_precision("bf16")
@@ -28,7 +29,7 @@ with torch.no_grad():
     torch.cuda.synchronize()
     be.lib.pn2_debug_trace(None)
 t = buf.cpu().view(5, 1024)
-names = {0x300: "gather_done", 0x600: "pool_done"}
+names = {0x300: "gather_done", 0x600: "pool_done"} if not (len(sys.argv) > 1 and sys.argv[1] == 'sa2' and os.environ.get('PN2_TC_COOP', '1') != '0') else {}
 def decode(v):
     ev, clk = (v >> 48) & 0xFFFF, v & 0xFFFFFFFFFFFF
     return ev, clk
@@ -38,6 +39,10 @@ for r in range(5):
     roles.append(evs)
 t0 = min(e[0][1] for e in roles if e)
 def name(ev):
+    if COOP:
+        if 0x400 <= ev < 0x410: return f"acc_ready l{(ev & 0xF) >> 1} u{ev & 1}"
+        if 0x500 <= ev < 0x510: return f"epi_done  l{(ev & 0xF) >> 1} u{ev & 1}"
+        if 0x600 <= ev < 0x610: return f"pool+gather done u{ev & 1}"
     if ev in names: return names[ev]
     k, l, u = ev & 0xF00, (ev >> 4) & 0xF, ev & 0xF
     if 0x610 <= ev < 0x640: return {0x610: "twin_issued", 0x620: "pool_ld", 0x630: "pool_blk"}[ev & 0xFF0] + (f" {ev & 0xF}" if ev != 0x610 else "")
@@ -56,6 +61,7 @@ for r, evs in enumerate(roles):
 # steady-state averages per unit: time between consecutive pool_done
 for r in range(4):
     pd = [clk for ev, clk in roles[r] if ev == 0x600]
+    if COOP and r == 0: print('coop: period per tile pair =', (pd[-1] - pd[4]) / max(1, len(pd) - 5))
     if len(pd) > 10:
         d = [b - a for a, b in zip(pd[4:-1], pd[5:])]
         print(f"unit {r}: tile period mean {sum(d)/len(d):.0f} cycles over {len(d)} tiles")
