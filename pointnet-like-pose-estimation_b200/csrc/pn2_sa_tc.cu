@@ -24,7 +24,7 @@ namespace pn2 {
 int64_t packed_bytes_bf16(int L, const int *dims)
 {
     const TcLayout t = tc_layout(L, dims);
-    return (int64_t)t.w_bytes + (int64_t)t.bias_floats * 4;
+    return (int64_t)t.total_bytes;
 }
 
 struct TcPackArgs {
@@ -53,6 +53,13 @@ __global__ void pack_bf16_kernel(TcPackArgs a, unsigned char *__restrict__ packe
                 float v = 0.f;
                 if (n < y.Cout) v = __fadd_rn(__fmul_rn(__fsub_rn(a.b[l][n], a.mu[l][n]), s), a.be[l][n]);
                 bias_out[y.b_off + n] = v;
+                if (l < a.lay.L - 1) {          // bias slice (see pn2_tc.cuh): hi and lo bf16 parts in k = 0, 1
+                    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+                    const __nv_bfloat16 lo = __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(hi)));
+                    __nv_bfloat16 *sl = reinterpret_cast<__nv_bfloat16 *>(packed + y.bs_off);
+                    for (int k2 = 0; k2 < BIAS_SLICE_K; ++k2)
+                        sl[(k2 / 8) * (y.Npad * 8) + n * 8 + (k2 % 8)] = k2 == 0 ? hi : (k2 == 1 ? lo : __float2bfloat16_rn(0.f));
+                }
                 continue;
             }
             int src = k;                       // column of the reference's weight matrix

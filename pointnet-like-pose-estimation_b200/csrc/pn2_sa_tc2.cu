@@ -2,28 +2,34 @@
 // shared memory next to the activations (every sa1 / sa2 configuration of the reference's SSG models and most
 // MSG branches).  Reference: model/pointnet2_utils.py:166-172 (SSG) and :204-218 (one MSG branch).
 //
-// One persistent CTA per SM runs U independent "units".  A unit is a warpgroup of 4 warps (128 threads, one
-// thread per row of a 128-row tile = one TMEM lane) that walks its tiles through the chain
+// A tile is 128 grouped rows (128 / K whole groups) = the 128 TMEM lanes of a cta_group::1, M = 128 tcgen05.mma.
+// One persistent CTA per SM keeps U tiles in flight ("units": an activation buffer in shared memory, written in
+// place by every layer's epilogue, and an accumulator region in TMEM) and walks each through
 //     gather -> [MMA l -> epilogue l] x (L-1) -> MMA L-1 -> max-pool -> store
-// and owns one activation buffer in shared memory (each layer's epilogue overwrites its own, fully consumed,
-// input) and one accumulator region in TMEM.  One extra warp issues every tcgen05.mma of the CTA (one elected
-// lane, descriptors on the uniform datapath: ~65 cycles per instruction, the tensor-pipe time of an N = 128
-// MMA): it serves the units round-robin, waiting on a unit's "operand ready" mbarrier (4 warp arrivals) and
-// committing to its "accumulator ready" mbarrier, so a unit's MMAs run back to back at pipe speed while the
-// other units drain TMEM or gather.
 // All weights (BN folded, bf16, canonical K-major core-matrix layout, written by pn2_pack_weights) are
 // bulk-copied (cp.async.bulk + mbarrier) into shared memory once per CTA.
 //
-//   epilogue (hidden layer): tcgen05.ld 32x32b.x32 -> +bias (FADD2) -> cvt.rn.relu.bf16x2 -> st.shared.v4
-//   last layer + pooling   : the product is issued TRANSPOSED, D^T[channel][row] = W (M operand) x X^T (N operand;
-//                            both are K-major in shared memory, so swapping roles costs nothing).  A thread then
-//                            owns one output channel (TMEM lane) and the rows of a group are consecutive TMEM
-//                            columns: the max over the K neighbours is a chain of FMNMX3 on the registers that
-//                            tcgen05.ld returns, bias + ReLU (which commute with the max) are applied once per
-//                            group, and a warp stores 32 consecutive channels of a group (128 B coalesced).
-//   gather                 : features of the previous set-abstraction layer arrive in bf16 (side output of this
-//                            kernel) and go global -> shared with cp.async, 16 B = one k-group of one row,
-//                            no registers; fp32 features / raw coordinates go through registers.
+//   hidden layer            : the folded bias is added INSIDE the MMA: one extra K = 16 step multiplies a constant
+//                             activation slice (channels 0, 1 = 1.0) with the layer's "bias slice" (bf16 hi and lo
+//                             parts of the fp32 bias, pn2_tc.cuh), so the epilogue is
+//                             tcgen05.ld 32x32b.x32 (two in flight) -> cvt.rn.relu.bf16x2 -> st.shared.v4
+//                             with compile-time swizzle offsets (one XOR per 16-byte chunk).
+//   last layer + pooling    : the product is issued TRANSPOSED, D^T[channel][row] = W (M operand) x X^T (N operand;
+//                             both are K-major in shared memory, so swapping roles costs nothing).  A thread then
+//                             owns one output channel (TMEM lane) and the rows of a group are consecutive TMEM
+//                             columns: the max over the K neighbours is a tree of FMNMX3 on the registers that
+//                             tcgen05.ld returns, bias + ReLU (which commute with the max) are applied once per
+//                             group, and a warp stores 32 consecutive channels of a group (128 B coalesced).
+//   gather                  : features of the previous set-abstraction layer arrive in bf16 (side output of this
+//                             kernel) by TMA tile::gather4 straight into the 128-byte-swizzled operand; fp32
+//                             features / raw coordinates go through registers.
+//
+// Two schedules share those pieces:
+//   sa_tc2_kernel  U (<= 4) units of four warps, thread = row; each unit's first warp issues the unit's MMAs (one
+//                  elected lane, descriptors on the uniform datapath) after a unit-wide named barrier.
+//   sa_tc3_kernel  for stacks that leave room for only TWO tiles per SM (sa2-sized): 16 worker warps serve both tiles
+//                  in a fixed (layer, unit) schedule, each epilogue / pooling phase split 16 ways, one extra warp
+//                  issues every MMA; the MMAs of one tile always run underneath the CUDA-core phase of the other.
 #include <cuda.h>
 #include <stdlib.h>
 #include "pn2_tc.cuh"
@@ -31,50 +37,104 @@
 namespace pn2 {
 
 constexpr int T2_MAX_UNITS = 4;
-constexpr int T2_MAX_THREADS = (4 * T2_MAX_UNITS + 1) * 32;   // 544: unit warps + the MMA-issue warp
+constexpr int T2_MAX_THREADS = 4 * T2_MAX_UNITS * 32;         // 512
 constexpr int T2_SMEM_LIMIT = 227 * 1024;
+constexpr int T2_MAX_L = 4;
+constexpr int ONES_BYTES = 2 * A_LBO;                         // constant activation slice [2][128][16 B]
+
+// per layer, precomputed on the host: everything the MMA issue needs, as descriptor words relative to the start of
+// the weight image in shared memory
+struct Tc2Layer {
+    uint32_t w_lo_rel;    // weight operand: (byte offset >> 4) | (LBO >> 4) << 16
+    uint32_t w_step;      // descriptor increment per K = 16 step
+    uint32_t bs_lo_rel;   // hidden layers: the bias slice, same encoding
+    uint32_t idesc;       // instruction descriptor (N = layer width; last layer: M = 128 channels, N = 128 rows)
+    int nks;              // K = 16 steps over the swizzled activation blocks (layer 0: the D feature channels)
+    int nb32;             // hidden layers: Npad / 32
+    int n_mh;             // last layer: Npad / 128
+    int Cout, b_off;
+};
 
 struct Tc2Params {
     const float *points; int64_t sb, sn, sc;
     const float *feat;   int64_t fb, fn, fc;
     const float *centres; const int32_t *idx32;
     int N, S, K, C, D, order;
-    TcLayout lay;
+    int L;
+    Tc2Layer ly[T2_MAX_L];
+    int img_bytes, bias_off;   // weight image = the whole packed buffer; fp32 biases at bias_off
     const unsigned char *packed;
     float *out; int64_t ob, os; int co_off;
     int64_t G, rows, tiles;
     int U, cols_per_unit, tmem_cols, a_unit_bytes, xyz_off, feat_fast;   // xyz_off: the no-swizzle coordinate block inside a unit's buffer
     const __nv_bfloat16 *feat_bf16; __nv_bfloat16 *out_bf16;
     unsigned long long *trace;   // debug timeline (pn2_debug_trace), CTA 0 only; nullptr = off
-    int unit_issue;              // 1: each unit's first warp issues its own MMAs (small stacks, U = 4); 0: the MMA warp does
     int use_tma, feat_rows;      // bf16 features gathered by TMA (tile::gather4) through `tmap` = [feat_rows = B*N][D]
     alignas(64) CUtensorMap tmap;
 };
 
-__device__ __forceinline__ float2 add2(float2 a, float2 b)
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
 {
-    unsigned long long x, y, z;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a.x), "f"(a.y));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(b.x), "f"(b.y));
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(z) : "l"(x), "l"(y));
-    float2 r;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(z));
-    return r;
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ uint32_t relu_pack_u(uint32_t lo, uint32_t hi) { return relu_pack_bf16x2(__uint_as_float(lo), __uint_as_float(hi)); }
 
-// hidden-layer epilogue of 32 accumulator columns [c0, c0+32) of this thread's row
-__device__ __forceinline__ void epi_block(const uint32_t (&r)[32], const float *bs, unsigned char *A, int c0, int row)
+// ReLU + bf16 of 32 accumulator columns of this thread's row -> chunks J0 .. J0+3 of a 64-channel swizzled block.
+// a_rowx = address of the row inside block 0 with (row & 7) << 4 already added: the 16-byte chunk j of the row lives
+// at a_rowx ^ (j << 4) (the block is 1024-byte aligned, so bits 4..6 of the row address are the swizzle term alone)
+template <int J0>
+__device__ __forceinline__ void epi_store32(const uint32_t (&r)[32], uint32_t a_rowx, uint32_t blk_off)
 {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float4 b0 = *reinterpret_cast<const float4 *>(bs + c0 + 8 * i);
-        const float4 b1 = *reinterpret_cast<const float4 *>(bs + c0 + 8 * i + 4);
-        const float2 v0 = add2(make_float2(__uint_as_float(r[8 * i + 0]), __uint_as_float(r[8 * i + 1])), make_float2(b0.x, b0.y));
-        const float2 v1 = add2(make_float2(__uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3])), make_float2(b0.z, b0.w));
-        const float2 v2 = add2(make_float2(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5])), make_float2(b1.x, b1.y));
-        const float2 v3 = add2(make_float2(__uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7])), make_float2(b1.z, b1.w));
-        *reinterpret_cast<uint4 *>(A + sw128_chunk_off(row, c0 / 8 + i)) =
-            make_uint4(relu_pack_bf16x2(v0.x, v0.y), relu_pack_bf16x2(v1.x, v1.y), relu_pack_bf16x2(v2.x, v2.y), relu_pack_bf16x2(v3.x, v3.y));
+    for (int i = 0; i < 4; ++i)
+        sts128((a_rowx ^ (uint32_t)((J0 + i) << 4)) + blk_off, relu_pack_u(r[8 * i + 0], r[8 * i + 1]), relu_pack_u(r[8 * i + 2], r[8 * i + 3]),
+               relu_pack_u(r[8 * i + 4], r[8 * i + 5]), relu_pack_u(r[8 * i + 6], r[8 * i + 7]));
+}
+// hidden-layer epilogue of NB consecutive 32-column blocks starting at column 0 (thread = row), two loads in flight
+template <int NB>
+__device__ __forceinline__ void epi_hidden(uint32_t tmem_row, uint32_t a_rowx)
+{
+#ifdef PN2_EPI_PAIR
+#pragma unroll
+    for (int b = 0; b < NB; b += 2) {
+        uint32_t r0[32], r1[32];
+        tmem_ld32_nowait(tmem_row + (uint32_t)(32 * b), r0);
+        if (b + 1 < NB) tmem_ld32_nowait(tmem_row + (uint32_t)(32 * b + 32), r1);
+        tmem_ld_wait();
+        epi_store32<0>(r0, a_rowx, (uint32_t)((b >> 1) * SW128_BLOCK));
+        if (b + 1 < NB) epi_store32<4>(r1, a_rowx, (uint32_t)((b >> 1) * SW128_BLOCK));
+    }
+#else
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        uint32_t r0[32];
+        tmem_ld32_nowait(tmem_row + (uint32_t)(32 * b), r0);
+        tmem_ld_wait();
+        if (b & 1) epi_store32<4>(r0, a_rowx, (uint32_t)((b >> 1) * SW128_BLOCK));
+        else epi_store32<0>(r0, a_rowx, (uint32_t)((b >> 1) * SW128_BLOCK));
+    }
+#endif
+}
+// any width, blocks b0, b0 + step, ... < nb
+__device__ __forceinline__ void epi_hidden_rt(uint32_t tmem_row, uint32_t a_rowx, int b0, int step, int nb)
+{
+#pragma unroll 1
+    for (int b = b0; b < nb; b += step) {
+        uint32_t r[32];
+        tmem_ld32_nowait(tmem_row + (uint32_t)(32 * b), r);
+        tmem_ld_wait();
+        epi_store32<0>(r, a_rowx ^ (uint32_t)((b & 1) << 6), (uint32_t)((b >> 1) * SW128_BLOCK));
+    }
+}
+__device__ __forceinline__ void epi_hidden_any(int nb32, uint32_t tmem_row, uint32_t a_rowx)
+{
+    switch (nb32) {
+    case 1: epi_hidden<1>(tmem_row, a_rowx); break;
+    case 2: epi_hidden<2>(tmem_row, a_rowx); break;
+    case 3: epi_hidden<3>(tmem_row, a_rowx); break;
+    case 4: epi_hidden<4>(tmem_row, a_rowx); break;
+    case 8: epi_hidden<8>(tmem_row, a_rowx); break;
+    default: epi_hidden_rt(tmem_row, a_rowx, 0, 1, nb32); break;
     }
 }
 
@@ -84,25 +144,118 @@ __device__ __forceinline__ float max3(float a, float b, float c)
     asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
     return d;
 }
-// max of r[OFF .. OFF+CNT) (CNT = 8, 16 or 32) as a tree of 3-input maxima
+// max of v[0..N) as a tree of 3-input maxima
+template <int N>
+__device__ __forceinline__ float max_all(const float (&v)[N])
+{
+    if constexpr (N == 1) return v[0];
+    else if constexpr (N == 2) return fmaxf(v[0], v[1]);
+    else if constexpr (N == 3) return max3(v[0], v[1], v[2]);
+    else {
+        constexpr int M = (N + 2) / 3;
+        float w[M];
+#pragma unroll
+        for (int i = 0; i < N / 3; ++i) w[i] = max3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+        if constexpr (N % 3 == 1) w[M - 1] = v[N - 1];
+        if constexpr (N % 3 == 2) w[M - 1] = fmaxf(v[N - 2], v[N - 1]);
+        return max_all<M>(w);
+    }
+}
 template <int OFF, int CNT>
 __device__ __forceinline__ float max_range(const uint32_t (&r)[32])
 {
-    float m = __uint_as_float(r[OFF]);
+    float v[CNT];
 #pragma unroll
-    for (int j = 1; j + 1 < CNT; j += 2) m = max3(m, __uint_as_float(r[OFF + j]), __uint_as_float(r[OFF + j + 1]));
-    return fmaxf(m, __uint_as_float(r[OFF + CNT - 1]));
+    for (int j = 0; j < CNT; ++j) v[j] = __uint_as_float(r[OFF + j]);
+    return max_all<CNT>(v);
 }
+
+// where the pooled value of (group, channel) goes; groups are visited in order
+struct PoolOut {
+    float *po; __nv_bfloat16 *pb;       // element (cloud 0, group 0, this thread's channel)
+    int64_t os, ob;
+    int S, gg, G;
+    float bv; bool c_ok, all_valid, has_bf, contig;      // contig: ob == S * os, group g lives at g * os
+    // group finished: max over its rows -> + bias -> ReLU -> [B,S,Ctot]; then step to the next group
+    __device__ __forceinline__ void emit(float m)
+    {
+        if (c_ok && gg < G && (all_valid || m > -INFINITY)) {
+            const float y = fmaxf(m + bv, 0.f);
+            int64_t off;
+            if (contig) off = (int64_t)gg * os;
+            else { const int b = (int)((unsigned)gg / (unsigned)S); off = (int64_t)b * ob + (int64_t)(gg - b * S) * os; }
+            po[off] = y;
+            if (has_bf) pb[off] = __float2bfloat16_rn(y);
+        }
+        ++gg;
+    }
+};
+__device__ __forceinline__ void mask_rows(uint32_t (&r)[32], uint32_t mk)
+{
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (!((mk >> j) & 1u)) r[j] = 0xff800000u;   // -inf
+}
+// one 32-row block of the transposed accumulator (this thread = one channel)
+template <int K>
+__device__ __forceinline__ void pool_block(const uint32_t (&r)[32], int blk, float &run, PoolOut &o)
+{
+    if constexpr (K == 32) o.emit(max_range<0, 32>(r));
+    else if constexpr (K > 32) {
+        run = fmaxf(run, max_range<0, 32>(r));
+        if ((((blk + 1) * 32) & (K - 1)) == 0) { o.emit(run); run = -INFINITY; }
+    } else if constexpr (K == 16) {
+        o.emit(max_range<0, 16>(r));
+        o.emit(max_range<16, 16>(r));
+    } else {
+        o.emit(max_range<0, 8>(r));
+        o.emit(max_range<8, 8>(r));
+        o.emit(max_range<16, 8>(r));
+        o.emit(max_range<24, 8>(r));
+    }
+}
+// blocks [b_lo, b_hi) of one 128-channel slice; taddr = TMEM address of (this warp's lanes, column of block 0);
+// vm = the tile's four valid-row ballots
+template <int K, bool PAIR>
+__device__ __forceinline__ void pool_slice(uint32_t taddr, int b_lo, int b_hi, const uint32_t *vm, PoolOut &o)
+{
+    float run = -INFINITY;
+    int blk = b_lo;
+#pragma unroll 1
+    for (; PAIR && blk + 1 < b_hi; blk += 2) {
+        uint32_t r0[32], r1[32];
+        tmem_ld32_nowait(taddr + (uint32_t)(blk * 32), r0);
+        tmem_ld32_nowait(taddr + (uint32_t)(blk * 32 + 32), r1);
+        tmem_ld_wait();
+        if (!o.all_valid) { mask_rows(r0, vm[blk]); mask_rows(r1, vm[blk + 1]); }   // padding rows / empty balls
+        pool_block<K>(r0, blk, run, o);
+        pool_block<K>(r1, blk + 1, run, o);
+    }
+#pragma unroll 1
+    for (; blk < b_hi; ++blk) {
+        uint32_t r0[32];
+        tmem_ld32_nowait(taddr + (uint32_t)(blk * 32), r0);
+        tmem_ld_wait();
+        if (!o.all_valid) mask_rows(r0, vm[blk]);
+        pool_block<K>(r0, blk, run, o);
+    }
+}
+template <bool PAIR>
+__device__ __forceinline__ void pool_slice_any(int logK, uint32_t taddr, int b_lo, int b_hi, const uint32_t *vm, PoolOut &o)
+{
+    switch (logK) {
+    case 3: pool_slice<8, PAIR>(taddr, b_lo, b_hi, vm, o); break;
+    case 4: pool_slice<16, PAIR>(taddr, b_lo, b_hi, vm, o); break;
+    case 5: pool_slice<32, PAIR>(taddr, b_lo, b_hi, vm, o); break;
+    case 6: pool_slice<64, PAIR>(taddr, b_lo, b_hi, vm, o); break;
+    default: pool_slice<128, PAIR>(taddr, b_lo, b_hi, vm, o); break;
+    }
+}
+
 __device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gsrc, bool pred)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(pred ? 16 : 0) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit_wait_all()
-{
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
 
-constexpr int T2_MAX_L = 4;
 constexpr int T2_TRACE_SLOTS = 1024;     // per role (units 0..3, MMA warp = 4)
 
 // debug timeline: (event << 48) | clock, appended to this role's slice of the trace buffer
@@ -115,120 +268,117 @@ struct Tracer {
     }
 };
 
-__device__ __forceinline__ uint64_t mk_desc(uint32_t lo, uint32_t hi)
-{
-    uint64_t d;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
-    return d;
-}
-// low / high words of a K-major no-swizzle descriptor (see smem_desc): stepping the start address by X bytes
-// is `lo += X >> 4`
-__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16); }
-constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);      // SBO = 128 B, descriptor version 1
+constexpr uint32_t DESC_HI = DESC_HI_NS;      // SBO = 128 B, descriptor version 1
 
+// Every tcgen05.mma of layer l for one tile (called by ONE elected lane; all arguments warp-uniform).
+//   wsm16  = shared address of the weight image >> 4      a_sw = descriptor low word of the unit's swizzled block 0
+//   a_xyz  = ... of the unit's coordinate block            ones = ... of the constant slice      d_tm = TMEM accumulator
+__device__ __forceinline__ void issue_layer_mmas(const Tc2Params &p, int l, uint32_t wsm16, uint32_t a_sw, uint32_t a_xyz, uint32_t ones,
+                                                 uint32_t d_tm)
+{
+    const Tc2Layer &y = p.ly[l];
+    const int nks = y.nks;
+    const uint32_t idesc = y.idesc, w_step = y.w_step;
+    if (l < p.L - 1) {
+        // D[row][channel] = X (M operand) x W^T, then + 1 x bias
+        uint32_t w = wsm16 + y.w_lo_rel, acc = 0;
+        for (int ks = 0; ks < nks; ++ks) {
+            umma_bf16(d_tm, mk_desc64(a_sw + (uint32_t)(((ks >> 2) << 10) + ((ks & 3) << 1)), DESC_HI_SW128), mk_desc64(w, DESC_HI), idesc, acc);
+            w += w_step; acc = 1u;
+        }
+        if (l == 0) { umma_bf16(d_tm, mk_desc64(a_xyz, DESC_HI), mk_desc64(w, DESC_HI), idesc, acc); }
+        umma_bf16(d_tm, mk_desc64(ones, DESC_HI), mk_desc64(wsm16 + y.bs_lo_rel, DESC_HI), idesc, 1u);
+    } else {
+        // transposed: D[channel][row] = W (128 output channels as M) x X^T (the tile's 128 rows as N)
+        for (int mh = 0; mh < y.n_mh; ++mh) {
+            uint32_t w = wsm16 + y.w_lo_rel + (uint32_t)(mh * TC_ROWS), acc = 0;
+            const uint32_t d = d_tm + (uint32_t)(mh * TC_ROWS);
+            for (int ks = 0; ks < nks; ++ks) {
+                umma_bf16(d, mk_desc64(w, DESC_HI), mk_desc64(a_sw + (uint32_t)(((ks >> 2) << 10) + ((ks & 3) << 1)), DESC_HI_SW128), idesc, acc);
+                w += w_step; acc = 1u;
+            }
+            if (l == 0) umma_bf16(d, mk_desc64(w, DESC_HI), mk_desc64(a_xyz, DESC_HI), idesc, acc);
+        }
+    }
+}
+
+// shared-memory carve-up, identical in both kernels
+struct Tc2Smem {
+    unsigned char *A_base, *ones, *Wsm;
+    float *bias_s;
+    uint32_t *vmask;                    // [U][2][4] valid-row ballots, by tile parity
+    uint64_t *acc_ready, *a_ready, *feat_ready, *w_bar;
+    uint32_t *tmem_slot;
+};
+__device__ __forceinline__ Tc2Smem carve(unsigned char *smem, const Tc2Params &p)
+{
+    Tc2Smem s;
+    // activation buffers first: their 128-byte-swizzled blocks need 1024-byte alignment
+    s.A_base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+    s.ones = s.A_base + (size_t)p.U * p.a_unit_bytes;
+    s.Wsm = s.ones + ONES_BYTES;
+    s.bias_s = reinterpret_cast<float *>(s.Wsm + p.bias_off);
+    s.vmask = reinterpret_cast<uint32_t *>(s.Wsm + p.img_bytes);
+    s.acc_ready = reinterpret_cast<uint64_t *>(s.vmask + 8 * T2_MAX_UNITS);
+    s.a_ready = s.acc_ready + T2_MAX_UNITS;
+    s.feat_ready = s.a_ready + T2_MAX_UNITS;
+    s.w_bar = s.feat_ready + T2_MAX_UNITS;
+    s.tmem_slot = reinterpret_cast<uint32_t *>(s.w_bar + 1);
+    return s;
+}
+static size_t tc2_smem_bytes(int U, int a_unit_bytes, int img_bytes)
+{
+    return (size_t)U * a_unit_bytes + ONES_BYTES + (size_t)img_bytes + 8 * T2_MAX_UNITS * 4 + (3 * T2_MAX_UNITS + 1) * 8 + 16 + 1024;   // + alignment slack
+}
+// start of every CTA: barriers, weight image (bulk copy), constant slice
+__device__ __forceinline__ void cta_prologue(const Tc2Smem &s, const Tc2Params &p, int tid, uint32_t a_ready_count)
+{
+    if (tid == 0) {
+        for (int u = 0; u < T2_MAX_UNITS; ++u) { mbar_init(s.acc_ready + u, 1); mbar_init(s.a_ready + u, a_ready_count); mbar_init(s.feat_ready + u, 1); }
+        mbar_init(s.w_bar, 1);
+        fence_mbar_init();
+        mbar_expect_tx(s.w_bar, (uint32_t)p.img_bytes);
+        for (int off = 0; off < p.img_bytes; off += 32768) {
+            const int nb = min(32768, p.img_bytes - off);
+            bulk_g2s(s.Wsm + off, p.packed + off, (uint32_t)nb, s.w_bar);
+        }
+    }
+    // constant slice: k-group 0 = {1, 1, 0, ...} per row, k-group 1 = 0
+    for (int i = tid; i < 2 * TC_ROWS; i += (int)blockDim.x)
+        *reinterpret_cast<uint4 *>(s.ones + i * 16) = make_uint4(i < TC_ROWS ? 0x3F803F80u : 0u, 0u, 0u, 0u);
+    fence_proxy_async();
+}
+
+// FMODE: how layer 0's feature channels arrive -- 0: none (D = 0), 1: bf16 rows by TMA gather4, 2: anything else
+// (bf16 rows by cp.async, fp32 rows through registers, strided fp32).  PRE_XYZ: C <= 4, coordinates prefetched one
+// tile ahead.  Separate instantiations keep the register allocation of the common cases free of spills (a spilled
+// prefetch register turns the prefetch into a blocking load).
+template <int FMODE, bool PRE_XYZ>
 __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const __grid_constant__ Tc2Params p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    const TcLayout &lay = p.lay;
+    const Tc2Smem sm = carve(smem, p);
     const int U = p.U;
-    // activation buffers first: their 128-byte-swizzled blocks need 1024-byte alignment
-    unsigned char *A_base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
-    unsigned char *Wsm = A_base + (size_t)U * p.a_unit_bytes;
-    float *bias_s = reinterpret_cast<float *>(Wsm + lay.w_bytes);
-    uint32_t *vmask_base = reinterpret_cast<uint32_t *>(bias_s + lay.bias_floats);   // [U][2][4] valid-row ballots, by tile parity
-    uint64_t *acc_ready = reinterpret_cast<uint64_t *>(vmask_base + 8 * T2_MAX_UNITS);
-    uint64_t *a_ready = acc_ready + T2_MAX_UNITS;        // per unit: operand written / TMEM drained (one arrival per warp)
-    uint64_t *feat_ready = a_ready + T2_MAX_UNITS;     // per unit: the TMA gather of the next tile's feature rows has landed
-    uint64_t *w_bar = feat_ready + T2_MAX_UNITS;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w_bar + 1);
-
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler (uniform datapath)
-    const int L = lay.L;
+    const int L = p.L;
 
-    if (tid == 0) {
-        for (int u = 0; u < T2_MAX_UNITS; ++u) { mbar_init(acc_ready + u, 1); mbar_init(a_ready + u, 4); mbar_init(feat_ready + u, 1); }
-        mbar_init(w_bar, 1);
-        fence_mbar_init();
-        // all weights, once per CTA, through the bulk-copy engine
-        mbar_expect_tx(w_bar, (uint32_t)lay.w_bytes);
-        for (int off = 0; off < lay.w_bytes; off += 32768) {
-            const int nb = min(32768, lay.w_bytes - off);
-            bulk_g2s(Wsm + off, p.packed + off, (uint32_t)nb, w_bar);
-        }
-    }
-    const int mma_warp = 4 * U;
-    if (warp == mma_warp) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-    {
-        const float *bsrc = reinterpret_cast<const float *>(p.packed + lay.w_bytes);
-        for (int i = tid; i < lay.bias_floats; i += blockDim.x) bias_s[i] = __ldg(bsrc + i);
-    }
+    cta_prologue(sm, p, tid, 4);
+    if (warp == 0) tmem_alloc(sm.tmem_slot, (uint32_t)p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = *sm.tmem_slot;
     const int tiles = (int)p.tiles;
     const int stride = (int)gridDim.x * U;
 
-    if (warp == mma_warp) {
-      if (!p.unit_issue) {
-        // =================================================================================================
-        // MMA warp: every tcgen05.mma of the CTA, units served round-robin.  The whole warp runs the loop
-        // (warp-uniform values -> uniform datapath), one elected lane issues.
-        // =================================================================================================
-        int n_max = 0;
-        for (int u = 0; u < U; ++u) {
-            const int gu = (int)blockIdx.x * U + u;
-            n_max = max(n_max, gu < tiles ? (tiles - gu + stride - 1) / stride : 0);
-        }
-        const int ks_xyz = p.D / 16;
-        mbar_wait(w_bar, 0);
-        uint32_t phases = 0;
-        for (int it = 0; it < n_max; ++it) {
-#pragma unroll
-            for (int l = 0; l < T2_MAX_L; ++l) {
-                if (l >= L) break;
-                const TcLayer &ly = lay.ly[l];
-                const bool last = (l == L - 1);
-                const uint32_t lbo = (uint32_t)(last ? ly.Npad : ly.NS) * 16u;
-                const uint32_t w_lo = desc_lo(smem_u32(Wsm) + (uint32_t)ly.w_off, lbo);
-                const uint32_t w_step = (2u * lbo) >> 4;
-                const uint32_t idesc = instr_desc_bf16(last ? TC_ROWS : ly.NS);
-                const int nks = ly.K / 16;
-                const int n_mh = last ? ly.Npad / TC_ROWS : 1;
-                for (int u = 0; u < U; ++u) {
-                    if ((int)blockIdx.x * U + u + it * stride >= tiles) continue;
-                    mbar_wait(a_ready + u, (phases >> u) & 1u);
-                    phases ^= 1u << u;
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(A_base) + (uint32_t)(u * p.a_unit_bytes);
-                    const uint32_t a_sw = desc_lo_sw128(a_addr);
-                    const uint32_t a_xyz = desc_lo(a_addr + (uint32_t)p.xyz_off, A_LBO);
-                    const uint32_t d_tm = tmem_base + (uint32_t)(u * p.cols_per_unit);
-                    if (elect_one()) {
-                        for (int mh = 0; mh < n_mh; ++mh)
-                            for (int ks = 0; ks < nks; ++ks) {
-                                const bool xyz = (l == 0 && ks == ks_xyz);
-                                const uint64_t act = xyz ? mk_desc(a_xyz, DESC_HI)
-                                                         : mk_desc(a_sw + (uint32_t)((ks >> 2) * (SW128_BLOCK / 16) + (ks & 3) * 2), DESC_HI_SW128);
-                                const uint64_t wgt = mk_desc(w_lo + (uint32_t)(mh * TC_ROWS) + (uint32_t)ks * w_step, DESC_HI);
-                                // hidden layers: D[row][channel] = X (M operand) x W^T; last layer, transposed:
-                                // D[channel][row] = W (128 output channels as M) x X^T (the tile's 128 rows as N)
-                                if (!last) umma_bf16(d_tm, act, wgt, idesc, ks ? 1u : 0u);
-                                else umma_bf16(d_tm + (uint32_t)(mh * TC_ROWS), wgt, act, idesc, ks ? 1u : 0u);
-                            }
-                        umma_commit(acc_ready + u);
-                    }
-                    __syncwarp();
-                }
-            }
-        }
-      }
-    } else {
+    {
         const int u = warp >> 2, q = warp & 3, row = q * 32 + lane;
-        unsigned char *A = A_base + (size_t)u * p.a_unit_bytes;
+        unsigned char *A = sm.A_base + (size_t)u * p.a_unit_bytes;
+        const uint32_t a_addr = smem_u32(A);
+        const uint32_t a_rowx = a_addr + (uint32_t)(row * 128 + ((row & 7) << 4));
         unsigned char *X_row = A + p.xyz_off + row * 16;            // this row in the coordinate block [2][128][16 B]
-        uint32_t *vmask_u = vmask_base + 8 * u;
+        uint32_t *vmask_u = sm.vmask + 8 * u;
         uint32_t parity = 0;
         const uint32_t tmem_row = tmem_base + (uint32_t)(u * p.cols_per_unit) + ((uint32_t)(q * 32) << 16);
         const int K = p.K, C = p.C, D = p.D, S = p.S, N = p.N;
@@ -237,9 +387,9 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const __grid_
         const int rows = (int)p.rows, G = (int)p.G;
         uint32_t acc_phase = 0;
         const int gu = (int)blockIdx.x * U + u;
-        uint64_t *my_acc_ready = acc_ready + u;
-        const bool twin = p.feat_fast && p.feat_bf16 != nullptr;    // bf16 features: cp.async straight into the operand
-        const bool pre_xyz = C <= 4;                                // coordinates prefetched one tile ahead
+        uint64_t *my_acc_ready = sm.acc_ready + u;
+        const bool twin = FMODE == 1 || (FMODE == 2 && p.feat_fast && p.feat_bf16 != nullptr);    // bf16 features: TMA / cp.async straight into the operand
+        constexpr bool pre_xyz = PRE_XYZ;                           // coordinates prefetched one tile ahead
 
         // raw neighbour index of this thread's row in `tile` (-1 outside the problem); no use of the value here,
         // so the load stays in flight
@@ -263,15 +413,12 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const __grid_
                 pp += p.sc;
             }
         };
-        // Feature rows -> operand buffer.  Lanes are mapped (4 rows) x (8 chunks of 16 B): eight lanes read 128
-        // contiguous bytes of one source row (bf16) and write one 128-byte swizzled line, so the copy is coalesced
-        // in global memory and conflict free in shared memory.  The row's neighbour index lives in the lane that
-        // owns the row (thread = row everywhere else) and is fetched with a shuffle.
-        // bf16 features: asynchronous (cp.async), the buffer must be free when this is called.
-        uint64_t *my_feat_ready = feat_ready + u;
+        // Feature rows -> operand buffer (bf16 features, asynchronous; the buffer must be free when this is called).
+        uint64_t *my_feat_ready = sm.feat_ready + u;
         uint32_t feat_phase = 0;
         auto issue_twin = [&](int tile, int n_mine) {
-            if (p.use_tma) {
+            if constexpr (FMODE == 0) return;
+            if constexpr (FMODE == 1) {
                 // TMA gather4: lane l < 8 moves rows 4l..4l+3 of this warp's 32 (one instruction per 64-channel
                 // block); invalid rows use an out-of-range row index and arrive as zeros
                 const int g = (tile * TC_ROWS + row) >> logK;
@@ -286,6 +433,8 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const __grid_
                         tma_gather4(A + (c0 >> 6) * SW128_BLOCK + (q * 32 + l4) * 128, &p.tmap, c0, r0, r1, r2, r3, my_feat_ready);
                 return;
             }
+            // cp.async: lanes are mapped (4 rows) x (8 chunks of 16 B): eight lanes read 128 contiguous bytes of one
+            // source row and write one 128-byte swizzled line (coalesced, conflict free)
             const int nv = is_valid(n_mine) ? n_mine : -1;
             const int ch = lane & 7;
 #pragma unroll 1
@@ -334,48 +483,31 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const __grid_
         };
 
         Tracer tr; tr.init(p.trace, u, blockIdx.x == 0 && q == 0 && lane == 0);
-        uint64_t *my_a_ready = a_ready + u;
-        const uint32_t a_sw = desc_lo_sw128(smem_u32(A));
-        const uint32_t a_xyz = desc_lo(smem_u32(A) + (uint32_t)p.xyz_off, A_LBO);
+        const uint32_t wsm16 = smem_u32(sm.Wsm) >> 4;
+        const uint32_t a_sw = desc_lo_sw128(a_addr);
+        const uint32_t a_xyz = desc_lo_ns(a_addr + (uint32_t)p.xyz_off, A_LBO);
+        const uint32_t ones_lo = desc_lo_ns(smem_u32(sm.ones), A_LBO);
         const uint32_t d_tm = tmem_base + (uint32_t)(u * p.cols_per_unit);
-        const int ks_xyz = D / 16;
         bool w_ready = false;
-        // operand written (and proxy-fenced) / TMEM drained by this warp.  Either tell the MMA warp, or (small
-        // stacks) meet the unit's other warps at a named barrier and let this unit's first warp issue the layer.
+        // operand written (and proxy-fenced) / TMEM drained by this warp: meet the unit's other warps at a named
+        // barrier, then the unit's first warp issues the layer
         auto issue_layer = [&](int l) {
-            if (!p.unit_issue) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(my_a_ready);
-                return;
-            }
             asm volatile("bar.sync %0, 128;" ::"r"(u + 1) : "memory");
             if (q == 0) {
-                if (!w_ready) { mbar_wait(w_bar, 0); w_ready = true; }
+                if (!w_ready) { mbar_wait(sm.w_bar, 0); w_ready = true; }
                 tc_fence_after();
-                const TcLayer &ly = lay.ly[l];
-                const bool last = (l == L - 1);
-                const uint32_t lbo = (uint32_t)(last ? ly.Npad : ly.NS) * 16u;
-                const uint32_t w_lo = desc_lo(smem_u32(Wsm) + (uint32_t)ly.w_off, lbo);
-                const uint32_t w_step = (2u * lbo) >> 4;
-                const uint32_t idesc = instr_desc_bf16(last ? TC_ROWS : ly.NS);
-                const int nks = ly.K / 16;
                 if (elect_one()) {
-                    const int n_mh = last ? ly.Npad / TC_ROWS : 1;
-                    for (int mh = 0; mh < n_mh; ++mh)
-                        for (int ks = 0; ks < nks; ++ks) {
-                            const bool xyz = (l == 0 && ks == ks_xyz);
-                            const uint64_t act = xyz ? mk_desc(a_xyz, DESC_HI)
-                                                     : mk_desc(a_sw + (uint32_t)((ks >> 2) * (SW128_BLOCK / 16) + (ks & 3) * 2), DESC_HI_SW128);
-                            const uint64_t wgt = mk_desc(w_lo + (uint32_t)(mh * TC_ROWS) + (uint32_t)ks * w_step, DESC_HI);
-                            if (!last) umma_bf16(d_tm, act, wgt, idesc, ks ? 1u : 0u);
-                            else umma_bf16(d_tm + (uint32_t)(mh * TC_ROWS), wgt, act, idesc, ks ? 1u : 0u);
-                        }
+                    issue_layer_mmas(p, l, wsm16, a_sw, a_xyz, ones_lo, d_tm);
                     umma_commit(my_acc_ready);
                 }
                 __syncwarp();
             }
         };
+        // Prefetch discipline: fence.proxy.async is a MEMBAR + proxy fence and stalls on every global load this
+        // thread still has in flight, so loads are only issued at the start of the pooling phase (the longest
+        // fence-free stretch): the neighbour index of the tile after next and the coordinates of the next tile.
         int n_cur = load_index(gu);
+        int n_next = load_index(gu + stride);
         float px[4], pc[4];
         if (gu < tiles) {
             if (twin) issue_twin(gu, n_cur);
@@ -386,14 +518,14 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const __grid_
             uint32_t *vmask_s = vmask_u + 4 * parity;    // a warp can run at most one tile ahead of its unit
             parity ^= 1u;
             const int n = n_cur;
-            const int n_next = load_index(tile + stride);          // used after the first epilogue at the earliest
+            int n_next2 = -1;
             const bool valid = is_valid(n);
             const int g = (tile * TC_ROWS + row) >> logK;      // group of this row
             const int b = (int)((unsigned)g / (unsigned)S);
 
             // ---- gather: features (swizzled blocks) were started earlier (bf16 twin) or are converted here (fp32);
             //      coordinates minus centre go to the unit's coordinate block: channels [D, D+16) of layer 0 ----------
-            if (D) {
+            if constexpr (FMODE == 2) {
                 if (p.feat_fast) { if (!twin) gather_f32(tile, n); }
                 else {
                     for (int k = 0; k < D; ++k) {
@@ -420,120 +552,75 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const __grid_
                 *reinterpret_cast<uint4 *>(X_row) = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
                 *reinterpret_cast<uint4 *>(X_row + A_LBO) = make_uint4(pack_bf16x2(x[8], x[9]), pack_bf16x2(x[10], x[11]), pack_bf16x2(x[12], x[13]), pack_bf16x2(x[14], x[15]));
             }
-            if (twin) {
-                if (p.use_tma) { mbar_wait(my_feat_ready, feat_phase); feat_phase ^= 1u; }
-                else asm volatile("cp.async.wait_group 0;" ::: "memory");
-            }
+            if constexpr (FMODE == 1) { mbar_wait(my_feat_ready, feat_phase); feat_phase ^= 1u; }
+            if constexpr (FMODE == 2) { if (twin) asm volatile("cp.async.wait_group 0;" ::: "memory"); }
             const unsigned vm = __ballot_sync(0xffffffffu, valid);
-            if (lane == 0) vmask_s[q] = vm;      // read by the whole unit in the pooling step (ordered by the mbarriers)
+            if (lane == 0) vmask_s[q] = vm;      // read by the whole unit in the pooling step (ordered by the barriers)
             fence_proxy_async();                 // generic-proxy stores -> visible to the tensor core (async proxy)
             tr.mark(0x300);
             issue_layer(0);
             tr.mark(0x700);
             const bool more = tile + stride < tiles;
 
-#pragma unroll
-            for (int l = 0; l < T2_MAX_L; ++l) {
-                if (l >= L) break;
-                const TcLayer &ly = lay.ly[l];
+#pragma unroll 1
+            for (int l = 0; l < L; ++l) {
                 mbar_wait(my_acc_ready, acc_phase);
                 acc_phase ^= 1u;
                 tc_fence_after();
                 tr.mark(0x400 + l);
-                const float *bs = bias_s + ly.b_off;
                 if (l < L - 1) {
-                    // ---- hidden layer: accumulator -> +bias -> ReLU -> bf16 -> the next layer's A operand (in place) --
-#pragma unroll 1
-                    for (int c0 = 0; c0 < ly.Npad; c0 += 32) {
-                        uint32_t r[32];
-                        tmem_ld32_nowait(tmem_row + (uint32_t)c0, r);
-                        tmem_ld_wait();
-                        epi_block(r, bs, A, c0, row);
-                    }
+                    // ---- hidden layer: accumulator (bias included) -> ReLU -> bf16 -> the next layer's A operand (in place) --
+                    epi_hidden_any(p.ly[l].nb32, tmem_row, a_rowx);
                     tc_fence_before();           // TMEM reads ordered before the next MMA's write to this region
                     fence_proxy_async();
                     tr.mark(0x500 + l);
                     issue_layer(l + 1);
                     tr.mark(0x700 + l + 1);
-                    // the next tile's index has arrived by now: start its coordinate loads (they land during the
-                    // remaining layers)
-                    if (l == 0 && L > 1 && more && pre_xyz) load_xyz4(tile + stride, n_next, px, pc);
                 } else {
                     // ---- last layer (transposed): this thread = channel mh*128 + row; columns = the tile's rows ------
                     // every MMA that reads the operand buffer has completed: the next tile's feature rows can start
                     // flowing in underneath the pooling
                     if (more) {
                         if (twin) issue_twin(tile + stride, n_next);
-                        if (L == 1 && pre_xyz) load_xyz4(tile + stride, n_next, px, pc);
+                        if (pre_xyz) load_xyz4(tile + stride, n_next, px, pc);
                     }
+                    n_next2 = load_index(tile + 2 * stride);
                     tr.mark(0x610);
-                    const uint32_t m0 = vmask_s[0], m1 = vmask_s[1], m2 = vmask_s[2], m3 = vmask_s[3];
-                    const bool all_valid = (m0 & m1 & m2 & m3) == 0xffffffffu;
+                    const Tc2Layer &ly = p.ly[l];
+                    const float *bs = sm.bias_s + ly.b_off;
+                    if (!w_ready) { mbar_wait(sm.w_bar, 0); w_ready = true; }     // the fp32 biases arrive with the weight image
+                    PoolOut o;
+                    o.all_valid = (vmask_s[0] & vmask_s[1] & vmask_s[2] & vmask_s[3]) == 0xffffffffu;
+                    o.has_bf = p.out_bf16 != nullptr;
+                    o.os = p.os; o.ob = p.ob; o.contig = p.ob == (int64_t)S * p.os; o.S = S; o.G = G;
                     const int g0 = tile * gpt;
-                    const int b0 = (int)((unsigned)g0 / (unsigned)S);
-                    const int s0 = g0 - b0 * S;
-                    const int64_t wrap = p.ob - (int64_t)S * p.os;      // offset correction when a group index rolls into the next cloud
-                    for (int mh = 0; mh < ly.Npad / TC_ROWS; ++mh) {
+                    for (int mh = 0; mh < ly.n_mh; ++mh) {
                         const int c = mh * TC_ROWS + row;
-                        const float bv = bs[c];
-                        const bool c_ok = c < ly.Cout;
-                        int64_t o = (int64_t)b0 * p.ob + (int64_t)s0 * p.os + p.co_off + c;   // output element of (group, channel)
-                        int ss = s0, gg = g0;
-                        // group finished: max over its rows -> + bias -> ReLU -> [B,S,Ctot]; then step to the next group
-                        auto emit = [&](float m) {
-                            if (c_ok && gg < G && (all_valid || m > -INFINITY)) {
-                                const float y = fmaxf(m + bv, 0.f);
-                                p.out[o] = y;
-                                if (p.out_bf16) p.out_bf16[o] = __float2bfloat16_rn(y);
-                            }
-                            ++gg; o += p.os;
-                            if (++ss == S) { ss = 0; o += wrap; }
-                        };
-                        float run = -INFINITY;
-#pragma unroll 1
-                        for (int blk = 0; blk < 4; ++blk) {
-                            uint32_t r[32];
-                            tmem_ld32_nowait(tmem_row + (uint32_t)(mh * TC_ROWS + blk * 32), r);
-                            tmem_ld_wait();
-                            tr.mark(0x620 + mh * 4 + blk);
-                            if (!all_valid) {        // padding rows / empty balls (never on the reference's configurations)
-                                const uint32_t mk = blk == 0 ? m0 : blk == 1 ? m1 : blk == 2 ? m2 : m3;
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) if (!((mk >> j) & 1u)) r[j] = 0xff800000u;   // -inf
-                            }
-                            if (K >= 32) {
-                                run = fmaxf(run, max_range<0, 32>(r));
-                                if ((((blk + 1) * 32) & (K - 1)) == 0) { emit(run); run = -INFINITY; }
-                            } else if (K == 16) {
-                                emit(max_range<0, 16>(r));
-                                emit(max_range<16, 16>(r));
-                            } else {
-                                emit(max_range<0, 8>(r));
-                                emit(max_range<8, 8>(r));
-                                emit(max_range<16, 8>(r));
-                                emit(max_range<24, 8>(r));
-                            }
-                            tr.mark(0x630 + mh * 4 + blk);
-                        }
+                        o.bv = bs[c];
+                        o.c_ok = c < ly.Cout;
+                        o.po = p.out + p.co_off + c;
+                        o.pb = p.out_bf16 + p.co_off + c;
+                        o.gg = g0;
+                        pool_slice_any<false>(logK, tmem_row + (uint32_t)(mh * TC_ROWS), 0, 4, vmask_s, o);
                     }
                     tc_fence_before();
                     tr.mark(0x600);
                 }
             }
-            n_cur = n_next;
+            n_cur = n_next; n_next = n_next2;
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == mma_warp) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 // ======================================================================================================
 // Cooperative variant, for stacks whose weights leave room for only TWO tiles per SM (sa2-sized).
 //
-// With two units of four warps each unit's chain (epilogue, pooling: a few hundred dependent instructions per
-// warp, ~8 cycles each) is far longer than its MMAs, and the two chains tend to run in phase, so the tensor
-// pipe idles.  Here all 16 worker warps serve BOTH tiles: the CTA walks a fixed schedule
+// With two units of four warps each unit's chain (epilogue, pooling) is far longer than its MMAs, and the two
+// chains tend to run in phase, so the tensor pipe idles.  Here all 16 worker warps serve BOTH tiles: the CTA
+// walks a fixed schedule
 //     for layer l: for unit u: wait acc(u,l) -> epilogue / pooling of (u,l) split 16 ways -> signal MMA warp
 // so every CUDA-core phase is four times shorter and the MMAs of one unit always run underneath the phase of
 // the other.  Warp w covers TMEM lane quarter w & 3 and column share w >> 2; threads of share 0 also own "their"
@@ -545,82 +632,43 @@ constexpr int T3_THREADS = (T3_WORKERS + 1) * 32;      // + the MMA-issue warp
 __global__ void __launch_bounds__(T3_THREADS, 1) sa_tc3_kernel(const __grid_constant__ Tc2Params p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    const TcLayout &lay = p.lay;
+    const Tc2Smem sm = carve(smem, p);
     constexpr int U = 2;
-    unsigned char *A_base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
-    unsigned char *Wsm = A_base + (size_t)U * p.a_unit_bytes;
-    float *bias_s = reinterpret_cast<float *>(Wsm + lay.w_bytes);
-    uint32_t *vmask_base = reinterpret_cast<uint32_t *>(bias_s + lay.bias_floats);   // [U][2][4] valid-row ballots, by tile parity
-    uint64_t *acc_ready = reinterpret_cast<uint64_t *>(vmask_base + 8 * T2_MAX_UNITS);
-    uint64_t *a_ready = acc_ready + T2_MAX_UNITS;        // per unit: 16 warp arrivals (+ the TMA bytes of a gather)
-    uint64_t *w_bar = a_ready + 2 * T2_MAX_UNITS;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w_bar + 1);
-
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    const int L = lay.L;
+    const int L = p.L;
 
-    if (tid == 0) {
-        for (int u = 0; u < U; ++u) { mbar_init(acc_ready + u, 1); mbar_init(a_ready + u, T3_WORKERS); }
-        mbar_init(w_bar, 1);
-        fence_mbar_init();
-        mbar_expect_tx(w_bar, (uint32_t)lay.w_bytes);
-        for (int off = 0; off < lay.w_bytes; off += 32768) {
-            const int nb = min(32768, lay.w_bytes - off);
-            bulk_g2s(Wsm + off, p.packed + off, (uint32_t)nb, w_bar);
-        }
-    }
-    if (warp == T3_WORKERS) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-    {
-        const float *bsrc = reinterpret_cast<const float *>(p.packed + lay.w_bytes);
-        for (int i = tid; i < lay.bias_floats; i += blockDim.x) bias_s[i] = __ldg(bsrc + i);
-    }
+    cta_prologue(sm, p, tid, T3_WORKERS);      // a_ready: 16 warp arrivals (+ the TMA bytes of a gather)
+    if (warp == T3_WORKERS) tmem_alloc(sm.tmem_slot, (uint32_t)p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = *sm.tmem_slot;
     const int tiles = (int)p.tiles;
     const int stride = (int)gridDim.x * U;
     const int first_tile = (int)blockIdx.x * U;
     const int n_iter = first_tile < tiles ? (tiles - first_tile + stride - 1) / stride : 0;   // trips of unit 0 (>= unit 1's)
+    uint64_t *acc_ready = sm.acc_ready, *a_ready = sm.a_ready;
 
     if (warp == T3_WORKERS) {
         // ---- MMA warp: same schedule as the workers, one elected lane issues ---------------------------------
-        const int ks_xyz = p.D / 16;
-        mbar_wait(w_bar, 0);
+        const uint32_t wsm16 = smem_u32(sm.Wsm) >> 4;
+        const uint32_t ones_lo = desc_lo_ns(smem_u32(sm.ones), A_LBO);
+        mbar_wait(sm.w_bar, 0);
         uint32_t phases = 0;
         for (int it = 0; it < n_iter; ++it) {
-#pragma unroll
-            for (int l = 0; l < T2_MAX_L; ++l) {
-                if (l >= L) break;
-                const TcLayer &ly = lay.ly[l];
-                const bool last = (l == L - 1);
-                const uint32_t lbo = (uint32_t)(last ? ly.Npad : ly.NS) * 16u;
-                const uint32_t w_lo = desc_lo(smem_u32(Wsm) + (uint32_t)ly.w_off, lbo);
-                const uint32_t w_step = (2u * lbo) >> 4;
-                const uint32_t idesc = instr_desc_bf16(last ? TC_ROWS : ly.NS);
-                const int nks = ly.K / 16;
-                const int n_mh = last ? ly.Npad / TC_ROWS : 1;
+#pragma unroll 1
+            for (int l = 0; l < L; ++l) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     if (first_tile + u + it * stride >= tiles) continue;
                     mbar_wait(a_ready + u, (phases >> u) & 1u);
                     phases ^= 1u << u;
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(A_base) + (uint32_t)(u * p.a_unit_bytes);
-                    const uint32_t a_sw = desc_lo_sw128(a_addr);
-                    const uint32_t a_xyz = desc_lo(a_addr + (uint32_t)p.xyz_off, A_LBO);
-                    const uint32_t d_tm = tmem_base + (uint32_t)(u * p.cols_per_unit);
+                    const uint32_t a_addr = smem_u32(sm.A_base) + (uint32_t)(u * p.a_unit_bytes);
                     if (elect_one()) {
-                        for (int mh = 0; mh < n_mh; ++mh)
-                            for (int ks = 0; ks < nks; ++ks) {
-                                const bool xyz = (l == 0 && ks == ks_xyz);
-                                const uint64_t act = xyz ? mk_desc(a_xyz, DESC_HI)
-                                                         : mk_desc(a_sw + (uint32_t)((ks >> 2) * (SW128_BLOCK / 16) + (ks & 3) * 2), DESC_HI_SW128);
-                                const uint64_t wgt = mk_desc(w_lo + (uint32_t)(mh * TC_ROWS) + (uint32_t)ks * w_step, DESC_HI);
-                                if (!last) umma_bf16(d_tm, act, wgt, idesc, ks ? 1u : 0u);
-                                else umma_bf16(d_tm + (uint32_t)(mh * TC_ROWS), wgt, act, idesc, ks ? 1u : 0u);
-                            }
+                        issue_layer_mmas(p, l, wsm16, desc_lo_sw128(a_addr), desc_lo_ns(a_addr + (uint32_t)p.xyz_off, A_LBO), ones_lo,
+                                         tmem_base + (uint32_t)(u * p.cols_per_unit));
                         umma_commit(acc_ready + u);
                     }
                     __syncwarp();
@@ -637,6 +685,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) sa_tc3_kernel(const __grid_cons
         const bool pre_xyz = C <= 4;
         const int n_blk_feat = D / 64;                  // the coop variant is only launched with TMA-gathered features (D % 64 == 0) or D == 0
         uint32_t acc_phase = 0;
+        bool w_ready = false;
         Tracer tr; tr.init(p.trace, 0, blockIdx.x == 0 && warp == 0 && lane == 0);
 
         auto load_index = [&](int tile) -> int {
@@ -662,7 +711,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) sa_tc3_kernel(const __grid_cons
         // the byte count on the unit's barrier
         auto issue_gather = [&](int u, int tile, int n_mine) {
             if (n_blk_feat == 0) return;
-            unsigned char *A = A_base + (size_t)u * p.a_unit_bytes;
+            unsigned char *A = sm.A_base + (size_t)u * p.a_unit_bytes;
             const int g = (tile * TC_ROWS + row) >> logK;
             const int b = (int)((unsigned)g / (unsigned)S);
             const int ri = is_valid(n_mine) ? b * N + n_mine : p.feat_rows;
@@ -677,7 +726,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) sa_tc3_kernel(const __grid_cons
         // coordinates minus centre (+ zero padding) of this thread's row -> unit u's coordinate block; valid-row ballot
         auto finish_gather = [&](int u, int tile, int n, const float (&px)[4], const float (&pc)[4], uint32_t par) {
             if (hb != 0) return;
-            unsigned char *X_row = A_base + (size_t)u * p.a_unit_bytes + p.xyz_off + row * 16;
+            unsigned char *X_row = sm.A_base + (size_t)u * p.a_unit_bytes + p.xyz_off + row * 16;
             const bool valid = is_valid(n);
             if (pre_xyz) {
                 *reinterpret_cast<uint4 *>(X_row) = make_uint4(pack_bf16x2(__fsub_rn(px[0], pc[0]), __fsub_rn(px[1], pc[1])),
@@ -700,7 +749,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) sa_tc3_kernel(const __grid_cons
                 *reinterpret_cast<uint4 *>(X_row + A_LBO) = make_uint4(pack_bf16x2(x[8], x[9]), pack_bf16x2(x[10], x[11]), pack_bf16x2(x[12], x[13]), pack_bf16x2(x[14], x[15]));
             }
             const unsigned vm = __ballot_sync(0xffffffffu, valid);
-            if (lane == 0) vmask_base[8 * u + 4 * par + q] = vm;
+            if (lane == 0) sm.vmask[8 * u + 4 * par + q] = vm;
         };
         auto arrive = [&](int u) {
             __syncwarp();
@@ -726,16 +775,14 @@ __global__ void __launch_bounds__(T3_THREADS, 1) sa_tc3_kernel(const __grid_cons
 
         for (int it = 0; it < n_iter; ++it) {
             const uint32_t par = (uint32_t)it & 1u;
-#pragma unroll
-            for (int l = 0; l < T2_MAX_L; ++l) {
-                if (l >= L) break;
-                const TcLayer &ly = lay.ly[l];
-                const float *bs = bias_s + ly.b_off;
+#pragma unroll 1
+            for (int l = 0; l < L; ++l) {
+                const Tc2Layer &ly = p.ly[l];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int tile = first_tile + u + it * stride;
                     if (tile >= tiles) continue;
-                    unsigned char *A = A_base + (size_t)u * p.a_unit_bytes;
+                    const uint32_t a_addr = smem_u32(sm.A_base) + (uint32_t)(u * p.a_unit_bytes);
                     const uint32_t tmem_row = tmem_base + (uint32_t)(u * p.cols_per_unit) + ((uint32_t)(q * 32) << 16);
                     const bool more = tile + stride < tiles;
                     if (l == 0) n_nxt[u] = load_index(tile + stride);      // needed after this tile's first epilogue at the earliest
@@ -745,13 +792,21 @@ __global__ void __launch_bounds__(T3_THREADS, 1) sa_tc3_kernel(const __grid_cons
                     tr.mark(0x400 + l * 2 + u);
                     if (l < L - 1) {
                         // hidden layer: this warp's 32-column blocks hb, hb+4, ...
-#pragma unroll 1
-                        for (int c0 = 32 * hb; c0 < ly.Npad; c0 += 128) {
+                        const uint32_t a_rowx = a_addr + (uint32_t)(row * 128 + ((row & 7) << 4));
+                        const uint32_t a_rowx_hb = (a_rowx ^ (uint32_t)((hb & 1) << 6)) + (uint32_t)((hb >> 1) * SW128_BLOCK);
+                        if (ly.nb32 == 4) {
                             uint32_t r[32];
-                            tmem_ld32_nowait(tmem_row + (uint32_t)c0, r);
+                            tmem_ld32_nowait(tmem_row + (uint32_t)(32 * hb), r);
                             tmem_ld_wait();
-                            epi_block(r, bs, A, c0, row);
-                        }
+                            epi_store32<0>(r, a_rowx_hb, 0u);
+                        } else if (ly.nb32 == 8) {
+                            uint32_t r0[32], r1[32];
+                            tmem_ld32_nowait(tmem_row + (uint32_t)(32 * hb), r0);
+                            tmem_ld32_nowait(tmem_row + (uint32_t)(32 * hb + 128), r1);
+                            tmem_ld_wait();
+                            epi_store32<0>(r0, a_rowx_hb, 0u);
+                            epi_store32<0>(r1, a_rowx_hb, (uint32_t)(2 * SW128_BLOCK));
+                        } else epi_hidden_rt(tmem_row, a_rowx, hb, 4, ly.nb32);
                         tc_fence_before();
                         fence_proxy_async();
                         arrive(u);
@@ -763,61 +818,32 @@ __global__ void __launch_bounds__(T3_THREADS, 1) sa_tc3_kernel(const __grid_cons
                             issue_gather(u, tile + stride, n_nxt[u]);
                             if (L == 1 && pre_xyz && hb == 0) load_xyz4(tile + stride, n_nxt[u], px[u], pc[u]);
                         }
-                        const uint32_t *vm = vmask_base + 8 * u + 4 * par;
-                        const bool all_valid = (vm[0] & vm[1] & vm[2] & vm[3]) == 0xffffffffu;
+                        const float *bs = sm.bias_s + ly.b_off;
+                        const uint32_t *vm = sm.vmask + 8 * u + 4 * par;
+                        if (!w_ready) { mbar_wait(sm.w_bar, 0); w_ready = true; }
+                        PoolOut o;
+                        o.all_valid = (vm[0] & vm[1] & vm[2] & vm[3]) == 0xffffffffu;
+                        o.has_bf = p.out_bf16 != nullptr;
+                        o.os = p.os; o.ob = p.ob; o.contig = p.ob == (int64_t)S * p.os; o.S = S; o.G = G;
                         const int g0 = tile * gpt;
-                        const int64_t wrap = p.ob - (int64_t)S * p.os;
                         // 16-way split of the (128-channel slice, 32-row block) items of this lane quarter: whole groups
                         // stay in one warp
-                        const int n_mh = ly.Npad / TC_ROWS;
+                        const int n_mh = ly.n_mh;
                         const int bpg = K >= 32 ? K / 32 : 1;                   // 32-row blocks per group
-                        int ipw = (n_mh * 4) / 4; if (ipw < bpg) ipw = bpg;     // items per warp
+                        int ipw = n_mh; if (ipw < bpg) ipw = bpg;               // items per warp
                         const int item0 = hb * ipw;
                         if (item0 < n_mh * 4) {
                             const int mh = item0 >> 2, blk_lo = item0 & 3, blk_hi = min(4, blk_lo + ipw);
                             for (int mhh = mh; mhh < n_mh && mhh * 4 < item0 + ipw; ++mhh) {
                                 const int c = mhh * TC_ROWS + row;
-                                const float bv = bs[c];
-                                const bool c_ok = c < ly.Cout;
+                                o.bv = bs[c];
+                                o.c_ok = c < ly.Cout;
                                 const int b_lo = (mhh == mh) ? blk_lo : 0;
                                 const int b_hi = (mhh == mh) ? blk_hi : min(4, item0 + ipw - mhh * 4);
-                                int gg = g0 + ((b_lo * 32) >> logK);
-                                const int bb = (int)((unsigned)gg / (unsigned)S);
-                                int ss = gg - bb * S;
-                                int64_t o = (int64_t)bb * p.ob + (int64_t)ss * p.os + p.co_off + c;
-                                auto emit = [&](float m) {
-                                    if (c_ok && gg < G && (all_valid || m > -INFINITY)) {
-                                        const float y = fmaxf(m + bv, 0.f);
-                                        p.out[o] = y;
-                                        if (p.out_bf16) p.out_bf16[o] = __float2bfloat16_rn(y);
-                                    }
-                                    ++gg; o += p.os;
-                                    if (++ss == S) { ss = 0; o += wrap; }
-                                };
-                                float run = -INFINITY;
-#pragma unroll 1
-                                for (int blk = b_lo; blk < b_hi; ++blk) {
-                                    uint32_t r[32];
-                                    tmem_ld32_nowait(tmem_row + (uint32_t)(mhh * TC_ROWS + blk * 32), r);
-                                    tmem_ld_wait();
-                                    if (!all_valid) {
-                                        const uint32_t mk = vm[blk];
-#pragma unroll
-                                        for (int j = 0; j < 32; ++j) if (!((mk >> j) & 1u)) r[j] = 0xff800000u;
-                                    }
-                                    if (K >= 32) {
-                                        run = fmaxf(run, max_range<0, 32>(r));
-                                        if ((((blk + 1) * 32) & (K - 1)) == 0) { emit(run); run = -INFINITY; }
-                                    } else if (K == 16) {
-                                        emit(max_range<0, 16>(r));
-                                        emit(max_range<16, 16>(r));
-                                    } else {
-                                        emit(max_range<0, 8>(r));
-                                        emit(max_range<8, 8>(r));
-                                        emit(max_range<16, 8>(r));
-                                        emit(max_range<24, 8>(r));
-                                    }
-                                }
+                                o.gg = g0 + ((b_lo * 32) >> logK);
+                                o.po = p.out + p.co_off + c;
+                                o.pb = p.out_bf16 + p.co_off + c;
+                                pool_slice_any<true>(logK, tmem_row + (uint32_t)(mhh * TC_ROWS), b_lo, b_hi, vm, o);
                             }
                         }
                         tc_fence_before();
@@ -854,8 +880,8 @@ static bool tc2_plan(int K, int C, int D, int order, const TcLayout &t, Tc2Plan 
     if (D % 16 != 0 || C < 1 || C > 16 || t.ly[0].K != D + 16) return false;
     if (order == PN2_ORDER_ALL) return false;                       // group_all stacks are wide: pn2_sa_tc.cu
     if (K < 8 || K > TC_ROWS || (K & (K - 1))) return false;
-    if (t.L > 4) return false;
-    if (t.L < 1 || t.ly[t.L - 1].Npad > 512) return false;
+    if (t.L > T2_MAX_L) return false;
+    if (t.L < 1 || t.ly[t.L - 1].Npad > 512 || t.ly[t.L - 1].nslab != 1) return false;
     int kmax = D, nmax = 0;                                         // widest feature part of any layer's operand
     for (int l = 0; l < t.L; ++l) {
         if (l < t.L - 1 && (t.ly[l].nslab != 1 || t.ly[l].NS > 256)) return false;
@@ -867,8 +893,7 @@ static bool tc2_plan(int K, int C, int D, int order, const TcLayout &t, Tc2Plan 
     pl->a_unit_bytes = pl->xyz_off + 2 * A_LBO;
     for (int U = T2_MAX_UNITS; U >= 1; U >>= 1) {
         if (U * pl->cols_per_unit > 512) continue;
-        const size_t smem = (size_t)t.w_bytes + (size_t)t.bias_floats * 4 + (size_t)U * pl->a_unit_bytes +
-                            8 * T2_MAX_UNITS * 4 + (3 * T2_MAX_UNITS + 1) * 8 + 16 + 1024;   // + alignment slack
+        const size_t smem = tc2_smem_bytes(U, pl->a_unit_bytes, t.total_bytes);
         if (smem > (size_t)T2_SMEM_LIMIT) continue;
         pl->U = U; pl->smem = smem; pl->tmem_cols = pow2_at_least(U * pl->cols_per_unit);
         return true;
@@ -894,7 +919,22 @@ int launch_sa_bf16_pipelined(const SaArgs &a, cudaStream_t st)
     p.feat = a.feat; p.fb = a.fb; p.fn = a.fn; p.fc = a.fc;
     p.centres = a.centres; p.idx32 = a.idx32;
     p.N = a.N; p.S = a.S; p.K = a.K; p.C = a.C; p.D = a.D; p.order = a.order;
-    p.lay = lay;
+    p.L = lay.L;
+    for (int l = 0; l < lay.L; ++l) {
+        const TcLayer &y = lay.ly[l];
+        const bool last = (l == lay.L - 1);
+        Tc2Layer &t = p.ly[l];
+        const uint32_t lbo = (uint32_t)(last ? y.Npad : y.NS) * 16u;
+        t.w_lo_rel = ((uint32_t)y.w_off >> 4) | ((lbo >> 4) << 16);
+        t.w_step = (2u * lbo) >> 4;
+        t.bs_lo_rel = ((uint32_t)y.bs_off >> 4) | ((lbo >> 4) << 16);
+        t.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((last ? TC_ROWS : y.NS) >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+        t.nks = (l == 0 ? a.D : y.K) / 16;
+        t.nb32 = y.Npad / 32;
+        t.n_mh = y.Npad / TC_ROWS;
+        t.Cout = y.Cout; t.b_off = y.b_off;
+    }
+    p.img_bytes = lay.total_bytes; p.bias_off = lay.w_bytes;
     p.packed = (const unsigned char *)a.packed;
     p.out = a.out; p.ob = a.ob; p.os = a.os; p.co_off = a.co_off;
     p.G = (int64_t)a.B * a.S;
@@ -908,8 +948,6 @@ int launch_sa_bf16_pipelined(const SaArgs &a, cudaStream_t st)
     p.feat_bf16 = (a.feat_bf16 && p.feat_fast && a.D > 0 && ((uintptr_t)a.feat_bf16 & 15) == 0) ? (const __nv_bfloat16 *)a.feat_bf16 : nullptr;
     p.out_bf16 = (__nv_bfloat16 *)a.out_bf16;
     p.trace = g_trace;
-    static const int issue_env = getenv("PN2_UNIT_ISSUE") ? atoi(getenv("PN2_UNIT_ISSUE")) : -1;
-    p.unit_issue = issue_env >= 0 ? issue_env : (pl.U == T2_MAX_UNITS);   // measured: profiles/README.md
     p.use_tma = 0; p.feat_rows = a.B * a.N;
     static const bool no_tma = getenv("PN2_NO_TMA_GATHER") != nullptr;
     if (p.feat_bf16 && a.D % 64 == 0 && (int64_t)a.B * a.N < (1ll << 31) - 1 && !no_tma) {
@@ -925,12 +963,19 @@ int launch_sa_bf16_pipelined(const SaArgs &a, cudaStream_t st)
         sa_tc3_kernel<<<(unsigned)grid3, T3_THREADS, pl.smem, st>>>(p);
         return launch_status("pn2_sa_fused(bf16, cooperative)");
     }
-    cudaError_t e = cudaFuncSetAttribute(sa_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
-    if (e != cudaSuccess) { set_error("sa_tc2: smem attribute (%zu B): %s", pl.smem, cudaGetErrorString(e)); return (int)e; }
     int64_t grid = (p.tiles + pl.U - 1) / pl.U;
     if (grid > 148) grid = 148;
-    sa_tc2_kernel<<<(unsigned)grid, (4 * pl.U + 1) * 32, pl.smem, st>>>(p);
-    return launch_status("pn2_sa_fused(bf16, pipelined)");
+    auto run = [&](auto kern) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+        if (e != cudaSuccess) { set_error("sa_tc2: smem attribute (%zu B): %s", pl.smem, cudaGetErrorString(e)); return (int)e; }
+        kern<<<(unsigned)grid, 4 * pl.U * 32, pl.smem, st>>>(p);
+        return launch_status("pn2_sa_fused(bf16, pipelined)");
+    };
+    const int fmode = a.D == 0 ? 0 : (p.use_tma ? 1 : 2);
+    const bool pre = a.C <= 4;
+    if (fmode == 0) return pre ? run(sa_tc2_kernel<0, true>) : run(sa_tc2_kernel<0, false>);
+    if (fmode == 1) return pre ? run(sa_tc2_kernel<1, true>) : run(sa_tc2_kernel<1, false>);
+    return pre ? run(sa_tc2_kernel<2, true>) : run(sa_tc2_kernel<2, false>);
 }
 
 }  // namespace pn2

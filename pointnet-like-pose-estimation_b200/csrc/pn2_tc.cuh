@@ -29,6 +29,7 @@ struct TcLayer {
     int nkb;      // number of 64-wide k blocks
     int w_off;    // byte offset of this layer's first chunk inside the packed buffer
     int b_off;    // float offset of this layer's bias inside the bias block
+    int bs_off;   // hidden layers: byte offset (from the start of the packed buffer) of the layer's bias slice
 };
 struct TcLayout {
     int L;
@@ -37,7 +38,13 @@ struct TcLayout {
     int bias_floats;   // sum of Npad
     int max_chunk;     // bytes of the largest chunk
     int n_chunks;
+    int total_bytes;   // weights + fp32 biases + bias slices
 };
+// Bias slice of a hidden layer (used by the pipelined kernels, pn2_sa_tc2.cu): one extra K = 16 slice of the weight
+// operand, [Npad] rows in the canonical K-major no-swizzle layout (k-groups at Npad*16 bytes), holding
+// k = 0: bf16(b), k = 1: bf16(b - bf16(b)), zeros elsewhere.  Multiplied by an activation slice whose channels 0 and 1
+// are 1.0 it adds the folded bias inside the MMA (to ~2^-17 relative), so the epilogue is ReLU + convert only.
+constexpr int BIAS_SLICE_K = 16;
 
 static __host__ __device__ inline int tc_chunk_bytes(const TcLayer &ly, int kb)
 {
@@ -72,6 +79,11 @@ static inline TcLayout tc_layout(int L, const int *dims)
         for (int kb = 0; kb < y.nkb; ++kb) { const int c = tc_chunk_bytes(y, kb); if (c > t.max_chunk) t.max_chunk = c; }
         t.n_chunks += y.nslab * y.nkb;
         K = y.Npad;
+    }
+    t.total_bytes = t.w_bytes + t.bias_floats * 4;
+    for (int l = 0; l < L; ++l) {
+        t.ly[l].bs_off = t.total_bytes;
+        if (l < L - 1) t.total_bytes += t.ly[l].Npad * BIAS_SLICE_K * 2;
     }
     return t;
 }
