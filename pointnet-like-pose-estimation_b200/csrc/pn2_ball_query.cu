@@ -16,6 +16,8 @@ namespace pn2 {
 
 constexpr int BQ_WARPS = 8;
 constexpr int BQ_THREADS = BQ_WARPS * 32;
+// centres scanned together by one warp (register budget: CPB * (2C + 2))
+template <int C> struct BQ_CPB { static constexpr int value = C <= 4 ? 4 : 2; };
 
 template <int C>
 __device__ __forceinline__ float sqnorm(const float (&v)[C], bool contig, bool tail)
@@ -60,7 +62,8 @@ ball_query_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, i
     extern __shared__ float smem[];
     float *sp = smem;                       // [C][NCH]
     float *sp2 = smem + (size_t)C * NCH;    // [NCH]
-    int *stage = (int *)(sp2 + NCH) + (threadIdx.x >> 5) * K;
+    constexpr int CPB = BQ_CPB<C>::value;
+    int *stage = (int *)(sp2 + NCH) + (threadIdx.x >> 5) * (CPB * K);      // [CPB][K] per warp
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
     const int s_begin = (blockIdx.x * BQ_WARPS + warp) * cpw;
@@ -105,41 +108,69 @@ ball_query_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, i
         __syncthreads();
 
         if (single_chunk) {
-            for (int ci = 0; ci < cpw; ++ci) {
-                const int sidx = s_begin + ci;
-                if (sidx >= S) break;
+            // CPB centres per pass: every pair of points read from shared memory is tested against all of them
+            // (shared-memory traffic, the limiter of the one-centre scan, drops by CPB; so do the loop instructions)
+            for (int ci = 0; ci < cpw; ci += CPB) {
+                f32x2 sv[CPB][C], s2v[CPB];
+                int cn[CPB];
 #pragma unroll
-                for (int k = 0; k < C; ++k) s[k] = __ldg(centres + (int64_t)b * csb + (int64_t)sidx * csn + (int64_t)k * csc);
-                s2 = sqnorm<C>(s, csc == 1, sidx >= (S & ~31));
-                cnt = 0;
-                f32x2 sv[C];
+                for (int c = 0; c < CPB; ++c) {
+                    const int sidx = s_begin + ci + c;
+                    const bool act = ci + c < cpw && sidx < S;
+                    float sc_[C];
 #pragma unroll
-                for (int k = 0; k < C; ++k) sv[k] = pk2(s[k], s[k]);
-                const f32x2 s2v = pk2(s2, s2), m2v = pk2(-2.0f, -2.0f);
-                for (int n0 = 0; n0 < NCH && cnt < K; n0 += 64) {
+                    for (int k = 0; k < C; ++k) sc_[k] = act ? __ldg(centres + (int64_t)b * csb + (int64_t)sidx * csn + (int64_t)k * csc) : 0.f;
+                    const float q2 = sqnorm<C>(sc_, csc == 1, sidx >= (S & ~31));
+#pragma unroll
+                    for (int k = 0; k < C; ++k) sv[c][k] = pk2(sc_[k], sc_[k]);
+                    s2v[c] = pk2(q2, q2);
+                    cn[c] = act ? 0 : K;              // an inactive slot counts as finished
+                }
+                const f32x2 m2v = pk2(-2.0f, -2.0f);
+                for (int n0 = 0; n0 < NCH; n0 += 64) {
+                    bool all_done = true;
+#pragma unroll
+                    for (int c = 0; c < CPB; ++c) all_done = all_done && cn[c] >= K;
+                    if (all_done) break;
                     // 64 points per trip, two consecutive ones per lane (rows are padded to a multiple of 64)
                     const int na = n0 + 2 * lane;
-                    const float2 d = pair_dist2<C>(sv, sp, NCH, na, s2v, m2v);
-                    const bool ina = !(d.x > r2), inb = !(d.y > r2);
-                    const unsigned ma = __ballot_sync(0xffffffffu, ina);
-                    const unsigned mb = __ballot_sync(0xffffffffu, inb);
-                    if (ma | mb) {                                                              // warp-uniform; most trips have no hit
-                        const int pa = cnt + __popc(ma & lt_mask) + __popc(mb & lt_mask);       // hits at lower indices
-                        if (ina && pa < K) stage[pa] = na;
-                        if (inb && pa + (int)ina < K) stage[pa + (int)ina] = na + 1;
-                        cnt += __popc(ma) + __popc(mb);
+                    f32x2 pv[C];
+#pragma unroll
+                    for (int k = 0; k < C; ++k) pv[k] = *reinterpret_cast<const f32x2 *>(sp + k * NCH + na);
+                    const f32x2 p2v = *reinterpret_cast<const f32x2 *>(sp2 + na);
+#pragma unroll
+                    for (int c = 0; c < CPB; ++c) {
+                        f32x2 dot = mul2(sv[c][0], pv[0]);
+#pragma unroll
+                        for (int k = 1; k < C; ++k) dot = fma2(sv[c][k], pv[k], dot);
+                        const float2 d = unpk2(add2(add2(mul2(m2v, dot), s2v[c]), p2v));
+                        const bool ina = !(d.x > r2), inb = !(d.y > r2);
+                        const unsigned ma = __ballot_sync(0xffffffffu, ina);
+                        const unsigned mb = __ballot_sync(0xffffffffu, inb);
+                        if (ma | mb) {                                                              // warp-uniform; most trips have no hit
+                            int *stg = stage + c * K;
+                            const int pa = cn[c] + __popc(ma & lt_mask) + __popc(mb & lt_mask);     // hits at lower indices
+                            if (ina && pa < K) stg[pa] = na;
+                            if (inb && pa + (int)ina < K) stg[pa + (int)ina] = na + 1;
+                            cn[c] += __popc(ma) + __popc(mb);
+                        }
                     }
                 }
                 __syncwarp();
-                first = cnt ? stage[0] : N;                                                     // hits are staged in index order
-                if (cnt > K) cnt = K;
-                if (cnt == 0 && lane == 0 && empty_flag) atomicOr(empty_flag, 1);
-                __syncwarp();
-                const int64_t o = ((int64_t)b * S + sidx) * K;
-                for (int j = lane; j < K; j += 32) {
-                    const int v = (j < cnt) ? stage[j] : first;
-                    if (idx64) idx64[o + j] = v;
-                    if (idx32) idx32[o + j] = v;
+#pragma unroll
+                for (int c = 0; c < CPB; ++c) {
+                    const int sidx = s_begin + ci + c;
+                    if (!(ci + c < cpw && sidx < S)) continue;
+                    const int *stg = stage + c * K;
+                    const int cc = cn[c] > K ? K : cn[c];
+                    const int frst = cc ? stg[0] : N;                                               // hits are staged in index order
+                    if (cc == 0 && lane == 0 && empty_flag) atomicOr(empty_flag, 1);
+                    const int64_t o = ((int64_t)b * S + sidx) * K;
+                    for (int j = lane; j < K; j += 32) {
+                        const int v = (j < cc) ? stg[j] : frst;
+                        if (idx64) idx64[o + j] = v;
+                        if (idx32) idx32[o + j] = v;
+                    }
                 }
                 __syncwarp();
             }
@@ -216,7 +247,7 @@ static int launch_bq_c(const float *centres, int64_t csb, int64_t csn, int64_t c
                        int B, int S, int N, float r2, int K,
                        int64_t *idx64, int32_t *idx32, int32_t *empty_flag, cudaStream_t st)
 {
-    const size_t stage_bytes = sizeof(int) * (size_t)BQ_WARPS * K;
+    const size_t stage_bytes = sizeof(int) * (size_t)BQ_WARPS * BQ_CPB<C>::value * K;
     const size_t budget = 200 * 1024 - stage_bytes;
     int NCH = (N + 63) & ~63, cpw;          // rows padded to 64 points: the packed inner loop scans 64 per trip, unguarded
     if ((size_t)(C + 1) * NCH * sizeof(float) > budget) {
@@ -224,7 +255,7 @@ static int launch_bq_c(const float *centres, int64_t csb, int64_t csn, int64_t c
         cpw = 1;  // multi-chunk path keeps one centre per warp in registers
     } else {
         // enough CTAs for ~4 waves of 148 SMs, but amortise the staging of the cloud over >= 8 centres/warp
-        cpw = 8;
+        cpw = 16;
         while (cpw > 1 && (int64_t)B * ((S + BQ_WARPS * cpw - 1) / (BQ_WARPS * cpw)) < 592) cpw >>= 1;
     }
     const size_t smem = (size_t)(C + 1) * NCH * sizeof(float) + stage_bytes;
