@@ -82,7 +82,18 @@ __device__ __forceinline__ float sum_order(const float (&t)[C], bool tail = fals
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ float2 unpk2(f32x2 v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+// Separately rounded product.  NOT mul.rn.f32x2: ptxas (12.9, sm_100a) contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2
+// despite the explicit rounding modifiers and -fmad=false (tools/probes/f32x2_contract.cu: 22 % of |p - c|^2 values one
+// ulp off, which moves an FPS argmax about once in ten clouds).  fma(a, b, +0) rounds the product once and cannot be
+// fused with a following add; the only difference from a multiply is that a -0 product comes out as +0, which none of the
+// callers can observe (squares, and dot products that only feed sums and comparisons).
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    const f32x2 zero = 0ull;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(zero));
+    return r;
+}
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 

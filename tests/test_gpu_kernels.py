@@ -70,6 +70,10 @@ FPS_CASES = [  # (B, N, C, S, layout, kind)
     (2, 100, 3, 512, "strided", "uni"), (2, 1000, 3, 100, "contig", "dup"), (2, 777, 10, 99, "contig", "dup"),
     (2, 3000, 10, 64, "strided", "uni"), (2, 300, 5, 64, "contig", "uni"), (2, 300, 16, 64, "strided", "uni"),
     (1, 2, 3, 4, "contig", "uni"), (2, 33, 8, 40, "contig", "uni"),
+    # many clouds: a one-ulp error in a distance only moves the argmax when the two farthest candidates are that close,
+    # about once in ten clouds (this is what catches a contracted multiply-add, see tools/probes/f32x2_contract.cu)
+    (256, 1024, 3, 512, "strided", "uni"), (256, 1024, 3, 512, "contig", "uni"), (96, 1024, 10, 512, "strided", "uni"),
+    (96, 512, 10, 128, "contig", "uni"),
 ]
 
 

@@ -3,7 +3,8 @@
 dominant opcodes per chunk of SASS; then the top individual instructions by stall samples."""
 import csv, sys
 rows = list(csv.reader(open(sys.argv[1])))
-hdr, data = rows[1], rows[2:]
+hdr = rows[1]
+data = [r for r in rows[2:] if len(r) >= len(hdr) - 2 and r[0].startswith('0x')]
 ia, isamp, isrc = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Source")
 tot_i = sum(int(r[ia]) for r in data); tot_s = sum(int(r[isamp]) for r in data)
 print("total warp-instructions", tot_i, "samples", tot_s, "sass lines", len(data))
