@@ -635,15 +635,17 @@ int launch_sa_bf16_pipelined(const SaArgs &a, cudaStream_t st)
     p.feat_bf16 = (a.feat_bf16 && p.feat_fast && a.D > 0 && ((uintptr_t)a.feat_bf16 & 15) == 0) ? (const __nv_bfloat16 *)a.feat_bf16 : nullptr;
     p.out_bf16 = (__nv_bfloat16 *)a.out_bf16;
     p.trace = g_trace;
-    p.use_tma = 0; p.feat_rows = a.B * a.N;
+    p.use_tma = 0; p.feat_rows = a.B * a.N; p.lsu_gather = 0;
     static const bool no_tma = getenv("PN2_NO_TMA_GATHER") != nullptr;
     if (p.feat_bf16 && a.D % 64 == 0 && (int64_t)a.B * a.N < (1ll << 31) - 1 && !no_tma) {
         if (make_row_gather_map(p.feat_bf16, (int64_t)a.B * a.N, a.D, &p.tmap) == 0) p.use_tma = 1;
     }
     if (p.tiles == 0) return 0;
-    // warp-specialised schedule (pn2_sa_tc4.cu), experimental: configurations whose layer-0 features are absent or bf16 rows
-    static const int tc4_env = getenv("PN2_TC4") ? atoi(getenv("PN2_TC4")) : 0;     // opt-in: see the status note in pn2_sa_tc4.cu
-    if (tc4_env && (a.D == 0 || (p.feat_bf16 && a.D % 64 == 0))) return launch_sa_tc4(p, pl.smem, st);
+    // warp-specialised schedule (pn2_sa_tc4.cu): configurations whose layer-0 features are absent or bf16 rows
+    // PN2_TC4: -1 (default) = two-unit stacks only (sa2-sized: 2.68 ms against 2.79 ms for the cooperative kernel below),
+    // 0 = never, 1 = every stack it covers (four-unit stacks are slower on it: 3.6 ms against 1.46 ms for sa1)
+    static const int tc4_env = getenv("PN2_TC4") ? atoi(getenv("PN2_TC4")) : -1;
+    if ((tc4_env > 0 || (tc4_env < 0 && pl.U == 2)) && (a.D == 0 || (p.feat_bf16 && a.D % 64 == 0))) return launch_sa_tc4(p, pl.smem, st);
     static const int coop_env = getenv("PN2_TC_COOP") ? atoi(getenv("PN2_TC_COOP")) : 1;
     if (coop_env && pl.U == 2 && (a.D == 0 || p.use_tma)) {
         cudaError_t e3 = cudaFuncSetAttribute(sa_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);

@@ -21,12 +21,12 @@
 //                      drift apart in phase by themselves, and the MMAs of one unit run underneath the CUDA-core
 //                      phases of the others.
 //
-// STATUS (round 1): correct (same parity tests as the default kernels, PN2_TC4=1) but NOT the default.  Measured on
-// B200, cls_ssg, B = 2048: sa1 3.6 ms against 1.46 ms for the unit kernel (a 16-column share per phase is all latency:
-// tcgen05.ld round trip + fences + arrive), sa2 3.8 ms against 2.76 ms for the cooperative kernel -- CTA 0 runs a tile
-// pair in 9.5-10.9 k cycles (cooperative: 11.7 k) but 10-20 % of the CTAs, different ones every launch, fall into a slow
-// mode (up to 1.6x) in which the two units run in phase; see profiles/README.md.  Kept as the test bed for the
-// producer / setmaxnreg machinery.
+// STATUS (round 1), cls_ssg at B = 2048 on B200: with the FIXED (layer, unit) schedule (default, PN2_TC4_STATIC=1: the
+// polling loops below block instead of moving on) this is the default for two-unit stacks -- sa2 2.68 ms against 2.79 ms
+// for the cooperative kernel with its TMA gather.  Four-unit stacks stay on the unit kernel (sa1: 3.6 ms here against
+// 1.46 ms; a 16-column share per phase is all latency).  With DYNAMIC polling (PN2_TC4_STATIC=0) CTA 0 runs an sa2 tile
+// pair in 9.5-10.9 k cycles, but 10-20 % of the CTAs, different ones every launch, fall into a slow mode (up to 1.6x)
+// with the two units in phase, and the launch takes 3.8 ms; see profiles/README.md.
 #include <stdlib.h>
 #include "pn2_sa_pipe.cuh"
 
@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(T4_THREADS, 1) sa_tc4_kernel(const __grid_cons
     auto n_it_of = [&](int u) -> int { const int t0 = first_tile + u; return t0 < tiles ? (tiles - t0 + stride - 1) / stride : 0; };
     const int K = p.K, C = p.C, D = p.D, S = p.S, N = p.N;
     const int logK = 31 - __clz(K);
+    const bool static_sched = p.lsu_gather != 0;      // (field reused as the schedule switch of this kernel)
 
     if (warp >= T4_MMA_WARP) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T4_REGS_MMA));
@@ -140,8 +141,13 @@ __global__ void __launch_bounds__(T4_THREADS, 1) sa_tc4_kernel(const __grid_cons
                 // layer 0 needs the gathered operand and (after the first tile) the previous tile's pool to have drained
                 // TMEM; layer l > 0 needs epilogue l-1.  full[u] cannot advance before this layer is issued, so probing
                 // it repeatedly without consuming it is safe.
-                if (l == 0 && !mbar_probe(full + u, (uint32_t)mit[u] & 1u, T4_POLL_NS)) continue;
-                if ((l > 0 || mit[u] > 0) && !mbar_probe(w_done + u, (wd_par >> u) & 1u, T4_POLL_NS)) continue;
+                if (static_sched) {          // fixed (layer, unit) order: block instead of moving on to the next unit
+                    if (l == 0) mbar_wait(full + u, (uint32_t)mit[u] & 1u);
+                    if (l > 0 || mit[u] > 0) mbar_wait(w_done + u, (wd_par >> u) & 1u);
+                } else {
+                    if (l == 0 && !mbar_probe(full + u, (uint32_t)mit[u] & 1u, T4_POLL_NS)) continue;
+                    if ((l > 0 || mit[u] > 0) && !mbar_probe(w_done + u, (wd_par >> u) & 1u, T4_POLL_NS)) continue;
+                }
                 if (l > 0 || mit[u] > 0) wd_par ^= 1u << u;
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(sm.A_base) + (uint32_t)(u * p.a_unit_bytes);
@@ -276,7 +282,8 @@ __global__ void __launch_bounds__(T4_THREADS, 1) sa_tc4_kernel(const __grid_cons
 #pragma unroll
             for (int u = 0; u < T2_MAX_UNITS; ++u) {
                 if (wit[u] >= nit[u]) continue;
-                if (!mbar_probe(acc_ready + u, (acc_par >> u) & 1u, T4_POLL_NS)) continue;
+                if (static_sched) mbar_wait(acc_ready + u, (acc_par >> u) & 1u);
+                else if (!mbar_probe(acc_ready + u, (acc_par >> u) & 1u, T4_POLL_NS)) continue;
                 acc_par ^= 1u << u;
                 tc_fence_after();
                 const int l = wl[u], it = wit[u];
@@ -335,8 +342,11 @@ __global__ void __launch_bounds__(T4_THREADS, 1) sa_tc4_kernel(const __grid_cons
     if (warp == T4_MMA_WARP) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
-int launch_sa_tc4(const Tc2Params &p, size_t smem, cudaStream_t st)
+int launch_sa_tc4(const Tc2Params &p_in, size_t smem, cudaStream_t st)
 {
+    Tc2Params p = p_in;
+    static const int static_env = getenv("PN2_TC4_STATIC") ? atoi(getenv("PN2_TC4_STATIC")) : 1;
+    p.lsu_gather = static_env;
     int64_t grid = (p.tiles + p.U - 1) / p.U;
     if (grid > 148) grid = 148;
     auto run = [&](auto kern) -> int {
