@@ -49,6 +49,10 @@ __global__ void __launch_bounds__(TMAX) fps_kernel(const float *__restrict__ poi
         dist[j + 1] = n1 < N ? 1e10f : 0.f;
     }
     int far = (int)min(max(start[b], (int64_t)0), (int64_t)N - 1);   // contract: start in [0,N); never index out of the cloud
+    // shared-memory addresses of the argmax slots, computed once (the compiler otherwise rebuilds them every iteration)
+    const uint32_t slot_wr = (uint32_t)__cvta_generic_to_shared(&s_slot[0][warp]);
+    const uint32_t slot_rd = (uint32_t)__cvta_generic_to_shared(&s_slot[0][lane < nwarps ? lane : 0]);
+    const bool slot_live = lane < nwarps;
     __syncthreads();
 
     for (int i = 0; i < S; ++i) {
@@ -101,9 +105,12 @@ __global__ void __launch_bounds__(TMAX) fps_kernel(const float *__restrict__ poi
         const unsigned bits = __float_as_uint(best);
         const unsigned wmax = redux_max(bits);
         const unsigned widx = redux_min(bits == wmax ? besti : 0xffffffffu);
-        if (lane == 0) s_slot[i & 1][warp] = make_uint2(wmax, widx);
+        const uint32_t par_off = (uint32_t)(i & 1) * (uint32_t)sizeof(s_slot[0]);
+        if (lane == 0) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(slot_wr + par_off), "r"(wmax), "r"(widx) : "memory");
         __syncthreads();
-        const uint2 sl = (lane < nwarps) ? s_slot[i & 1][lane] : make_uint2(0u, 0xffffffffu);
+        uint2 sl;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(sl.x), "=r"(sl.y) : "r"(slot_rd + par_off) : "memory");
+        if (!slot_live) sl = make_uint2(0u, 0xffffffffu);
         const unsigned gmax = redux_max(sl.x);
         far = (int)redux_min(sl.x == gmax ? sl.y : 0xffffffffu);
     }
