@@ -260,6 +260,9 @@ class Native:
             _need_cuda("feature", feature, torch.float32)
             D = feature.shape[-1]
             fptr, fstr = feature.data_ptr(), feature.stride()
+        elif feature_bf16 is not None:          # bf16 rows only (bf16 mode): strides of the contiguous [B,N,D] tensor
+            D = feature_bf16.shape[-1]
+            fstr = (N * D, D, 1)
         if order == ORDER_ALL:
             S, K = 1, N
             iptr = cptr = None

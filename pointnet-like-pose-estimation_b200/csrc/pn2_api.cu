@@ -127,7 +127,9 @@ int pn2_sa_fused(const float *points, int64_t sb, int64_t sn, int64_t sc,
     PN2_REQUIRE(order >= 0 && order <= 2, "pn2_sa_fused: bad order %d", order);
     PN2_REQUIRE(order == PN2_ORDER_ALL || (idx32 && centres), "pn2_sa_fused: idx/centres required");
     PN2_REQUIRE(order != PN2_ORDER_ALL || (S == 1 && K == N), "pn2_sa_fused: group_all needs S=1, K=N");
-    PN2_REQUIRE((D == 0) == (feat == nullptr), "pn2_sa_fused: feat pointer / D mismatch");
+    // features may be given as the bf16 side tensor alone (bf16 mode; the launcher refuses configurations whose kernel
+    // would need the fp32 rows)
+    PN2_REQUIRE((D == 0) == (feat == nullptr && !(prec == PN2_PREC_BF16 && feat_bf16)), "pn2_sa_fused: feat pointer / D mismatch");
     PN2_REQUIRE(dims[0] == C + D, "pn2_sa_fused: first layer expects %d channels, rows have %d (+%d)", dims[0], C, D);
     PN2_REQUIRE(B >= 0 && N >= 1 && S >= 1 && K >= 1 && C >= 1, "pn2_sa_fused: bad sizes");
     SaArgs a;

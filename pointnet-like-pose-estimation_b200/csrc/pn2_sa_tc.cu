@@ -511,6 +511,7 @@ int launch_sa_bf16(const SaArgs &a, cudaStream_t st)
         const int rc = launch_sa_bf16_pipelined(a, st);
         if (rc != -100) return rc;
     }
+    PN2_REQUIRE(a.D == 0 || a.feat, "pn2_sa_fused(bf16): this configuration needs the fp32 feature rows (bf16-only features are gathered by the pipelined kernels)");
     TcPlan pl;
     PN2_REQUIRE(tc_plan(a.K, a.L, a.dims, &pl), "pn2_sa_fused(bf16): layer widths do not fit shared memory");
     TcParams p;

@@ -646,6 +646,7 @@ int launch_sa_bf16_pipelined(const SaArgs &a, cudaStream_t st)
     // 0 = never, 1 = every stack it covers (four-unit stacks are slower on it: 3.6 ms against 1.46 ms for sa1)
     static const int tc4_env = getenv("PN2_TC4") ? atoi(getenv("PN2_TC4")) : -1;
     if ((tc4_env > 0 || (tc4_env < 0 && pl.U == 2)) && (a.D == 0 || (p.feat_bf16 && a.D % 64 == 0))) return launch_sa_tc4(p, pl.smem, st);
+    if (a.D > 0 && !a.feat && !p.use_tma) return -100;           // bf16-only features: the remaining kernels gather them by TMA
     static const int coop_env = getenv("PN2_TC_COOP") ? atoi(getenv("PN2_TC_COOP")) : 1;
     if (coop_env && pl.U == 2 && (a.D == 0 || p.use_tma)) {
         cudaError_t e3 = cudaFuncSetAttribute(sa_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);

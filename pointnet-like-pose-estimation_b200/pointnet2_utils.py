@@ -36,6 +36,7 @@ __all__ = ["square_distance", "index_points", "farthest_point_sample", "query_ba
 _native = None              # created on first use; tests may monkeypatch this attribute
 _precision = os.environ.get("PN2_PRECISION", "fp32")
 _reference_strides = False
+_factorise_first_layer = os.environ.get("PN2_FACTORISE", "1") != "0"     # see _FactorisedFirstLayer
 _start_source = None        # optional callable (B, N) -> int64 CPU tensor [B]; default = torch.randint
 
 
@@ -176,6 +177,47 @@ class _FoldedMLP:
         return self.packed, self.dims, prec
 
 
+class _FactorisedFirstLayer:
+    """Derived cache for the first-layer factorisation of an MSG branch (bf16 mode).
+
+    The first layer is linear in the concatenated row [feat[n], xyz[n] - centre] (:208-217), so its feature part does not
+    depend on the group a point was gathered into:
+        y0 = relu(s (Wf feat[n] + Wx (xyz[n] - c) + b - mu) + beta) = relu(P[n] + (s Wx)(xyz[n] - c) + b'),   P = feat (s Wf)^T
+    P is computed ONCE PER POINT (a plain library GEMM, bf16 inputs / fp32 accumulation like the fused kernel) instead of
+    once per grouped row, and the fused kernel gathers the N0-wide rows of P through an identity block in place of the
+    D-wide feature rows: for cls_msg's sa2 (D = 320, N0 = 64 / 128, K = 32 / 64 / 128 neighbours) the first layer's
+    work drops 16-64x, the stack's weights fit shared memory again (the pipelined kernel instead of the streaming one)
+    and the gather moves 2.5-5x fewer bytes.  Exactly the reference's arithmetic up to the extra bf16 rounding of P."""
+
+    def __init__(self):
+        self.key = None
+        self.packed = self.dims = self.wf = None
+
+    def get(self, convs, bns, C, D):
+        tensors = []
+        for conv, bn in zip(convs, bns):
+            tensors += [conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        key = (C, D, tuple((t.data_ptr(), t._version) for t in tensors))
+        if key != self.key:
+            conv0, bn0 = convs[0], bns[0]
+            n0 = conv0.out_channels
+            w0 = conv0.weight.detach().reshape(n0, D + C)                       # MSG channel order: [feat(D), xyz(C)]
+            scale = bn0.weight.detach() / torch.sqrt(bn0.running_var + bn0.eps)
+            bias = (conv0.bias.detach() - bn0.running_mean) * scale + bn0.bias.detach()
+            self.wf = (w0[:, :D] * scale[:, None]).to(torch.bfloat16).contiguous()    # [N0, D]
+            w_syn = torch.cat([torch.eye(n0, dtype=w0.dtype, device=w0.device), w0[:, D:] * scale[:, None]], dim=1)
+            one, zero = torch.ones_like(bias), torch.zeros_like(bias)
+            eps = bn0.eps
+            layers = [(w_syn.contiguous(), bias.contiguous(), one, zero, zero, one - eps)]     # folds to scale 1, bias `bias`
+            layers += [(conv.weight.detach().reshape(conv.out_channels, conv.in_channels), conv.bias.detach(),
+                        bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var)
+                       for conv, bn in zip(list(convs)[1:], list(bns)[1:])]
+            assert all(bn.eps == eps for bn in bns)
+            self.packed, self.dims = _backend().pack(layers, eps, PREC_BF16, C, ORDER_MSG)
+            self.key = key
+        return self.packed, self.dims, self.wf
+
+
 def _finish(new_points_bsc, pooled_bsc, pooled_bf16=None):
     new_points = new_points_bsc.permute(0, 2, 1)       # view of contiguous [B,S,C], like the reference (:173)
     new_feature = pooled_bsc.permute(0, 2, 1)
@@ -296,6 +338,17 @@ class PointNetSetAbstractionMsg(nn.Module):
             self.conv_blocks.append(convs)
             self.bn_blocks.append(bns)
         self._folded = [_FoldedMLP() for _ in mlp_list]
+        self._factorised = [_FactorisedFirstLayer() for _ in mlp_list]
+
+    def _use_factorised(self, i, K, C, D):
+        """bf16 mode, features wider than the branch's first layer, and the pipelined kernel covers the factorised stack."""
+        if _precision != "bf16" or not _factorise_first_layer or D == 0:
+            return False
+        n0 = self.conv_blocks[i][0].out_channels
+        if D <= n0 or n0 % 64 != 0:
+            return False
+        dims = [n0 + C] + [c.out_channels for c in self.conv_blocks[i]]
+        return bool(_backend().sa_bf16_side_io(K, C, ORDER_MSG, dims, PREC_BF16))
 
     def forward(self, points, feature):
         be = _backend()
@@ -307,10 +360,17 @@ class PointNetSetAbstractionMsg(nn.Module):
         if self.training:
             return self._forward_train(pts, feat, start)
         _, _, new_points = be.fps(pts, start, S, want_idx64=False, want_new_points=True)
-        plans = []
+        plans, fact = [], []
+        D = feat.shape[-1] if feat is not None else 0
         for i in range(len(self.radius_list)):
-            packed, dims, prec = self._folded[i].get(self.conv_blocks[i], self.bn_blocks[i], C, ORDER_MSG)
-            plans.append((packed, dims, prec))
+            if self._use_factorised(i, self.sample_number_list[i], C, D):
+                packed, dims, wf = self._factorised[i].get(self.conv_blocks[i], self.bn_blocks[i], C, D)
+                plans.append((packed, dims, PREC_BF16))
+                fact.append(wf)
+            else:
+                packed, dims, prec = self._folded[i].get(self.conv_blocks[i], self.bn_blocks[i], C, ORDER_MSG)
+                plans.append((packed, dims, prec))
+                fact.append(None)
         total = sum(d[-1] for _, d, _ in plans)
         zero = any(be.sa_needs_zero(S, K, d, prec) for K, (_, d, prec) in zip(self.sample_number_list, plans))
         pooled = (torch.zeros if zero else torch.empty)(B, S, total, dtype=torch.float32, device=pts.device)
@@ -319,10 +379,19 @@ class PointNetSetAbstractionMsg(nn.Module):
         # the bf16 twin of the concatenated output is only complete if every branch's kernel writes its slice
         twin_out = torch.empty(B, S, total, dtype=torch.bfloat16, device=pts.device) if all(sides) else None
         co = 0
-        for radius, K, (packed, dims, prec) in zip(self.radius_list, self.sample_number_list, plans):
+        feat_bf16 = None
+        for radius, K, (packed, dims, prec), wf in zip(self.radius_list, self.sample_number_list, plans, fact):
             _, idx32 = be.ball_query(new_points, pts, _radius_sq(radius), K, want_idx64=False, want_idx32=True)
-            be.sa_fused(pts, feat, new_points, idx32, ORDER_MSG, dims, packed, prec, pooled, co,   # branch concat (:222) is the channel offset
-                        feature_bf16=twin_in, out_bf16=twin_out)
+            if wf is not None:
+                # first layer factorised: P = feat (s Wf)^T once per point, gathered in place of the feature rows
+                if feat_bf16 is None:
+                    feat_bf16 = twin_in if twin_in is not None else feat.to(torch.bfloat16).contiguous()
+                p_rows = torch.matmul(feat_bf16, wf.t())                       # [B,N,N0] bf16, fp32 accumulation (cuBLAS)
+                be.sa_fused(pts, None, new_points, idx32, ORDER_MSG, dims, packed, prec, pooled, co,
+                            feature_bf16=p_rows, out_bf16=twin_out)
+            else:
+                be.sa_fused(pts, feat, new_points, idx32, ORDER_MSG, dims, packed, prec, pooled, co,   # branch concat (:222) is the channel offset
+                            feature_bf16=twin_in, out_bf16=twin_out)
             co += dims[-1]
         return _finish(new_points, pooled, twin_out)
 
