@@ -40,7 +40,7 @@ struct Tc2Params {
     const __nv_bfloat16 *feat_bf16; __nv_bfloat16 *out_bf16;
     unsigned long long *trace;   // debug timeline (pn2_debug_trace), CTA 0 only; nullptr = off
     int use_tma, feat_rows;      // bf16 features gathered by TMA (tile::gather4) through `tmap` = [feat_rows = B*N][D]
-    int lsu_gather;              // pn2_sa_tc4.cu: 1 = fixed (layer, unit) schedule, 0 = units polled dynamically
+    int static_sched;            // pn2_sa_tc4.cu: 1 = fixed (layer, unit) schedule, 0 = units polled dynamically
     alignas(64) CUtensorMap tmap;
 };
 

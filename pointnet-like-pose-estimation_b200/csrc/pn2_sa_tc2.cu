@@ -635,7 +635,7 @@ int launch_sa_bf16_pipelined(const SaArgs &a, cudaStream_t st)
     p.feat_bf16 = (a.feat_bf16 && p.feat_fast && a.D > 0 && ((uintptr_t)a.feat_bf16 & 15) == 0) ? (const __nv_bfloat16 *)a.feat_bf16 : nullptr;
     p.out_bf16 = (__nv_bfloat16 *)a.out_bf16;
     p.trace = g_trace;
-    p.use_tma = 0; p.feat_rows = a.B * a.N; p.lsu_gather = 0;
+    p.use_tma = 0; p.feat_rows = a.B * a.N; p.static_sched = 1;
     static const bool no_tma = getenv("PN2_NO_TMA_GATHER") != nullptr;
     if (p.feat_bf16 && a.D % 64 == 0 && (int64_t)a.B * a.N < (1ll << 31) - 1 && !no_tma) {
         if (make_row_gather_map(p.feat_bf16, (int64_t)a.B * a.N, a.D, &p.tmap) == 0) p.use_tma = 1;

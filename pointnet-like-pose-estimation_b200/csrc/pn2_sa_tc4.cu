@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(T4_THREADS, 1) sa_tc4_kernel(const __grid_cons
     auto n_it_of = [&](int u) -> int { const int t0 = first_tile + u; return t0 < tiles ? (tiles - t0 + stride - 1) / stride : 0; };
     const int K = p.K, C = p.C, D = p.D, S = p.S, N = p.N;
     const int logK = 31 - __clz(K);
-    const bool static_sched = p.lsu_gather != 0;      // (field reused as the schedule switch of this kernel)
+    const bool static_sched = p.static_sched != 0;
 
     if (warp >= T4_MMA_WARP) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T4_REGS_MMA));
@@ -346,7 +346,7 @@ int launch_sa_tc4(const Tc2Params &p_in, size_t smem, cudaStream_t st)
 {
     Tc2Params p = p_in;
     static const int static_env = getenv("PN2_TC4_STATIC") ? atoi(getenv("PN2_TC4_STATIC")) : 1;
-    p.lsu_gather = static_env;
+    p.static_sched = static_env;
     int64_t grid = (p.tiles + p.U - 1) / p.U;
     if (grid > 148) grid = 148;
     auto run = [&](auto kern) -> int {

@@ -282,3 +282,17 @@ def test_tma_gather4_matches_the_swizzled_operand_layout(nat):
             want_row = srcb[rows[r], col0 * 2: col0 * 2 + 128].view(8, 16) if rows[r] < R else torch.zeros(8, 16, dtype=torch.uint8)
             for j in range(8):
                 assert torch.equal(img[r, j ^ (r & 7)], want_row[j]), (col0, r, j)
+
+
+@pytest.mark.parametrize("env", [{"PN2_TC4": "0"}, {"PN2_TC4": "1", "PN2_TC4_STATIC": "0"}, {"PN2_TC4": "0", "PN2_TC_COOP": "0"},
+                                 {"PN2_FACTORISE": "0"}])
+def test_alternative_schedules_keep_parity(env):
+    """The kernel-selection switches are read once per process: run the bf16 parity cases in a child process with the
+    cooperative TMA kernel (PN2_TC4=0), the dynamically polled warp-specialised schedule, the unit kernel everywhere, and
+    the unfactorised MSG branches."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ, **env)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_kernels.py"), os.path.join(root, "tests", "test_gpu_models.py"),
+                        "-m", "gpu", "-q", "-x", "-k", "bf16 and not alternative"], env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
