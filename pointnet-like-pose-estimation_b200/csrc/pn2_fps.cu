@@ -9,6 +9,7 @@
 //
 // Exactness contract: d = sum_order_k( fl( fl(p_k - c_k)^2 ) ) with separately rounded sub, mul
 // and adds; dist = d if d < dist (NaN never replaces -> fminf); argmax with lowest index on ties.
+#include <stdlib.h>
 #include "pn2_common.cuh"
 
 namespace pn2 {
@@ -116,6 +117,158 @@ __global__ void __launch_bounds__(TMAX) fps_kernel(const float *__restrict__ poi
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Cluster variant: ONE CLOUD PER THREAD-BLOCK CLUSTER of FPS_CS CTAs, for few large clouds (BASELINE configs[2]: B = 16,
+// N = 8192 -> 2048: sixteen single CTAs would leave 132 SMs idle and spend 1650 cycles per iteration on 8 points per
+// thread).  Every CTA keeps the whole cloud in shared memory (centroid lookup) and 1/FPS_CS of the points + running
+// distances in registers.  Per iteration: local argmax as above, then each CTA's first FPS_CS threads store its (distance
+// bits, index) into the slot array of EVERY CTA of the cluster through distributed shared memory (st.shared::cluster,
+// double-buffered by iteration parity, tagged with the iteration number), every warp polls its own CTA's slots until all
+// FPS_CS carry the current tag and reduces them locally: same maximum, lowest index among equals, so the result is bit-identical to the one-CTA kernel.
+// ------------------------------------------------------------------------------------------------------
+constexpr int FPS_CS = 8;
+
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int C, int PPT, bool CONTIG>
+__global__ void __launch_bounds__(256) fps_cluster_kernel(const float *__restrict__ points, int64_t sb, int64_t sn, int64_t sc, int N,
+                                                          const int64_t *__restrict__ start, int S,
+                                                          int64_t *__restrict__ idx64, int32_t *__restrict__ idx32, float *__restrict__ new_points)
+{
+    extern __shared__ float s_pts[];            // [C][Nall]: the WHOLE cloud (Nall = FPS_CS * PPT * blockDim.x >= N)
+    __shared__ uint2 s_slot[2][32];             // per-warp (dist bits, index), double-buffered
+    __shared__ uint2 c_slot[2][FPS_CS];         // per-CTA results of the cluster, written by the peers
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+    unsigned rank;
+    asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int b = blockIdx.x / FPS_CS;
+    const int Nc = PPT * T, Nall = FPS_CS * Nc;
+    const float *P = points + (int64_t)b * sb;
+    static_assert(PPT % 2 == 0 && C <= 4, "two points per register pair; packed arithmetic needs C <= 4 on strided clouds");
+
+    for (int n = tid; n < Nall; n += T) {
+#pragma unroll
+        for (int k = 0; k < C; ++k) s_pts[k * Nall + n] = n < N ? __ldg(P + (int64_t)n * sn + (int64_t)k * sc) : 0.f;
+    }
+    __syncthreads();
+    const int base = (int)rank * Nc;            // this CTA's points: base + tid + j*T
+    f32x2 pp[PPT / 2][C];
+    float dist[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; j += 2) {
+        const int n0 = base + tid + j * T, n1 = n0 + T;
+#pragma unroll
+        for (int k = 0; k < C; ++k) pp[j / 2][k] = pk2(s_pts[k * Nall + n0], s_pts[k * Nall + n1]);
+        dist[j] = n0 < N ? 1e10f : 0.f;
+        dist[j + 1] = n1 < N ? 1e10f : 0.f;
+    }
+    int far = (int)min(max(start[b], (int64_t)0), (int64_t)N - 1);
+    const uint32_t slot_wr = (uint32_t)__cvta_generic_to_shared(&s_slot[0][warp]);
+    const uint32_t slot_rd = (uint32_t)__cvta_generic_to_shared(&s_slot[0][lane < nwarps ? lane : 0]);
+    const uint32_t cslot_rd = (uint32_t)__cvta_generic_to_shared(&c_slot[0][lane < FPS_CS ? lane : 0]);
+    uint32_t cslot_peer = 0;                    // address of c_slot[0][rank] inside CTA `tid` of the cluster (threads < FPS_CS)
+    if (tid < FPS_CS) {
+        const uint32_t mine = (uint32_t)__cvta_generic_to_shared(&c_slot[0][rank]);
+        asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(cslot_peer) : "r"(mine), "r"((uint32_t)tid));
+    }
+    if (tid < 2 * FPS_CS) (&c_slot[0][0])[tid] = make_uint2(0u, 0u);      // tag 0 = "no iteration yet"
+    cluster_sync_all();                         // every CTA of the cluster is resident (and its slots cleared) before anyone writes to a peer
+
+    for (int i = 0; i < S; ++i) {
+        float c[C];
+#pragma unroll
+        for (int k = 0; k < C; ++k) c[k] = s_pts[k * Nall + far];
+        if (rank == 0) {
+            if (tid == 0) {
+                if (idx64) idx64[(int64_t)b * S + i] = far;
+                if (idx32) idx32[(int64_t)b * S + i] = far;
+            }
+            if (new_points && tid < C) new_points[((int64_t)b * S + i) * C + tid] = s_pts[tid * Nall + far];
+        }
+        float best = -1.f;
+        unsigned besti = 0xffffffffu;
+        f32x2 nc[C];
+#pragma unroll
+        for (int k = 0; k < C; ++k) nc[k] = pk2(-c[k], -c[k]);
+#pragma unroll
+        for (int j = 0; j < PPT; j += 2) {
+            f32x2 t[C];
+#pragma unroll
+            for (int k = 0; k < C; ++k) {
+                const f32x2 df = add2(pp[j / 2][k], nc[k]);
+                t[k] = mul2(df, df);
+            }
+            const float2 d = unpk2(sum_order2<C, CONTIG>(t));
+            dist[j] = fminf(dist[j], d.x);
+            dist[j + 1] = fminf(dist[j + 1], d.y);
+            if (dist[j] > best) { best = dist[j]; besti = (unsigned)(base + tid + j * T); }
+            if (dist[j + 1] > best) { best = dist[j + 1]; besti = (unsigned)(base + tid + (j + 1) * T); }
+        }
+        const unsigned bits = __float_as_uint(best);
+        const unsigned wmax = redux_max(bits);
+        const unsigned widx = redux_min(bits == wmax ? besti : 0xffffffffu);
+        const uint32_t par_off = (uint32_t)(i & 1) * (uint32_t)sizeof(s_slot[0]);
+        if (lane == 0) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(slot_wr + par_off), "r"(wmax), "r"(widx) : "memory");
+        __syncthreads();
+        uint2 sl;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(sl.x), "=r"(sl.y) : "r"(slot_rd + par_off) : "memory");
+        if (lane >= nwarps) sl = make_uint2(0u, 0xffffffffu);
+        const unsigned cmax = redux_max(sl.x);
+        const unsigned cidx = redux_min(sl.x == cmax ? sl.y : 0xffffffffu);
+        // this CTA's result -> slot [parity][rank] of every CTA of the cluster (thread t writes to CTA t)
+        const uint32_t cpar = (uint32_t)(i & 1) * (uint32_t)sizeof(c_slot[0]);
+        // (no cluster barrier: ~1000 cycles.)  The 8-byte slot carries the iteration number in the index word's upper half;
+        // every warp polls its own CTA's slots until all FPS_CS of them show this iteration.  A slot of parity p is only
+        // rewritten two iterations later, which needs every CTA's result of the iteration in between, i.e. every CTA has
+        // finished reading this one.
+        const unsigned tag = ((unsigned)(i + 1) & 0xffffu) << 16;
+        if (tid < FPS_CS) asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(cslot_peer + cpar), "r"(cmax), "r"(cidx | tag) : "memory");
+        uint2 cl;
+        bool ok;
+        do {
+            asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cl.x), "=r"(cl.y) : "r"(cslot_rd + cpar) : "memory");
+            ok = (cl.y & 0xffff0000u) == tag;
+        } while (!__all_sync(0xffffffffu, ok));
+        cl.y &= 0xffffu;
+        if (lane >= FPS_CS) cl = make_uint2(0u, 0xffffffffu);
+        const unsigned gmax = redux_max(cl.x);
+        far = (int)redux_min(cl.x == gmax ? cl.y : 0xffffffffu);
+    }
+    cluster_sync_all();                         // no CTA may exit while a peer can still store into its slots
+}
+
+// returns -100 when the cluster variant does not apply
+template <int C>
+static int launch_fps_cluster(const float *points, int64_t sb, int64_t sn, int64_t sc, int B, int N,
+                              const int64_t *start, int S, int64_t *idx64, int32_t *idx32, float *new_points, cudaStream_t st)
+{
+    static const int env = getenv("PN2_FPS_CLUSTER") ? atoi(getenv("PN2_FPS_CLUSTER")) : 1;
+    // few, large clouds only: the cluster barrier costs more than it saves when a single CTA already has little to do
+    if (!env || N < 4096 || N > FPS_CS * 256 * 4 || (int64_t)B * FPS_CS > 2 * 148) return -100;
+    if (sc != 1 && (N & 31)) return -100;       // strided clouds with leftover points use the scalar order (single-CTA kernel)
+    const int threads = 256;
+    const int ppt = N <= FPS_CS * threads * 2 ? 2 : 4;
+    const size_t smem = sizeof(float) * (size_t)C * FPS_CS * ppt * threads;
+    auto run = [&](auto kern) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("fps(cluster): smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(B * FPS_CS)); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = FPS_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kern, points, sb, sn, sc, N, start, S, idx64, idx32, new_points);
+        if (e != cudaSuccess) { set_error("fps(cluster): launch: %s", cudaGetErrorString(e)); return (int)e; }
+        return launch_status("pn2_fps_f32(cluster)");
+    };
+    if (ppt == 2) return sc == 1 ? run(fps_cluster_kernel<C, 2, true>) : run(fps_cluster_kernel<C, 2, false>);
+    return sc == 1 ? run(fps_cluster_kernel<C, 4, true>) : run(fps_cluster_kernel<C, 4, false>);
+}
+
 // Generic fallback: any C <= PN2_MAX_COORD, any N whose distance array fits in shared memory; points are
 // re-read from global memory (L1/L2) every iteration.
 __global__ void fps_generic_kernel(const float *__restrict__ points, int64_t sb, int64_t sn, int64_t sc, int N, int C,
@@ -209,6 +362,8 @@ int launch_fps(const float *points, int64_t sb, int64_t sn, int64_t sc, int B, i
 {
     if (B == 0 || S == 0) return 0;
     int rc = -100;
+    if (C == 3) rc = launch_fps_cluster<3>(points, sb, sn, sc, B, N, start, S, idx64, idx32, new_points, st);
+    if (rc != -100) return rc;
     if (C == 3) rc = launch_fps_c<3>(points, sb, sn, sc, B, N, start, S, idx64, idx32, new_points, st);
     else if (C == 10) rc = launch_fps_c<10>(points, sb, sn, sc, B, N, start, S, idx64, idx32, new_points, st);
     if (rc != -100) return rc;
