@@ -14,8 +14,7 @@
 
 namespace pn2 {
 
-constexpr int BQ_WARPS = 8;
-constexpr int BQ_THREADS = BQ_WARPS * 32;
+constexpr int BQ_WARPS_SMALL = 8, BQ_WARPS_BIG = 32;     // warps per CTA; 32 when the staged cloud allows only one CTA per SM
 // centres scanned together by one warp (register budget: CPB * (2C + 2))
 template <int C> struct BQ_CPB { static constexpr int value = C <= 4 ? 4 : 2; };
 
@@ -52,13 +51,14 @@ __device__ __forceinline__ float pair_dist(const float (&s)[C], const float *sp,
 }
 
 // smem: [C+1][NCH] floats (coords SoA then |p|^2), then per-warp staging rows [BQ_WARPS][K] int
-template <int C>
-__global__ void __launch_bounds__(BQ_THREADS)
+template <int C, int BQ_WARPS>
+__global__ void __launch_bounds__(BQ_WARPS * 32)
 ball_query_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, int64_t csc,
                   const float *__restrict__ points, int64_t sb, int64_t sn, int64_t sc,
                   int S, int N, int NCH, int cpw /*centres per warp*/, float r2, int K,
                   int64_t *__restrict__ idx64, int32_t *__restrict__ idx32, int32_t *__restrict__ empty_flag)
 {
+    constexpr int BQ_THREADS = BQ_WARPS * 32;
     extern __shared__ float smem[];
     float *sp = smem;                       // [C][NCH]
     float *sp2 = smem + (size_t)C * NCH;    // [NCH]
@@ -241,8 +241,8 @@ __global__ void ball_query_generic_kernel(const float *__restrict__ centres, int
     }
 }
 
-template <int C>
-static int launch_bq_c(const float *centres, int64_t csb, int64_t csn, int64_t csc,
+template <int C, int BQ_WARPS>
+static int launch_bq_w(const float *centres, int64_t csb, int64_t csn, int64_t csc,
                        const float *points, int64_t sb, int64_t sn, int64_t sc,
                        int B, int S, int N, float r2, int K,
                        int64_t *idx64, int32_t *idx32, int32_t *empty_flag, cudaStream_t st)
@@ -257,17 +257,32 @@ static int launch_bq_c(const float *centres, int64_t csb, int64_t csn, int64_t c
         // enough CTAs for ~4 waves of 148 SMs, but amortise the staging of the cloud over >= 8 centres/warp
         cpw = 16;
         while (cpw > 1 && (int64_t)B * ((S + BQ_WARPS * cpw - 1) / (BQ_WARPS * cpw)) < 592) cpw >>= 1;
+        if (BQ_WARPS == BQ_WARPS_BIG && cpw < BQ_CPB<C>::value) cpw = BQ_CPB<C>::value;      // one CTA per SM: at least one full pass per warp
     }
     const size_t smem = (size_t)(C + 1) * NCH * sizeof(float) + stage_bytes;
-    auto kern = ball_query_kernel<C>;
+    auto kern = ball_query_kernel<C, BQ_WARPS>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("ball_query: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
     }
     dim3 grid((S + BQ_WARPS * cpw - 1) / (BQ_WARPS * cpw), B);
-    kern<<<grid, BQ_THREADS, smem, st>>>(centres, csb, csn, csc, points, sb, sn, sc, S, N, NCH, cpw, r2, K,
-                                         idx64, idx32, empty_flag);
+    kern<<<grid, BQ_WARPS * 32, smem, st>>>(centres, csb, csn, csc, points, sb, sn, sc, S, N, NCH, cpw, r2, K,
+                                            idx64, idx32, empty_flag);
     return launch_status("pn2_ball_query_f32");
+}
+
+template <int C>
+static int launch_bq_c(const float *centres, int64_t csb, int64_t csn, int64_t csc,
+                       const float *points, int64_t sb, int64_t sn, int64_t sc,
+                       int B, int S, int N, float r2, int K,
+                       int64_t *idx64, int32_t *idx32, int32_t *empty_flag, cudaStream_t st)
+{
+    // a staged cloud of more than ~100 KB leaves room for one CTA per SM: give it 32 warps instead of 8 (C <= 4 only: the
+    // C = 10 kernel needs more than the 64 registers a 1024-thread CTA can have)
+    const size_t cloud = (size_t)(C + 1) * ((N + 63) & ~63) * sizeof(float);
+    if (C <= 4 && cloud > 100 * 1024 && cloud + sizeof(int) * (size_t)BQ_WARPS_BIG * BQ_CPB<C>::value * K <= 200 * 1024)
+        return launch_bq_w<C, BQ_WARPS_BIG>(centres, csb, csn, csc, points, sb, sn, sc, B, S, N, r2, K, idx64, idx32, empty_flag, st);
+    return launch_bq_w<C, BQ_WARPS_SMALL>(centres, csb, csn, csc, points, sb, sn, sc, B, S, N, r2, K, idx64, idx32, empty_flag, st);
 }
 
 int launch_ball_query(const float *centres, int64_t csb, int64_t csn, int64_t csc,
