@@ -403,8 +403,29 @@ class PointNetSetAbstractionMsg(nn.Module):
         for i, radius in enumerate(self.radius_list):
             K = self.sample_number_list[i]
             _, idx32 = be.ball_query(new_points, pts.detach(), _radius_sq(radius), K, want_idx64=False, want_idx32=True)
-            rows = be.group(pts.detach(), None, idx32, new_points, ORDER_MSG)
+            rows = be.group(pts.detach(), None, idx32, new_points, ORDER_MSG)            # [B,S,K,C] xyz - centre
+            convs, bns = self.conv_blocks[i], self.bn_blocks[i]
+            if feat is not None and _factorise_first_layer and feat.shape[-1] > convs[0].out_channels:
+                outs.append(_msg_branch_train_factorised(rows, feat, idx32, convs, bns))
+                continue
             if feat is not None:
                 rows = torch.cat([_gather_rows(feat, idx32), rows], dim=-1)
-            outs.append(_shared_mlp_train(rows.permute(0, 3, 2, 1), self.conv_blocks[i], self.bn_blocks[i]))
+            outs.append(_shared_mlp_train(rows.permute(0, 3, 2, 1), convs, bns))
         return new_points.permute(0, 2, 1), torch.cat(outs, dim=1)
+
+
+def _msg_branch_train_factorised(rows_xyz, feat, idx32, convs, bns):
+    """Training-mode MSG branch with the first convolution factorised (see _FactorisedFirstLayer): the 1x1 convolution is
+    linear in [feat[n], xyz[n] - c], so its feature part is evaluated once per POINT and gathered, instead of gathering the
+    D-wide rows and convolving every grouped copy.  Same function as `_shared_mlp_train(cat([gather(feat), xyz]))` up to
+    fp32 reassociation (the sum is split in two); BatchNorm sees the same pre-activations, autograd the same graph
+    leaves.  The [B, D+C, K, S] tensor of the reference (:209) is never built."""
+    conv0, bn0 = convs[0], bns[0]
+    D = feat.shape[-1]
+    w = conv0.weight.reshape(conv0.out_channels, -1)                  # [N0, D + C], MSG order [feat, xyz] (:209)
+    p_rows = torch.matmul(feat, w[:, :D].t())                         # [B, N, N0] once per point
+    y = _gather_rows(p_rows, idx32) + torch.matmul(rows_xyz, w[:, D:].t()) + conv0.bias      # [B, S, K, N0]
+    x = F.relu(bn0(y.permute(0, 3, 2, 1)))
+    for conv, bn in zip(list(convs)[1:], list(bns)[1:]):
+        x = F.relu(bn(conv(x)))
+    return torch.max(x, 2)[0]

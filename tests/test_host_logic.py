@@ -169,3 +169,30 @@ def test_training_mode_runs_autograd_through_the_host_path(fake_native):
     f2.sum().backward()
     assert sa1.conv_blocks[0][0].weight.grad is not None and sa2.mlp_convs[0].weight.grad.abs().sum() > 0
     assert int(sa1.bn_blocks[0][0].num_batches_tracked) == 1
+
+
+def test_training_mode_factorised_msg_branch_matches_the_direct_form(fake_native):
+    """MSG training forward / backward with the first convolution factorised (feature part once per point) equals the
+    direct form (gather the D-wide rows, convolve every grouped copy) to fp32 rounding."""
+    import torch
+    pu = fake_native
+    torch.manual_seed(0)
+    mod = pu.PointNetSetAbstractionMsg(16, [4, 8], [0.4, 0.8], 24, [[8, 8, 16], [16, 16, 32]], num_category=0).train()
+    pts = (torch.rand(3, 3, 40) * 2 - 1)
+    feat = torch.randn(3, 24, 40, requires_grad=True)
+    outs, grads = [], []
+    for flag in (True, False):
+        pu._factorise_first_layer = flag
+        mod.zero_grad()
+        if feat.grad is not None:
+            feat.grad = None
+        torch.manual_seed(5)
+        _, f = mod(pts, feat)
+        f.square().sum().backward()
+        outs.append(f.detach().clone())
+        grads.append([p.grad.clone() for p in mod.parameters()] + [feat.grad.clone()])
+    pu._factorise_first_layer = True
+    assert float((outs[0] - outs[1]).abs().max() / outs[1].abs().max()) < 1e-5
+    scale = max(float(b.abs().max()) for b in grads[1])     # a convolution bias in front of BatchNorm has zero gradient: noise only
+    for a, b in zip(*grads):
+        assert float((a - b).abs().max()) / scale < 1e-5
