@@ -35,6 +35,11 @@ __global__ void __launch_bounds__(TMAX) fps_kernel(const float *__restrict__ poi
     static_assert(PPT % 2 == 0, "points are kept as register pairs");
     f32x2 pp[PPT / 2][C];                       // this thread's points (tid + j*T), two per 64-bit register
     float dist[PPT];
+    // The pose heads feed xyz + a one-hot category vector as "coordinates" (rotation_ssg.py:27, provider.py:166-180): the
+    // channels from 3 on are the same finite constants for every point of a cloud, so p_k - c_k = +0 exactly there and the
+    // squared distance is the three-channel one -- adding +0 terms changes no fp32 sum, and every summation order of
+    // DESIGN.md section 2 restricted to its non-zero terms is ((t0 + t1) + t2).  Detected per cloud, bit-identical.
+    bool tail_same = C > 4;
 #pragma unroll
     for (int j = 0; j < PPT; j += 2) {
         const int n0 = tid + j * T, n1 = n0 + T;
@@ -45,6 +50,11 @@ __global__ void __launch_bounds__(TMAX) fps_kernel(const float *__restrict__ poi
             pp[j / 2][k] = pk2(v0, v1);
             s_pts[k * Npad + n0] = v0;
             s_pts[k * Npad + n1] = v1;
+            if (C > 4 && k >= 3) {
+                const float ref = __ldg(P + (int64_t)k * sc);          // point 0
+                const bool fin = fabsf(ref) <= 3.0e38f;                 // finite: x - x = +0 (false for NaN / inf)
+                tail_same = tail_same && fin && (n0 >= N || v0 == ref) && (n1 >= N || v1 == ref);
+            }
         }
         dist[j] = n0 < N ? 1e10f : 0.f;         // padding can never win: dist 0 and index >= N
         dist[j + 1] = n1 < N ? 1e10f : 0.f;
@@ -54,7 +64,50 @@ __global__ void __launch_bounds__(TMAX) fps_kernel(const float *__restrict__ poi
     const uint32_t slot_wr = (uint32_t)__cvta_generic_to_shared(&s_slot[0][warp]);
     const uint32_t slot_rd = (uint32_t)__cvta_generic_to_shared(&s_slot[0][lane < nwarps ? lane : 0]);
     const bool slot_live = lane < nwarps;
-    __syncthreads();
+    const bool tail_uniform = __syncthreads_and(tail_same ? 1 : 0) != 0 && C > 4;
+
+    if (tail_uniform) {
+        // three-channel loop (see above); sequential sum = every layout's order restricted to the non-zero terms
+        constexpr int CE = C > 4 ? 3 : C;
+        for (int i = 0; i < S; ++i) {
+            f32x2 nc[CE];
+#pragma unroll
+            for (int k = 0; k < CE; ++k) { const float ck = s_pts[k * Npad + far]; nc[k] = pk2(-ck, -ck); }
+            if (tid == 0) {
+                if (idx64) idx64[(int64_t)b * S + i] = far;
+                if (idx32) idx32[(int64_t)b * S + i] = far;
+            }
+            if (new_points && tid < C) new_points[((int64_t)b * S + i) * C + tid] = s_pts[tid * Npad + far];
+            float best = -1.f;
+            unsigned besti = 0xffffffffu;
+#pragma unroll
+            for (int j = 0; j < PPT; j += 2) {
+                f32x2 t[CE];
+#pragma unroll
+                for (int k = 0; k < CE; ++k) {
+                    const f32x2 df = add2(pp[j / 2][k], nc[k]);
+                    t[k] = mul2(df, df);
+                }
+                const float2 d = unpk2(sum_order2<CE, false>(t));
+                dist[j] = fminf(dist[j], d.x);
+                dist[j + 1] = fminf(dist[j + 1], d.y);
+                if (dist[j] > best) { best = dist[j]; besti = (unsigned)(tid + j * T); }
+                if (dist[j + 1] > best) { best = dist[j + 1]; besti = (unsigned)(tid + (j + 1) * T); }
+            }
+            const unsigned bits = __float_as_uint(best);
+            const unsigned wmax = redux_max(bits);
+            const unsigned widx = redux_min(bits == wmax ? besti : 0xffffffffu);
+            const uint32_t par_off = (uint32_t)(i & 1) * (uint32_t)sizeof(s_slot[0]);
+            if (lane == 0) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(slot_wr + par_off), "r"(wmax), "r"(widx) : "memory");
+            __syncthreads();
+            uint2 sl;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(sl.x), "=r"(sl.y) : "r"(slot_rd + par_off) : "memory");
+            if (!slot_live) sl = make_uint2(0u, 0xffffffffu);
+            const unsigned gmax = redux_max(sl.x);
+            far = (int)redux_min(sl.x == gmax ? sl.y : 0xffffffffu);
+        }
+        return;
+    }
 
     for (int i = 0; i < S; ++i) {
         float c[C];

@@ -74,6 +74,9 @@ FPS_CASES = [  # (B, N, C, S, layout, kind)
     # about once in ten clouds (this is what catches a contracted multiply-add, see tools/probes/f32x2_contract.cu)
     (256, 1024, 3, 512, "strided", "uni"), (256, 1024, 3, 512, "contig", "uni"), (96, 1024, 10, 512, "strided", "uni"),
     (96, 512, 10, 128, "contig", "uni"),
+    # C = 10 without / with a broken constant tail: the general ten-channel loop, not the three-channel shortcut
+    (8, 1024, 10, 512, "strided", "mix"), (8, 512, 10, 128, "contig", "mix"), (8, 1024, 10, 512, "strided", "odd1"),
+    (8, 512, 10, 128, "contig", "odd1"),
 ]
 
 
@@ -83,6 +86,12 @@ def make_cloud(B, N, C, kind, seed):
         base = cloudgen.duplicate_heavy(base, 0.6, seed + 1)
     if C == 3:
         return base
+    if C == 10 and kind == "mix":          # ten genuinely varying coordinates (no one-hot tail)
+        return torch.cat([base, torch.rand(B, N, 7, generator=torch.Generator().manual_seed(seed + 3))], -1)
+    if C == 10 and kind == "odd1":         # one-hot tail except for ONE point of every cloud: the uniform-tail test must fail
+        x = cloudgen.with_category(base).clone()
+        x[:, N // 2, 5] += 0.25
+        return x
     if C == 10:
         return cloudgen.with_category(base)
     g = torch.Generator().manual_seed(seed + 2)
