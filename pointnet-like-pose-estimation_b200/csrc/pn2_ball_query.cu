@@ -87,12 +87,21 @@ ball_query_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, i
     for (int n_base = 0; n_base < N; n_base += NCH) {
         const int nc = min(NCH, N - n_base);
         if (n_base) __syncthreads();
+        // The pose heads' "coordinates" are xyz + a one-hot category vector (rotation_ssg.py:27): channels 3.. are the same
+        // finite constants e_k for every point (and centre) of the cloud, at most one of them non-zero.  The dot-product chain
+        // then continues past k = 2 with fma(e_k, e_k, dot): a no-op for e_k = 0, one fused add of e_k^2 for the non-zero one --
+        // no shared-memory reads, three channels of arithmetic, bit-identical.  |p|^2 and |s|^2 keep their full sums.
+        bool tail_same = C > 4 && single_chunk;
         for (int n = tid; n < nc; n += BQ_THREADS) {
             float v[C];
 #pragma unroll
             for (int k = 0; k < C; ++k) {
                 v[k] = __ldg(P + (int64_t)(n_base + n) * sn + (int64_t)k * sc);
                 sp[k * NCH + n] = v[k];
+                if (C > 4 && k >= 3) {
+                    const float ref = __ldg(P + (int64_t)k * sc);       // point 0
+                    tail_same = tail_same && fabsf(ref) <= 3.0e38f && v[k] == ref;
+                }
             }
             sp2[n] = sqnorm<C>(v, pcontig, n_base + n >= (N & ~31));
         }
@@ -105,7 +114,16 @@ ball_query_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, i
                 sp2[n] = INFINITY;
             }
         }
-        __syncthreads();
+        const bool tail_uniform = __syncthreads_and(tail_same ? 1 : 0) != 0 && C > 4;
+        // the tail's constants: usable by the short chain when at most one is non-zero
+        float e_nz = 0.f;
+        bool tail_short = tail_uniform;
+        if (C > 4 && tail_uniform) {
+            int nz = 0;
+#pragma unroll
+            for (int k = 3; k < C; ++k) { const float ek = sp[k * NCH]; if (ek != 0.f) { ++nz; e_nz = ek; } }
+            tail_short = nz <= 1;
+        }
 
         if (single_chunk) {
             // CPB centres per pass: every pair of points read from shared memory is tested against all of them
@@ -113,6 +131,7 @@ ball_query_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, i
             for (int ci = 0; ci < cpw; ci += CPB) {
                 f32x2 sv[CPB][C], s2v[CPB];
                 int cn[CPB];
+                bool grp_short = tail_short;
 #pragma unroll
                 for (int c = 0; c < CPB; ++c) {
                     const int sidx = s_begin + ci + c;
@@ -125,8 +144,45 @@ ball_query_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, i
                     for (int k = 0; k < C; ++k) sv[c][k] = pk2(sc_[k], sc_[k]);
                     s2v[c] = pk2(q2, q2);
                     cn[c] = act ? 0 : K;              // an inactive slot counts as finished
+                    if (C > 4 && act) {               // the centres must carry the cloud's tail as well (they do when they are its points)
+#pragma unroll
+                        for (int k = 3; k < C; ++k) grp_short = grp_short && sc_[k] == sp[k * NCH];
+                    }
                 }
                 const f32x2 m2v = pk2(-2.0f, -2.0f);
+                if (C > 4 && grp_short) {
+                    // ---- three channels from shared memory + one constant fused add (see the staging comment) ----------------
+                    const f32x2 ev = pk2(e_nz, e_nz);
+                    for (int n0 = 0; n0 < NCH; n0 += 64) {
+                        bool all_done = true;
+#pragma unroll
+                        for (int c = 0; c < CPB; ++c) all_done = all_done && cn[c] >= K;
+                        if (all_done) break;
+                        const int na = n0 + 2 * lane;
+                        f32x2 pv[3];
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) pv[k] = *reinterpret_cast<const f32x2 *>(sp + k * NCH + na);
+                        const f32x2 p2v = *reinterpret_cast<const f32x2 *>(sp2 + na);
+#pragma unroll
+                        for (int c = 0; c < CPB; ++c) {
+                            f32x2 dot = mul2(sv[c][0], pv[0]);
+                            dot = fma2(sv[c][1], pv[1], dot);
+                            dot = fma2(sv[c][2], pv[2], dot);
+                            if (e_nz != 0.f) dot = fma2(ev, ev, dot);
+                            const float2 d = unpk2(add2(add2(mul2(m2v, dot), s2v[c]), p2v));
+                            const bool ina = !(d.x > r2), inb = !(d.y > r2);
+                            const unsigned ma = __ballot_sync(0xffffffffu, ina);
+                            const unsigned mb = __ballot_sync(0xffffffffu, inb);
+                            if (ma | mb) {
+                                int *stg = stage + c * K;
+                                const int pa = cn[c] + __popc(ma & lt_mask) + __popc(mb & lt_mask);
+                                if (ina && pa < K) stg[pa] = na;
+                                if (inb && pa + (int)ina < K) stg[pa + (int)ina] = na + 1;
+                                cn[c] += __popc(ma) + __popc(mb);
+                            }
+                        }
+                    }
+                } else
                 for (int n0 = 0; n0 < NCH; n0 += 64) {
                     bool all_done = true;
 #pragma unroll

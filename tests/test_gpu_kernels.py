@@ -122,6 +122,10 @@ BQ_CASES = [  # (B, N, C, S, K, r, layout, kind)
     (1, 20000, 3, 64, 48, 0.1, "contig", "uni"), (1, 6000, 10, 70, 20, 0.3, "contig", "uni"),
     (2, 300, 5, 64, 7, 0.5, "contig", "uni"), (2, 300, 16, 64, 300, 5.0, "strided", "uni"),
     (2, 64, 3, 64, 64, 10.0, "contig", "uni"), (2, 500, 3, 37, 1, 0.05, "contig", "dup"),
+    # C = 10 whose tail is NOT one constant one-hot vector: the full ten-channel chain, not the three-channel shortcut
+    (4, 1024, 10, 512, 32, 0.9, "strided", "mix"), (4, 512, 10, 128, 64, 1.2, "contig", "mix"),
+    (4, 1024, 10, 512, 32, 0.2, "strided", "odd1"), (4, 512, 10, 128, 64, 0.4, "contig", "odd1"),
+    (24, 1024, 10, 512, 128, 0.4, "strided", "uni"), (24, 512, 10, 128, 32, 0.2, "contig", "uni"),
 ]
 
 
