@@ -347,6 +347,19 @@ def run_ours(args, rank, local_rank, world):
             ev1.record()
             torch.cuda.synchronize(dev)
             extra["b24_clouds_per_s"] = CPU_BATCH * 20 / (1e-3 * ev0.elapsed_time(ev1))
+            # the same 24-cloud forward replayed as one CUDA graph (pn2_graph.GraphedForward: launch latency removed,
+            # FPS start indices still drawn on the CPU generator per forward and uploaded by the graph's memcpy nodes)
+            import pn2_graph
+            g = pn2_graph.GraphedForward(model, xb)
+            for _ in range(5):
+                g(xb)
+            torch.cuda.synchronize(dev)
+            ev0.record()
+            for _ in range(20):
+                g(xb)
+            ev1.record()
+            torch.cuda.synchronize(dev)
+            extra["b24_graph_clouds_per_s"] = CPU_BATCH * 20 / (1e-3 * ev0.elapsed_time(ev1))
             other = "fp32" if args.precision == "bf16" else "bf16"
             pu.set_precision(other)
             with pu.fps_start_source(src):

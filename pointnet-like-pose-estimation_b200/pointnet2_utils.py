@@ -86,7 +86,7 @@ def _draw_start(B: int, N: int, device) -> torch.Tensor:
         start = _start_source(B, N)
     else:
         start = torch.randint(0, N, (B,), dtype=torch.long)
-    return start.to(device)
+    return start.to(device, non_blocking=start.is_pinned())     # pinned sources (pn2_graph.py) must not synchronise
 
 
 def _radius_sq(radius) -> float:

@@ -176,3 +176,35 @@ def test_training_mode_runs_and_backpropagates(pu):
     out.square().sum().backward()
     g = model.sa1.conv_blocks[0][0].weight.grad
     assert g is not None and torch.isfinite(g).all() and g.abs().sum() > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,prec", [("pointnet2_cls_ssg", "bf16"), ("rotation_msg", "bf16"), ("translation_ssg", "fp32")])
+def test_graphed_forward_replays_the_eager_sequence(pu, name, prec):
+    """pn2_graph.GraphedForward: a seeded sequence of graph replays equals the same sequence of eager forwards bit for bit
+    (same FPS draws from the CPU generator, same kernels)."""
+    import pn2_graph
+    import pn2_models
+    dev = "cuda:0"
+    torch.manual_seed(0)
+    model = pn2_models.get_model(name, 7)
+    pn2_models.randomize_bn_(model)
+    model = model.eval().to(dev)
+    xyz = cloudgen.uniform_cloud(24, 1024, 3)
+    pose = not name.startswith("pointnet2_cls")
+    x = cloudgen.channels_first(cloudgen.with_category(xyz) if pose else xyz).to(dev)
+    args = (x, xyz[:, :3, :].mean(1).to(dev)) if name.startswith("translation") else (x,)
+    prev = pu.get_precision()
+    pu.set_precision(prec)
+    try:
+        g = pn2_graph.GraphedForward(model, *args)
+        first = lambda o: (o[0] if isinstance(o, (tuple, list)) else o)
+        torch.manual_seed(11)
+        got = [first(g(*args)).clone() for _ in range(3)]
+        torch.manual_seed(11)
+        with torch.no_grad():
+            exp = [first(model(*args)).clone() for _ in range(3)]
+    finally:
+        pu.set_precision(prev)
+    assert all(torch.equal(a, b) for a, b in zip(got, exp))
+    assert not torch.equal(exp[0], exp[1])          # different draws per forward
