@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PN2_ABI_VERSION 5
+#define PN2_ABI_VERSION 6
 #define PN2_MAX_COORD 16 /* exact summation-order rules are verified against ATen for C <= 16 */
 #define PN2_MAX_LAYERS 8
 
@@ -113,6 +113,14 @@ int pn2_sa_fused(const float *points, int64_t sb, int64_t sn, int64_t sc,
                  int L, const int *dims, const void *packed, int prec,
                  float *out, int64_t ob, int64_t os, int co_off,
                  const void *feat_bf16, void *out_bf16, void *stream);
+
+/* Input preparation of the pose heads, fused -- provider.py:5-21 (normalization: subtract the centroid, divide by the
+ * largest norm, per cloud) followed by provider.py:166-180 (splice_torch: append the one-hot category vector) and the
+ * transpose of train_rotation.py:116.  xyz [B,N,3] with element strides; category[B] int64 (device) in [0,num_category);
+ * out [B, 3+num_category, N] contiguous = the tensor the models consume.  num_category = 0 gives plain normalisation.
+ * fp32 like the reference's numpy path; sums are tree reductions, so results agree to rounding (<= 1e-5 on coordinates in [-1, 1]), not bitwise. */
+int pn2_normalize_splice_f32(const float *xyz, int64_t sb, int64_t sn, int64_t sc, int B, int N,
+                             const int64_t *category, int num_category, float *out, void *stream);
 
 /* Device self-test of the tcgen05 building blocks (one 128xN tile against a scalar loop in the same
  * launch).  Returns 0 and writes max|err| to *max_err (device float). */

@@ -218,3 +218,30 @@ def set_abstraction_msg(points_bcn, feature_bdn, point_number, sample_number_lis
         outs.append(pooled.permute(0, 2, 1))
         gidxs.append(gidx)
     return new_points.permute(0, 2, 1), torch.cat(outs, 1), fps_idx, gidxs
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# input preparation (host-side numpy in the reference; provider.py cannot be imported here -- it imports open3d at :3)
+def normalization(point_cloud):
+    """provider.py:5-21, the same numpy operations in the same order (float32 in -> float64 container, like the reference)."""
+    import numpy as np
+    B, N, C = point_cloud.shape
+    normalize = np.zeros((B, N, C))
+    for i in range(B):
+        pc = point_cloud[i]
+        centroid = np.mean(pc, axis=0)
+        pc = pc - centroid
+        m = np.max(np.sqrt(np.sum(pc ** 2, axis=1)))
+        pc = pc / m
+        normalize[i] = pc
+    return normalize
+
+
+def splice_torch(point_cloud, category, num_category=7):
+    """provider.py:166-180."""
+    point_cloud = point_cloud.transpose(2, 1)
+    B, C, N = point_cloud.size()
+    class_vector = torch.zeros(B, num_category, N)
+    for i in range(B):
+        class_vector[i, category[i].item(), :] = 1
+    return torch.cat([point_cloud, class_vector], 1).transpose(2, 1)

@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(_HERE, LIB_NAME)
 ORDER_SSG, ORDER_MSG, ORDER_ALL = 0, 1, 2
 PREC_F32, PREC_BF16 = 0, 1
 MAX_COORD = 16
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _i64, _i32, _f32, _vp = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p
 
@@ -43,6 +43,7 @@ _SIGNATURES = {
     "pn2_sa_fused": ([_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _vp,
                       _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32,
                       _vp, _i64, _i64, _i32, _vp, _vp, _vp], _i32),
+    "pn2_normalize_splice_f32": ([_vp, _i64, _i64, _i64, _i32, _i32, _vp, _i32, _vp, _vp], _i32),
     "pn2_selftest_umma": ([_i32, _i32, _i32, _vp, _vp, _vp], _i32),
     "pn2_debug_trace": ([_vp], _i32),
     "pn2_selftest_tma_gather": ([_vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp], _i32),
@@ -286,6 +287,23 @@ class Native:
                                          out.data_ptr(), out.stride(0), out.stride(1), int(co_off),
                                          feature_bf16.data_ptr() if feature_bf16 is not None else None,
                                          out_bf16.data_ptr() if out_bf16 is not None else None, _stream(points)))
+        return out
+
+    def normalize_splice(self, xyz, category=None, num_category=0):
+        """provider.normalization + provider.splice_torch + transpose, fused: xyz [B,N,3] -> [B, 3+num_category, N]."""
+        _need_cuda("xyz", xyz, torch.float32)
+        B, N, C = xyz.shape
+        if C != 3:
+            raise ValueError("normalize_splice expects xyz [B,N,3]")
+        cptr = None
+        if num_category:
+            _need_cuda("category", category, torch.int64)
+            assert category.shape == (B,) and category.is_contiguous()
+            cptr = category.data_ptr()
+        out = torch.empty(B, 3 + num_category, N, dtype=torch.float32, device=xyz.device)
+        with torch.cuda.device(xyz.device), self._span("normalize_splice", B=B, N=N):
+            _check(self.lib.pn2_normalize_splice_f32(xyz.data_ptr(), *xyz.stride(), B, N, cptr, int(num_category),
+                                                     out.data_ptr(), _stream(xyz)))
         return out
 
     def selftest_umma(self, n_cols, k_dim, variant, device="cuda:0", dump=False):

@@ -147,6 +147,15 @@ int pn2_sa_fused(const float *points, int64_t sb, int64_t sn, int64_t sc,
     PN2_REQUIRE(false, "pn2_sa_fused: unknown precision %d", prec);
 }
 
+int pn2_normalize_splice_f32(const float *xyz, int64_t sb, int64_t sn, int64_t sc, int B, int N,
+                             const int64_t *category, int num_category, float *out, void *stream)
+{
+    PN2_REQUIRE(xyz && out, "pn2_normalize_splice_f32: null pointer");
+    PN2_REQUIRE(B >= 0 && N >= 1, "pn2_normalize_splice_f32: bad sizes B=%d N=%d", B, N);
+    PN2_REQUIRE(num_category >= 0 && num_category <= 1024 && (num_category == 0 || category), "pn2_normalize_splice_f32: bad category arguments");
+    return launch_normalize_splice(xyz, sb, sn, sc, B, N, category, num_category, out, (cudaStream_t)stream);
+}
+
 int pn2_selftest_tma_gather(const void *src_bf16, int64_t rows, int cols, const int32_t *rows4, int n_inst, int col0, void *out, void *stream)
 {
     return launch_selftest_tma_gather(src_bf16, rows, cols, rows4, n_inst, col0, out, (cudaStream_t)stream);

@@ -204,6 +204,8 @@ int launch_sa_bf16(const SaArgs &a, cudaStream_t st);
 int launch_sa_bf16_pipelined(const SaArgs &a, cudaStream_t st);   // -100: configuration not covered
 int sa_bf16_pipelined_covers(int K, int C, int D, int order, int L, const int *dims);
 void set_debug_trace(void *buf);
+int launch_normalize_splice(const float *xyz, int64_t sb, int64_t sn, int64_t sc, int B, int N,
+                            const int64_t *category, int num_category, float *out, cudaStream_t st);
 int make_row_gather_map(const void *base, int64_t rows, int cols, void *out_map);
 int launch_selftest_tma_gather(const void *src_bf16, int64_t rows, int cols, const int32_t *rows4, int n_inst, int col0, void *out, cudaStream_t st);
 int launch_selftest_umma(int n_cols, int k_dim, int variant, float *max_err, float *dump, cudaStream_t st);

@@ -81,4 +81,59 @@ int launch_group(const float *points, int64_t sb, int64_t sn, int64_t sc,
     return launch_status("pn2_group_f32");
 }
 
+// ---------------------------------------------------------------------------------------------------
+// provider.normalization (provider.py:5-21) + provider.splice_torch (:166-180) + transpose (train_rotation.py:116):
+// one CTA per cloud, three passes over the (L1/L2-resident) cloud: centroid, largest norm, write-out.
+__device__ __forceinline__ float block_sum(float v, float *scratch)
+{
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += scratch[w];
+    return t;
+}
+__global__ void __launch_bounds__(256) normalize_splice_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sn, int64_t sc, int N,
+                                                               const int64_t *__restrict__ category, int num_category, float *__restrict__ out)
+{
+    __shared__ float scratch[8];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float *P = xyz + (int64_t)b * sb;
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    for (int n = tid; n < N; n += blockDim.x) {
+        sx += __ldg(P + (int64_t)n * sn); sy += __ldg(P + (int64_t)n * sn + sc); sz += __ldg(P + (int64_t)n * sn + 2 * sc);
+    }
+    const float cx = __fdiv_rn(block_sum(sx, scratch), (float)N), cy = __fdiv_rn(block_sum(sy, scratch), (float)N),
+                cz = __fdiv_rn(block_sum(sz, scratch), (float)N);
+    float m2 = 0.f;
+    for (int n = tid; n < N; n += blockDim.x) {
+        const float x = __fsub_rn(__ldg(P + (int64_t)n * sn), cx), y = __fsub_rn(__ldg(P + (int64_t)n * sn + sc), cy),
+                    z = __fsub_rn(__ldg(P + (int64_t)n * sn + 2 * sc), cz);
+        m2 = fmaxf(m2, __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+    }
+    for (int o = 16; o; o >>= 1) m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+    __syncthreads();
+    if ((tid & 31) == 0) scratch[tid >> 5] = m2;
+    __syncthreads();
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m2 = fmaxf(m2, scratch[w]);
+    const float m = __fsqrt_rn(m2);                      // max of sqrt = sqrt of max (monotonic, correctly rounded)
+    const int Ct = 3 + num_category;
+    float *O = out + (int64_t)b * Ct * N;
+    const int cat = num_category ? (int)category[b] : -1;
+    for (int n = tid; n < N; n += blockDim.x) {
+        O[n] = __fdiv_rn(__fsub_rn(__ldg(P + (int64_t)n * sn), cx), m);
+        O[N + n] = __fdiv_rn(__fsub_rn(__ldg(P + (int64_t)n * sn + sc), cy), m);
+        O[2 * N + n] = __fdiv_rn(__fsub_rn(__ldg(P + (int64_t)n * sn + 2 * sc), cz), m);
+        for (int k = 0; k < num_category; ++k) O[(int64_t)(3 + k) * N + n] = (k == cat) ? 1.f : 0.f;
+    }
+}
+int launch_normalize_splice(const float *xyz, int64_t sb, int64_t sn, int64_t sc, int B, int N,
+                            const int64_t *category, int num_category, float *out, cudaStream_t st)
+{
+    if (B == 0) return 0;
+    normalize_splice_kernel<<<B, 256, 0, st>>>(xyz, sb, sn, sc, N, category, num_category, out);
+    return launch_status("pn2_normalize_splice_f32");
+}
+
 }  // namespace pn2
