@@ -169,7 +169,7 @@ ball_query_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, i
                             dot = fma2(sv[c][1], pv[1], dot);
                             dot = fma2(sv[c][2], pv[2], dot);
                             if (e_nz != 0.f) dot = fma2(ev, ev, dot);
-                            const float2 d = unpk2(add2(add2(mul2(m2v, dot), s2v[c]), p2v));
+                            const float2 d = unpk2(add2(fma2(m2v, dot, s2v[c]), p2v));   // fl(-2 dot + |s|^2): -2 dot is exact, one rounding either way
                             const bool ina = !(d.x > r2), inb = !(d.y > r2);
                             const unsigned ma = __ballot_sync(0xffffffffu, ina);
                             const unsigned mb = __ballot_sync(0xffffffffu, inb);
@@ -199,7 +199,7 @@ ball_query_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, i
                         f32x2 dot = mul2(sv[c][0], pv[0]);
 #pragma unroll
                         for (int k = 1; k < C; ++k) dot = fma2(sv[c][k], pv[k], dot);
-                        const float2 d = unpk2(add2(add2(mul2(m2v, dot), s2v[c]), p2v));
+                        const float2 d = unpk2(add2(fma2(m2v, dot, s2v[c]), p2v));   // fl(-2 dot + |s|^2): -2 dot is exact, one rounding either way
                         const bool ina = !(d.x > r2), inb = !(d.y > r2);
                         const unsigned ma = __ballot_sync(0xffffffffu, ina);
                         const unsigned mb = __ballot_sync(0xffffffffu, inb);
