@@ -275,6 +275,28 @@ def test_sa_fused_bf16_side_tensors(nat, oracle, K, order):
     assert rel_err(outs[0][0], exp) <= TOL_BF16
 
 
+@pytest.mark.parametrize("D,K,order,mlp", [(128, 64, 0, [128, 128, 256]), (192, 32, 1, [64, 64, 128]), (256, 64, 0, [64, 64, 128]),
+                                          (256, 16, 1, [32, 64]), (64, 128, 1, [128, 128, 256])])
+def test_sa_fused_bf16_rows_only(nat, oracle, D, K, order, mlp):
+    """Features given as the bf16 side tensor ALONE (no fp32 rows: the factorised MSG branches do this), several
+    64-channel blocks per row (the producer warps' batches), one and several hidden layers, two- and four-unit stacks."""
+    B, N, C, S, r = 3, 512, 3, 128, 0.7
+    x = make_cloud(B, N, C, "uni", 91)
+    f = torch.randn(B, N, D, generator=torch.Generator().manual_seed(16)).bfloat16()
+    dims = [C + D] + mlp
+    layers = rand_layers(dims, 17)
+    start = torch.randint(0, N, (B,), generator=torch.Generator().manual_seed(8), dtype=torch.long)
+    cen = oracle.index_points(x, oracle.farthest_point_sample(x, S, start)).contiguous()
+    idx = oracle.query_ball_point(r, K, x, cen)
+    assert nat.sa_bf16_side_io(K, C, order, dims, 1)
+    packed, _ = nat.pack([tuple(dev(t) for t in l) for l in layers], 1e-5, 1, C, order)
+    out = torch.full((B, S, mlp[-1]), -7.0, device="cuda:0")
+    nat.sa_fused(dev(x), None, dev(cen), dev(idx.int()), order, dims, packed, 1, out, 0, feature_bf16=f.cuda().contiguous())
+    rows = oracle.group(x, f.float(), idx, cen, order)
+    exp = oracle.mlp_max(rows.reshape(B * S, K, C + D), layers).reshape(B, S, -1)
+    assert rel_err(out.cpu(), exp) <= TOL_BF16
+
+
 def test_tma_gather4_matches_the_swizzled_operand_layout(nat):
     """cp.async.bulk.tensor tile::gather4 + 128-byte swizzle: 4 arbitrary rows -> 4 consecutive swizzled smem rows
     (chunk j of row r at r*128 + ((j ^ (r & 7)) << 4)); rows outside the tensor read as zeros."""
