@@ -397,6 +397,13 @@ static int launch_fps_c(const float *points, int64_t sb, int64_t sn, int64_t sc,
                         const int64_t *start, int S, int64_t *idx64, int32_t *idx32, float *new_points, cudaStream_t st)
 {
 #define PN2_FPS_GO(P, TM, T) return launch_fps_t<C, P, TM>(points, sb, sn, sc, B, N, T, start, S, idx64, idx32, new_points, st)
+    // Many clouds (the SMs are full either way): the kernel is issue-bound, and the per-warp cost of the argmax / barrier
+    // (~60 instructions per iteration) outweighs the arithmetic of 4 points per thread (~34): 8 points per thread and half
+    // the warps execute a third fewer instructions per cloud.  Few clouds stay latency-optimised (more threads).
+    if constexpr (C <= 4) {
+        if (B >= 4 * 148 && N > 256 && N <= 512)  PN2_FPS_GO(8, 512, 64);
+        if (B >= 4 * 148 && N > 512 && N <= 1024) PN2_FPS_GO(8, 512, 128);      // 0.78 -> 0.54 ms at B = 2048 (16 per thread: 0.58)
+    }
     if (N <= 128)  PN2_FPS_GO(2, 128, 64);
     if (N <= 256)  PN2_FPS_GO(2, 128, 128);
     if (N <= 512)  PN2_FPS_GO(4, 512, 128);

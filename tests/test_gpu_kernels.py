@@ -77,6 +77,8 @@ FPS_CASES = [  # (B, N, C, S, layout, kind)
     # C = 10 without / with a broken constant tail: the general ten-channel loop, not the three-channel shortcut
     (8, 1024, 10, 512, "strided", "mix"), (8, 512, 10, 128, "contig", "mix"), (8, 1024, 10, 512, "strided", "odd1"),
     (8, 512, 10, 128, "contig", "odd1"),
+    # >= 592 clouds: the issue-optimised launch shape (8 points per thread)
+    (600, 1024, 3, 512, "strided", "uni"), (600, 512, 3, 128, "contig", "uni"), (600, 1000, 3, 100, "contig", "dup"),
 ]
 
 
