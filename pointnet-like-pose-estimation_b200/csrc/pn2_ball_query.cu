@@ -182,8 +182,9 @@ ball_query_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, i
                             }
                         }
                     }
-                } else
-                for (int n0 = 0; n0 < NCH; n0 += 64) {
+                } else {
+                const float *prow = sp + 2 * lane;            // this lane's pair of points in channel 0; bumped by 64 per trip
+                for (int n0 = 0; n0 < NCH; n0 += 64, prow += 64) {
                     bool all_done = true;
 #pragma unroll
                     for (int c = 0; c < CPB; ++c) all_done = all_done && cn[c] >= K;
@@ -192,8 +193,8 @@ ball_query_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, i
                     const int na = n0 + 2 * lane;
                     f32x2 pv[C];
 #pragma unroll
-                    for (int k = 0; k < C; ++k) pv[k] = *reinterpret_cast<const f32x2 *>(sp + k * NCH + na);
-                    const f32x2 p2v = *reinterpret_cast<const f32x2 *>(sp2 + na);
+                    for (int k = 0; k < C; ++k) pv[k] = *reinterpret_cast<const f32x2 *>(prow + k * NCH);
+                    const f32x2 p2v = *reinterpret_cast<const f32x2 *>(prow + C * NCH);
 #pragma unroll
                     for (int c = 0; c < CPB; ++c) {
                         f32x2 dot = mul2(sv[c][0], pv[0]);
@@ -211,6 +212,7 @@ ball_query_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, i
                             cn[c] += __popc(ma) + __popc(mb);
                         }
                     }
+                }
                 }
                 __syncwarp();
 #pragma unroll
