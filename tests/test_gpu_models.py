@@ -208,3 +208,48 @@ def test_graphed_forward_replays_the_eager_sequence(pu, name, prec):
         pu.set_precision(prev)
     assert all(torch.equal(a, b) for a, b in zip(got, exp))
     assert not torch.equal(exp[0], exp[1])          # different draws per forward
+
+
+@pytest.mark.gpu
+def test_full_size_properties_of_the_bench_workload(pu):
+    """BASELINE-sized run (pointnet2_cls_ssg, B = 2048, N = 1024, bf16 mode) checked through size-independent properties:
+    FPS picks distinct in-range points starting at the drawn index; every ball-query row is ascending up to its padding,
+    padded with its first entry, and in radius; the forward is per-cloud independent (a slice of the batch gives bitwise
+    the same rows as the whole batch) and repeatable."""
+    import pn2_models
+    B, N = 2048, 1024
+    torch.manual_seed(0)
+    model = pn2_models.get_model("pointnet2_cls_ssg", 7)
+    pn2_models.randomize_bn_(model)
+    model = model.eval().to(DEV)
+    x = cloudgen.channels_first(cloudgen.uniform_cloud(B, N, 4242)).to(DEV)
+    be = pu._backend()
+    pts = x.permute(0, 2, 1)
+    start = torch.randint(0, N, (B,), generator=torch.Generator().manual_seed(9), dtype=torch.long).to(DEV)
+    idx, _, cen = be.fps(pts, start, 512, want_idx64=True, want_new_points=True)
+    assert torch.equal(idx[:, 0], start) and int(idx.min()) >= 0 and int(idx.max()) < N
+    assert int((idx.sort(dim=1).values.diff(dim=1) == 0).sum()) == 0                      # distinct points -> distinct picks
+    assert torch.equal(cen, torch.gather(pts, 1, idx[..., None].expand(-1, -1, 3)))
+    K, r = 32, 0.2
+    ball, _ = be.ball_query(cen, pts, pu._radius_sq(r), K, want_idx64=True)
+    assert int(ball.min()) >= 0 and int(ball.max()) < N
+    first = ball[:, :, :1]
+    pad = ball == first
+    pad[:, :, 0] = False
+    inc = ball.diff(dim=2) > 0
+    # a row is strictly ascending until the first padded slot, padded (= first entry) from there on
+    n_real = K - pad.sum(dim=2)
+    pos = torch.arange(K, device=DEV)
+    assert bool(((pos[None, None, 1:] < n_real[..., None]) <= inc).all()) and bool(((pos[None, None, :] >= n_real[..., None]) <= (pad | (pos == 0))).all())
+    d2 = (torch.gather(pts, 1, ball.reshape(B, -1, 1).expand(-1, -1, 3)).view(B, 512, K, 3).double() - cen[:, :, None, :].double()).square().sum(-1)
+    assert float(d2.max()) <= r * r * (1 + 1e-5)                                          # fp32 rounding of the expanded form
+    pu.set_precision("bf16")
+    with torch.no_grad(), pu.fps_start_source(lambda B_, N_: start[:B_] % N_):
+        whole = model(x)[0]
+    with torch.no_grad(), pu.fps_start_source(lambda B_, N_: start[:B_] % N_):
+        again = model(x)[0]
+    with torch.no_grad(), pu.fps_start_source(lambda B_, N_: start[:B_] % N_):
+        part = model(x[:160])[0]
+    assert torch.isfinite(whole).all() and torch.equal(whole, again)
+    # the set-abstraction path is per cloud; the FC head behind it is a library GEMM whose blocking depends on the batch size
+    assert torch.allclose(part, whole[:160], rtol=1e-4, atol=1e-5)
