@@ -12,14 +12,14 @@
 //                      in fence.proxy.async (a MEMBAR that waits for the thread's loads in flight); TMA gather4 was
 //                      measured at ~4000 cycles per 32 KB tile (latency-bound inside the TMA unit), the load/store
 //                      path lands a tile in ~1000.
-//   1 MMA warp         polls the units; whenever a unit's next layer has its operand (full[u] / w_done[u]) it issues
-//                      the layer (one elected lane, descriptors on the uniform datapath) and commits to acc_ready[u]
-//                      (+ buf_free[u] after the last layer).
-//   16 worker warps    warp (q, hb) covers TMEM lane quarter q and column share hb of EVERY tile: it polls the
-//                      units' acc_ready barriers and runs its share of whichever epilogue / pooling phase is ready,
-//                      then arrives on w_done[u].  A phase is 4x shorter than with one warpgroup per tile, the units
-//                      drift apart in phase by themselves, and the MMAs of one unit run underneath the CUDA-core
-//                      phases of the others.
+//   1 MMA warp         walks the (layer, unit) schedule; when a unit's next layer has its operand (full[u] / w_done[u]) it
+//                      issues the layer (one elected lane, descriptors on the uniform datapath) and commits to
+//                      acc_ready[u] (+ buf_free[u] after the last layer).
+//   16 worker warps    warp (q, hb) covers TMEM lane quarter q and column share hb of EVERY tile: it waits on the units'
+//                      acc_ready barriers in the same order and runs its share of the epilogue / pooling phase, then
+//                      arrives on w_done[u].  A phase is 4x shorter than with one warpgroup per tile and the MMAs of one
+//                      unit run underneath the CUDA-core phases of the other.  (Both loops can also POLL the units and
+//                      take whichever is ready, PN2_TC4_STATIC=0; see the status note.)
 //
 // STATUS (round 1), cls_ssg at B = 2048 on B200: with the FIXED (layer, unit) schedule (default, PN2_TC4_STATIC=1: the
 // polling loops below block instead of moving on) this is the default for two-unit stacks -- sa2 2.68 ms against 2.79 ms
@@ -39,7 +39,7 @@ constexpr int T4_MMA_WARP = T4_WORKERS + T4_PRODUCERS;    // warp 20
 constexpr int T4_THREADS = 24 * 32;                       // 768 threads: 80 registers per thread at launch
 constexpr int T4_REGS_PRODUCER = 120, T4_REGS_MMA = 40;   // producers +40 x 128 threads, MMA warpgroup -40 x 128
 constexpr uint32_t T4_POLL_NS = 20;
-constexpr bool T4_POOL_PAIR = false;                 // 21 warps leave 80 registers per thread: one tcgen05.ld in flight in the pool
+constexpr bool T4_POOL_PAIR = false;                      // workers stay at the launch allocation of 80 registers: one tcgen05.ld in flight in the pool
 
 __device__ __forceinline__ void sts_relu8(uint32_t addr, const uint32_t *r)
 {
