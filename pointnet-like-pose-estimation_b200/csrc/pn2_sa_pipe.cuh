@@ -147,6 +147,7 @@ struct PoolOut {
     int64_t os, ob;
     int S, gg, G;
     float bv; bool c_ok, all_valid, has_bf, contig;      // contig: ob == S * os, group g lives at g * os
+    bool use_atomic = false;                             // a tile is only part of its group (K > 128): combine with atomicMax
     // group finished: max over its rows -> + bias -> ReLU -> [B,S,Ctot]; then step to the next group
     __device__ __forceinline__ void emit(float m)
     {
@@ -155,7 +156,8 @@ struct PoolOut {
             int64_t off;
             if (contig) off = (int64_t)gg * os;
             else { const int b = (int)((unsigned)gg / (unsigned)S); off = (int64_t)b * ob + (int64_t)(gg - b * S) * os; }
-            po[off] = y;
+            if (use_atomic) atomicMax(reinterpret_cast<int *>(po + off), __float_as_int(y));      // y >= 0: int order = float order
+            else po[off] = y;
             if (has_bf) pb[off] = __float2bfloat16_rn(y);
         }
         ++gg;

@@ -17,7 +17,7 @@
 // LBO bytes.  For A, LBO = 128*16: a k-group column holds the 128 rows back to back, so a warp that writes
 // 32 consecutive rows of one k-group (gather and epilogue both do) stores 512 contiguous bytes.
 #include <stdlib.h>
-#include "pn2_tc.cuh"
+#include "pn2_sa_pipe.cuh"
 
 namespace pn2 {
 
@@ -122,6 +122,7 @@ struct TcParams {
     int64_t n_iter;    // tile-loop trips, identical for every CTA (a CTA without a tile still takes part in the ring)
     int a_bytes[2];    // activation buffers (a_bytes[1] == 0: one buffer, each layer's epilogue overwrites its own input)
     int pool_cols;     // columns of the cross-warp pooling scratch (0 if direct)
+    int pipelined_last;   // last layer transposed + pipelined over 128-column TMEM buffers (needs 128-channel slabs)
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
@@ -139,7 +140,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
     uint64_t *empty_bar = full_bar + TC_MAX_STAGES;
     uint64_t *acc_bar = empty_bar + TC_MAX_STAGES;
     uint64_t *slot_free = acc_bar + 1;      // in cluster rank 0: every CTA of the cluster has released ring slot s
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(slot_free + TC_MAX_STAGES);
+    uint64_t *acc_full = slot_free + TC_MAX_STAGES;     // last layer, per 128-column TMEM buffer: slab's MMAs retired
+    uint64_t *acc_empty = acc_full + 4;                  // ... and its pooling done (4 warp arrivals)
+    uint32_t *vm_s = reinterpret_cast<uint32_t *>(acc_empty + 4);       // valid-row ballots of the tile
+    uint32_t *tmem_slot = vm_s + 4;
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform for the compiler (MMA descriptors on the uniform datapath)
@@ -148,6 +152,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
     if (tid == 0) {
         for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); mbar_init(slot_free + s, (uint32_t)p.cs); }
         mbar_init(acc_bar, 1);
+        for (int i = 0; i < 4; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -226,7 +231,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
         const int half = warp >> 2;         // which 32-column blocks of a round this warp drains
         const int row = q4 * 32 + lane;     // the tile row (= TMEM lane) this thread owns in the epilogue
         const int K = p.K, C = p.C, D = p.D;
-        uint32_t acc_phase = 0, wq = 0;
+        uint32_t acc_phase = 0, wq = 0, gsl = 0;      // gsl: last-layer slabs issued / pooled so far (TMEM buffer ring position)
         if (p.resident && warp == 0) mbar_wait(full_bar, 0);
 
         for (int64_t it = 0; it < p.n_iter; ++it) {
@@ -313,6 +318,82 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
                 unsigned char *a_out = A[(l + 1) & 1];
                 const int slabs_per_round = p.tmem_cols / ly.NS;
                 const uint32_t idesc = instr_desc_bf16(ly.NS);
+                if (last && p.pipelined_last) {
+                    // ---- last layer, TRANSPOSED and PIPELINED (128-channel slabs): D^T[channel][row] = W slab (M operand)
+                    //      x X^T (the tile's 128 rows as N).  Warp 0 issues slab after slab into a ring of 128-column
+                    //      TMEM buffers as the weight chunks arrive; warps 4-7 (one per lane quarter = 32 channels) pool
+                    //      a finished slab in registers (max over the rows = TMEM columns, FMNMX3 tree, no shuffles) while
+                    //      the next slabs' MMAs run; warps 1-3 rest.  (The non-pipelined form below issues a round of
+                    //      slabs, waits, and reduces over rows with warp shuffles, all warps in lock step.) ------------
+                    const int nbuf = p.tmem_cols / TC_ROWS;
+                    tc_fence_before();
+                    cbar_sync();                                   // the layer's A operand is complete
+                    if (warp == 0) {
+                        tc_fence_after();
+                        for (int sl = 0; sl < ly.nslab; ++sl, ++gsl) {
+                            const int buf = (int)(gsl % (uint32_t)nbuf);
+                            const uint32_t use = gsl / (uint32_t)nbuf;
+                            if (use > 0) { mbar_wait(acc_empty + buf, (use - 1u) & 1u); tc_fence_after(); }
+                            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * TC_ROWS);
+                            for (int kb = 0; kb < ly.nkb; ++kb) {
+                                uint32_t w_addr;
+                                int s = 0;
+                                if (p.resident) {
+                                    w_addr = smem_u32(Wsm) + (uint32_t)(ly.w_off + sl * ly.NS * ly.K * 2 + kb * ly.NS * KBLK * 2);
+                                } else {
+                                    s = wq % p.nstage;
+                                    mbar_wait(full_bar + s, (wq / p.nstage) & 1u);
+                                    tc_fence_after();
+                                    w_addr = smem_u32(Wsm) + (uint32_t)(s * p.stage_bytes);
+                                    ++wq;
+                                }
+                                const int kw = min(KBLK, ly.K - kb * KBLK);
+                                const uint32_t a_lo = desc_lo_ns(a_in + (uint32_t)(kb * 8 * A_LBO), A_LBO);
+                                const uint32_t b_lo = desc_lo_ns(w_addr, (uint32_t)(ly.NS * 16));
+                                if (elect_one()) {
+                                    for (int j = 0; j < kw / 16; ++j)      // weights as the M operand, activations as N
+                                        umma_bf16(d_tmem, mk_desc64(b_lo + (uint32_t)(j * 2 * ly.NS), DESC_HI_NS),
+                                                  mk_desc64(a_lo + (uint32_t)(j * 2 * A_LBO / 16), DESC_HI_NS), idesc, (kb | j) ? 1u : 0u);
+                                    if (!p.resident) umma_commit(empty_bar + s);
+                                }
+                                __syncwarp();
+                            }
+                            if (elect_one()) umma_commit(acc_full + buf);
+                            __syncwarp();
+                        }
+                    } else if (warp >= 4) {
+                        // valid-row ballots of the tile (rows without a neighbour pool as -inf), shared by the four pooling warps
+                        const unsigned vmw = __ballot_sync(0xffffffffu, s_n[q4 * 32 + lane] >= 0);
+                        if (lane == 0) vm_s[q4] = vmw;
+                        asm volatile("bar.sync 2, 128;" ::: "memory");
+                        PoolOut o;
+                        o.all_valid = (vm_s[0] & vm_s[1] & vm_s[2] & vm_s[3]) == 0xffffffffu;
+                        o.has_bf = false; o.pb = nullptr;
+                        o.use_atomic = p.use_atomic != 0;
+                        o.os = p.os; o.ob = p.ob; o.contig = p.ob == (int64_t)p.S * p.os; o.S = p.S; o.G = (int)p.G;
+                        const int logKe = 31 - __clz(TC_ROWS / p.gpt);      // rows per group inside a tile
+                        const int g_first = (int)(p.cpg == 1 ? tile * p.gpt : tile / p.cpg);
+                        const bool tile_ok = tile < p.tiles;
+                        for (int sl = 0; sl < ly.nslab; ++sl, ++gsl) {
+                            const int buf = (int)(gsl % (uint32_t)nbuf);
+                            const uint32_t use = gsl / (uint32_t)nbuf;
+                            mbar_wait(acc_full + buf, use & 1u);
+                            tc_fence_after();
+                            const int c = sl * TC_ROWS + row;
+                            o.bv = bias_s[ly.b_off + c];
+                            o.c_ok = tile_ok && c < ly.Cout;
+                            o.po = p.out + p.co_off + c;
+                            o.gg = g_first;
+                            pool_slice_any<false>(logKe, tmem_base + (uint32_t)(buf * TC_ROWS) + ((uint32_t)(q4 * 32) << 16), 0, 4, vm_s, o);
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(acc_empty + buf);
+                        }
+                    } else {
+                        gsl += (uint32_t)ly.nslab;                 // warps 1-3: keep the slab counter in step
+                    }
+                    continue;
+                }
                 for (int sl0 = 0; sl0 < ly.nslab; sl0 += slabs_per_round) {
                     const int sl1 = min(ly.nslab, sl0 + slabs_per_round);
                     tc_fence_before();
@@ -457,7 +538,7 @@ static bool tc_plan(int K, int L, const int *dims, TcPlan *pl)
     else if (K <= TC_ROWS)     { pl->gpt = 1; pl->cpg = 1; pl->Kl = 32; pl->direct = 0; pl->use_atomic = 0; }
     else                       { pl->gpt = 1; pl->cpg = (K + TC_ROWS - 1) / TC_ROWS; pl->Kl = 32; pl->direct = 0; pl->use_atomic = 1; }
     const int last_npad = t.ly[L - 1].Npad;
-    const size_t misc = (size_t)t.bias_floats * 4 + 2 * TC_ROWS * 4 + (3 * TC_MAX_STAGES + 1) * 8 + 16;
+    const size_t misc = (size_t)t.bias_floats * 4 + 2 * TC_ROWS * 4 + (3 * TC_MAX_STAGES + 1 + 8) * 8 + 16 + 16;
     // Candidates: two CTAs per SM with 256 TMEM columns each (one CTA's epilogue overlaps the other's MMAs),
     // or one CTA per SM with all 512 columns.  Weights stay resident in shared memory when they fit, else
     // they stream through an mbarrier ring.  Preference: resident x2, resident x1, ring x2, ring x1.
@@ -529,6 +610,8 @@ int launch_sa_bf16(const SaArgs &a, cudaStream_t st)
     p.feat_fast = (a.D == 0) || (a.fc == 1 && a.D % 8 == 0 && a.fn % 4 == 0 && a.fb % 4 == 0 && ((uintptr_t)a.feat & 15) == 0);
     p.tmem_cols = pl.tmem_cols; p.resident = pl.resident; p.nstage = pl.nstage; p.stage_bytes = pl.stage_bytes;
     p.a_bytes[0] = pl.a_bytes[0]; p.a_bytes[1] = pl.a_bytes[1]; p.pool_cols = pl.pool_cols;
+    static const int pipe_env = getenv("PN2_RING_PIPELINED") ? atoi(getenv("PN2_RING_PIPELINED")) : 1;
+    p.pipelined_last = (pipe_env && pl.lay.ly[a.L - 1].NS == TC_ROWS && pl.tmem_cols >= 2 * TC_ROWS && TC_ROWS / pl.gpt >= 8) ? 1 : 0;
     if (p.tiles == 0) return 0;
     cudaError_t e = cudaFuncSetAttribute(sa_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) { set_error("sa_tc: smem attribute (%zu B): %s", pl.smem, cudaGetErrorString(e)); return (int)e; }
