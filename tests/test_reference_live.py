@@ -98,3 +98,43 @@ def import_reference_utils():
         _ref_utils = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(_ref_utils)
     return _ref_utils
+
+
+@pytest.mark.parametrize("kind", ["ssg", "msg", "all"])
+def test_training_mode_matches_the_reference_modules(fake_native, kind):
+    """Training mode (batch-statistics BatchNorm, autograd): our modules -- sampling / grouping through the native layer,
+    MLP on ATen, MSG branches with the factorised first convolution -- against the reference's own modules with the same
+    parameters, inputs and FPS draws: outputs, parameter gradients, feature gradients and running statistics."""
+    pu = fake_native
+    ref = import_reference_utils()
+    torch.manual_seed(3)
+    if kind == "ssg":
+        mk = lambda m: m.PointNetSetAbstraction(24, 8, 0.6, 20 + 3, [16, 16, 32], False)
+    elif kind == "msg":
+        mk = lambda m: m.PointNetSetAbstractionMsg(24, [4, 8], [0.4, 0.8], 20, [[8, 8, 16], [16, 16, 32]], num_category=0)
+    else:
+        mk = lambda m: m.PointNetSetAbstraction(None, None, None, 20 + 3, [16, 32], True)
+    torch.manual_seed(1)
+    ours = mk(pu).train()
+    torch.manual_seed(1)
+    theirs = mk(ref).train()
+    theirs.load_state_dict(ours.state_dict())
+    g = torch.Generator().manual_seed(9)
+    pts = torch.rand(3, 3, 60, generator=g) * 2 - 1
+    fa = torch.randn(3, 20, 60, generator=g, requires_grad=True)
+    fb = fa.detach().clone().requires_grad_(True)
+    torch.manual_seed(77)
+    pa, ya = ours(pts, fa)
+    torch.manual_seed(77)
+    pb, yb = theirs(pts, fb)
+    assert torch.equal(pa, pb) and ya.shape == yb.shape
+    assert float((ya - yb).abs().max() / yb.abs().max()) < 1e-5
+    w = torch.randn(ya.shape, generator=g)
+    (ya * w).sum().backward()
+    (yb * w).sum().backward()
+    scale = max(float(p.grad.abs().max()) for p in theirs.parameters())
+    for (na, a), (nb, b) in zip(ours.named_parameters(), theirs.named_parameters()):
+        assert na == nb and float((a.grad - b.grad).abs().max()) / scale < 1e-5, na
+    assert float((fa.grad - fb.grad).abs().max() / fb.grad.abs().max()) < 1e-5
+    for (na, a), (nb, b) in zip(ours.named_buffers(), theirs.named_buffers()):
+        assert na == nb and torch.allclose(a.float(), b.float(), rtol=1e-5, atol=1e-6), na      # running statistics
