@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PN2_ABI_VERSION 6
+#define PN2_ABI_VERSION 7
 #define PN2_MAX_COORD 16 /* exact summation-order rules are verified against ATen for C <= 16 */
 #define PN2_MAX_LAYERS 8
 
@@ -121,6 +121,20 @@ int pn2_sa_fused(const float *points, int64_t sb, int64_t sn, int64_t sc,
  * fp32 like the reference's numpy path; sums are tree reductions, so results agree to rounding (<= 1e-5 on coordinates in [-1, 1]), not bitwise. */
 int pn2_normalize_splice_f32(const float *xyz, int64_t sb, int64_t sn, int64_t sc, int B, int N,
                              const int64_t *category, int num_category, float *out, void *stream);
+
+/* The reference's numpy copies of farthest point sampling -- provider.py:183-204, data_utils/ModelDataLoader.py:10-31,
+ * point_collect/transformer.py:120-141 (called per file by the data generators and loaders, and per DBSCAN cluster by
+ * point_collect/collect.py:64-68).  They sample on the FIRST THREE columns of an [N,C] array in the array's dtype:
+ * float64 for np.loadtxt / generated clouds, float32 where the loader casts first (ModelNetDataLoader.py:102-105).
+ * points [B,N,>=3] with element strides (B clouds of equal N; the reference handles one per call); start[B] = the
+ * np.random.randint(0, N) draw of :193 (int64, device); idx64 [B,S] = `centroids`.  Any N >= 1: clouds whose four
+ * N-element arrays do not fit in shared memory need `scratch` of pn2_fps_xyz_scratch_bytes(B, N, sizeof(element))
+ * bytes (0 = none needed).  Bit-exact with numpy: sub, square and the sequential 3-term sum rounded separately. */
+int64_t pn2_fps_xyz_scratch_bytes(int B, int N, int elem_bytes);
+int pn2_fps_xyz_f64(const double *points, int64_t sb, int64_t sn, int64_t sc, int B, int N,
+                    const int64_t *start, int S, int64_t *idx64, void *scratch, void *stream);
+int pn2_fps_xyz_f32(const float *points, int64_t sb, int64_t sn, int64_t sc, int B, int N,
+                    const int64_t *start, int S, int64_t *idx64, void *scratch, void *stream);
 
 /* Device self-test of the tcgen05 building blocks (one 128xN tile against a scalar loop in the same
  * launch).  Returns 0 and writes max|err| to *max_err (device float). */

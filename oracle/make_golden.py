@@ -180,6 +180,99 @@ def gen_models():
     print("models.npz:", len(names), "models")
 
 
+def gen_v1():
+    """The four PointNet-v1-like pose heads (model/width.py, rotation.py, translation.py, sign.py): seeded construction,
+    randomised BN, eval forward at B=4, N=256.  Weights are not stored (they are reproduced by seeded construction and
+    checked through a checksum); inputs, the pooled 1024-wide feature and the head outputs are."""
+    flat = {}
+    for i, name in enumerate(["width", "rotation", "translation", "sign"]):
+        sys.modules.pop("pointnet_utils", None)
+        mod = ref_module(name)
+        torch.manual_seed(0)
+        model = mod.get_model(num_category=7).eval()
+        rand_bn_(model, 7)
+        xyz = cloudgen.uniform_cloud(4, 256, 300 + i)
+        pts = cloudgen.with_category(xyz)
+        if name == "width":                          # width.py:12 normal_channel=True -> 6 + num_category channels
+            nrm = torch.randn(4, 256, 3, generator=torch.Generator().manual_seed(400))
+            pts = torch.cat([xyz, nrm, pts[..., 3:]], -1)
+        x = cloudgen.channels_first(pts)
+        mean = xyz[:, :3, :].mean(1)
+        args = (x, mean) if name == "translation" else (x,)
+        with torch.no_grad():
+            out = model(*args)
+            h = x
+            for conv, bn in zip(model.conv, model.bn_conv):      # the point-wise stack + max the fused kernel replaces
+                h = torch.relu(bn(conv(h)))
+            pooled = h.max(2)[0]
+        outs = out if isinstance(out, tuple) else (out,)
+        flat[f"{name}/points"] = pts.numpy()
+        flat[f"{name}/mean"] = mean.numpy()
+        flat[f"{name}/pooled"] = pooled.numpy()
+        for j, o in enumerate(outs):
+            flat[f"{name}/out{j}"] = o.contiguous().numpy()
+        sd = model.state_dict()
+        flat[f"{name}/sd_checksum"] = np.array([float(sum(v.double().abs().sum() for v in sd.values()))])
+        flat[f"{name}/sd_keys"] = np.array(list(sd.keys()))
+        print(f"  v1/{name}: {[tuple(o.shape) for o in outs]}")
+    np.savez_compressed(os.path.join(OUT, "v1.npz"), **flat)
+    print("v1.npz: 4 heads")
+
+
+def np_cloud(N, C, dtype, seed, dup=False):
+    """Seeded numpy cloud for the numpy-FPS fixtures (regenerated by the tests for the large cases; sha-guarded)."""
+    rng = np.random.default_rng(seed)
+    pc = rng.standard_normal((N, C)).astype(dtype)
+    if dup:
+        pc[rng.random(N) < 0.5] = pc[0]                # like provider.random_point_dropout (:157-164)
+    return pc
+
+
+NPFPS_SPECS = [  # name, N, C, dtype, number, seed, dup, store input
+    ("f64_small", 300, 3, "float64", 64, 1, False, True),
+    ("f64_cols6", 500, 6, "float64", 128, 2, False, True),
+    ("f64_dup", 400, 3, "float64", 450, 3, True, True),          # number > N and duplicates: ties, zero distances
+    ("f32_small", 300, 3, "float32", 64, 4, False, True),
+    ("f32_modelnet", 10000, 6, "float32", 1024, 5, False, False),  # ModelNetDataLoader.py:102-105 sizes
+    ("f64_scratch", 7000, 3, "float64", 256, 6, False, False),     # beyond the on-chip limit of the CUDA kernel
+    ("f32_scratch", 13000, 3, "float32", 128, 7, False, False),
+]
+
+
+def gen_npfps():
+    """The numpy copies of FPS, run live: data_utils/ModelDataLoader.py:10-31 and point_collect/transformer.py:120-141
+    (provider.py:183-204 is the same text but cannot be imported: open3d)."""
+    import hashlib
+    sys.path.insert(0, "/root/reference/data_utils"); sys.path.insert(0, "/root/reference/point_collect")
+    try:
+        import ModelDataLoader as mdl
+        import transformer as tr
+    finally:
+        sys.path.remove("/root/reference/data_utils"); sys.path.remove("/root/reference/point_collect")
+    assert mdl.__file__.startswith("/root/reference") and tr.__file__.startswith("/root/reference")
+    flat = {}
+    for name, N, C, dt, number, seed, dup, store in NPFPS_SPECS:
+        pc = np_cloud(N, C, np.dtype(dt), seed, dup)
+        np.random.seed(1000 + seed)
+        ref = mdl.farthest_point_sample(pc.copy(), number)
+        np.random.seed(1000 + seed)
+        ref2 = tr.farthest_point_sample(pc.copy(), number)
+        np.random.seed(1000 + seed)
+        start = np.random.randint(0, N)
+        assert np.array_equal(ref, ref2)
+        got, idx = orc.farthest_point_sample_np(pc, number, start)
+        assert np.array_equal(got, ref), name                    # the C restatement reproduces the live reference
+        if store:
+            flat[f"{name}/points"] = pc
+        flat[f"{name}/sha"] = np.array([hashlib.sha256(pc.tobytes()).hexdigest()])
+        flat[f"{name}/start"] = np.array([start])
+        flat[f"{name}/rows_sha"] = np.array([hashlib.sha256(np.ascontiguousarray(ref).tobytes()).hexdigest()])
+        flat[f"{name}/idx"] = idx.astype(np.int32)
+        print(f"  npfps/{name}: N={N} C={C} {dt} -> {ref.shape}")
+    np.savez_compressed(os.path.join(OUT, "npfps.npz"), **flat)
+    print("npfps.npz:", len(NPFPS_SPECS), "cases")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     orc.build()
@@ -187,6 +280,8 @@ def main():
     gen_indices(ref)
     gen_modules(ref)
     gen_models()
+    gen_v1()
+    gen_npfps()
 
 
 if __name__ == "__main__":

@@ -106,6 +106,46 @@ int pn2o_fps(const float *pts, int64_t sb, int64_t sn, int64_t sc, int B, int N,
 }
 
 /* ---------------------------------------------------------------------------------------------
+ * The numpy copies of farthest point sampling (provider.py:183-204, data_utils/ModelDataLoader.py:10-31,
+ * point_collect/transformer.py:120-141): one cloud, first three columns of an [N,C] array, arithmetic in the
+ * array's dtype.  numpy evaluates `xyz - centroid` (:196), `** 2` and `np.sum(., -1)` as three array passes, so
+ * every sub, square and add is rounded on its own, and a 3-term contiguous sum is sequential (probed: 200 000
+ * random triples, float64 and float32).  `distance` is float64 in the reference (:191) even for float32 input; a
+ * float32 value widens exactly, so keeping it in the array's dtype decides `dist < distance` (:197) and
+ * np.argmax (:199, first of equal maxima) identically.
+ * ------------------------------------------------------------------------------------------- */
+#define PN2O_FPS_XYZ(NAME, T)                                                                       \
+    int NAME(const T *pts, int64_t sn, int64_t sc, int N, int64_t start, int S, int64_t *out)       \
+    {                                                                                               \
+        if (N < 1 || S < 0 || start < 0 || start >= N) return -1;                                   \
+        T *dist = (T *)malloc(sizeof(T) * (size_t)N);                                               \
+        if (!dist) return -2;                                                                       \
+        for (int n = 0; n < N; ++n) dist[n] = (T)1e10;                                              \
+        int64_t far = start;                                                                        \
+        for (int i = 0; i < S; ++i) {                                                               \
+            out[i] = far;                                                                           \
+            const T cx = pts[far * sn], cy = pts[far * sn + sc], cz = pts[far * sn + 2 * sc];       \
+            T best = (T)-1;                                                                         \
+            int64_t besti = 0;                                                                      \
+            for (int n = 0; n < N; ++n) {                                                           \
+                volatile T dx = pts[(int64_t)n * sn] - cx;                                          \
+                volatile T dy = pts[(int64_t)n * sn + sc] - cy;                                     \
+                volatile T dz = pts[(int64_t)n * sn + 2 * sc] - cz;                                 \
+                volatile T qx = dx * dx, qy = dy * dy, qz = dz * dz;                                \
+                volatile T s = qx + qy;                                                             \
+                T d = s + qz;                                                                       \
+                if (d < dist[n]) dist[n] = d;                                                       \
+                if (dist[n] > best) { best = dist[n]; besti = n; }                                  \
+            }                                                                                       \
+            far = besti;                                                                            \
+        }                                                                                           \
+        free(dist);                                                                                 \
+        return 0;                                                                                   \
+    }
+PN2O_FPS_XYZ(pn2o_fps_xyz_f64, double)
+PN2O_FPS_XYZ(pn2o_fps_xyz_f32, float)
+
+/* ---------------------------------------------------------------------------------------------
  * square_distance as the reference evaluates it (pointnet2_utils.py:23-25): expanded form
  *   dot = s0*p0; dot = fma(s_k, p_k, dot) k=1..C-1   (what MKL sgemm does for this K; :23)
  *   d = -2*dot; d += sum_order(s^2) [src always contiguous]; d += sum_order(p^2) [dst layout]

@@ -49,6 +49,9 @@ def lib():
         L.pn2o_mlp_max.argtypes = [_ptr, _i64, _int, _int, _ptr, _ptr, _f32, _ptr]
         L.pn2o_sum_order.argtypes = [_ptr, _int, _int]
         L.pn2o_sum_order.restype = _f32
+        for f in (L.pn2o_fps_xyz_f64, L.pn2o_fps_xyz_f32):
+            f.argtypes = [_ptr, _i64, _i64, _int, _i64, _int, _ptr]
+            f.restype = _int
         for f in (L.pn2o_fps, L.pn2o_square_distance, L.pn2o_ball_query, L.pn2o_group, L.pn2o_mlp_max):
             f.restype = _int
         _lib = L
@@ -235,6 +238,23 @@ def normalization(point_cloud):
         pc = pc / m
         normalize[i] = pc
     return normalize
+
+
+def farthest_point_sample_np(point_cloud, number, start):
+    """provider.py:183-204 / data_utils/ModelDataLoader.py:10-31 / point_collect/transformer.py:120-141 with the :193
+    np.random.randint draw passed in: [N, C] float64 | float32 array -> (sampled rows [number, C], indices [number])."""
+    import numpy as np
+    assert point_cloud.ndim == 2 and point_cloud.shape[1] >= 3 and point_cloud.dtype in (np.float64, np.float32)
+    N = point_cloud.shape[0]
+    es = point_cloud.itemsize
+    assert point_cloud.strides[0] % es == 0 and point_cloud.strides[1] % es == 0
+    idx = np.empty(number, dtype=np.int64)
+    fn = lib().pn2o_fps_xyz_f64 if point_cloud.dtype == np.float64 else lib().pn2o_fps_xyz_f32
+    rc = fn(point_cloud.ctypes.data, point_cloud.strides[0] // es, point_cloud.strides[1] // es, N, int(start), int(number),
+            idx.ctypes.data)
+    if rc:
+        raise RuntimeError(f"pn2o_fps_xyz rc={rc}")
+    return point_cloud[idx.astype(np.int32)], idx
 
 
 def splice_torch(point_cloud, category, num_category=7):

@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(_HERE, LIB_NAME)
 ORDER_SSG, ORDER_MSG, ORDER_ALL = 0, 1, 2
 PREC_F32, PREC_BF16 = 0, 1
 MAX_COORD = 16
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _i64, _i32, _f32, _vp = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p
 
@@ -44,6 +44,9 @@ _SIGNATURES = {
                       _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32,
                       _vp, _i64, _i64, _i32, _vp, _vp, _vp], _i32),
     "pn2_normalize_splice_f32": ([_vp, _i64, _i64, _i64, _i32, _i32, _vp, _i32, _vp, _vp], _i32),
+    "pn2_fps_xyz_scratch_bytes": ([_i32, _i32, _i32], _i64),
+    "pn2_fps_xyz_f64": ([_vp, _i64, _i64, _i64, _i32, _i32, _vp, _i32, _vp, _vp, _vp], _i32),
+    "pn2_fps_xyz_f32": ([_vp, _i64, _i64, _i64, _i32, _i32, _vp, _i32, _vp, _vp, _vp], _i32),
     "pn2_selftest_umma": ([_i32, _i32, _i32, _vp, _vp, _vp], _i32),
     "pn2_debug_trace": ([_vp], _i32),
     "pn2_selftest_tma_gather": ([_vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp], _i32),
@@ -305,6 +308,26 @@ class Native:
             _check(self.lib.pn2_normalize_splice_f32(xyz.data_ptr(), *xyz.stride(), B, N, cptr, int(num_category),
                                                      out.data_ptr(), _stream(xyz)))
         return out
+
+    def fps_xyz(self, points, start, S):
+        """The numpy FPS copies (provider.py:183-204 ...): points [B,N,>=3] float64 | float32 (first three columns are
+        sampled), start [B] int64 -> idx [B,S] int64.  Arithmetic in the tensor's dtype, bit-exact with numpy."""
+        if points.dtype not in (torch.float64, torch.float32):
+            raise RuntimeError(f"pn2: `points` must be float64 or float32 (got {points.dtype})")
+        _need_cuda("points", points, points.dtype)
+        _need_cuda("start", start, torch.int64)
+        B, N, C = points.shape
+        if C < 3:
+            raise ValueError("fps_xyz samples on the first three columns; the array has fewer")
+        assert start.shape == (B,) and start.is_contiguous()
+        idx = torch.empty(B, S, dtype=torch.int64, device=points.device)
+        nbytes = self.lib.pn2_fps_xyz_scratch_bytes(B, N, points.element_size())
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=points.device) if nbytes > 0 else None
+        fn = self.lib.pn2_fps_xyz_f64 if points.dtype == torch.float64 else self.lib.pn2_fps_xyz_f32
+        with torch.cuda.device(points.device), self._span("fps_xyz", B=B, N=N, S=S):
+            _check(fn(points.data_ptr(), *points.stride(), B, N, start.data_ptr(), int(S), idx.data_ptr(),
+                      scratch.data_ptr() if scratch is not None else None, _stream(points)))
+        return idx
 
     def selftest_umma(self, n_cols, k_dim, variant, device="cuda:0", dump=False):
         err = torch.full((1,), -1.0, dtype=torch.float32, device=device)

@@ -156,6 +156,27 @@ int pn2_normalize_splice_f32(const float *xyz, int64_t sb, int64_t sn, int64_t s
     return launch_normalize_splice(xyz, sb, sn, sc, B, N, category, num_category, out, (cudaStream_t)stream);
 }
 
+int64_t pn2_fps_xyz_scratch_bytes(int B, int N, int elem_bytes)
+{
+    return (B < 0 || N < 1 || (elem_bytes != 4 && elem_bytes != 8)) ? -1 : fps_np_scratch_bytes(B, N, elem_bytes);
+}
+
+int pn2_fps_xyz_f64(const double *points, int64_t sb, int64_t sn, int64_t sc, int B, int N,
+                    const int64_t *start, int S, int64_t *idx64, void *scratch, void *stream)
+{
+    PN2_REQUIRE(points && start && idx64, "pn2_fps_xyz_f64: null pointer");
+    PN2_REQUIRE(B >= 0 && N >= 1 && S >= 0, "pn2_fps_xyz_f64: bad sizes B=%d N=%d S=%d", B, N, S);
+    return launch_fps_np_f64(points, sb, sn, sc, B, N, start, S, idx64, scratch, (cudaStream_t)stream);
+}
+
+int pn2_fps_xyz_f32(const float *points, int64_t sb, int64_t sn, int64_t sc, int B, int N,
+                    const int64_t *start, int S, int64_t *idx64, void *scratch, void *stream)
+{
+    PN2_REQUIRE(points && start && idx64, "pn2_fps_xyz_f32: null pointer");
+    PN2_REQUIRE(B >= 0 && N >= 1 && S >= 0, "pn2_fps_xyz_f32: bad sizes B=%d N=%d S=%d", B, N, S);
+    return launch_fps_np_f32(points, sb, sn, sc, B, N, start, S, idx64, scratch, (cudaStream_t)stream);
+}
+
 int pn2_selftest_tma_gather(const void *src_bf16, int64_t rows, int cols, const int32_t *rows4, int n_inst, int col0, void *out, void *stream)
 {
     return launch_selftest_tma_gather(src_bf16, rows, cols, rows4, n_inst, col0, out, (cudaStream_t)stream);

@@ -204,6 +204,11 @@ int launch_sa_bf16(const SaArgs &a, cudaStream_t st);
 int launch_sa_bf16_pipelined(const SaArgs &a, cudaStream_t st);   // -100: configuration not covered
 int sa_bf16_pipelined_covers(int K, int C, int D, int order, int L, const int *dims);
 void set_debug_trace(void *buf);
+int64_t fps_np_scratch_bytes(int B, int N, int elem_bytes);
+int launch_fps_np_f64(const double *points, int64_t sb, int64_t sn, int64_t sc, int B, int N, const int64_t *start, int S,
+                      int64_t *idx64, void *scratch, cudaStream_t stream);
+int launch_fps_np_f32(const float *points, int64_t sb, int64_t sn, int64_t sc, int B, int N, const int64_t *start, int S,
+                      int64_t *idx64, void *scratch, cudaStream_t stream);
 int launch_normalize_splice(const float *xyz, int64_t sb, int64_t sn, int64_t sc, int B, int N,
                             const int64_t *category, int num_category, float *out, cudaStream_t st);
 int make_row_gather_map(const void *base, int64_t rows, int cols, void *out_map);

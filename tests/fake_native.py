@@ -4,6 +4,7 @@ Lets the `not gpu` suite exercise the host logic of pointnet2_utils.py (RNG call
 channel orders, branch concatenation, views / strides, weight-cache invalidation) and run the reference's
 unchanged model files on top of it.  Nothing under pointnet-like-pose-estimation_b200/ imports this file.
 """
+import numpy as np
 import torch
 
 import pn2_oracle as orc
@@ -21,6 +22,11 @@ class OracleNative:
         idx = orc.farthest_point_sample(points, number, start)
         return (idx if want_idx64 else None, idx.int() if want_idx32 else None,
                 orc.index_points(points, idx).contiguous() if want_new_points else None)
+
+    def fps_xyz(self, points, start, S):
+        self.calls.append("fps_xyz")
+        rows = [orc.farthest_point_sample_np(points[b].numpy(), S, int(start[b]))[1] for b in range(points.shape[0])]
+        return torch.from_numpy(np.stack(rows))
 
     def index_points(self, src, idx, check=True):
         self.calls.append("index_points")

@@ -48,3 +48,89 @@ def test_prepare_pose_input_on_the_gpu(oracle, B, N, layout):
     assert float((got[:, :3] - exp[:, :3]).abs().max()) <= 1e-5                  # normalised coordinates lie in [-1, 1]: the fp32 tolerance of the path
     plain = pn2_preprocess.normalization(xin.cuda()).cpu()
     assert plain.shape == (B, N, 3) and torch.equal(plain, got[:, :3].permute(0, 2, 1))
+
+
+# ---- the numpy copies of farthest point sampling + random_sample (provider.py:183-204, ModelDataLoader.py:10-46) ----
+
+import hashlib
+
+import golden_io
+
+NPFPS = golden_io.npfps_cases()
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _case(name):
+    d = NPFPS[name]
+    if not d["input_ok"]:
+        pytest.skip("this numpy's default_rng stream differs from the build container's; input not reproducible")
+    return d
+
+
+@pytest.mark.parametrize("name", sorted(NPFPS))
+def test_numpy_fps_restatement_matches_the_golden_vectors(oracle, name):
+    d = _case(name)
+    rows, idx = oracle.farthest_point_sample_np(d["points"], d["number"], d["start"])
+    assert np.array_equal(idx, d["idx"])
+    assert _sha(rows) == str(d["rows_sha"][0]) and rows.dtype == d["points"].dtype
+
+
+@pytest.mark.parametrize("name", ["f64_small", "f64_cols6", "f64_dup", "f32_small"])
+def test_numpy_fps_drop_in_draws_like_the_reference(fake_native, name):
+    import pn2_preprocess
+    d = _case(name)
+    seed = 1000 + [s[5] for s in _specs() if s[0] == name][0]
+    np.random.seed(seed)
+    rows = pn2_preprocess.farthest_point_sample(d["points"], d["number"], device="cpu")
+    after = np.random.get_state()[1].copy()
+    np.random.seed(seed)
+    np.random.randint(0, d["points"].shape[0])                          # exactly one draw, the reference's (:193)
+    assert np.array_equal(after, np.random.get_state()[1])
+    assert _sha(rows) == str(d["rows_sha"][0])
+    assert fake_native._native.calls == ["fps_xyz"]
+
+
+def _specs():
+    src = open(golden_io.os.path.join(golden_io.os.path.dirname(golden_io.GOLDEN), "..", "oracle", "make_golden.py")).read()
+    ns = {"np": np}
+    exec(src[src.index("NPFPS_SPECS = ["):src.index("def gen_npfps(")], ns)
+    return ns["NPFPS_SPECS"]
+
+
+def test_random_sample_keeps_the_reference_draw():
+    import pn2_preprocess
+    pc = np.random.default_rng(0).standard_normal((50, 4))
+    np.random.seed(3)
+    got = pn2_preprocess.random_sample(pc, 20)
+    np.random.seed(3)
+    exp = pc[np.random.choice(50, 20, replace=False)]                    # ModelDataLoader.py:44-45
+    assert np.array_equal(got, exp)
+    assert pn2_preprocess.random_sample(pc, 50) is pc and pn2_preprocess.random_sample(pc, 64) is pc      # :42-43
+    np.random.seed(3)
+    assert np.array_equal(pn2_preprocess.random_sample(torch.from_numpy(pc), 20).numpy(), exp)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(NPFPS))
+def test_numpy_fps_on_the_gpu(name):
+    import pn2_preprocess
+    import pointnet2_utils as pu
+    d = _case(name)
+    pc, number = d["points"], d["number"]
+    seed = 1000 + [s[5] for s in _specs() if s[0] == name][0]
+    np.random.seed(seed)
+    rows = pn2_preprocess.farthest_point_sample(pc, number)
+    assert rows.dtype == pc.dtype and rows.shape == (number, pc.shape[1])
+    assert _sha(rows) == str(d["rows_sha"][0])
+    # the kernel on the array as it lies (row stride C, no xyz copy), three clouds per launch with different starts
+    N = pc.shape[0]
+    starts = torch.tensor([d["start"], 0, N - 1])
+    stack = torch.from_numpy(np.stack([pc, pc[::-1].copy(), pc])).cuda()
+    idx = pu._backend().fps_xyz(stack, starts.cuda(), number).cpu().numpy()
+    assert np.array_equal(idx[0], d["idx"])
+    import pn2_oracle
+    for b, cloud in enumerate([pc, pc[::-1].copy(), pc]):
+        assert np.array_equal(idx[b], pn2_oracle.farthest_point_sample_np(cloud, number, int(starts[b]))[1]), (name, b)

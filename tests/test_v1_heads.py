@@ -101,3 +101,60 @@ def test_fused_head_on_the_gpu(name, prec, tol):
     assert err <= tol, (name, prec, err)                     # max|a-b| / max|b|, the tolerance of DESIGN.md §2
     outs = out if isinstance(out, tuple) else (out,)
     assert all(torch.isfinite(o).all() for o in outs)
+
+
+# ---- golden vectors from the live reference (tests/golden/v1.npz, written by oracle/make_golden.py:gen_v1) ----
+
+def _golden_head(name):
+    import golden_io
+    d = golden_io.v1_cases()[name]
+    torch.manual_seed(0)
+    model = pn2_v1.get_v1_model(name, 7).eval()
+    pn2_models.randomize_bn_(model, 7)
+    sd = model.state_dict()
+    assert list(sd.keys()) == [str(k) for k in d["sd_keys"]]
+    checksum = float(sum(v.double().abs().sum() for v in sd.values()))
+    if abs(checksum - float(d["sd_checksum"][0])) > 1e-6 * checksum:
+        pytest.skip("seeded initialisation differs from the build container's torch; weights not reproducible")
+    x = cloudgen.channels_first(torch.from_numpy(d["points"]))
+    return model, d, x, torch.from_numpy(d["mean"])
+
+
+def _check_outputs(name, outs, d, tol):
+    exp0 = torch.from_numpy(d["out0"])
+    assert float((outs[0] - exp0).abs().max() / exp0.abs().max()) <= 5 * tol, name
+    if name == "sign" and tol <= 1e-5:
+        assert torch.equal(outs[1], torch.from_numpy(d["out1"]))
+
+
+@pytest.mark.parametrize("name", sorted(pn2_v1.V1_ARCH))
+def test_golden_head_through_the_oracle_backed_entry_point(fake_native, name):
+    model, d, x, mean = _golden_head(name)
+    with torch.no_grad():
+        pooled = pn2_v1.pointwise_mlp_max(x, model.conv, model.bn_conv)
+        out = model(x, mean) if name == "translation" else model(x)         # CPU tensor: the ATen op sequence
+    exp = torch.from_numpy(d["pooled"])
+    assert float((pooled - exp).abs().max() / exp.abs().max()) <= 1e-5
+    _check_outputs(name, out if isinstance(out, tuple) else (out,), d, 1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-5), ("bf16", 2e-2)])
+@pytest.mark.parametrize("name", sorted(pn2_v1.V1_ARCH))
+def test_golden_head_on_the_gpu(name, prec, tol):
+    import pointnet2_utils as pu
+    model, d, x, mean = _golden_head(name)
+    model, x, mean = model.to("cuda:0"), x.to("cuda:0"), mean.to("cuda:0")
+    prev = pu.get_precision()
+    pu.set_precision(prec)
+    try:
+        with torch.no_grad():
+            pooled = pn2_v1.pointwise_mlp_max(x, model.conv, model.bn_conv).cpu()
+            out = model(x, mean) if name == "translation" else model(x)
+    finally:
+        pu.set_precision(prev)
+    exp = torch.from_numpy(d["pooled"])
+    err = float((pooled - exp).abs().max() / exp.abs().max())
+    assert err <= tol, (name, prec, err)
+    outs = tuple(o.cpu() for o in (out if isinstance(out, tuple) else (out,)))
+    _check_outputs(name, outs, d, tol)
