@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PN2_ABI_VERSION 7
+#define PN2_ABI_VERSION 8
 #define PN2_MAX_COORD 16 /* exact summation-order rules are verified against ATen for C <= 16 */
 #define PN2_MAX_LAYERS 8
 
@@ -135,6 +135,21 @@ int pn2_fps_xyz_f64(const double *points, int64_t sb, int64_t sn, int64_t sc, in
                     const int64_t *start, int S, int64_t *idx64, void *scratch, void *stream);
 int pn2_fps_xyz_f32(const float *points, int64_t sb, int64_t sn, int64_t sc, int B, int N,
                     const int64_t *start, int S, int64_t *idx64, void *scratch, void *stream);
+
+/* Training-mode BatchNorm2d + ReLU of the shared MLP -- relu(bn(conv(x))) of pointnet2_utils.py:170 / :217 with batch
+ * statistics (nn.BatchNorm2d in train(): biased variance over all B*K*S positions) -- on channels-last rows
+ * y [M, C] = the 1x1 convolution's output WITHOUT its bias (a bias in front of a batch-statistics BatchNorm cancels).
+ *   forward : stats [5][C] <- mean, biased var, invstd, a = gamma*invstd, b = beta - mean*a;  z = max(0, y*a + b).
+ *             K = 0: z [M, C].  K > 0: the max over each group of K consecutive rows (:172 / :218) is fused:
+ *             z [M/K, C] pooled maximum, arg [M/K, C] int32 = its first row, and the full z never reaches HBM.
+ *   backward: dz = gradient of z (K = 0: [M, C]; K > 0: [M/K, C] with the forward's arg); dy [M, C] = gradient of y;
+ *             sums [2][C] <- dbeta, dgamma.  The ReLU mask is recomputed from y and stats.
+ * ws = pn2_bn_train_ws_bytes(C) bytes of scratch (per-CTA fp64 partial sums, added in a fixed order: deterministic). */
+int64_t pn2_bn_train_ws_bytes(int C);
+int pn2_bn_relu_train_fwd_f32(const float *y, int64_t M, int C, int K, const float *gamma, const float *beta, float eps,
+                              void *ws, float *stats, float *z, int32_t *arg, void *stream);
+int pn2_bn_relu_train_bwd_f32(const float *dz, const float *y, const int32_t *arg, int64_t M, int C, int K,
+                              const float *stats, void *ws, float *sums, float *dy, void *stream);
 
 /* Device self-test of the tcgen05 building blocks (one 128xN tile against a scalar loop in the same
  * launch).  Returns 0 and writes max|err| to *max_err (device float). */

@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(_HERE, LIB_NAME)
 ORDER_SSG, ORDER_MSG, ORDER_ALL = 0, 1, 2
 PREC_F32, PREC_BF16 = 0, 1
 MAX_COORD = 16
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 _i64, _i32, _f32, _vp = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p
 
@@ -47,6 +47,9 @@ _SIGNATURES = {
     "pn2_fps_xyz_scratch_bytes": ([_i32, _i32, _i32], _i64),
     "pn2_fps_xyz_f64": ([_vp, _i64, _i64, _i64, _i32, _i32, _vp, _i32, _vp, _vp, _vp], _i32),
     "pn2_fps_xyz_f32": ([_vp, _i64, _i64, _i64, _i32, _i32, _vp, _i32, _vp, _vp, _vp], _i32),
+    "pn2_bn_train_ws_bytes": ([_i32], _i64),
+    "pn2_bn_relu_train_fwd_f32": ([_vp, _i64, _i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp], _i32),
+    "pn2_bn_relu_train_bwd_f32": ([_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp], _i32),
     "pn2_selftest_umma": ([_i32, _i32, _i32, _vp, _vp, _vp], _i32),
     "pn2_debug_trace": ([_vp], _i32),
     "pn2_selftest_tma_gather": ([_vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp], _i32),
@@ -328,6 +331,40 @@ class Native:
             _check(fn(points.data_ptr(), *points.stride(), B, N, start.data_ptr(), int(S), idx.data_ptr(),
                       scratch.data_ptr() if scratch is not None else None, _stream(points)))
         return idx
+
+    def bn_relu_train_fwd(self, y, gamma, beta, eps, K=0):
+        """Training-mode relu(bn(y)) on rows y [M, C] (batch statistics): -> (z, stats [5, C], arg).
+        K = 0: z [M, C], arg None.  K > 0: z [M/K, C] = max over each group of K rows, arg [M/K, C] int32."""
+        _need_cuda("y", y, torch.float32)
+        _need_cuda("gamma", gamma, torch.float32)
+        _need_cuda("beta", beta, torch.float32)
+        M, C = y.shape
+        assert y.is_contiguous() and gamma.is_contiguous() and beta.is_contiguous() and gamma.numel() == C == beta.numel()
+        if M < 2:
+            raise ValueError(f"Expected more than 1 value per channel when training, got input size {tuple(y.shape)}")
+        ws = torch.empty(self.lib.pn2_bn_train_ws_bytes(C), dtype=torch.uint8, device=y.device)
+        stats = torch.empty(5, C, dtype=torch.float32, device=y.device)
+        z = torch.empty(M // K if K else M, C, dtype=torch.float32, device=y.device)
+        arg = torch.empty(M // K, C, dtype=torch.int32, device=y.device) if K else None
+        with torch.cuda.device(y.device), self._span("bn_relu_train_fwd", M=M, C=C, K=K):
+            _check(self.lib.pn2_bn_relu_train_fwd_f32(y.data_ptr(), M, C, int(K), gamma.data_ptr(), beta.data_ptr(), float(eps),
+                                                      ws.data_ptr(), stats.data_ptr(), z.data_ptr(),
+                                                      arg.data_ptr() if K else None, _stream(y)))
+        return z, stats, arg
+
+    def bn_relu_train_bwd(self, dz, y, arg, stats, K=0):
+        """Backward of bn_relu_train_fwd: dz (gradient of z) -> (dy [M, C], sums [2, C] = dbeta, dgamma)."""
+        _need_cuda("dz", dz, torch.float32)
+        M, C = y.shape
+        dz = dz.contiguous()
+        assert dz.shape == ((M // K, C) if K else (M, C))
+        ws = torch.empty(self.lib.pn2_bn_train_ws_bytes(C), dtype=torch.uint8, device=y.device)
+        sums = torch.empty(2, C, dtype=torch.float32, device=y.device)
+        dy = torch.empty_like(y)
+        with torch.cuda.device(y.device), self._span("bn_relu_train_bwd", M=M, C=C, K=K):
+            _check(self.lib.pn2_bn_relu_train_bwd_f32(dz.data_ptr(), y.data_ptr(), arg.data_ptr() if K else None, M, C, int(K),
+                                                      stats.data_ptr(), ws.data_ptr(), sums.data_ptr(), dy.data_ptr(), _stream(y)))
+        return dy, sums
 
     def selftest_umma(self, n_cols, k_dim, variant, device="cuda:0", dump=False):
         err = torch.full((1,), -1.0, dtype=torch.float32, device=device)

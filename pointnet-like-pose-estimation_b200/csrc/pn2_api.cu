@@ -177,6 +177,26 @@ int pn2_fps_xyz_f32(const float *points, int64_t sb, int64_t sn, int64_t sc, int
     return launch_fps_np_f32(points, sb, sn, sc, B, N, start, S, idx64, scratch, (cudaStream_t)stream);
 }
 
+int64_t pn2_bn_train_ws_bytes(int C) { return C >= 1 ? bn_train_ws_bytes(C) : -1; }
+
+int pn2_bn_relu_train_fwd_f32(const float *y, int64_t M, int C, int K, const float *gamma, const float *beta, float eps,
+                              void *ws, float *stats, float *z, int32_t *arg, void *stream)
+{
+    PN2_REQUIRE(y && gamma && beta && ws && stats && z, "pn2_bn_relu_train_fwd_f32: null pointer");
+    PN2_REQUIRE(M >= 2 && C >= 1, "pn2_bn_relu_train_fwd_f32: batch statistics need more than one value per channel (M=%lld, C=%d)", (long long)M, C);
+    PN2_REQUIRE(K == 0 || (K > 0 && M % K == 0 && arg), "pn2_bn_relu_train_fwd_f32: K=%d must divide M=%lld and needs arg", K, (long long)M);
+    return launch_bn_fwd(y, M, C, K, gamma, beta, eps, ws, stats, z, arg, (cudaStream_t)stream);
+}
+
+int pn2_bn_relu_train_bwd_f32(const float *dz, const float *y, const int32_t *arg, int64_t M, int C, int K,
+                              const float *stats, void *ws, float *sums, float *dy, void *stream)
+{
+    PN2_REQUIRE(dz && y && stats && ws && sums && dy, "pn2_bn_relu_train_bwd_f32: null pointer");
+    PN2_REQUIRE(M >= 2 && C >= 1, "pn2_bn_relu_train_bwd_f32: bad sizes M=%lld C=%d", (long long)M, C);
+    PN2_REQUIRE(K == 0 || (K > 0 && M % K == 0 && arg), "pn2_bn_relu_train_bwd_f32: K=%d must divide M=%lld and needs arg", K, (long long)M);
+    return launch_bn_bwd(dz, y, arg, M, C, K, stats, ws, sums, dy, (cudaStream_t)stream);
+}
+
 int pn2_selftest_tma_gather(const void *src_bf16, int64_t rows, int cols, const int32_t *rows4, int n_inst, int col0, void *out, void *stream)
 {
     return launch_selftest_tma_gather(src_bf16, rows, cols, rows4, n_inst, col0, out, (cudaStream_t)stream);

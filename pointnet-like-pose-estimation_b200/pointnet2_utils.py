@@ -37,6 +37,7 @@ _native = None              # created on first use; tests may monkeypatch this a
 _precision = os.environ.get("PN2_PRECISION", "fp32")
 _reference_strides = False
 _factorise_first_layer = os.environ.get("PN2_FACTORISE", "1") != "0"     # see _FactorisedFirstLayer
+_train_fused = os.environ.get("PN2_TRAIN_FUSED", "1") != "0"            # see _shared_mlp_train_rows
 _start_source = None        # optional callable (B, N) -> int64 CPU tensor [B]; default = torch.randint
 
 
@@ -242,9 +243,99 @@ def _bf16_twin(feature_bdn, B, N, D):
 
 
 def _shared_mlp_train(x, convs, bns):
+    """The reference's op sequence on ATen (:168-172 / :214-218); x [B, Cin, K, S].  Kept as the comparator of the fused
+    training path (PN2_TRAIN_FUSED=0 selects it)."""
     for conv, bn in zip(convs, bns):
         x = F.relu(bn(conv(x)))
     return torch.max(x, 2)[0]
+
+
+class _gemm_precision_of_the_reference_convs:
+    """The reference's 1x1 convolutions run through cuDNN, whose TF32 switch is ``torch.backends.cudnn.allow_tf32``
+    (default True); the GEMMs that stand in for them follow that switch instead of the matmul one (default False)."""
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = bool(torch.backends.cudnn.allow_tf32)
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+
+
+class _RowsLinear(torch.autograd.Function):
+    """y [M, Cout] = x [M, Cin] @ w[Cout, Cin]^T: a 1x1 convolution on channels-last rows, bias left to the BatchNorm."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        with _gemm_precision_of_the_reference_convs():
+            return torch.mm(x, w.t())
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dx = dw = None
+        with _gemm_precision_of_the_reference_convs():
+            if ctx.needs_input_grad[0]:
+                dx = torch.mm(dy, w)
+            if ctx.needs_input_grad[1]:
+                dw = torch.mm(dy.t(), x)
+        return dx, dw
+
+
+class _BnReluRows(torch.autograd.Function):
+    """relu(batch_norm(y + bias)) on rows y [M, C] with batch statistics, optionally followed by the max over groups of K
+    rows -- the product kernels of csrc/pn2_bn_train.cu.  The bias of the convolution cancels against the batch mean, so
+    it is not added (its gradient is exactly zero; the running mean is shifted by it outside)."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, bias, eps, K):
+        z, stats, arg = _backend().bn_relu_train_fwd(y, gamma, beta, eps, K)
+        ctx.save_for_backward(y, stats, arg)
+        ctx.K = K
+        ctx.has_bias = bias is not None
+        ctx.mark_non_differentiable(stats)
+        return z, stats
+
+    @staticmethod
+    def backward(ctx, dz, _dstats):
+        y, stats, arg = ctx.saved_tensors
+        dy, sums = _backend().bn_relu_train_bwd(dz, y, arg, stats, ctx.K)
+        dbias = torch.zeros_like(sums[0]) if ctx.has_bias else None
+        return dy, sums[1], sums[0], dbias, None, None
+
+
+def _bn_relu_rows(y, conv_bias, bn, K=0):
+    """One ``relu(bn(.))`` of the shared MLP in training mode on rows [M, C] (+ fused max over K rows): product kernels
+    for the data, nn.BatchNorm2d's bookkeeping (running statistics, momentum, num_batches_tracked) here."""
+    M = y.shape[0]
+    z, stats = _BnReluRows.apply(y, bn.weight, bn.bias, conv_bias, bn.eps, K)
+    if bn.track_running_stats and bn.running_mean is not None:
+        with torch.no_grad():
+            bn.num_batches_tracked += 1
+            f = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+            mean = stats[0] + conv_bias if conv_bias is not None else stats[0]
+            bn.running_mean.mul_(1.0 - f).add_(mean, alpha=f)
+            bn.running_var.mul_(1.0 - f).add_(stats[1], alpha=f * M / (M - 1))            # unbiased, like ATen
+    return z
+
+
+def _shared_mlp_train_rows(rows, convs, bns, first=None):
+    """Training-mode shared MLP + max over K on the grouped rows [B, S, K, Cin] as they leave the grouping kernel:
+    per layer one GEMM and the fused BatchNorm + ReLU kernels; the last layer's max-pool is fused into its BatchNorm, so
+    its activations never reach HBM.  ``first`` = pre-activations of layer 0 [B, S, K, C0] when the caller has already
+    evaluated the first convolution (factorised MSG branch).  Returns [B, Cout, S] like torch.max(x, 2)[0] of (:172)."""
+    B, S, K = rows.shape[:3]
+    convs, bns = list(convs), list(bns)
+    x = rows.reshape(B * S * K, -1)
+    for i, (conv, bn) in enumerate(zip(convs, bns)):
+        if i == 0 and first is not None:
+            y = first.reshape(B * S * K, -1)
+        else:
+            y = _RowsLinear.apply(x, conv.weight.view(conv.out_channels, -1))
+        x = _bn_relu_rows(y, conv.bias, bn, K if i == len(convs) - 1 else 0)
+    out = x.view(B, S, -1).permute(0, 2, 1)
+    return out.contiguous() if _reference_strides else out
 
 
 class PointNetSetAbstraction(nn.Module):
@@ -308,7 +399,10 @@ class PointNetSetAbstraction(nn.Module):
             rows = be.group(pts.detach(), None, idx32, new_points, ORDER_SSG)
             if feat is not None:
                 rows = torch.cat([rows, _gather_rows(feat, idx32)], dim=-1)
-        pooled = _shared_mlp_train(rows.permute(0, 3, 2, 1), self.mlp_convs, self.mlp_bns)
+        if _train_fused:
+            pooled = _shared_mlp_train_rows(rows, self.mlp_convs, self.mlp_bns)
+        else:
+            pooled = _shared_mlp_train(rows.permute(0, 3, 2, 1), self.mlp_convs, self.mlp_bns)
         return new_points.permute(0, 2, 1), pooled
 
 
@@ -410,7 +504,10 @@ class PointNetSetAbstractionMsg(nn.Module):
                 continue
             if feat is not None:
                 rows = torch.cat([_gather_rows(feat, idx32), rows], dim=-1)
-            outs.append(_shared_mlp_train(rows.permute(0, 3, 2, 1), convs, bns))
+            if _train_fused:
+                outs.append(_shared_mlp_train_rows(rows, convs, bns))
+            else:
+                outs.append(_shared_mlp_train(rows.permute(0, 3, 2, 1), convs, bns))
         return new_points.permute(0, 2, 1), torch.cat(outs, dim=1)
 
 
@@ -424,6 +521,10 @@ def _msg_branch_train_factorised(rows_xyz, feat, idx32, convs, bns):
     D = feat.shape[-1]
     w = conv0.weight.reshape(conv0.out_channels, -1)                  # [N0, D + C], MSG order [feat, xyz] (:209)
     p_rows = torch.matmul(feat, w[:, :D].t())                         # [B, N, N0] once per point
+    if _train_fused:       # bias left to the BatchNorm (it cancels against the batch mean)
+        with _gemm_precision_of_the_reference_convs():
+            y = _gather_rows(p_rows, idx32) + torch.matmul(rows_xyz, w[:, D:].t())
+        return _shared_mlp_train_rows(rows_xyz, convs, bns, first=y)
     y = _gather_rows(p_rows, idx32) + torch.matmul(rows_xyz, w[:, D:].t()) + conv0.bias      # [B, S, K, N0]
     x = F.relu(bn0(y.permute(0, 3, 2, 1)))
     for conv, bn in zip(list(convs)[1:], list(bns)[1:]):

@@ -28,6 +28,37 @@ class OracleNative:
         rows = [orc.farthest_point_sample_np(points[b].numpy(), S, int(start[b]))[1] for b in range(points.shape[0])]
         return torch.from_numpy(np.stack(rows))
 
+    def bn_relu_train_fwd(self, y, gamma, beta, eps, K=0):
+        self.calls.append("bn_relu_train_fwd")
+        M, C = y.shape
+        if M < 2:
+            raise ValueError("Expected more than 1 value per channel when training")
+        yd = y.double()
+        mean, var = yd.mean(0), yd.var(0, unbiased=False)
+        invstd = (1.0 / torch.sqrt(var + eps)).float()
+        a = gamma * invstd
+        b = torch.addcmul(beta, -mean.float(), a)
+        stats = torch.stack([mean.float(), var.float(), invstd, a, b])
+        z = torch.relu(torch.addcmul(b, y, a))
+        if not K:
+            return z, stats, None
+        zm, arg = z.view(M // K, K, C).max(1)
+        return zm.contiguous(), stats, arg.int()
+
+    def bn_relu_train_bwd(self, dz, y, arg, stats, K=0):
+        self.calls.append("bn_relu_train_bwd")
+        M, C = y.shape
+        mean, invstd, a, b = stats[0], stats[2], stats[3], stats[4]
+        if K:
+            full = torch.zeros(M // K, K, C).scatter_(1, arg.long().unsqueeze(1), dz.view(M // K, 1, C)).view(M, C)
+        else:
+            full = dz
+        g = torch.where(torch.addcmul(b, y, a) > 0, full, torch.zeros_like(full))
+        xh = (y - mean) * invstd
+        s1, s2 = g.double().sum(0), (g.double() * xh.double()).sum(0)
+        dy = a * (g - (s1 / M).float() - xh * (s2 / M).float())
+        return dy, torch.stack([s1.float(), s2.float()])
+
     def index_points(self, src, idx, check=True):
         self.calls.append("index_points")
         N = src.shape[1]
