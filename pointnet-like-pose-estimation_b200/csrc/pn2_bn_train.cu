@@ -138,15 +138,40 @@ __global__ void __launch_bounds__(BN_THREADS) bn_fwd_stats_kernel(const float *_
     cta_partials<V, 2>(m, C, acc, ws);
 }
 
-// mean, biased variance, invstd, a, b from the per-CTA partials (fixed order).
-__global__ void bn_fwd_finalize_kernel(const double *__restrict__ ws, int nctas, int64_t M, int C,
+// Sum of the per-CTA partials of 32 channels by a (32, FIN_LANES) thread block: lane ly adds partials ly, ly + FIN_LANES,
+// ... (coalesced 256-byte reads), lane 0 then adds the FIN_LANES sub-sums in order -- a fixed order, so deterministic.
+constexpr int FIN_LANES = 16;
+
+__device__ __forceinline__ bool finalize_sums(const double *__restrict__ ws, int nctas, int C, double &s, double &q)
+{
+    __shared__ double s_part[2][FIN_LANES][32];
+    const int c = blockIdx.x * 32 + threadIdx.x, ly = threadIdx.y;
+    double a0 = 0.0, a1 = 0.0;
+    if (c < C) {
+#pragma unroll 4
+        for (int i = ly; i < nctas; i += FIN_LANES) {
+            a0 += ws[(int64_t)i * C + c];
+            a1 += ws[((int64_t)nctas + i) * C + c];
+        }
+    }
+    s_part[0][ly][threadIdx.x] = a0;
+    s_part[1][ly][threadIdx.x] = a1;
+    __syncthreads();
+    if (ly != 0 || c >= C) return false;
+    s = q = 0.0;
+#pragma unroll
+    for (int l = 0; l < FIN_LANES; ++l) { s += s_part[0][l][threadIdx.x]; q += s_part[1][l][threadIdx.x]; }
+    return true;
+}
+
+// mean, biased variance, invstd, a, b from the per-CTA partials.
+__global__ void __launch_bounds__(32 * FIN_LANES) bn_fwd_finalize_kernel(const double *__restrict__ ws, int nctas, int64_t M, int C,
                                        const float *__restrict__ gamma, const float *__restrict__ beta, float eps,
                                        float *__restrict__ stats)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double s = 0.0, q = 0.0;
-    for (int i = 0; i < nctas; ++i) { s += ws[(int64_t)i * C + c]; q += ws[((int64_t)nctas + i) * C + c]; }
+    double s, q;
+    if (!finalize_sums(ws, nctas, C, s, q)) return;
+    const int c = blockIdx.x * 32 + threadIdx.x;
     const double mean = s / (double)M;
     double var = q / (double)M - mean * mean;
     var = var > 0.0 ? var : 0.0;
@@ -175,6 +200,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_fwd_apply_kernel(const float *_
         int64_t r0, r1;
         row_range(M, r0, r1);
         float *o = z + (int64_t)m.cv * V;
+#pragma unroll 4
         for (int64_t r = r0 + m.rl; r < r1; r += m.RL) {
             float v[V];
             ldv<V>(p + r * C, v);
@@ -189,6 +215,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_fwd_apply_kernel(const float *_
             int bi[V];
 #pragma unroll
             for (int j = 0; j < V; ++j) { best[j] = -1.f; bi[j] = 0; }
+#pragma unroll 4
             for (int k = 0; k < K; ++k) {
                 float v[V];
                 ldv<V>(p + (g * K + k) * C, v);
@@ -226,6 +253,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_stats_kernel(const float *_
             int64_t r0, r1;
             row_range(M, r0, r1);
             const float *pg = dz + (int64_t)m.cv * V;
+#pragma unroll 4
             for (int64_t r = r0 + m.rl; r < r1; r += m.RL) {
                 float v[V], g[V];
                 ldv<V>(py + r * C, v);
@@ -259,12 +287,11 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_stats_kernel(const float *_
     cta_partials<V, 2>(m, C, acc, ws);
 }
 
-__global__ void bn_bwd_finalize_kernel(const double *__restrict__ ws, int nctas, int C, float *__restrict__ sums)
+__global__ void __launch_bounds__(32 * FIN_LANES) bn_bwd_finalize_kernel(const double *__restrict__ ws, int nctas, int C, float *__restrict__ sums)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double s1 = 0.0, s2 = 0.0;
-    for (int i = 0; i < nctas; ++i) { s1 += ws[(int64_t)i * C + c]; s2 += ws[((int64_t)nctas + i) * C + c]; }
+    double s1, s2;
+    if (!finalize_sums(ws, nctas, C, s1, s2)) return;
+    const int c = blockIdx.x * 32 + threadIdx.x;
     sums[c] = (float)s1;
     sums[C + c] = (float)s2;
 }
@@ -293,6 +320,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const float *_
         int64_t r0, r1;
         row_range(M, r0, r1);
         const float *pg = dz + (int64_t)m.cv * V;
+#pragma unroll 4
         for (int64_t r = r0 + m.rl; r < r1; r += m.RL) {
             float v[V], g[V];
             ldv<V>(py + r * C, v);
@@ -313,6 +341,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const float *_
             ldv<V>(dz + g * C + (int64_t)m.cv * V, gr);
 #pragma unroll
             for (int j = 0; j < V; ++j) ak[j] = arg[g * C + m.cv * V + j];
+#pragma unroll 4
             for (int k = 0; k < K; ++k) {
                 float v[V];
                 ldv<V>(py + (g * K + k) * C, v);
@@ -361,7 +390,7 @@ int launch_bn_fwd(const float *y, int64_t M, int C, int K, const float *gamma, c
     double *w = reinterpret_cast<double *>(ws);
     if (g.V == 4) bn_fwd_stats_kernel<4><<<g.grid, BN_THREADS, g.smem, st>>>(y, M, C, w);
     else bn_fwd_stats_kernel<1><<<g.grid, BN_THREADS, g.smem, st>>>(y, M, C, w);
-    bn_fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(w, (int)g.grid.x, M, C, gamma, beta, eps, stats);
+    bn_fwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(w, (int)g.grid.x, M, C, gamma, beta, eps, stats);
     if (K <= 0) {
         if (g.V == 4) bn_fwd_apply_kernel<4, false><<<g.grid, BN_THREADS, 0, st>>>(y, M, C, 1, stats, z, nullptr);
         else bn_fwd_apply_kernel<1, false><<<g.grid, BN_THREADS, 0, st>>>(y, M, C, 1, stats, z, nullptr);
@@ -381,14 +410,14 @@ int launch_bn_bwd(const float *dz, const float *y, const int32_t *arg, int64_t M
         const Grid g = plan(M, C);
         if (g.V == 4) bn_bwd_stats_kernel<4, false><<<g.grid, BN_THREADS, g.smem, st>>>(dz, y, nullptr, M, C, 1, stats, w);
         else bn_bwd_stats_kernel<1, false><<<g.grid, BN_THREADS, g.smem, st>>>(dz, y, nullptr, M, C, 1, stats, w);
-        bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(w, (int)g.grid.x, C, sums);
+        bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(w, (int)g.grid.x, C, sums);
         if (g.V == 4) bn_bwd_apply_kernel<4, false><<<g.grid, BN_THREADS, 0, st>>>(dz, y, nullptr, M, C, 1, stats, sums, dy);
         else bn_bwd_apply_kernel<1, false><<<g.grid, BN_THREADS, 0, st>>>(dz, y, nullptr, M, C, 1, stats, sums, dy);
     } else {
         const Grid p = plan(M / K, C);
         if (p.V == 4) bn_bwd_stats_kernel<4, true><<<p.grid, BN_THREADS, p.smem, st>>>(dz, y, arg, M, C, K, stats, w);
         else bn_bwd_stats_kernel<1, true><<<p.grid, BN_THREADS, p.smem, st>>>(dz, y, arg, M, C, K, stats, w);
-        bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(w, (int)p.grid.x, C, sums);
+        bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(w, (int)p.grid.x, C, sums);
         if (p.V == 4) bn_bwd_apply_kernel<4, true><<<p.grid, BN_THREADS, 0, st>>>(dz, y, arg, M, C, K, stats, sums, dy);
         else bn_bwd_apply_kernel<1, true><<<p.grid, BN_THREADS, 0, st>>>(dz, y, arg, M, C, K, stats, sums, dy);
     }
