@@ -19,6 +19,7 @@ What is deliberately different from the reference (all documented in DESIGN.md):
 from __future__ import annotations
 
 import contextlib
+import math
 import os
 
 import numpy as np
@@ -279,8 +280,21 @@ class _RowsLinear(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 dx = torch.mm(dy, w)
             if ctx.needs_input_grad[1]:
-                dw = torch.mm(dy.t(), x)
+                dw = _rows_outer(dy, x)
         return dx, dw
+
+
+def _rows_outer(dy, x, chunk=8192):
+    """dy^T x for tall operands [M, Cout], [M, Cin] (the weight gradient of a 1x1 convolution: M = B*S*K in the millions,
+    a few thousand output elements).  A single GEMM call leaves cuBLAS with a split-K problem it runs at a third of the
+    HBM rate; as a batch of M/chunk independent GEMMs plus a small sum it streams both operands once at full rate
+    (B200, TF32: 386 -> 211 us for 2.1 M x 96 x 64, 691 -> 233 us for Cin = 10)."""
+    M = dy.shape[0]
+    c = math.gcd(M, chunk)
+    if c < 1024 or M // c < 2:
+        return torch.mm(dy.t(), x)
+    P = M // c
+    return torch.bmm(dy.reshape(P, c, -1).transpose(1, 2), x.reshape(P, c, -1)).sum(0)
 
 
 class _BnReluRows(torch.autograd.Function):
@@ -520,11 +534,13 @@ def _msg_branch_train_factorised(rows_xyz, feat, idx32, convs, bns):
     conv0, bn0 = convs[0], bns[0]
     D = feat.shape[-1]
     w = conv0.weight.reshape(conv0.out_channels, -1)                  # [N0, D + C], MSG order [feat, xyz] (:209)
-    p_rows = torch.matmul(feat, w[:, :D].t())                         # [B, N, N0] once per point
     if _train_fused:       # bias left to the BatchNorm (it cancels against the batch mean)
-        with _gemm_precision_of_the_reference_convs():
-            y = _gather_rows(p_rows, idx32) + torch.matmul(rows_xyz, w[:, D:].t())
+        B, N = feat.shape[:2]
+        p_rows = _RowsLinear.apply(feat.reshape(B * N, D), w[:, :D]).view(B, N, -1)
+        y = _gather_rows(p_rows, idx32)
+        y += _RowsLinear.apply(rows_xyz.reshape(-1, rows_xyz.shape[-1]), w[:, D:]).view(y.shape)
         return _shared_mlp_train_rows(rows_xyz, convs, bns, first=y)
+    p_rows = torch.matmul(feat, w[:, :D].t())                         # [B, N, N0] once per point
     y = _gather_rows(p_rows, idx32) + torch.matmul(rows_xyz, w[:, D:].t()) + conv0.bias      # [B, S, K, N0]
     x = F.relu(bn0(y.permute(0, 3, 2, 1)))
     for conv, bn in zip(list(convs)[1:], list(bns)[1:]):
