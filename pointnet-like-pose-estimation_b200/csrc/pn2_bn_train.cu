@@ -2,7 +2,7 @@
 //
 // The reference's training step (train_rotation.py:95-123 through pointnet2_utils.py:166-172 / :212-218) evaluates
 // relu(bn(conv(x))) on the grouped [B, C, K, S] tensor; on a GPU that is cuDNN's per-channel NCHW BatchNorm plus separate
-// bias-add / ReLU / threshold kernels, which take 75 % of the configs[4] step (profiles/r01_j_train_profile.txt: the
+// bias-add / ReLU / threshold kernels, which take 75 % of the configs[4] step (profiles/r01_j_train_profile_aten.txt: the
 // 1x1 convolutions themselves are under 10 %).  Here the grouped rows stay in the [M = B*S*K, C] layout the grouping
 // kernel writes, the convolution is a plain GEMM on them, and the rest of the layer is four streaming kernels:
 //

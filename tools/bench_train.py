@@ -6,7 +6,8 @@ NCCL gradient all-reduce, 32 clouds per GPU (256 at 8 GPUs), weak scaling.
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/bench_train.py
 
 Prints one JSON line on rank 0: clouds/s over all ranks (device time, max over ranks), ms per step and the all-reduce's
-share.  Training-mode MLP + BatchNorm run on ATen (autograd); sampling / grouping on the product kernels."""
+share.  Sampling, grouping and the BatchNorm / ReLU / max-pool of the shared MLP run on the product kernels, the 1x1
+convolutions as cuBLAS GEMMs on the grouped rows (PN2_TRAIN_FUSED=0: the reference's op sequence on ATen, for comparison)."""
 import argparse, json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in ("pointnet-like-pose-estimation_b200", "tests"):
