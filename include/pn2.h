@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PN2_ABI_VERSION 8
+#define PN2_ABI_VERSION 9
 #define PN2_MAX_COORD 16 /* exact summation-order rules are verified against ATen for C <= 16 */
 #define PN2_MAX_LAYERS 8
 
@@ -121,6 +121,17 @@ int pn2_sa_fused(const float *points, int64_t sb, int64_t sn, int64_t sc,
  * fp32 like the reference's numpy path; sums are tree reductions, so results agree to rounding (<= 1e-5 on coordinates in [-1, 1]), not bitwise. */
 int pn2_normalize_splice_f32(const float *xyz, int64_t sb, int64_t sn, int64_t sc, int B, int N,
                              const int64_t *category, int num_category, float *out, void *stream);
+
+/* query_ball_point for the n_radii balls of one PointNetSetAbstractionMsg layer in one scan -- the loop of
+ * pointnet2_utils.py:203-204 calls :70-90 once per radius on the same centres and cloud; the distances do not depend on
+ * the radius.  r2[n_radii], K[n_radii] are HOST arrays (r2 as in pn2_ball_query_f32); idx64[n_radii] / idx32[n_radii] are
+ * host arrays of device pointers [B,S,K[r]] (either array, or single entries, may be NULL).  Each list is bit-identical
+ * to a separate pn2_ball_query_f32 call; n_radii in 1..3.  Radii that are not ascending, widths other than 3 / 10 and
+ * clouds beyond the one-pass shared-memory budget are served by one query per radius internally. */
+int pn2_ball_query_multi_f32(const float *centres, int64_t csb, int64_t csn, int64_t csc,
+                             const float *points, int64_t sb, int64_t sn, int64_t sc,
+                             int B, int S, int N, int C, int n_radii, const float *r2, const int *K,
+                             int64_t *const *idx64, int32_t *const *idx32, int32_t *empty_flag, void *stream);
 
 /* The reference's numpy copies of farthest point sampling -- provider.py:183-204, data_utils/ModelDataLoader.py:10-31,
  * point_collect/transformer.py:120-141 (called per file by the data generators and loaders, and per DBSCAN cluster by

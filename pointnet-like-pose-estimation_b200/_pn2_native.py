@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(_HERE, LIB_NAME)
 ORDER_SSG, ORDER_MSG, ORDER_ALL = 0, 1, 2
 PREC_F32, PREC_BF16 = 0, 1
 MAX_COORD = 16
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 _i64, _i32, _f32, _vp = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p
 
@@ -34,6 +34,8 @@ _SIGNATURES = {
     "pn2_square_distance_f32": ([_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp], _i32),
     "pn2_ball_query_f32": ([_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _i32,
                             _vp, _vp, _vp, _vp], _i32),
+    "pn2_ball_query_multi_f32": ([_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32,
+                                  _vp, _vp, _vp, _vp, _vp, _vp], _i32),
     "pn2_group_f32": ([_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _vp,
                        _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp], _i32),
     "pn2_packed_bytes": ([_i32, _vp, _i32], _i64),
@@ -188,6 +190,29 @@ class Native:
                                                i64.data_ptr() if want_idx64 else None,
                                                i32.data_ptr() if want_idx32 else None, None, _stream(points)))
         return i64, i32
+
+    def ball_query_multi(self, centres, points, r2_list, numbers, want_idx64=False, want_idx32=True):
+        """All radii of one MSG layer in one scan: -> list of (idx64 | None, idx32 | None) [B,S,K_r] per radius; every list
+        is bit-identical to ball_query(centres, points, r2_list[r], numbers[r])."""
+        _need_cuda("new_points", centres, torch.float32)
+        _need_cuda("points", points, torch.float32)
+        B, N, C = points.shape
+        S = centres.shape[1]
+        R = len(r2_list)
+        dev = points.device
+        if R > 3:
+            return [self.ball_query(centres, points, r2, K, want_idx64, want_idx32) for r2, K in zip(r2_list, numbers)]
+        outs = [(torch.empty(B, S, int(K), dtype=torch.int64, device=dev) if want_idx64 else None,
+                 torch.empty(B, S, int(K), dtype=torch.int32, device=dev) if want_idx32 else None) for K in numbers]
+        r2 = (ctypes.c_float * R)(*[float(v) for v in r2_list])
+        ks = (ctypes.c_int * R)(*[int(K) for K in numbers])
+        p64 = (ctypes.c_void_p * R)(*[o[0].data_ptr() if o[0] is not None else None for o in outs])
+        p32 = (ctypes.c_void_p * R)(*[o[1].data_ptr() if o[1] is not None else None for o in outs])
+        with torch.cuda.device(dev), self._span("ball_query_multi", B=B, N=N, C=C, S=S, K=[int(K) for K in numbers]):
+            _check(self.lib.pn2_ball_query_multi_f32(centres.data_ptr(), *centres.stride(), points.data_ptr(), *points.stride(),
+                                                     B, S, N, C, R, r2, ks, p64 if want_idx64 else None,
+                                                     p32 if want_idx32 else None, None, _stream(points)))
+        return outs
 
     # -- grouping ------------------------------------------------------------------------------------------
     def group(self, points, feature, idx32, centres, order):

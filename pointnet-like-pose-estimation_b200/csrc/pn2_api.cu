@@ -68,6 +68,24 @@ int pn2_ball_query_f32(const float *centres, int64_t csb, int64_t csn, int64_t c
                              (cudaStream_t)stream);
 }
 
+int pn2_ball_query_multi_f32(const float *centres, int64_t csb, int64_t csn, int64_t csc,
+                             const float *points, int64_t sb, int64_t sn, int64_t sc,
+                             int B, int S, int N, int C, int n_radii, const float *r2, const int *K,
+                             int64_t *const *idx64, int32_t *const *idx32, int32_t *empty_flag, void *stream)
+{
+    PN2_REQUIRE(centres && points && r2 && K, "pn2_ball_query_multi_f32: null pointer");
+    PN2_REQUIRE(n_radii >= 1 && n_radii <= 3, "pn2_ball_query_multi_f32: n_radii=%d outside [1,3]", n_radii);
+    PN2_REQUIRE(idx64 || idx32, "pn2_ball_query_multi_f32: no output requested");
+    PN2_REQUIRE(C >= 1 && C <= PN2_MAX_COORD, "pn2_ball_query_multi_f32: C=%d outside [1,%d]", C, PN2_MAX_COORD);
+    for (int r = 0; r < n_radii; ++r) {
+        PN2_REQUIRE((idx64 && idx64[r]) || (idx32 && idx32[r]), "pn2_ball_query_multi_f32: no output requested for radius %d", r);
+        PN2_REQUIRE(K[r] >= 1 && K[r] <= N, "pn2_ball_query_multi_f32: number=%d must be in [1, N=%d] (the reference raises for K > N)", K[r], N);
+        PN2_REQUIRE(K[r] <= 4096, "pn2_ball_query_multi_f32: number=%d > 4096 unsupported", K[r]);
+    }
+    return launch_ball_query_multi(centres, csb, csn, csc, points, sb, sn, sc, B, S, N, C, n_radii, r2, K, idx64, idx32,
+                                   empty_flag, (cudaStream_t)stream);
+}
+
 int pn2_group_f32(const float *points, int64_t sb, int64_t sn, int64_t sc,
                   const float *feat, int64_t fb, int64_t fn, int64_t fc,
                   const int32_t *idx32, const float *centres,

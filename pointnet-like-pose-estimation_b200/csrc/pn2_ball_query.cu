@@ -10,6 +10,7 @@
 //
 // Exactness contract: dot = fl(s0*p0), dot = fma(s_k, p_k, dot) ascending k (MKL sgemm, :23);
 // d = fl(fl(-2*dot + |s|^2) + |p|^2); in radius <=> !(d > r2).
+#include <type_traits>
 #include "pn2_common.cuh"
 
 namespace pn2 {
@@ -258,6 +259,170 @@ ball_query_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, i
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Multi-radius ball query: the MSG layers (pointnet2_utils.py:203-204) query the same centres against the same cloud once
+// per radius.  The distances do not depend on the radius, so one scan serves all NR of them: d is evaluated once per
+// (centre, point) and compared against the ascending radii, largest first -- a point outside the largest ball is outside
+// all (the common case costs one compare + two ballots, like the single-radius kernel), and the hit bookkeeping of the
+// smaller balls runs only on trips that have a hit in the largest.  The scan of a centre group stops when every list of
+// every centre is full.  Same staging, distance arithmetic and output convention as ball_query_kernel (single-chunk
+// path: the cloud fits in shared memory), so each list is bit-identical to a separate query.
+struct BqMulti {
+    float r2[3];
+    int K[3];
+    int koff[3];            // offset of radius r's staging row inside a centre's [ktot] block
+    int ktot;
+    int64_t *idx64[3];
+    int32_t *idx32[3];
+};
+
+template <int C, int BQ_WARPS, int NR>
+__global__ void __launch_bounds__(BQ_WARPS * 32)
+ball_query_multi_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, int64_t csc,
+                        const float *__restrict__ points, int64_t sb, int64_t sn, int64_t sc,
+                        int S, int N, int NCH, int cpw, const BqMulti q, int32_t *__restrict__ empty_flag)
+{
+    constexpr int BQ_THREADS = BQ_WARPS * 32;
+    constexpr int CPB = BQ_CPB<C>::value;
+    extern __shared__ float smem[];
+    float *sp = smem;                       // [C][NCH]
+    float *sp2 = smem + (size_t)C * NCH;    // [NCH]
+    int *stage = (int *)(sp2 + NCH) + (threadIdx.x >> 5) * (CPB * q.ktot);       // [CPB][ktot] per warp
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    const int s_begin = (blockIdx.x * BQ_WARPS + warp) * cpw;
+    const float *P = points + (int64_t)b * sb;
+    const bool pcontig = (sc == 1);
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    // staging: identical to ball_query_kernel's single-chunk path (one-hot tail detection, rows padded to 64 with +inf)
+    bool tail_same = C > 4;
+    for (int n = tid; n < N; n += BQ_THREADS) {
+        float v[C];
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            v[k] = __ldg(P + (int64_t)n * sn + (int64_t)k * sc);
+            sp[k * NCH + n] = v[k];
+            if (C > 4 && k >= 3) {
+                const float ref = __ldg(P + (int64_t)k * sc);
+                tail_same = tail_same && fabsf(ref) <= 3.0e38f && v[k] == ref;
+            }
+        }
+        sp2[n] = sqnorm<C>(v, pcontig, n >= (N & ~31));
+    }
+    for (int n = N + tid; n < NCH; n += BQ_THREADS) {
+#pragma unroll
+        for (int k = 0; k < C; ++k) sp[k * NCH + n] = 0.f;
+        sp2[n] = INFINITY;
+    }
+    const bool tail_uniform = __syncthreads_and(tail_same ? 1 : 0) != 0 && C > 4;
+    float e_nz = 0.f;
+    bool tail_short = tail_uniform;
+    if (C > 4 && tail_uniform) {
+        int nz = 0;
+#pragma unroll
+        for (int k = 3; k < C; ++k) { const float ek = sp[k * NCH]; if (ek != 0.f) { ++nz; e_nz = ek; } }
+        tail_short = nz <= 1;
+    }
+
+    for (int ci = 0; ci < cpw; ci += CPB) {
+        f32x2 sv[CPB][C], s2v[CPB];
+        int cn[CPB][NR];
+        bool grp_short = tail_short;
+#pragma unroll
+        for (int c = 0; c < CPB; ++c) {
+            const int sidx = s_begin + ci + c;
+            const bool act = ci + c < cpw && sidx < S;
+            float sc_[C];
+#pragma unroll
+            for (int k = 0; k < C; ++k) sc_[k] = act ? __ldg(centres + (int64_t)b * csb + (int64_t)sidx * csn + (int64_t)k * csc) : 0.f;
+            const float q2 = sqnorm<C>(sc_, csc == 1, sidx >= (S & ~31));
+#pragma unroll
+            for (int k = 0; k < C; ++k) sv[c][k] = pk2(sc_[k], sc_[k]);
+            s2v[c] = pk2(q2, q2);
+#pragma unroll
+            for (int r = 0; r < NR; ++r) cn[c][r] = act ? 0 : q.K[r];
+            if (C > 4 && act) {
+#pragma unroll
+                for (int k = 3; k < C; ++k) grp_short = grp_short && sc_[k] == sp[k * NCH];
+            }
+        }
+        const f32x2 m2v = pk2(-2.0f, -2.0f);
+        const f32x2 ev = pk2(e_nz, e_nz);
+
+        auto scan = [&](auto short_tag) {
+            constexpr bool SHORT = decltype(short_tag)::value;
+            constexpr int CE = SHORT ? 3 : C;
+            const float *prow = sp + 2 * lane;
+            for (int n0 = 0; n0 < NCH; n0 += 64, prow += 64) {
+                bool all_done = true;
+#pragma unroll
+                for (int c = 0; c < CPB; ++c)
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) all_done = all_done && cn[c][r] >= q.K[r];
+                if (all_done) break;
+                const int na = n0 + 2 * lane;
+                f32x2 pv[CE];
+#pragma unroll
+                for (int k = 0; k < CE; ++k) pv[k] = *reinterpret_cast<const f32x2 *>(prow + k * NCH);
+                const f32x2 p2v = *reinterpret_cast<const f32x2 *>(prow + C * NCH);
+#pragma unroll
+                for (int c = 0; c < CPB; ++c) {
+                    f32x2 dot = mul2(sv[c][0], pv[0]);
+#pragma unroll
+                    for (int k = 1; k < CE; ++k) dot = fma2(sv[c][k], pv[k], dot);
+                    if (SHORT && e_nz != 0.f) dot = fma2(ev, ev, dot);
+                    const float2 d = unpk2(add2(fma2(m2v, dot, s2v[c]), p2v));
+                    bool ina = !(d.x > q.r2[NR - 1]), inb = !(d.y > q.r2[NR - 1]);
+                    unsigned ma = __ballot_sync(0xffffffffu, ina);
+                    unsigned mb = __ballot_sync(0xffffffffu, inb);
+                    if (ma | mb) {                                          // warp-uniform
+#pragma unroll
+                        for (int r = NR - 1; r >= 0; --r) {
+                            if (r < NR - 1) {                               // next smaller ball: a subset of the previous hits
+                                ina = !(d.x > q.r2[r]); inb = !(d.y > q.r2[r]);
+                                ma = __ballot_sync(0xffffffffu, ina);
+                                mb = __ballot_sync(0xffffffffu, inb);
+                                if (!(ma | mb)) break;
+                            }
+                            if (cn[c][r] < q.K[r]) {
+                                int *stg = stage + c * q.ktot + q.koff[r];
+                                const int pa = cn[c][r] + __popc(ma & lt_mask) + __popc(mb & lt_mask);
+                                if (ina && pa < q.K[r]) stg[pa] = na;
+                                if (inb && pa + (int)ina < q.K[r]) stg[pa + (int)ina] = na + 1;
+                                cn[c][r] += __popc(ma) + __popc(mb);
+                            }
+                        }
+                    }
+                }
+            }
+        };
+        if (C > 4 && grp_short) scan(std::true_type{});
+        else scan(std::false_type{});
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < CPB; ++c) {
+            const int sidx = s_begin + ci + c;
+            if (!(ci + c < cpw && sidx < S)) continue;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const int K = q.K[r];
+                const int *stg = stage + c * q.ktot + q.koff[r];
+                const int cc = cn[c][r] > K ? K : cn[c][r];
+                const int frst = cc ? stg[0] : N;
+                if (cc == 0 && lane == 0 && empty_flag) atomicOr(empty_flag, 1);
+                const int64_t o = ((int64_t)b * S + sidx) * K;
+                for (int j = lane; j < K; j += 32) {
+                    const int v = (j < cc) ? stg[j] : frst;
+                    if (q.idx64[r]) q.idx64[r][o + j] = v;
+                    if (q.idx32[r]) q.idx32[r][o + j] = v;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // Run-time-C fallback (C <= PN2_MAX_COORD): one thread per centre, points streamed from global memory.
 __global__ void ball_query_generic_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, int64_t csc,
                                           const float *__restrict__ points, int64_t sb, int64_t sn, int64_t sc,
@@ -356,6 +521,61 @@ int launch_ball_query(const float *centres, int64_t csb, int64_t csn, int64_t cs
     ball_query_generic_kernel<<<(unsigned)((G + 127) / 128), 128, 0, st>>>(centres, csb, csn, csc, points, sb, sn, sc,
                                                                             B, S, N, C, r2, K, idx64, idx32, empty_flag);
     return launch_status("pn2_ball_query_f32(generic)");
+}
+
+template <int C, int NR>
+static int launch_bq_multi(const float *centres, int64_t csb, int64_t csn, int64_t csc,
+                           const float *points, int64_t sb, int64_t sn, int64_t sc,
+                           int B, int S, int N, int NCH, const BqMulti &q, int32_t *empty_flag, cudaStream_t st)
+{
+    constexpr int W = BQ_WARPS_SMALL;
+    int cpw = 16;
+    while (cpw > 1 && (int64_t)B * ((S + W * cpw - 1) / (W * cpw)) < 592) cpw >>= 1;
+    const size_t smem = (size_t)(C + 1) * NCH * sizeof(float) + sizeof(int) * (size_t)W * BQ_CPB<C>::value * q.ktot;
+    auto kern = ball_query_multi_kernel<C, W, NR>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("ball_query_multi: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    dim3 grid((S + W * cpw - 1) / (W * cpw), B);
+    kern<<<grid, W * 32, smem, st>>>(centres, csb, csn, csc, points, sb, sn, sc, S, N, NCH, cpw, q, empty_flag);
+    return launch_status("pn2_ball_query_multi_f32");
+}
+
+// Host arrays r2[NR] (ascending), K[NR], idx64[NR] / idx32[NR] (device pointers, entries or the arrays may be NULL).
+int launch_ball_query_multi(const float *centres, int64_t csb, int64_t csn, int64_t csc,
+                            const float *points, int64_t sb, int64_t sn, int64_t sc,
+                            int B, int S, int N, int C, int NR, const float *r2, const int *K,
+                            int64_t *const *idx64, int32_t *const *idx32, int32_t *empty_flag, cudaStream_t st)
+{
+    if (B == 0 || S == 0) return 0;
+    PN2_REQUIRE(B <= 65535, "pn2_ball_query_multi_f32: B=%d exceeds gridDim.y", B);
+    BqMulti q;
+    q.ktot = 0;
+    bool ascending = true;
+    for (int r = 0; r < NR; ++r) {
+        q.r2[r] = r2[r]; q.K[r] = K[r]; q.koff[r] = q.ktot; q.ktot += K[r];
+        q.idx64[r] = idx64 ? idx64[r] : nullptr;
+        q.idx32[r] = idx32 ? idx32[r] : nullptr;
+        if (r && !(r2[r - 1] <= r2[r])) ascending = false;
+    }
+    for (int r = NR; r < 3; ++r) { q.r2[r] = 0.f; q.K[r] = 0; q.koff[r] = 0; q.idx64[r] = nullptr; q.idx32[r] = nullptr; }
+    const int NCH = (N + 63) & ~63;
+    const size_t cloud = (size_t)(C + 1) * NCH * sizeof(float);
+    const size_t stage = sizeof(int) * (size_t)BQ_WARPS_SMALL * (C <= 4 ? 4 : 2) * q.ktot;
+    const bool fused = ascending && (NR == 2 || NR == 3) && (C == 3 || C == 10) && cloud <= 100 * 1024 && cloud + stage <= 200 * 1024;
+    if (!fused) {         // one query per radius (unsorted radii, other widths, clouds that need the chunked / 32-warp kernel)
+        for (int r = 0; r < NR; ++r) {
+            const int rc = launch_ball_query(centres, csb, csn, csc, points, sb, sn, sc, B, S, N, C, r2[r], K[r],
+                                             q.idx64[r], q.idx32[r], empty_flag, st);
+            if (rc) return rc;
+        }
+        return 0;
+    }
+    if (C == 3) return NR == 2 ? launch_bq_multi<3, 2>(centres, csb, csn, csc, points, sb, sn, sc, B, S, N, NCH, q, empty_flag, st)
+                               : launch_bq_multi<3, 3>(centres, csb, csn, csc, points, sb, sn, sc, B, S, N, NCH, q, empty_flag, st);
+    return NR == 2 ? launch_bq_multi<10, 2>(centres, csb, csn, csc, points, sb, sn, sc, B, S, N, NCH, q, empty_flag, st)
+                   : launch_bq_multi<10, 3>(centres, csb, csn, csc, points, sb, sn, sc, B, S, N, NCH, q, empty_flag, st);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -204,6 +204,10 @@ int launch_sa_bf16(const SaArgs &a, cudaStream_t st);
 int launch_sa_bf16_pipelined(const SaArgs &a, cudaStream_t st);   // -100: configuration not covered
 int sa_bf16_pipelined_covers(int K, int C, int D, int order, int L, const int *dims);
 void set_debug_trace(void *buf);
+int launch_ball_query_multi(const float *centres, int64_t csb, int64_t csn, int64_t csc,
+                            const float *points, int64_t sb, int64_t sn, int64_t sc,
+                            int B, int S, int N, int C, int NR, const float *r2, const int *K,
+                            int64_t *const *idx64, int32_t *const *idx32, int32_t *empty_flag, cudaStream_t st);
 int64_t fps_np_scratch_bytes(int B, int N, int elem_bytes);
 int launch_fps_np_f64(const double *points, int64_t sb, int64_t sn, int64_t sc, int B, int N, const int64_t *start, int S,
                       int64_t *idx64, void *scratch, cudaStream_t stream);

@@ -488,8 +488,9 @@ class PointNetSetAbstractionMsg(nn.Module):
         twin_out = torch.empty(B, S, total, dtype=torch.bfloat16, device=pts.device) if all(sides) else None
         co = 0
         feat_bf16 = None
-        for radius, K, (packed, dims, prec), wf in zip(self.radius_list, self.sample_number_list, plans, fact):
-            _, idx32 = be.ball_query(new_points, pts, _radius_sq(radius), K, want_idx64=False, want_idx32=True)
+        # one scan of the cloud serves every radius of the layer (the distances do not depend on it)
+        groups = be.ball_query_multi(new_points, pts, [_radius_sq(r) for r in self.radius_list], self.sample_number_list)
+        for (_, idx32), K, (packed, dims, prec), wf in zip(groups, self.sample_number_list, plans, fact):
             if wf is not None:
                 # first layer factorised: P = feat (s Wf)^T once per point, gathered in place of the feature rows
                 if feat_bf16 is None:
@@ -508,9 +509,8 @@ class PointNetSetAbstractionMsg(nn.Module):
         S = self.point_number
         _, _, new_points = be.fps(pts.detach(), start, S, want_idx64=False, want_new_points=True)
         outs = []
-        for i, radius in enumerate(self.radius_list):
-            K = self.sample_number_list[i]
-            _, idx32 = be.ball_query(new_points, pts.detach(), _radius_sq(radius), K, want_idx64=False, want_idx32=True)
+        groups = be.ball_query_multi(new_points, pts.detach(), [_radius_sq(r) for r in self.radius_list], self.sample_number_list)
+        for i, (_, idx32) in enumerate(groups):
             rows = be.group(pts.detach(), None, idx32, new_points, ORDER_MSG)            # [B,S,K,C] xyz - centre
             convs, bns = self.conv_blocks[i], self.bn_blocks[i]
             if feat is not None and _factorise_first_layer and feat.shape[-1] > convs[0].out_channels:

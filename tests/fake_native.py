@@ -23,6 +23,13 @@ class OracleNative:
         return (idx if want_idx64 else None, idx.int() if want_idx32 else None,
                 orc.index_points(points, idx).contiguous() if want_new_points else None)
 
+    def ball_query_multi(self, centres, points, r2_list, numbers, want_idx64=False, want_idx32=True):
+        self.calls.append("ball_query_multi")
+        n = len(self.calls)
+        outs = [self.ball_query(centres, points, r2, K, want_idx64, want_idx32) for r2, K in zip(r2_list, numbers)]
+        del self.calls[n:]
+        return outs
+
     def fps_xyz(self, points, start, S):
         self.calls.append("fps_xyz")
         rows = [orc.farthest_point_sample_np(points[b].numpy(), S, int(start[b]))[1] for b in range(points.shape[0])]

@@ -146,6 +146,35 @@ def test_ball_query_vs_oracle(nat, oracle, B, N, C, S, K, r, layout, kind):
     assert torch.equal(sd.cpu(), oracle.square_distance(cen[:, :8], x))
 
 
+BQ_MULTI_CASES = [  # (B, N, C, S, Ks, radii, layout, kind) -- the MSG layers (pointnet2_cls_msg.py:9-10, translation_msg.py:11) + edge cases
+    (4, 1024, 3, 512, [16, 32, 128], [0.1, 0.2, 0.4], "strided", "uni"), (4, 512, 3, 128, [32, 64, 128], [0.2, 0.4, 0.8], "contig", "uni"),
+    (4, 1024, 10, 512, [16, 32, 128], [0.1, 0.2, 0.4], "strided", "surf"), (4, 512, 10, 128, [32, 64, 128], [0.2, 0.4, 0.8], "contig", "uni"),
+    (3, 1024, 10, 512, [16, 32, 64], [0.1, 0.2, 0.4], "strided", "dup"), (3, 2048, 10, 512, [16, 32, 128], [0.1, 0.2, 0.4], "strided", "uni"),
+    (3, 1000, 10, 300, [8, 200], [0.3, 0.3], "contig", "mix"), (3, 777, 10, 99, [64, 5, 32], [0.2, 0.2, 0.9], "strided", "odd1"),
+    (2, 333, 3, 70, [333, 1], [0.05, 50.0], "contig", "dup"),
+    (2, 512, 3, 128, [16, 32, 64], [0.4, 0.2, 0.1], "contig", "uni"),        # descending radii: served by one query per radius
+    (2, 300, 5, 64, [7, 9], [0.5, 0.6], "contig", "uni"),                    # other widths: generic kernel per radius
+    (1, 6000, 3, 64, [16, 32], [0.05, 0.1], "contig", "uni"),                # large cloud
+    (40, 1024, 10, 512, [16, 32, 128], [0.1, 0.2, 0.4], "strided", "uni"),
+]
+
+
+@pytest.mark.parametrize("B,N,C,S,Ks,radii,layout,kind", BQ_MULTI_CASES)
+def test_multi_radius_ball_query_equals_one_query_per_radius(nat, oracle, B, N, C, S, Ks, radii, layout, kind):
+    x = lay(make_cloud(B, N, C, kind, 3000 + N + C + sum(Ks)), layout)
+    start = torch.randint(0, N, (B,), generator=torch.Generator().manual_seed(9), dtype=torch.long)
+    cen = oracle.index_points(x, oracle.farthest_point_sample(x, S, start)).contiguous()
+    r2 = [oracle.radius_sq_f32(r) for r in radii]
+    outs = nat.ball_query_multi(dev(cen), dev(x), r2, Ks, want_idx64=True, want_idx32=True)
+    assert len(outs) == len(Ks)
+    for (i64, i32), r, K in zip(outs, radii, Ks):
+        exp = oracle.query_ball_point(r, K, x, cen)
+        assert torch.equal(i64.cpu(), exp), (r, K)
+        assert torch.equal(i32.cpu().long(), exp)
+    only32 = nat.ball_query_multi(dev(cen), dev(x), r2, Ks)
+    assert all(a is None and torch.equal(b, o[1]) for (a, b), o in zip(only32, outs))
+
+
 def test_ball_query_empty_rows_are_flagged_not_oob(nat, oracle):
     """No point in radius: the reference writes N and fails in index_points; we fill N and never read OOB."""
     x = cloudgen.uniform_cloud(1, 256, 5)
