@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PN2_ABI_VERSION 9
+#define PN2_ABI_VERSION 10
 #define PN2_MAX_COORD 16 /* exact summation-order rules are verified against ATen for C <= 16 */
 #define PN2_MAX_LAYERS 8
 
@@ -153,12 +153,16 @@ int pn2_fps_xyz_f32(const float *points, int64_t sb, int64_t sn, int64_t sc, int
  *   forward : stats [5][C] <- mean, biased var, invstd, a = gamma*invstd, b = beta - mean*a;  z = max(0, y*a + b).
  *             K = 0: z [M, C].  K > 0: the max over each group of K consecutive rows (:172 / :218) is fused:
  *             z [M/K, C] pooled maximum, arg [M/K, C] int32 = its first row, and the full z never reaches HBM.
+ *             running_mean / running_var [C] (both or neither; may be NULL): nn.BatchNorm2d's bookkeeping in the same
+ *             launch, running <- (1 - factor) * running + factor * batch, with the mean shifted by conv_bias [C] (the
+ *             bias left out of y; may be NULL) and the variance unbiased (M / (M - 1)).
  *   backward: dz = gradient of z (K = 0: [M, C]; K > 0: [M/K, C] with the forward's arg); dy [M, C] = gradient of y;
  *             sums [2][C] <- dbeta, dgamma.  The ReLU mask is recomputed from y and stats.
  * ws = pn2_bn_train_ws_bytes(C) bytes of scratch (per-CTA fp64 partial sums, added in a fixed order: deterministic). */
 int64_t pn2_bn_train_ws_bytes(int C);
 int pn2_bn_relu_train_fwd_f32(const float *y, int64_t M, int C, int K, const float *gamma, const float *beta, float eps,
-                              void *ws, float *stats, float *z, int32_t *arg, void *stream);
+                              void *ws, float *stats, float *z, int32_t *arg,
+                              float *running_mean, float *running_var, const float *conv_bias, float factor, void *stream);
 int pn2_bn_relu_train_bwd_f32(const float *dz, const float *y, const int32_t *arg, int64_t M, int C, int K,
                               const float *stats, void *ws, float *sums, float *dy, void *stream);
 

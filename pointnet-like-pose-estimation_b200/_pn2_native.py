@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(_HERE, LIB_NAME)
 ORDER_SSG, ORDER_MSG, ORDER_ALL = 0, 1, 2
 PREC_F32, PREC_BF16 = 0, 1
 MAX_COORD = 16
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 _i64, _i32, _f32, _vp = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p
 
@@ -50,7 +50,7 @@ _SIGNATURES = {
     "pn2_fps_xyz_f64": ([_vp, _i64, _i64, _i64, _i32, _i32, _vp, _i32, _vp, _vp, _vp], _i32),
     "pn2_fps_xyz_f32": ([_vp, _i64, _i64, _i64, _i32, _i32, _vp, _i32, _vp, _vp, _vp], _i32),
     "pn2_bn_train_ws_bytes": ([_i32], _i64),
-    "pn2_bn_relu_train_fwd_f32": ([_vp, _i64, _i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp], _i32),
+    "pn2_bn_relu_train_fwd_f32": ([_vp, _i64, _i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp], _i32),
     "pn2_bn_relu_train_bwd_f32": ([_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp], _i32),
     "pn2_selftest_umma": ([_i32, _i32, _i32, _vp, _vp, _vp], _i32),
     "pn2_debug_trace": ([_vp], _i32),
@@ -357,9 +357,10 @@ class Native:
                       scratch.data_ptr() if scratch is not None else None, _stream(points)))
         return idx
 
-    def bn_relu_train_fwd(self, y, gamma, beta, eps, K=0):
+    def bn_relu_train_fwd(self, y, gamma, beta, eps, K=0, running=None):
         """Training-mode relu(bn(y)) on rows y [M, C] (batch statistics): -> (z, stats [5, C], arg).
-        K = 0: z [M, C], arg None.  K > 0: z [M/K, C] = max over each group of K rows, arg [M/K, C] int32."""
+        K = 0: z [M, C], arg None.  K > 0: z [M/K, C] = max over each group of K rows, arg [M/K, C] int32.
+        running = (running_mean, running_var, conv_bias | None, factor): updated in place in the same launch."""
         _need_cuda("y", y, torch.float32)
         _need_cuda("gamma", gamma, torch.float32)
         _need_cuda("beta", beta, torch.float32)
@@ -371,10 +372,18 @@ class Native:
         stats = torch.empty(5, C, dtype=torch.float32, device=y.device)
         z = torch.empty(M // K if K else M, C, dtype=torch.float32, device=y.device)
         arg = torch.empty(M // K, C, dtype=torch.int32, device=y.device) if K else None
+        rm = rv = cb = None
+        factor = 0.0
+        if running is not None:
+            rm_t, rv_t, cb_t, factor = running
+            for name, t in (("running_mean", rm_t), ("running_var", rv_t)) + ((("conv_bias", cb_t),) if cb_t is not None else ()):
+                _need_cuda(name, t, torch.float32)
+                assert t.is_contiguous() and t.numel() == C
+            rm, rv, cb = rm_t.data_ptr(), rv_t.data_ptr(), (cb_t.data_ptr() if cb_t is not None else None)
         with torch.cuda.device(y.device), self._span("bn_relu_train_fwd", M=M, C=C, K=K):
             _check(self.lib.pn2_bn_relu_train_fwd_f32(y.data_ptr(), M, C, int(K), gamma.data_ptr(), beta.data_ptr(), float(eps),
                                                       ws.data_ptr(), stats.data_ptr(), z.data_ptr(),
-                                                      arg.data_ptr() if K else None, _stream(y)))
+                                                      arg.data_ptr() if K else None, rm, rv, cb, float(factor), _stream(y)))
         return z, stats, arg
 
     def bn_relu_train_bwd(self, dz, y, arg, stats, K=0):

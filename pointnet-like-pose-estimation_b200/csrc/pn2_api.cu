@@ -198,12 +198,15 @@ int pn2_fps_xyz_f32(const float *points, int64_t sb, int64_t sn, int64_t sc, int
 int64_t pn2_bn_train_ws_bytes(int C) { return C >= 1 ? bn_train_ws_bytes(C) : -1; }
 
 int pn2_bn_relu_train_fwd_f32(const float *y, int64_t M, int C, int K, const float *gamma, const float *beta, float eps,
-                              void *ws, float *stats, float *z, int32_t *arg, void *stream)
+                              void *ws, float *stats, float *z, int32_t *arg,
+                              float *running_mean, float *running_var, const float *conv_bias, float factor, void *stream)
 {
+    PN2_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "pn2_bn_relu_train_fwd_f32: running_mean and running_var go together");
     PN2_REQUIRE(y && gamma && beta && ws && stats && z, "pn2_bn_relu_train_fwd_f32: null pointer");
     PN2_REQUIRE(M >= 2 && C >= 1, "pn2_bn_relu_train_fwd_f32: batch statistics need more than one value per channel (M=%lld, C=%d)", (long long)M, C);
     PN2_REQUIRE(K == 0 || (K > 0 && M % K == 0 && arg), "pn2_bn_relu_train_fwd_f32: K=%d must divide M=%lld and needs arg", K, (long long)M);
-    return launch_bn_fwd(y, M, C, K, gamma, beta, eps, ws, stats, z, arg, (cudaStream_t)stream);
+    return launch_bn_fwd(y, M, C, K, gamma, beta, eps, ws, stats, z, arg, running_mean, running_var, conv_bias, factor,
+                         (cudaStream_t)stream);
 }
 
 int pn2_bn_relu_train_bwd_f32(const float *dz, const float *y, const int32_t *arg, int64_t M, int C, int K,

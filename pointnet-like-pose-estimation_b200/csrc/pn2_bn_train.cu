@@ -165,9 +165,12 @@ __device__ __forceinline__ bool finalize_sums(const double *__restrict__ ws, int
 }
 
 // mean, biased variance, invstd, a, b from the per-CTA partials.
+// With running_mean / running_var it also does nn.BatchNorm2d's bookkeeping: running <- (1 - f) running + f batch, the
+// mean shifted by the convolution bias that was left out of y, the variance unbiased (M / (M - 1)) like ATen.
 __global__ void __launch_bounds__(32 * FIN_LANES) bn_fwd_finalize_kernel(const double *__restrict__ ws, int nctas, int64_t M, int C,
                                        const float *__restrict__ gamma, const float *__restrict__ beta, float eps,
-                                       float *__restrict__ stats)
+                                       float *__restrict__ stats, float *__restrict__ running_mean,
+                                       float *__restrict__ running_var, const float *__restrict__ conv_bias, float factor)
 {
     double s, q;
     if (!finalize_sums(ws, nctas, C, s, q)) return;
@@ -182,6 +185,11 @@ __global__ void __launch_bounds__(32 * FIN_LANES) bn_fwd_finalize_kernel(const d
     stats[2 * C + c] = invstd;
     stats[3 * C + c] = a;
     stats[4 * C + c] = fmaf(-(float)mean, a, beta[c]);
+    if (running_mean) {
+        const float mb = (float)mean + (conv_bias ? conv_bias[c] : 0.f);
+        running_mean[c] = fmaf(factor, mb, (1.f - factor) * running_mean[c]);
+        running_var[c] = fmaf(factor, (float)(var * ((double)M / (double)(M - 1))), (1.f - factor) * running_var[c]);
+    }
 }
 
 // z = max(0, y * a + b).  POOLED: rows come in groups of K; only max over the group and its first argmax row are kept.
@@ -384,13 +392,15 @@ Grid plan(int64_t rows, int C)
 int64_t bn_train_ws_bytes(int C) { return (int64_t)2 * BN_MAX_CTAS * C * sizeof(double); }
 
 int launch_bn_fwd(const float *y, int64_t M, int C, int K, const float *gamma, const float *beta, float eps,
-                  void *ws, float *stats, float *z, int32_t *arg, cudaStream_t st)
+                  void *ws, float *stats, float *z, int32_t *arg,
+                  float *running_mean, float *running_var, const float *conv_bias, float factor, cudaStream_t st)
 {
     const Grid g = plan(M, C);
     double *w = reinterpret_cast<double *>(ws);
     if (g.V == 4) bn_fwd_stats_kernel<4><<<g.grid, BN_THREADS, g.smem, st>>>(y, M, C, w);
     else bn_fwd_stats_kernel<1><<<g.grid, BN_THREADS, g.smem, st>>>(y, M, C, w);
-    bn_fwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(w, (int)g.grid.x, M, C, gamma, beta, eps, stats);
+    bn_fwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(w, (int)g.grid.x, M, C, gamma, beta, eps, stats,
+                                                                               running_mean, running_var, conv_bias, factor);
     if (K <= 0) {
         if (g.V == 4) bn_fwd_apply_kernel<4, false><<<g.grid, BN_THREADS, 0, st>>>(y, M, C, 1, stats, z, nullptr);
         else bn_fwd_apply_kernel<1, false><<<g.grid, BN_THREADS, 0, st>>>(y, M, C, 1, stats, z, nullptr);

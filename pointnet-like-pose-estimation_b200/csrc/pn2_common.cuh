@@ -215,7 +215,8 @@ int launch_fps_np_f32(const float *points, int64_t sb, int64_t sn, int64_t sc, i
                       int64_t *idx64, void *scratch, cudaStream_t stream);
 int64_t bn_train_ws_bytes(int C);
 int launch_bn_fwd(const float *y, int64_t M, int C, int K, const float *gamma, const float *beta, float eps,
-                  void *ws, float *stats, float *z, int32_t *arg, cudaStream_t st);
+                  void *ws, float *stats, float *z, int32_t *arg,
+                  float *running_mean, float *running_var, const float *conv_bias, float factor, cudaStream_t st);
 int launch_bn_bwd(const float *dz, const float *y, const int32_t *arg, int64_t M, int C, int K, const float *stats,
                   void *ws, float *sums, float *dy, cudaStream_t st);
 int launch_normalize_splice(const float *xyz, int64_t sb, int64_t sn, int64_t sc, int B, int N,

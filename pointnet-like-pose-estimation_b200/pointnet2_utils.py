@@ -303,8 +303,8 @@ class _BnReluRows(torch.autograd.Function):
     it is not added (its gradient is exactly zero; the running mean is shifted by it outside)."""
 
     @staticmethod
-    def forward(ctx, y, gamma, beta, bias, eps, K):
-        z, stats, arg = _backend().bn_relu_train_fwd(y, gamma, beta, eps, K)
+    def forward(ctx, y, gamma, beta, bias, eps, K, running):
+        z, stats, arg = _backend().bn_relu_train_fwd(y, gamma, beta, eps, K, running)
         ctx.save_for_backward(y, stats, arg)
         ctx.K = K
         ctx.has_bias = bias is not None
@@ -316,21 +316,19 @@ class _BnReluRows(torch.autograd.Function):
         y, stats, arg = ctx.saved_tensors
         dy, sums = _backend().bn_relu_train_bwd(dz, y, arg, stats, ctx.K)
         dbias = torch.zeros_like(sums[0]) if ctx.has_bias else None
-        return dy, sums[1], sums[0], dbias, None, None
+        return dy, sums[1], sums[0], dbias, None, None, None
 
 
 def _bn_relu_rows(y, conv_bias, bn, K=0):
     """One ``relu(bn(.))`` of the shared MLP in training mode on rows [M, C] (+ fused max over K rows): product kernels
     for the data, nn.BatchNorm2d's bookkeeping (running statistics, momentum, num_batches_tracked) here."""
-    M = y.shape[0]
-    z, stats = _BnReluRows.apply(y, bn.weight, bn.bias, conv_bias, bn.eps, K)
+    running = None
     if bn.track_running_stats and bn.running_mean is not None:
         with torch.no_grad():
             bn.num_batches_tracked += 1
-            f = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
-            mean = stats[0] + conv_bias if conv_bias is not None else stats[0]
-            bn.running_mean.mul_(1.0 - f).add_(mean, alpha=f)
-            bn.running_var.mul_(1.0 - f).add_(stats[1], alpha=f * M / (M - 1))            # unbiased, like ATen
+        f = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)     # cumulative average: one sync
+        running = (bn.running_mean, bn.running_var, conv_bias.detach() if conv_bias is not None else None, float(f))
+    z, _ = _BnReluRows.apply(y, bn.weight, bn.bias, conv_bias, bn.eps, K, running)            # running statistics in the same launch
     return z
 
 

@@ -35,7 +35,7 @@ class OracleNative:
         rows = [orc.farthest_point_sample_np(points[b].numpy(), S, int(start[b]))[1] for b in range(points.shape[0])]
         return torch.from_numpy(np.stack(rows))
 
-    def bn_relu_train_fwd(self, y, gamma, beta, eps, K=0):
+    def bn_relu_train_fwd(self, y, gamma, beta, eps, K=0, running=None):
         self.calls.append("bn_relu_train_fwd")
         M, C = y.shape
         if M < 2:
@@ -46,6 +46,10 @@ class OracleNative:
         a = gamma * invstd
         b = torch.addcmul(beta, -mean.float(), a)
         stats = torch.stack([mean.float(), var.float(), invstd, a, b])
+        if running is not None:
+            rm, rv, cb, f = running
+            rm.mul_(1.0 - f).add_(mean.float() + (cb if cb is not None else 0.0), alpha=f)
+            rv.mul_(1.0 - f).add_(var.float(), alpha=f * M / (M - 1))
         z = torch.relu(torch.addcmul(b, y, a))
         if not K:
             return z, stats, None
