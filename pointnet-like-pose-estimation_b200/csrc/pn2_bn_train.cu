@@ -123,10 +123,15 @@ __global__ void __launch_bounds__(BN_THREADS) bn_fwd_stats_kernel(const float *_
             float v[4][V];
 #pragma unroll
             for (int u = 0; u < 4; ++u) ldv<V>(p + (r + u * m.RL) * C, v[u]);
+            // four rows are first added in fp32 (sum and sum of squares: four-term partials, error far below the rounding
+            // of y itself), then once into the fp64 accumulators: the fp64 pipe would otherwise co-limit this pure-read kernel
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-#pragma unroll
-                for (int j = 0; j < V; ++j) { const double d = v[u][j]; acc[0][j] += d; acc[1][j] = fma(d, d, acc[1][j]); }
+            for (int j = 0; j < V; ++j) {
+                const float s4 = (v[0][j] + v[1][j]) + (v[2][j] + v[3][j]);
+                const float q4 = fmaf(v[3][j], v[3][j], fmaf(v[2][j], v[2][j], fmaf(v[1][j], v[1][j], v[0][j] * v[0][j])));
+                acc[0][j] += (double)s4;
+                acc[1][j] += (double)q4;
+            }
         }
         for (; r < r1; r += m.RL) {
             float v[V];
@@ -138,14 +143,14 @@ __global__ void __launch_bounds__(BN_THREADS) bn_fwd_stats_kernel(const float *_
     cta_partials<V, 2>(m, C, acc, ws);
 }
 
-// Sum of the per-CTA partials of 32 channels by a (32, FIN_LANES) thread block: lane ly adds partials ly, ly + FIN_LANES,
-// ... (coalesced 256-byte reads), lane 0 then adds the FIN_LANES sub-sums in order -- a fixed order, so deterministic.
-constexpr int FIN_LANES = 16;
+// Sum of the per-CTA partials of FIN_CH channels by a (FIN_CH, FIN_LANES) thread block: lane ly adds partials ly,
+// ly + FIN_LANES, ... (64-byte segments), lane 0 then adds the FIN_LANES sub-sums in order -- a fixed order, so deterministic.
+constexpr int FIN_LANES = 64, FIN_CH = 8;
 
 __device__ __forceinline__ bool finalize_sums(const double *__restrict__ ws, int nctas, int C, double &s, double &q)
 {
-    __shared__ double s_part[2][FIN_LANES][32];
-    const int c = blockIdx.x * 32 + threadIdx.x, ly = threadIdx.y;
+    __shared__ double s_part[2][FIN_LANES][FIN_CH];
+    const int c = blockIdx.x * FIN_CH + threadIdx.x, ly = threadIdx.y;
     double a0 = 0.0, a1 = 0.0;
     if (c < C) {
 #pragma unroll 4
@@ -159,22 +164,21 @@ __device__ __forceinline__ bool finalize_sums(const double *__restrict__ ws, int
     __syncthreads();
     if (ly != 0 || c >= C) return false;
     s = q = 0.0;
-#pragma unroll
+#pragma unroll 8
     for (int l = 0; l < FIN_LANES; ++l) { s += s_part[0][l][threadIdx.x]; q += s_part[1][l][threadIdx.x]; }
     return true;
 }
 
-// mean, biased variance, invstd, a, b from the per-CTA partials.
 // With running_mean / running_var it also does nn.BatchNorm2d's bookkeeping: running <- (1 - f) running + f batch, the
 // mean shifted by the convolution bias that was left out of y, the variance unbiased (M / (M - 1)) like ATen.
-__global__ void __launch_bounds__(32 * FIN_LANES) bn_fwd_finalize_kernel(const double *__restrict__ ws, int nctas, int64_t M, int C,
+__global__ void __launch_bounds__(FIN_CH * FIN_LANES) bn_fwd_finalize_kernel(const double *__restrict__ ws, int nctas, int64_t M, int C,
                                        const float *__restrict__ gamma, const float *__restrict__ beta, float eps,
                                        float *__restrict__ stats, float *__restrict__ running_mean,
                                        float *__restrict__ running_var, const float *__restrict__ conv_bias, float factor)
 {
     double s, q;
     if (!finalize_sums(ws, nctas, C, s, q)) return;
-    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int c = blockIdx.x * FIN_CH + threadIdx.x;
     const double mean = s / (double)M;
     double var = q / (double)M - mean * mean;
     var = var > 0.0 ? var : 0.0;
@@ -295,11 +299,11 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_stats_kernel(const float *_
     cta_partials<V, 2>(m, C, acc, ws);
 }
 
-__global__ void __launch_bounds__(32 * FIN_LANES) bn_bwd_finalize_kernel(const double *__restrict__ ws, int nctas, int C, float *__restrict__ sums)
+__global__ void __launch_bounds__(FIN_CH * FIN_LANES) bn_bwd_finalize_kernel(const double *__restrict__ ws, int nctas, int C, float *__restrict__ sums)
 {
     double s1, s2;
     if (!finalize_sums(ws, nctas, C, s1, s2)) return;
-    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int c = blockIdx.x * FIN_CH + threadIdx.x;
     sums[c] = (float)s1;
     sums[C + c] = (float)s2;
 }
@@ -399,7 +403,7 @@ int launch_bn_fwd(const float *y, int64_t M, int C, int K, const float *gamma, c
     double *w = reinterpret_cast<double *>(ws);
     if (g.V == 4) bn_fwd_stats_kernel<4><<<g.grid, BN_THREADS, g.smem, st>>>(y, M, C, w);
     else bn_fwd_stats_kernel<1><<<g.grid, BN_THREADS, g.smem, st>>>(y, M, C, w);
-    bn_fwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(w, (int)g.grid.x, M, C, gamma, beta, eps, stats,
+    bn_fwd_finalize_kernel<<<(C + FIN_CH - 1) / FIN_CH, dim3(FIN_CH, FIN_LANES), 0, st>>>(w, (int)g.grid.x, M, C, gamma, beta, eps, stats,
                                                                                running_mean, running_var, conv_bias, factor);
     if (K <= 0) {
         if (g.V == 4) bn_fwd_apply_kernel<4, false><<<g.grid, BN_THREADS, 0, st>>>(y, M, C, 1, stats, z, nullptr);
@@ -420,14 +424,14 @@ int launch_bn_bwd(const float *dz, const float *y, const int32_t *arg, int64_t M
         const Grid g = plan(M, C);
         if (g.V == 4) bn_bwd_stats_kernel<4, false><<<g.grid, BN_THREADS, g.smem, st>>>(dz, y, nullptr, M, C, 1, stats, w);
         else bn_bwd_stats_kernel<1, false><<<g.grid, BN_THREADS, g.smem, st>>>(dz, y, nullptr, M, C, 1, stats, w);
-        bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(w, (int)g.grid.x, C, sums);
+        bn_bwd_finalize_kernel<<<(C + FIN_CH - 1) / FIN_CH, dim3(FIN_CH, FIN_LANES), 0, st>>>(w, (int)g.grid.x, C, sums);
         if (g.V == 4) bn_bwd_apply_kernel<4, false><<<g.grid, BN_THREADS, 0, st>>>(dz, y, nullptr, M, C, 1, stats, sums, dy);
         else bn_bwd_apply_kernel<1, false><<<g.grid, BN_THREADS, 0, st>>>(dz, y, nullptr, M, C, 1, stats, sums, dy);
     } else {
         const Grid p = plan(M / K, C);
         if (p.V == 4) bn_bwd_stats_kernel<4, true><<<p.grid, BN_THREADS, p.smem, st>>>(dz, y, arg, M, C, K, stats, w);
         else bn_bwd_stats_kernel<1, true><<<p.grid, BN_THREADS, p.smem, st>>>(dz, y, arg, M, C, K, stats, w);
-        bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(w, (int)p.grid.x, C, sums);
+        bn_bwd_finalize_kernel<<<(C + FIN_CH - 1) / FIN_CH, dim3(FIN_CH, FIN_LANES), 0, st>>>(w, (int)p.grid.x, C, sums);
         if (p.V == 4) bn_bwd_apply_kernel<4, true><<<p.grid, BN_THREADS, 0, st>>>(dz, y, arg, M, C, K, stats, sums, dy);
         else bn_bwd_apply_kernel<1, true><<<p.grid, BN_THREADS, 0, st>>>(dz, y, arg, M, C, K, stats, sums, dy);
     }
