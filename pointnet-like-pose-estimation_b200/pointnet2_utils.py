@@ -284,6 +284,15 @@ class _RowsLinear(torch.autograd.Function):
         return dx, dw
 
 
+def _rows_linear(x, w):
+    """x [M, Cin] @ w[Cout, Cin]^T.  Rows that are not a multiple of 16 bytes (the 10 / 13-wide grouped coordinates of the
+    pose heads, 330-wide MSG inputs) are padded with zero columns: cuBLAS only has its slow element-aligned kernels for them."""
+    pad = (-x.shape[1]) % 4
+    if pad:
+        x, w = F.pad(x, (0, pad)), F.pad(w, (0, pad))
+    return _RowsLinear.apply(x, w)
+
+
 def _rows_outer(dy, x, chunk=8192):
     """dy^T x for tall operands [M, Cout], [M, Cin] (the weight gradient of a 1x1 convolution: M = B*S*K in the millions,
     a few thousand output elements).  A single GEMM call leaves cuBLAS with a split-K problem it runs at a third of the
@@ -344,7 +353,7 @@ def _shared_mlp_train_rows(rows, convs, bns, first=None):
         if i == 0 and first is not None:
             y = first.reshape(B * S * K, -1)
         else:
-            y = _RowsLinear.apply(x, conv.weight.view(conv.out_channels, -1))
+            y = _rows_linear(x, conv.weight.view(conv.out_channels, -1))
         x = _bn_relu_rows(y, conv.bias, bn, K if i == len(convs) - 1 else 0)
     out = x.view(B, S, -1).permute(0, 2, 1)
     return out.contiguous() if _reference_strides else out
@@ -534,9 +543,9 @@ def _msg_branch_train_factorised(rows_xyz, feat, idx32, convs, bns):
     w = conv0.weight.reshape(conv0.out_channels, -1)                  # [N0, D + C], MSG order [feat, xyz] (:209)
     if _train_fused:       # bias left to the BatchNorm (it cancels against the batch mean)
         B, N = feat.shape[:2]
-        p_rows = _RowsLinear.apply(feat.reshape(B * N, D), w[:, :D]).view(B, N, -1)
+        p_rows = _rows_linear(feat.reshape(B * N, D), w[:, :D]).view(B, N, -1)
         y = _gather_rows(p_rows, idx32)
-        y += _RowsLinear.apply(rows_xyz.reshape(-1, rows_xyz.shape[-1]), w[:, D:]).view(y.shape)
+        y += _rows_linear(rows_xyz.reshape(-1, rows_xyz.shape[-1]), w[:, D:]).view(y.shape)
         return _shared_mlp_train_rows(rows_xyz, convs, bns, first=y)
     p_rows = torch.matmul(feat, w[:, :D].t())                         # [B, N, N0] once per point
     y = _gather_rows(p_rows, idx32) + torch.matmul(rows_xyz, w[:, D:].t()) + conv0.bias      # [B, S, K, N0]
