@@ -67,6 +67,38 @@ __global__ void group_kernel(const float *__restrict__ points, int64_t sb, int64
     }
 }
 
+// Coordinates only (D = 0) and at most 16 of them -- the grouped rows of training mode: one warp per output row would
+// use 3 to 10 of its lanes and write 12 to 40 bytes per instruction.  Here a warp takes 32 consecutive rows, one per lane
+// (gather + centre subtraction into shared memory), and writes the 32 * C floats as contiguous 128-byte lines.
+__global__ void __launch_bounds__(256) group_rows_small_kernel(const float *__restrict__ points, int64_t sb, int64_t sn, int64_t sc,
+                                                               const int32_t *__restrict__ idx32, const float *__restrict__ centres,
+                                                               int S, int K, int C, int order, int64_t rows, float *__restrict__ out)
+{
+    __shared__ float s_rows[8][32 * 16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float *sr = s_rows[warp];
+    for (int64_t base = warp0 * 32; base < rows; base += nwarps * 32) {
+        const int64_t r = base + lane;
+        if (r < rows) {
+            const int64_t g = r / K;
+            const int64_t b = g / S;
+            const int n = (order == PN2_ORDER_ALL) ? (int)(r % K) : idx32[r];
+            const float *p = points + b * sb + (int64_t)n * sn;
+            for (int k = 0; k < C; ++k) {
+                float x = __ldg(p + (int64_t)k * sc);
+                if (order != PN2_ORDER_ALL) x = __fsub_rn(x, __ldg(centres + g * C + k));
+                sr[lane * C + k] = x;
+            }
+        }
+        __syncwarp();
+        const int cnt = (int)((rows - base < 32 ? rows - base : 32) * C);
+        for (int i = lane; i < cnt; i += 32) out[base * C + i] = sr[i];
+        __syncwarp();
+    }
+}
+
 int launch_group(const float *points, int64_t sb, int64_t sn, int64_t sc,
                  const float *feat, int64_t fb, int64_t fn, int64_t fc,
                  const int32_t *idx32, const float *centres,
@@ -74,6 +106,12 @@ int launch_group(const float *points, int64_t sb, int64_t sn, int64_t sc,
 {
     const int64_t rows = (int64_t)B * S * K;
     if (rows == 0) return 0;
+    if (D == 0 && C <= 16) {
+        int64_t blocks = (rows + 255) / 256;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        group_rows_small_kernel<<<(unsigned)blocks, 256, 0, st>>>(points, sb, sn, sc, idx32, centres, S, K, C, order, rows, out);
+        return launch_status("pn2_group_f32");
+    }
     int64_t blocks = (rows + 7) / 8;
     if (blocks > 148 * 32) blocks = 148 * 32;
     group_kernel<<<(unsigned)blocks, 256, 0, st>>>(points, sb, sn, sc, feat, fb, fn, fc, idx32, centres,

@@ -200,6 +200,14 @@ def test_index_points_and_group_vs_oracle(nat, oracle):
                 assert torch.equal(got.cpu(), exp)
         exp = oracle.group(xs, fs, None, None, 2)
         assert torch.equal(nat.group(dev(xs), dev(fs), None, None, 2).cpu(), exp)
+        # coordinates only (training mode's grouped rows): the 32-rows-per-warp kernel, C = 10 and C = 3, ragged row counts
+        assert torch.equal(nat.group(dev(xs), None, None, None, 2).cpu(), oracle.group(xs, None, None, None, 2))
+        x3 = lay(x[..., :3].contiguous(), layout)
+        for order in (0, 1):
+            for cut in (12, 7):
+                exp = oracle.group(x3, None, idx[:, :, :cut].contiguous(), cen[..., :3].contiguous(), order)
+                got = nat.group(dev(x3), None, dev(idx[:, :, :cut].int().contiguous()), dev(cen[..., :3].contiguous()), order)
+                assert torch.equal(got.cpu(), exp)
     with pytest.raises(IndexError):
         nat.index_points(dev(x), dev(torch.full((3, 4), 400, dtype=torch.long)))
 
