@@ -22,28 +22,36 @@ __all__ = ["GraphedForward"]
 class _PinnedStarts:
     """fps_start_source for capture / replay: one pinned [B] int64 buffer per draw of a forward."""
 
-    def __init__(self):
+    def __init__(self, source=None):
         self.buffers = []          # (pinned tensor, N)
         self.capturing = True
+        self.source = source       # (B, N) -> int64 CPU tensor [B]; default = the reference's torch.randint draw
+
+    def _draw(self, B, N):
+        if self.source is None:
+            return torch.randint(0, N, (B,), dtype=torch.long)
+        return self.source(B, N).to("cpu", torch.long)
 
     def __call__(self, B, N):
         assert self.capturing, "the graphed forward draws its start indices through refill()"
         buf = torch.empty(B, dtype=torch.long).pin_memory()
-        buf.copy_(torch.randint(0, N, (B,), dtype=torch.long))
+        buf.copy_(self._draw(B, N))
         self.buffers.append((buf, N))
         return buf
 
     def refill(self):
         for buf, N in self.buffers:            # same order, same generator as the eager path
-            buf.copy_(torch.randint(0, N, (buf.shape[0],), dtype=torch.long))
+            buf.copy_(self._draw(buf.shape[0], N))
 
 
 class GraphedForward:
     """``g = GraphedForward(model, *example_inputs); out = g(*inputs)`` -- eval mode, fixed shapes, CUDA tensors.
 
-    Outputs are the graph's static output tensors (overwritten by the next call); clone them to keep them."""
+    Outputs are the graph's static output tensors (overwritten by the next call); clone them to keep them.
+    ``start_source``: optional ``(B, N) -> int64 CPU tensor [B]`` that replaces the torch.randint draw of the FPS start
+    indices, e.g. a ``pn2_shard.GlobalStarts`` so that batch-sharded replays pick the centroids of the unsharded run."""
 
-    def __init__(self, model: torch.nn.Module, *example_inputs: torch.Tensor, warmup: int = 3):
+    def __init__(self, model: torch.nn.Module, *example_inputs: torch.Tensor, warmup: int = 3, start_source=None):
         if model.training:
             raise ValueError("GraphedForward captures the eval-mode forward; call model.eval() first")
         if not example_inputs or not all(t.is_cuda for t in example_inputs):
@@ -57,7 +65,7 @@ class GraphedForward:
                 model(*self.static_in)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.starts = _PinnedStarts()
+        self.starts = _PinnedStarts(start_source)
         self.graph = torch.cuda.CUDAGraph()
         with torch.no_grad(), _pu.fps_start_source(self.starts), torch.cuda.graph(self.graph):
             self.static_out = model(*self.static_in)

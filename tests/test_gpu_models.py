@@ -211,6 +211,34 @@ def test_graphed_forward_replays_the_eager_sequence(pu, name, prec):
 
 
 @pytest.mark.gpu
+def test_graphed_forward_on_shards_equals_the_unsharded_eager_run(pu):
+    """GraphedForward(start_source=GlobalStarts): two half-batch graphs replayed with the global FPS draws give, concatenated,
+    bitwise the eager forward of the whole batch under the same draws."""
+    import pn2_graph
+    import pn2_models
+    import pn2_shard
+    dev = "cuda:0"
+    torch.manual_seed(0)
+    model = pn2_models.get_model("rotation_ssg", 7)
+    pn2_models.randomize_bn_(model)
+    model = model.eval().to(dev)
+    x = cloudgen.channels_first(cloudgen.with_category(cloudgen.uniform_cloud(12, 1024, 8))).to(dev)
+    prev = pu.get_precision()
+    pu.set_precision("bf16")
+    try:
+        halves = [pn2_graph.GraphedForward(model, x[lo:hi], start_source=pn2_shard.GlobalStarts(12, 2, r, seed=77))
+                  for r, (lo, hi) in enumerate([(0, 6), (6, 12)])]
+        for g, r in zip(halves, range(2)):                       # capture consumed draws: restart both streams
+            g.starts.source = pn2_shard.GlobalStarts(12, 2, r, seed=78)
+        got = [torch.cat([g(x[lo:hi]).clone() for g, (lo, hi) in zip(halves, [(0, 6), (6, 12)])]) for _ in range(2)]
+        with torch.no_grad(), pn2_shard.sharded_starts(12, 1, 0, seed=78):
+            exp = [model(x).clone() for _ in range(2)]
+    finally:
+        pu.set_precision(prev)
+    assert all(torch.equal(a, b) for a, b in zip(got, exp))
+
+
+@pytest.mark.gpu
 def test_full_size_properties_of_the_bench_workload(pu):
     """BASELINE-sized run (pointnet2_cls_ssg, B = 2048, N = 1024, bf16 mode) checked through size-independent properties:
     FPS picks distinct in-range points starting at the drawn index; every ball-query row is ascending up to its padding,

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--precision", choices=["bf16", "fp32"], default="bf16")
+    ap.add_argument("--graph", type=int, default=0, help="1: every head replayed as one CUDA graph (pn2_graph.GraphedForward)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -53,6 +54,17 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     head_ms = {n: 0.0 for n in HEADS}
 
+    graphs = {}
+    if args.graph:
+        from pn2_graph import GraphedForward
+        src = pn2_shard.GlobalStarts(B, world, rank, seed=7)             # global draws, this rank's slice: as in the eager path
+        xyz0 = raw.to(dev)
+        x0 = pn2_preprocess.prepare_pose_input(xyz0, category.to(dev), 7)
+        ex = {"x": x0, "mean": xyz0[:, :3, :].mean(1), "xw": torch.cat([x0[:, :3], normals.to(dev).permute(0, 2, 1), x0[:, 3:]], 1)}
+        for n in HEADS:
+            a = (ex["xw"],) if n == "v1/width" else ((ex["x"], ex["mean"]) if n.startswith("translation") else (ex["x"],))
+            graphs[n] = GraphedForward(models[n], *a, start_source=src)
+
     def step(i, timed):
         xyz = raw.to(dev, non_blocking=True)
         nrm = normals.to(dev, non_blocking=True)
@@ -63,12 +75,13 @@ def main():
         with torch.no_grad(), pn2_shard.sharded_starts(B, world, rank, seed=42 + i, device=dev):
             for n in HEADS:
                 ev[n][0].record()
+                run = graphs[n] if args.graph else models[n]
                 if n == "v1/width":
-                    out = models[n](xw)
+                    out = run(xw)
                 elif n.startswith("translation"):
-                    out = models[n](x, mean)
+                    out = run(x, mean)
                 else:
-                    out = models[n](x)
+                    out = run(x)
                 out = out if isinstance(out, tuple) else (out,)
                 outs_host[n] = [o.to("cpu", non_blocking=True) for o in out]
                 ev[n][1].record()
@@ -97,7 +110,8 @@ def main():
                           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "scaling": "strong",
                           "dtype": args.precision, "data": "synthetic",
                           "config": {"workload": f"configs[3]: {', '.join(HEADS)} on B={B} clouds, {hi - lo} per GPU, host buffers in and out",
-                                     "parallelism": f"batch-sharded x{world}, no collective"},
+                                     "parallelism": f"batch-sharded x{world}, no collective",
+                                     "cuda_graphs": bool(args.graph)},
                           "head_ms_rank0": {n: round(head_ms[n] / args.steps, 3) for n in HEADS},
                           "h2d_bytes_per_step": (raw.numel() + normals.numel()) * 4 + category.numel() * 8,
                           "d2h_bytes_per_step": sum(o.numel() * o.element_size() for v in outs_host.values() for o in v)}))
