@@ -13,8 +13,9 @@ namespace pn2 {
 
 constexpr int SA_THREADS = 256;
 constexpr int SA_KC = 16;        // k rows of W per staged chunk
+constexpr int SA_CW = 8;         // output channels per thread (x 4 rows)
 constexpr int F32_CIN_ALIGN = 16;
-constexpr int F32_COUT_ALIGN = 128;
+constexpr int F32_COUT_ALIGN = 256;   // a pass covers up to 256 output channels (R = 32)
 
 static inline int rup(int x, int a) { return (x + a - 1) / a * a; }
 
@@ -103,8 +104,8 @@ template <int R>
 __global__ void __launch_bounds__(SA_THREADS) sa_f32_kernel(const SaF32Params p)
 {
     constexpr int TXN = R / 4;              // thread columns over rows (4 rows each)
-    constexpr int TYN = SA_THREADS / TXN;   // thread rows over output channels (4 each)
-    constexpr int CCH = 4 * TYN;            // output channels per pass (64 for R=64, 128 for R=32)
+    constexpr int TYN = SA_THREADS / TXN;   // thread rows over output channels (SA_CW each)
+    constexpr int CCH = SA_CW * TYN;        // output channels per pass (128 for R=64, 256 for R=32)
     constexpr int W4 = SA_KC * CCH / 4 / SA_THREADS;  // float4 per thread per staged W chunk
 
     extern __shared__ __align__(16) float smem[];
@@ -185,11 +186,15 @@ __global__ void __launch_bounds__(SA_THREADS) sa_f32_kernel(const SaF32Params p)
             const int nk = cip / SA_KC;
 
             for (int co0 = 0; co0 < cout; co0 += CCH) {
-                float acc[4][4];
+                // accumulators as packed pairs over two adjacent output channels: Blackwell's FP32 pipe issues one scalar FFMA
+                // every other cycle per scheduler, fma.rn.f32x2 does two in the same slot -- same per-element rounding
+                // 4 rows x 8 channels per thread: one activation quad + two weight quads from shared memory feed 32 FMAs
+                // (the 4 x 4 tile this replaces was bound by shared-memory bandwidth, 3 wavefronts per 16 FMAs).
+                f32x2 acc2[4][SA_CW / 2];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+                    for (int j = 0; j < SA_CW / 2; ++j) acc2[i][j] = pk2(0.f, 0.f);
 
                 auto prefetch = [&](int kc) {
                     float *dst = Ws + (kc & 1) * SA_KC * CCH;
@@ -201,36 +206,49 @@ __global__ void __launch_bounds__(SA_THREADS) sa_f32_kernel(const SaF32Params p)
                     }
                     cp_async_commit();
                 };
+                const bool active = co0 + SA_CW * ty < cout;
                 prefetch(0);
                 for (int kc = 0; kc < nk; ++kc) {
                     cp_async_wait_all();
                     __syncthreads();
                     if (kc + 1 < nk) prefetch(kc + 1);
-                    const float *wsb = Ws + (kc & 1) * SA_KC * CCH + 4 * ty;
+                    const float *wsb = Ws + (kc & 1) * SA_KC * CCH + SA_CW * ty;
                     const float *xb = Xin + (size_t)(kc * SA_KC) * R + 4 * tx;
+                    if (!active) continue;             // this thread's channels are padding of a narrow layer (whole warps: ty is warp-uniform up to 2 values)
 #pragma unroll
                     for (int kk = 0; kk < SA_KC; ++kk) {
                         const float4 a = *reinterpret_cast<const float4 *>(xb + kk * R);
                         const float4 w = *reinterpret_cast<const float4 *>(wsb + kk * CCH);
-                        const float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
+                        const float4 u = *reinterpret_cast<const float4 *>(wsb + kk * CCH + 4);
+                        const f32x2 wv[4] = {pk2(w.x, w.y), pk2(w.z, w.w), pk2(u.x, u.y), pk2(u.z, u.w)};
+                        const f32x2 av[4] = {pk2(a.x, a.x), pk2(a.y, a.y), pk2(a.z, a.z), pk2(a.w, a.w)};
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+                            for (int j = 0; j < SA_CW / 2; ++j) acc2[i][j] = fma2(av[i], wv[j], acc2[i][j]);
                     }
                 }
-                // ---- epilogue: bias + ReLU ---------------------------------------------------------------------
-                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + co0 + 4 * ty));
-                const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+                float acc[4][SA_CW];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaxf(acc[i][j] + bv[j], 0.f);
+                    for (int j = 0; j < SA_CW / 2; ++j) {
+                        const float2 v = unpk2(acc2[i][j]);
+                        acc[i][2 * j] = v.x; acc[i][2 * j + 1] = v.y;
+                    }
+                // ---- epilogue: bias + ReLU ---------------------------------------------------------------------
+                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + co0 + SA_CW * ty));
+                const float4 b5 = __ldg(reinterpret_cast<const float4 *>(bias + co0 + SA_CW * ty + 4));
+                const float bv[SA_CW] = {b4.x, b4.y, b4.z, b4.w, b5.x, b5.y, b5.z, b5.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < SA_CW; ++j) acc[i][j] = fmaxf(acc[i][j] + bv[j], 0.f);
 
                 if (!last) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int co = co0 + 4 * ty + j;
+                    for (int j = 0; j < SA_CW; ++j) {
+                        const int co = co0 + SA_CW * ty + j;
                         if (co < next_cip)
                             *reinterpret_cast<float4 *>(Xout + (size_t)co * R + 4 * tx) =
                                 make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
@@ -240,9 +258,9 @@ __global__ void __launch_bounds__(SA_THREADS) sa_f32_kernel(const SaF32Params p)
                     const int rows_per_group = p.gpt ? K : R;   // rows of one group inside this tile
                     const bool pow2 = (rows_per_group >= 4) && ((rows_per_group & (rows_per_group - 1)) == 0);
                     if (pow2) {
-                        float m[4];
+                        float m[SA_CW];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
+                        for (int j = 0; j < SA_CW; ++j) {
                             m[j] = 0.f;                               // post-ReLU values are >= 0
 #pragma unroll
                             for (int i = 0; i < 4; ++i) if (s_n[4 * tx + i] >= 0) m[j] = fmaxf(m[j], acc[i][j]);
@@ -250,14 +268,14 @@ __global__ void __launch_bounds__(SA_THREADS) sa_f32_kernel(const SaF32Params p)
                         const int q = rows_per_group / 4;             // thread columns per group
                         for (int o = 1; o < q; o <<= 1)
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) m[j] = fmaxf(m[j], __shfl_xor_sync(0xffffffffu, m[j], o));
+                            for (int j = 0; j < SA_CW; ++j) m[j] = fmaxf(m[j], __shfl_xor_sync(0xffffffffu, m[j], o));
                         if (tx % q == 0) {
                             const int64_t g = s_g[4 * tx];
                             if (g < p.G && s_n[4 * tx] >= 0) {
-                                float *o = p.out + (g / p.S) * p.ob + (g % p.S) * p.os + p.co_off + co0 + 4 * ty;
+                                float *o = p.out + (g / p.S) * p.ob + (g % p.S) * p.os + p.co_off + co0 + SA_CW * ty;
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    if (co0 + 4 * ty + j < cout) {
+                                for (int j = 0; j < SA_CW; ++j) {
+                                    if (co0 + SA_CW * ty + j < cout) {
                                         if (p.gpt) o[j] = m[j];
                                         else atomicMax(reinterpret_cast<int *>(o + j), __float_as_int(m[j]));
                                     }
@@ -268,8 +286,8 @@ __global__ void __launch_bounds__(SA_THREADS) sa_f32_kernel(const SaF32Params p)
                         // generic K: stage the chunk in the free buffer, then one thread per (channel, group)
                         float *Y = Xout;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            *reinterpret_cast<float4 *>(Y + (size_t)(4 * ty + j) * R + 4 * tx) =
+                        for (int j = 0; j < SA_CW; ++j)
+                            *reinterpret_cast<float4 *>(Y + (size_t)(SA_CW * ty + j) * R + 4 * tx) =
                                 make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
                         __syncthreads();
                         const int ng = p.gpt ? p.gpt : 1;
@@ -299,7 +317,7 @@ static void f32_plan(int S, int K, int L, const int *dims, int *R_out, int bufc[
 {
     (void)S; (void)K;
     for (int R = 64; R >= 32; R >>= 1) {
-        const int CCH = 4 * (SA_THREADS / (R / 4));
+        const int CCH = SA_CW * (SA_THREADS / (R / 4));
         int c[2] = {0, 0};
         for (int l = 0; l < L; ++l) {
             const int cip = rup(dims[l], F32_CIN_ALIGN);
