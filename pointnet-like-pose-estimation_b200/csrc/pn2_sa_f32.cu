@@ -109,8 +109,10 @@ __global__ void __launch_bounds__(SA_THREADS) sa_f32_kernel(const SaF32Params p)
     constexpr int W4 = SA_KC * CCH / 4 / SA_THREADS;  // float4 per thread per staged W chunk
 
     extern __shared__ __align__(16) float smem[];
-    float *buf[2] = {smem, smem + (size_t)p.bufc[0] * R};
-    float *Ws = buf[1] + (size_t)p.bufc[1] * R;        // [2][SA_KC][CCH]
+    // the two activation buffers as offsets from `smem` (an indexed array of pointers would demote every access to a
+    // generic load / store)
+    const int buf1_off = p.bufc[0] * R;
+    float *Ws = smem + buf1_off + (size_t)p.bufc[1] * R;        // [2][SA_KC][CCH]
     int *s_n = (int *)(Ws + 2 * SA_KC * CCH);          // [R] source point of each row, -1 = padding row
     int64_t *s_g = (int64_t *)(s_n + R);               // [R] group of each row
 
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(SA_THREADS) sa_f32_kernel(const SaF32Params p)
         }
         __syncthreads();
         // ---- gather layer-0 activations X0[c][r] ----------------------------------------------------------
-        float *X0 = buf[0];
+        float *X0 = smem;
         const int cip0 = (Cin0 + F32_CIN_ALIGN - 1) / F32_CIN_ALIGN * F32_CIN_ALIGN;
         for (int i = tid; i < R * (cip0 - Cin0); i += SA_THREADS) X0[(Cin0 + i / R) * R + i % R] = 0.f;
         for (int i = tid; i < R * C; i += SA_THREADS) {
@@ -179,8 +181,8 @@ __global__ void __launch_bounds__(SA_THREADS) sa_f32_kernel(const SaF32Params p)
             const int cip = (cin + F32_CIN_ALIGN - 1) / F32_CIN_ALIGN * F32_CIN_ALIGN;
             const int cop = (cout + F32_COUT_ALIGN - 1) / F32_COUT_ALIGN * F32_COUT_ALIGN;
             const float *Wt = wl, *bias = wl + (size_t)cip * cop;
-            const float *Xin = buf[l & 1];
-            float *Xout = buf[(l + 1) & 1];
+            const float *Xin = smem + ((l & 1) ? buf1_off : 0);
+            float *Xout = smem + ((l & 1) ? 0 : buf1_off);
             const bool last = (l == p.L - 1);
             const int next_cip = last ? 0 : (cout + F32_CIN_ALIGN - 1) / F32_CIN_ALIGN * F32_CIN_ALIGN;
             const int nk = cip / SA_KC;
@@ -215,11 +217,18 @@ __global__ void __launch_bounds__(SA_THREADS) sa_f32_kernel(const SaF32Params p)
                     const float *wsb = Ws + (kc & 1) * SA_KC * CCH + SA_CW * ty;
                     const float *xb = Xin + (size_t)(kc * SA_KC) * R + 4 * tx;
                     if (!active) continue;             // this thread's channels are padding of a narrow layer (whole warps: ty is warp-uniform up to 2 values)
+                    // operands of step kk + 1 are requested before the FMAs of step kk (register double buffer)
+                    float4 a_n = *reinterpret_cast<const float4 *>(xb);
+                    float4 w_n = *reinterpret_cast<const float4 *>(wsb);
+                    float4 u_n = *reinterpret_cast<const float4 *>(wsb + 4);
 #pragma unroll
                     for (int kk = 0; kk < SA_KC; ++kk) {
-                        const float4 a = *reinterpret_cast<const float4 *>(xb + kk * R);
-                        const float4 w = *reinterpret_cast<const float4 *>(wsb + kk * CCH);
-                        const float4 u = *reinterpret_cast<const float4 *>(wsb + kk * CCH + 4);
+                        const float4 a = a_n, w = w_n, u = u_n;
+                        if (kk + 1 < SA_KC) {
+                            a_n = *reinterpret_cast<const float4 *>(xb + (kk + 1) * R);
+                            w_n = *reinterpret_cast<const float4 *>(wsb + (kk + 1) * CCH);
+                            u_n = *reinterpret_cast<const float4 *>(wsb + (kk + 1) * CCH + 4);
+                        }
                         const f32x2 wv[4] = {pk2(w.x, w.y), pk2(w.z, w.w), pk2(u.x, u.y), pk2(u.z, u.w)};
                         const f32x2 av[4] = {pk2(a.x, a.x), pk2(a.y, a.y), pk2(a.z, a.z), pk2(a.w, a.w)};
 #pragma unroll
