@@ -129,7 +129,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     // carve-up (all offsets multiples of 16)
-    unsigned char *A[2] = {smem, p.a_bytes[1] ? smem + p.a_bytes[0] : smem};
+    // the two activation buffers as offsets from `smem`: indexing an array of pointers with the layer number would demote
+    // every activation store of the epilogue to a generic ST.E
+    const uint32_t a1_off = p.a_bytes[1] ? (uint32_t)p.a_bytes[0] : 0u;
     unsigned char *Wsm = smem + p.a_bytes[0] + p.a_bytes[1];
     const int w_region = p.resident ? p.lay.w_bytes : p.nstage * p.stage_bytes;
     float *bias_s = reinterpret_cast<float *>(Wsm + w_region);
@@ -252,7 +254,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
             cbar_sync();
             // ---- gather: layer-0 A operand, internal channel order [feat(D), xyz(C), zero pad] ------------
             {
-                unsigned char *A0 = A[0];
+                unsigned char *A0 = smem;
                 const int K0 = lay.ly[0].K;
                 if (p.feat_fast) {
                     const int cpr = D / 8;                               // 16-byte chunks per row
@@ -314,8 +316,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
             for (int l = 0; l < lay.L; ++l) {
                 const TcLayer ly = lay.ly[l];
                 const bool last = (l == lay.L - 1);
-                const uint32_t a_in = smem_u32(A[l & 1]);
-                unsigned char *a_out = A[(l + 1) & 1];
+                const uint32_t a_in = smem_u32(smem + ((l & 1) ? a1_off : 0u));
+                unsigned char *a_out = smem + ((l & 1) ? 0u : a1_off);
                 const int slabs_per_round = p.tmem_cols / ly.NS;
                 const uint32_t idesc = instr_desc_bf16(ly.NS);
                 if (last && p.pipelined_last) {
