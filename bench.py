@@ -126,6 +126,14 @@ def cpu_port_throughput(budget_s, threads):
     return CPU_BATCH / statistics.median(times), len(times)
 
 
+def workload_config(B, world, precision):
+    """The `config` object of the JSON line -- the same workload for both arms (the reference arm adds its bounded sample)."""
+    return {"workload": f"{MODEL} forward, N={N_POINTS} xyz (configs[0] architecture and input recipe), B={B} clouds per GPU per step",
+            "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"batch-sharded x{world}, no collective",
+            "l2": f"{N_ROTATING} rotating input batches; per-step working set (l1 features {B * 512 * 128 * 4 / 1e6:.0f} MB) exceeds the 126 MB L2",
+            "precision_mode": precision}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -150,7 +158,8 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "PointNet++ SSG fwd clouds/sec (N=1024)", "value": value, "unit": "clouds/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{MODEL} forward N={N_POINTS}, CPU port of the reference path (ATen/MKL/oneDNN), B={CPU_BATCH} per step"},
+        "config": dict(workload_config(args.batch, 1, "fp32"), sample=sample + "; CPU port of the reference path (ATen/MKL/oneDNN), "
+                       f"{threads} host threads, no GPU"),
         "cpu_baseline": {"value": value, "unit": "clouds/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -394,10 +403,7 @@ def run_ours(args, rank, local_rank, world):
         "metric": "PointNet++ SSG fwd clouds/sec (N=1024)", "value": value, "unit": "clouds/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": f"{MODEL} forward, N={N_POINTS} xyz (configs[0] architecture and input recipe), B={B} clouds per GPU per step",
-                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"batch-sharded x{world}, no collective",
-                   "l2": f"{N_ROTATING} rotating input batches; per-step working set (l1 features {B * 512 * 128 * 4 / 1e6:.0f} MB) exceeds the 126 MB L2",
-                   "precision_mode": args.precision},
+        "config": workload_config(B, world, args.precision),
         "e2e": {"value": B * world * K / (1e-3 * ms_e2e), "unit": "clouds/s", "h2d_bytes_per_step": B * 3 * N_POINTS * 4,
                 "d2h_bytes_per_step": B * 7 * 4 + B * 8},
         "gpu_launches": launches,

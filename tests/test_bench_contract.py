@@ -1,0 +1,46 @@
+"""bench.py's JSON-line contract on a machine without a GPU: the reference arm (CPU port of the reference path)
+must run here, print exactly one JSON line and describe the same workload as the product arm."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _bench(*flags, timeout=600):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *flags], capture_output=True, text=True,
+                         timeout=timeout, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    return json.loads(lines[0])
+
+
+def test_reference_arm_line():
+    line = _bench("--impl", "reference", "--steps", "1", "--warmup", "1")
+    assert line["impl"] == "reference"
+    assert line["metric"] == "PointNet++ SSG fwd clouds/sec (N=1024)" and line["unit"] == "clouds/s"
+    assert line["higher_is_better"] is True and line["value"] > 0
+    assert line["n_gpus"] == 1 and line["steps"] == 1 and line["gpu_launches"] == 0
+    cpu = line["cpu_baseline"]
+    assert cpu["kind"] == "port" and cpu["cores"] >= 1 and cpu["value"] == line["value"] and "24 clouds" in cpu["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # same workload description as the product arm; the bounded sample is stated next to it
+    sys.path.insert(0, ROOT)
+    import bench
+    ours = bench.workload_config(2048, 1, "fp32")
+    for k, v in ours.items():
+        assert line["config"][k] == v
+    assert "sample" in line["config"]
+
+
+def test_product_arm_fails_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("GPU present")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode != 0          # no CPU fallback: the product arm must not print a number here
+    assert not any(ln.startswith("{") for ln in out.stdout.splitlines())
