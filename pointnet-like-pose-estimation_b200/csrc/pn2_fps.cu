@@ -171,13 +171,15 @@ __global__ void __launch_bounds__(TMAX) fps_kernel(const float *__restrict__ poi
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Cluster variant: ONE CLOUD PER THREAD-BLOCK CLUSTER of FPS_CS CTAs, for few large clouds (BASELINE configs[2]: B = 16,
+// Cluster variant: ONE CLOUD PER THREAD-BLOCK CLUSTER of CS (4 or 8) CTAs, for few large clouds (BASELINE configs[2]: B = 16,
 // N = 8192 -> 2048: sixteen single CTAs would leave 132 SMs idle and spend 1650 cycles per iteration on 8 points per
-// thread).  Every CTA keeps the whole cloud in shared memory (centroid lookup) and 1/FPS_CS of the points + running
-// distances in registers.  Per iteration: local argmax as above, then each CTA's first FPS_CS threads store its (distance
-// bits, index) into the slot array of EVERY CTA of the cluster through distributed shared memory (st.shared::cluster,
-// double-buffered by iteration parity, tagged with the iteration number), every warp polls its own CTA's slots until all
-// FPS_CS carry the current tag and reduces them locally: same maximum, lowest index among equals, so the result is bit-identical to the one-CTA kernel.
+// thread).  Every CTA keeps the whole cloud in shared memory (centroid lookup) and 1/CS of the points + running distances
+// in registers.  Per iteration: argmax inside each warp as above, then (DIRECT) lanes 0..CS-1 of EVERY WARP store the warp's
+// (distance bits, index) into that warp's slot in the slot array of every CTA of the cluster through distributed shared
+// memory (st.shared::cluster, double-buffered by iteration parity, tagged with the iteration number); every warp polls the
+// CS x 8 slots of its own CTA (one or two per lane) until all carry the current tag and reduces them: same maximum, lowest
+// index among equals, so the result is bit-identical to the one-CTA kernel.  There is no block or cluster barrier inside the
+// loop.  (DIRECT = false is the first version: a block-level reduction, one slot per CTA; kept for PN2_FPS_CLUSTER=1.)
 // ------------------------------------------------------------------------------------------------------
 constexpr int FPS_CS = 8;
 
@@ -186,19 +188,23 @@ __device__ __forceinline__ void cluster_sync_all()
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int C, int PPT, bool CONTIG>
-__global__ void __launch_bounds__(256) fps_cluster_kernel(const float *__restrict__ points, int64_t sb, int64_t sn, int64_t sc, int N,
+template <int C, int PPT, bool CONTIG, bool DIRECT, int CS, int CW>     // CS CTAs per cluster, CW warps per CTA
+__global__ void __launch_bounds__(CW * 32) fps_cluster_kernel(const float *__restrict__ points, int64_t sb, int64_t sn, int64_t sc, int N,
                                                           const int64_t *__restrict__ start, int S,
                                                           int64_t *__restrict__ idx64, int32_t *__restrict__ idx32, float *__restrict__ new_points)
 {
-    extern __shared__ float s_pts[];            // [C][Nall]: the WHOLE cloud (Nall = FPS_CS * PPT * blockDim.x >= N)
+    extern __shared__ float s_pts[];            // [C][Nall]: the WHOLE cloud (Nall = CS * PPT * blockDim.x >= N)
     __shared__ uint2 s_slot[2][32];             // per-warp (dist bits, index), double-buffered
-    __shared__ uint2 c_slot[2][FPS_CS];         // per-CTA results of the cluster, written by the peers
+    // DIRECT: one slot per WARP of the cluster (the CTA-level reduction, its barrier and two REDUX leave the dependent chain)
+    constexpr int NSLOT = DIRECT ? CS * CW : CS;
+    constexpr int SPL = NSLOT > 32 ? 2 : 1;      // DIRECT: slots polled per lane (fewer than 32 slots: lanes wrap around, duplicates do not change a maximum)
+    static_assert(!DIRECT || NSLOT == 16 || NSLOT == 32 || NSLOT == 64, "one or two slots per lane");
+    __shared__ __align__(16) uint2 c_slot[2][NSLOT];        // results of the cluster, written by the peers
     const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
     unsigned rank;
     asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-    const int b = blockIdx.x / FPS_CS;
-    const int Nc = PPT * T, Nall = FPS_CS * Nc;
+    const int b = blockIdx.x / CS;
+    const int Nc = PPT * T, Nall = CS * Nc;
     const float *P = points + (int64_t)b * sb;
     static_assert(PPT % 2 == 0 && C <= 4, "two points per register pair; packed arithmetic needs C <= 4 on strided clouds");
 
@@ -221,13 +227,13 @@ __global__ void __launch_bounds__(256) fps_cluster_kernel(const float *__restric
     int far = (int)min(max(start[b], (int64_t)0), (int64_t)N - 1);
     const uint32_t slot_wr = (uint32_t)__cvta_generic_to_shared(&s_slot[0][warp]);
     const uint32_t slot_rd = (uint32_t)__cvta_generic_to_shared(&s_slot[0][lane < nwarps ? lane : 0]);
-    const uint32_t cslot_rd = (uint32_t)__cvta_generic_to_shared(&c_slot[0][lane < FPS_CS ? lane : 0]);
-    uint32_t cslot_peer = 0;                    // address of c_slot[0][rank] inside CTA `tid` of the cluster (threads < FPS_CS)
-    if (tid < FPS_CS) {
-        const uint32_t mine = (uint32_t)__cvta_generic_to_shared(&c_slot[0][rank]);
-        asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(cslot_peer) : "r"(mine), "r"((uint32_t)tid));
+    const uint32_t cslot_rd = (uint32_t)__cvta_generic_to_shared(DIRECT ? &c_slot[0][(SPL * lane) % NSLOT] : &c_slot[0][lane < CS ? lane : 0]);
+    uint32_t cslot_peer = 0;                    // address of this CTA's (DIRECT: this warp's) slot inside CTA `tid` (DIRECT: `lane`) of the cluster
+    if (DIRECT ? lane < CS : tid < CS) {
+        const uint32_t mine = (uint32_t)__cvta_generic_to_shared(DIRECT ? &c_slot[0][rank * CW + warp] : &c_slot[0][rank]);
+        asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(cslot_peer) : "r"(mine), "r"((uint32_t)(DIRECT ? lane : tid)));
     }
-    if (tid < 2 * FPS_CS) (&c_slot[0][0])[tid] = make_uint2(0u, 0u);      // tag 0 = "no iteration yet"
+    for (int t = tid; t < 2 * NSLOT; t += T) (&c_slot[0][0])[t] = make_uint2(0u, 0u);       // tag 0 = "no iteration yet"
     cluster_sync_all();                         // every CTA of the cluster is resident (and its slots cleared) before anyone writes to a peer
 
     for (int i = 0; i < S; ++i) {
@@ -263,32 +269,63 @@ __global__ void __launch_bounds__(256) fps_cluster_kernel(const float *__restric
         const unsigned bits = __float_as_uint(best);
         const unsigned wmax = redux_max(bits);
         const unsigned widx = redux_min(bits == wmax ? besti : 0xffffffffu);
-        const uint32_t par_off = (uint32_t)(i & 1) * (uint32_t)sizeof(s_slot[0]);
-        if (lane == 0) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(slot_wr + par_off), "r"(wmax), "r"(widx) : "memory");
-        __syncthreads();
-        uint2 sl;
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(sl.x), "=r"(sl.y) : "r"(slot_rd + par_off) : "memory");
-        if (lane >= nwarps) sl = make_uint2(0u, 0xffffffffu);
-        const unsigned cmax = redux_max(sl.x);
-        const unsigned cidx = redux_min(sl.x == cmax ? sl.y : 0xffffffffu);
-        // this CTA's result -> slot [parity][rank] of every CTA of the cluster (thread t writes to CTA t)
         const uint32_t cpar = (uint32_t)(i & 1) * (uint32_t)sizeof(c_slot[0]);
-        // (no cluster barrier: ~1000 cycles.)  The 8-byte slot carries the iteration number in the index word's upper half;
-        // every warp polls its own CTA's slots until all FPS_CS of them show this iteration.  A slot of parity p is only
-        // rewritten two iterations later, which needs every CTA's result of the iteration in between, i.e. every CTA has
-        // finished reading this one.
         const unsigned tag = ((unsigned)(i + 1) & 0xffffu) << 16;
-        if (tid < FPS_CS) asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(cslot_peer + cpar), "r"(cmax), "r"(cidx | tag) : "memory");
-        uint2 cl;
-        bool ok;
-        do {
-            asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cl.x), "=r"(cl.y) : "r"(cslot_rd + cpar) : "memory");
-            ok = (cl.y & 0xffff0000u) == tag;
-        } while (!__all_sync(0xffffffffu, ok));
-        cl.y &= 0xffffu;
-        if (lane >= FPS_CS) cl = make_uint2(0u, 0xffffffffu);
-        const unsigned gmax = redux_max(cl.x);
-        far = (int)redux_min(cl.x == gmax ? cl.y : 0xffffffffu);
+        if constexpr (DIRECT) {
+            // every warp posts its own result to all CTAs (lane l -> CTA l) and polls the CS * CW slots of its own CTA,
+            // two per lane.  No block barrier in the loop: a warp rewrites a parity two iterations later, which needs every
+            // warp's post of the iteration in between, and a warp posts only after it has read the previous iteration.
+            if (lane < CS) asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(cslot_peer + cpar), "r"(wmax), "r"(widx | tag) : "memory");
+            unsigned m2, i2;
+            if constexpr (SPL == 2) {
+                uint4 cl;
+                bool ok;
+                do {
+                    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(cl.x), "=r"(cl.y), "=r"(cl.z), "=r"(cl.w) : "r"(cslot_rd + cpar) : "memory");
+                    ok = (cl.y & 0xffff0000u) == tag && (cl.w & 0xffff0000u) == tag;
+                } while (!__all_sync(0xffffffffu, ok));
+                cl.y &= 0xffffu;
+                cl.w &= 0xffffu;
+                m2 = max(cl.x, cl.z);
+                i2 = min(cl.x == m2 ? cl.y : 0xffffffffu, cl.z == m2 ? cl.w : 0xffffffffu);
+            } else {
+                uint2 cl;
+                bool ok;
+                do {
+                    asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cl.x), "=r"(cl.y) : "r"(cslot_rd + cpar) : "memory");
+                    ok = (cl.y & 0xffff0000u) == tag;
+                } while (!__all_sync(0xffffffffu, ok));
+                m2 = cl.x;
+                i2 = cl.y & 0xffffu;
+            }
+            const unsigned gmax = redux_max(m2);
+            far = (int)redux_min(m2 == gmax ? i2 : 0xffffffffu);
+        } else {
+            const uint32_t par_off = (uint32_t)(i & 1) * (uint32_t)sizeof(s_slot[0]);
+            if (lane == 0) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(slot_wr + par_off), "r"(wmax), "r"(widx) : "memory");
+            __syncthreads();
+            uint2 sl;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(sl.x), "=r"(sl.y) : "r"(slot_rd + par_off) : "memory");
+            if (lane >= nwarps) sl = make_uint2(0u, 0xffffffffu);
+            const unsigned cmax = redux_max(sl.x);
+            const unsigned cidx = redux_min(sl.x == cmax ? sl.y : 0xffffffffu);
+            // this CTA's result -> slot [parity][rank] of every CTA of the cluster (thread t writes to CTA t)
+            // (no cluster barrier: ~1000 cycles.)  The 8-byte slot carries the iteration number in the index word's upper half;
+            // every warp polls its own CTA's slots until all CS of them show this iteration.  A slot of parity p is only
+            // rewritten two iterations later, which needs every CTA's result of the iteration in between, i.e. every CTA has
+            // finished reading this one.
+            if (tid < CS) asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(cslot_peer + cpar), "r"(cmax), "r"(cidx | tag) : "memory");
+            uint2 cl;
+            bool ok;
+            do {
+                asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cl.x), "=r"(cl.y) : "r"(cslot_rd + cpar) : "memory");
+                ok = (cl.y & 0xffff0000u) == tag;
+            } while (!__all_sync(0xffffffffu, ok));
+            cl.y &= 0xffffu;
+            if (lane >= CS) cl = make_uint2(0u, 0xffffffffu);
+            const unsigned gmax = redux_max(cl.x);
+            far = (int)redux_min(cl.x == gmax ? cl.y : 0xffffffffu);
+        }
     }
     cluster_sync_all();                         // no CTA may exit while a peer can still store into its slots
 }
@@ -298,28 +335,50 @@ template <int C>
 static int launch_fps_cluster(const float *points, int64_t sb, int64_t sn, int64_t sc, int B, int N,
                               const int64_t *start, int S, int64_t *idx64, int32_t *idx32, float *new_points, cudaStream_t st)
 {
-    static const int env = getenv("PN2_FPS_CLUSTER") ? atoi(getenv("PN2_FPS_CLUSTER")) : 1;
-    // few, large clouds only: the cluster barrier costs more than it saves when a single CTA already has little to do
-    if (!env || N < 4096 || N > FPS_CS * 256 * 4 || (int64_t)B * FPS_CS > 2 * 148) return -100;
+    // PN2_FPS_CLUSTER: 0 = off, 1 = 8 CTAs with per-CTA slots, 2 = 8 CTAs with per-warp slots, 4 = 4 CTAs with per-warp slots,
+    // default (-1) = per-warp slots, cluster size by the number of clouds
+    static const int env = getenv("PN2_FPS_CLUSTER") ? atoi(getenv("PN2_FPS_CLUSTER")) : -1;
+    // few, large clouds only: the exchange costs more than it saves when a single CTA already has little to do
+    if (!env || N < 4096 || N > 8192 || (int64_t)B * FPS_CS > 2 * 148) return -100;
     if (sc != 1 && (N & 31)) return -100;       // strided clouds with leftover points use the scalar order (single-CTA kernel)
+    // 8-CTA clusters of more than a few clouds no longer find an SM per CTA (two CTAs share one: x1.15 per iteration at 12
+    // clouds, x1.3 at 16); 4-CTA clusters of twice the points per thread run every B <= 37 at the same speed
+    // (configs[2], B = 16, N = 8192 -> 2048: 1047 us with 8 CTAs and per-CTA slots, 981 us with per-warp slots, 778 us with 4 CTAs)
+    // Other shapes measured at B = 16 (tools/fps_micro.py, profiles/r01_k_fps_cluster_variants.txt): 4 CTAs x 16 warps x 4 points
+    // 909 us, 2 CTAs x 16 warps x 8 points 1074 us, 8 CTAs x 4 warps x 8 points 817 us (755 us up to 14 clouds), 4 CTAs x 4 warps x
+    // 16 points 884 us: more warps per CTA lengthen the poll, fewer CTAs or warps lengthen the arithmetic.
+    const int cs = env == 4 ? 4 : (env == 1 || env == 2) ? 8 : (B > 4 ? 4 : 8);
     const int threads = 256;
-    const int ppt = N <= FPS_CS * threads * 2 ? 2 : 4;
-    const size_t smem = sizeof(float) * (size_t)C * FPS_CS * ppt * threads;
+    const int per_cta = (N + cs - 1) / cs;
+    const int ppt = per_cta <= threads * 2 ? 2 : per_cta <= threads * 4 ? 4 : 8;
+    const size_t smem = sizeof(float) * (size_t)C * cs * ppt * threads;
     auto run = [&](auto kern) -> int {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("fps(cluster): smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)(B * FPS_CS)); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cfg.gridDim = dim3((unsigned)(B * cs)); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = FPS_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         e = cudaLaunchKernelEx(&cfg, kern, points, sb, sn, sc, N, start, S, idx64, idx32, new_points);
         if (e != cudaSuccess) { set_error("fps(cluster): launch: %s", cudaGetErrorString(e)); return (int)e; }
         return launch_status("pn2_fps_f32(cluster)");
     };
-    if (ppt == 2) return sc == 1 ? run(fps_cluster_kernel<C, 2, true>) : run(fps_cluster_kernel<C, 2, false>);
-    return sc == 1 ? run(fps_cluster_kernel<C, 4, true>) : run(fps_cluster_kernel<C, 4, false>);
+#define PN2_FPS_CL(P, D, CSZ, CWP) \
+    return sc == 1 ? run(fps_cluster_kernel<C, P, true, D, CSZ, CWP>) : run(fps_cluster_kernel<C, P, false, D, CSZ, CWP>)
+    if (cs == 4) {
+        if (ppt == 2) PN2_FPS_CL(2, true, 4, 8);
+        if (ppt == 4) PN2_FPS_CL(4, true, 4, 8);
+        PN2_FPS_CL(8, true, 4, 8);
+    }
+    if (env == 1) {
+        if (ppt == 2) PN2_FPS_CL(2, false, 8, 8);
+        PN2_FPS_CL(4, false, 8, 8);
+    }
+    if (ppt == 2) PN2_FPS_CL(2, true, 8, 8);
+    PN2_FPS_CL(4, true, 8, 8);
+#undef PN2_FPS_CL
 }
 
 // Generic fallback: any C <= PN2_MAX_COORD, any N whose distance array fits in shared memory; points are
