@@ -207,29 +207,37 @@ def summarise_trace(trace, steps, pk):
     return table, roof
 
 
+def device_time_us(fn, reps=30, warm=5, flush=None):
+    """Median device time of one call of `fn` in us: CUDA events around every call, NO host synchronisation between the calls
+    (the host enqueues ahead of the GPU, so the bracket holds the kernel and not the Python / ctypes launch latency -- with a
+    synchronize per call a 100 us kernel reads 40 us longer), an L2 flush (`flush`: a buffer larger than the 126 MB L2,
+    rewritten outside the brackets) before every call."""
+    evs = []
+    for i in range(warm + reps):
+        if flush is not None:
+            flush.add_(1)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        evs.append((s, e))
+    torch.cuda.synchronize()
+    return statistics.median(1e3 * s.elapsed_time(e) for s, e in evs[warm:])
+
+
 def micro_cfg3(dev, be):
-    """configs[2]: FPS + ball query at B=16, N=8192 -> 2048 centroids, r=0.2, nsample=32 (median of 20, us)."""
+    """configs[2]: FPS + ball query at B=16, N=8192 -> 2048 centroids, r=0.2, nsample=32 (median of 30 launches, us;
+    device time, L2 flushed before every launch)."""
     import cloudgen
     import pointnet2_utils as pu
     x = cloudgen.uniform_cloud(16, 8192, 1003).to(dev)
     start = torch.randint(0, 8192, (16,), generator=torch.Generator().manual_seed(42), dtype=torch.long).to(dev)
     r2 = pu._radius_sq(0.2)
-    res = {}
-    new_pts = None
-    for name in ("fps", "ball_query"):
-        ts = []
-        for i in range(25):
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            if name == "fps":
-                _, _, new_pts = be.fps(x, start, 2048, want_idx64=True, want_new_points=True)
-            else:
-                be.ball_query(new_pts, x, r2, 32, want_idx64=True)
-            e.record()
-            e.synchronize()
-            if i >= 5:
-                ts.append(s.elapsed_time(e) * 1e3)
-        res[name + "_us"] = statistics.median(ts)
+    flush = torch.zeros(64 * 1024 * 1024, dtype=torch.int32, device=dev)          # 256 MB
+    _, _, new_pts = be.fps(x, start, 2048, want_idx64=True, want_new_points=True)
+    res = {"fps_us": device_time_us(lambda: be.fps(x, start, 2048, want_idx64=True, want_new_points=True), flush=flush),
+           "ball_query_us": device_time_us(lambda: be.ball_query(new_pts, x, r2, 32, want_idx64=True), flush=flush)}
+    del flush
     return res
 
 

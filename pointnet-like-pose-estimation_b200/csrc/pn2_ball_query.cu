@@ -10,6 +10,7 @@
 //
 // Exactness contract: dot = fl(s0*p0), dot = fma(s_k, p_k, dot) ascending k (MKL sgemm, :23);
 // d = fl(fl(-2*dot + |s|^2) + |p|^2); in radius <=> !(d > r2).
+#include <stdlib.h>
 #include <type_traits>
 #include "pn2_common.cuh"
 
@@ -480,7 +481,11 @@ static int launch_bq_w(const float *centres, int64_t csb, int64_t csn, int64_t c
         // enough CTAs for ~4 waves of 148 SMs, but amortise the staging of the cloud over >= 8 centres/warp
         cpw = 16;
         while (cpw > 1 && (int64_t)B * ((S + BQ_WARPS * cpw - 1) / (BQ_WARPS * cpw)) < 592) cpw >>= 1;
-        if (BQ_WARPS == BQ_WARPS_BIG && cpw < BQ_CPB<C>::value) cpw = BQ_CPB<C>::value;      // one CTA per SM: at least one full pass per warp
+        // at least one FULL pass per warp: a pass costs the same with idle centre slots (few clouds used to run passes of one or
+        // two centres in four slots on up to four times the CTAs; B = 16, N = 4096, S = 1024: 88 -> 57 us at 8 per warp)
+        if (cpw < BQ_CPB<C>::value) cpw = BQ_CPB<C>::value;
+        static const int cpw_env = getenv("PN2_BQ_CPW") ? atoi(getenv("PN2_BQ_CPW")) : 0;
+        if (cpw_env > 0) cpw = cpw_env;
     }
     const size_t smem = (size_t)(C + 1) * NCH * sizeof(float) + stage_bytes;
     auto kern = ball_query_kernel<C, BQ_WARPS>;
@@ -530,7 +535,7 @@ static int launch_bq_multi(const float *centres, int64_t csb, int64_t csn, int64
 {
     constexpr int W = BQ_WARPS_SMALL;
     int cpw = 16;
-    while (cpw > 1 && (int64_t)B * ((S + W * cpw - 1) / (W * cpw)) < 592) cpw >>= 1;
+    while (cpw > BQ_CPB<C>::value && (int64_t)B * ((S + W * cpw - 1) / (W * cpw)) < 592) cpw >>= 1;      // never less than one full pass
     const size_t smem = (size_t)(C + 1) * NCH * sizeof(float) + sizeof(int) * (size_t)W * BQ_CPB<C>::value * q.ktot;
     auto kern = ball_query_multi_kernel<C, W, NR>;
     if (smem > 48 * 1024) {

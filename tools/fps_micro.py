@@ -1,23 +1,19 @@
 #!/usr/bin/env python
-"""configs[2] FPS microbench (B = 16, N = 8192 -> 2048): median of 30 launches in us.  PN2_FPS_CLUSTER selects the variant
+"""configs[2] FPS microbench (B = 16, N = 8192 -> 2048): median device time of 30 launches in us (bench.device_time_us: no host sync between launches, L2 flushed).  PN2_FPS_CLUSTER selects the variant
 (0 = one CTA per cloud, 1 = cluster with per-CTA slots, 2 = cluster with per-warp slots)."""
 import os, statistics, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (os.path.join(ROOT, "pointnet-like-pose-estimation_b200"), os.path.join(ROOT, "tests")):
+for p in (ROOT, os.path.join(ROOT, "pointnet-like-pose-estimation_b200"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import torch
 import cloudgen
 import pointnet2_utils as pu
+from bench import device_time_us
 be = pu._backend()
+flush = torch.zeros(64 * 1024 * 1024, dtype=torch.int32, device="cuda")
 for B, N, S in [(16, 8192, 2048), (16, 4096, 1024), (4, 8192, 2048), (12, 8192, 2048), (14, 8192, 2048), (32, 8192, 2048)]:
     x = cloudgen.uniform_cloud(B, N, 1003).cuda()
     start = torch.randint(0, N, (B,), generator=torch.Generator().manual_seed(42), dtype=torch.long).cuda()
-    ts = []
-    for i in range(35):
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        idx, _, _ = be.fps(x, start, S, want_idx64=True, want_new_points=True)
-        e.record()
-        torch.cuda.synchronize()
-        ts.append(1e3 * s.elapsed_time(e))
-    print(f"PN2_FPS_CLUSTER={os.environ.get('PN2_FPS_CLUSTER', '(default)')} B={B} N={N} S={S}: {statistics.median(ts[5:]):.1f} us  checksum {int(idx.sum())}")
+    idx, _, _ = be.fps(x, start, S, want_idx64=True, want_new_points=True)
+    us = device_time_us(lambda: be.fps(x, start, S, want_idx64=True, want_new_points=True), flush=flush)
+    print(f"PN2_FPS_CLUSTER={os.environ.get('PN2_FPS_CLUSTER', '(default)')} B={B} N={N} S={S}: {us:.1f} us  checksum {int(idx.sum())}")
