@@ -94,6 +94,9 @@ ball_query_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, i
         // then continues past k = 2 with fma(e_k, e_k, dot): a no-op for e_k = 0, one fused add of e_k^2 for the non-zero one --
         // no shared-memory reads, three channels of arithmetic, bit-identical.  |p|^2 and |s|^2 keep their full sums.
         bool tail_same = C > 4 && single_chunk;
+        // one CTA per SM (large clouds): four points in flight per thread, the staging is a chain of global-load latencies
+        // (configs[2]: 135 -> 131 us; with several CTAs per SM the other CTAs hide it and the unrolled loop is 2 % slower)
+#pragma unroll((C <= 4 && BQ_WARPS == BQ_WARPS_BIG) ? 4 : 1)
         for (int n = tid; n < nc; n += BQ_THREADS) {
             float v[C];
 #pragma unroll
