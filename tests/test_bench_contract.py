@@ -44,3 +44,14 @@ def test_product_arm_fails_loudly_without_a_gpu():
                          capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode != 0          # no CPU fallback: the product arm must not print a number here
     assert not any(ln.startswith("{") for ln in out.stdout.splitlines())
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29541", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, lines
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
