@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """configs[2] FPS microbench (B = 16, N = 8192 -> 2048): median device time of 30 launches in us (bench.device_time_us: no host sync between launches, L2 flushed).  PN2_FPS_CLUSTER selects the variant
-(0 = one CTA per cloud, 1 = cluster with per-CTA slots, 2 = cluster with per-warp slots)."""
+(0 = one CTA per cloud, 1 = 8-CTA cluster with per-CTA slots, 2 = 8-CTA cluster with per-warp slots, 4 = 4-CTA cluster with per-warp slots; default: per-warp slots, 8 CTAs up to four clouds, 4 beyond)."""
 import os, statistics, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "pointnet-like-pose-estimation_b200"), os.path.join(ROOT, "tests")):
