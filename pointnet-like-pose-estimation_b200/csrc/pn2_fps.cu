@@ -181,7 +181,6 @@ __global__ void __launch_bounds__(TMAX) fps_kernel(const float *__restrict__ poi
 // index among equals, so the result is bit-identical to the one-CTA kernel.  There is no block or cluster barrier inside the
 // loop.  (DIRECT = false is the first version: a block-level reduction, one slot per CTA; kept for PN2_FPS_CLUSTER=1.)
 // ------------------------------------------------------------------------------------------------------
-constexpr int FPS_CS = 8;
 
 __device__ __forceinline__ void cluster_sync_all()
 {
@@ -339,7 +338,10 @@ static int launch_fps_cluster(const float *points, int64_t sb, int64_t sn, int64
     // default (-1) = per-warp slots, cluster size by the number of clouds
     static const int env = getenv("PN2_FPS_CLUSTER") ? atoi(getenv("PN2_FPS_CLUSTER")) : -1;
     // few, large clouds only: the exchange costs more than it saves when a single CTA already has little to do
-    if (!env || N < 4096 || N > 8192 || (int64_t)B * FPS_CS > 2 * 148) return -100;
+    // up to 64 clouds = 256 CTAs, two per SM (N = 8192 -> 2048: 778 us up to 37 clouds, 1050 - 1080 us at 48 - 64 against 1702 us on
+    // one CTA per cloud; 74 clouds no longer fit one wave: 1675 us)
+    static const int bmax = getenv("PN2_FPS_CLUSTER_BMAX") ? atoi(getenv("PN2_FPS_CLUSTER_BMAX")) : 64;
+    if (!env || N < 4096 || N > 8192 || B > bmax) return -100;
     if (sc != 1 && (N & 31)) return -100;       // strided clouds with leftover points use the scalar order (single-CTA kernel)
     // 8-CTA clusters of more than a few clouds no longer find an SM per CTA (two CTAs share one: x1.15 per iteration at 12
     // clouds, x1.3 at 16); 4-CTA clusters of twice the points per thread run every B <= 37 at the same speed

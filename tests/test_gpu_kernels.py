@@ -68,6 +68,7 @@ FPS_CASES = [  # (B, N, C, S, layout, kind)
     (3, 512, 10, 128, "contig", "surf"), (2, 2048, 10, 512, "strided", "surf"), (2, 2048, 3, 512, "contig", "dup"),
     (2, 4096, 3, 1024, "contig", "uni"), (2, 8192, 3, 2048, "contig", "uni"), (2, 8192, 3, 64, "strided", "surf"),
     (16, 8192, 3, 2048, "contig", "uni"), (3, 6000, 3, 700, "contig", "dup"), (5, 4128, 3, 300, "strided", "uni"),   # one cloud per cluster
+    (48, 4096, 3, 96, "contig", "uni"), (64, 5000, 3, 64, "contig", "dup"),      # 4-CTA clusters, two CTAs per SM
     (2, 100, 3, 512, "strided", "uni"), (2, 1000, 3, 100, "contig", "dup"), (2, 777, 10, 99, "contig", "dup"),
     (2, 3000, 10, 64, "strided", "uni"), (2, 300, 5, 64, "contig", "uni"), (2, 300, 16, 64, "strided", "uni"),
     (1, 2, 3, 4, "contig", "uni"), (2, 33, 8, 40, "contig", "uni"),

@@ -11,7 +11,7 @@ import pointnet2_utils as pu
 from bench import device_time_us
 be = pu._backend()
 flush = torch.zeros(64 * 1024 * 1024, dtype=torch.int32, device="cuda")
-for B, N, S in [(16, 8192, 2048), (16, 4096, 1024), (4, 8192, 2048), (12, 8192, 2048), (14, 8192, 2048), (32, 8192, 2048)]:
+for B, N, S in [(16, 8192, 2048), (16, 4096, 1024), (4, 8192, 2048), (12, 8192, 2048), (14, 8192, 2048), (32, 8192, 2048), (48, 8192, 2048), (64, 8192, 2048), (74, 8192, 2048), (64, 4096, 1024)]:
     x = cloudgen.uniform_cloud(B, N, 1003).cuda()
     start = torch.randint(0, N, (B,), generator=torch.Generator().manual_seed(42), dtype=torch.long).cuda()
     idx, _, _ = be.fps(x, start, S, want_idx64=True, want_new_points=True)
