@@ -1,3 +1,5 @@
+"""Debug helper (not collected by pytest): one fused set-abstraction launch against the oracle, printing where they differ.
+Lives under tests/ because only tests/, smoke() and bench.py's CPU legs may use oracle/."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in ("pointnet-like-pose-estimation_b200", "tests", "oracle"):
