@@ -372,3 +372,16 @@ def test_alternative_schedules_keep_parity(env):
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_kernels.py"), os.path.join(root, "tests", "test_gpu_models.py"),
                         "-m", "gpu", "-q", "-x", "-k", "bf16 and not alternative"], env=e, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
+
+
+@pytest.mark.parametrize("variant", ["0", "1", "2", "4"])
+def test_fps_cluster_variants_keep_parity(variant):
+    """PN2_FPS_CLUSTER (read once per process) selects how few large clouds are sampled: 0 = one CTA per cloud, 1 = 8-CTA
+    cluster with a block reduction and per-CTA slots, 2 / 4 = 8- / 4-CTA cluster with per-warp slots (the default picks between
+    the last two by the number of clouds).  Every variant must return the oracle's indices."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ, PN2_FPS_CLUSTER=variant)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_kernels.py"), "-m", "gpu", "-q", "-x",
+                        "-k", "test_fps_vs_oracle and (4096 or 8192 or 6000 or 4128 or 5000)"], env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
