@@ -65,3 +65,22 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "pn2_oracle" not in text and "pn2_torch_port" not in text, f
+
+
+def test_tensor_core_kernels_do_not_spill():
+    """A spilled prefetch register in the fused set-abstraction kernels blocks `fence.proxy.async` on the spill store (DESIGN.md,
+    prefetch discipline: a ~1000-cycle stall per fence).  Guard it at build time: no stack frame, no local memory."""
+    import re
+    import shutil
+    import subprocess
+    import _pn2_native
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    out = subprocess.run(["cuobjdump", "--dump-resource-usage", _pn2_native.LIB_PATH], capture_output=True, text=True, timeout=120).stdout
+    seen = 0
+    for fn, usage in re.findall(r"Function (\S+):\n\s*(REG:.*)", out):
+        if re.search(r"sa_tc\d?_kernel", fn):
+            seen += 1
+            stack, local = int(re.search(r"STACK:(\d+)", usage).group(1)), int(re.search(r"LOCAL:(\d+)", usage).group(1))
+            assert stack == 0 and local == 0, (fn, usage)
+    assert seen >= 4, "the tensor-core kernels were not found in the library"
