@@ -174,8 +174,9 @@ class Native:
                                                     B, S, N, C, out.data_ptr(), _stream(src)))
         return out
 
-    def ball_query(self, centres, points, r2, number, want_idx64=True, want_idx32=False):
-        """centres [B,S,C], points [B,N,C] (any strides), r2 = fp32(radius**2) -> (idx64 | None, idx32 | None) [B,S,K]."""
+    def ball_query(self, centres, points, r2, number, want_idx64=True, want_idx32=False, empty_flag=None):
+        """centres [B,S,C], points [B,N,C] (any strides), r2 = fp32(radius**2) -> (idx64 | None, idx32 | None) [B,S,K].
+        empty_flag: optional int32 [1] device tensor, OR-ed with 1 when some centre has no point in radius (its row is N)."""
         _need_cuda("new_points", centres, torch.float32)
         _need_cuda("points", points, torch.float32)
         B, N, C = points.shape
@@ -188,10 +189,11 @@ class Native:
             _check(self.lib.pn2_ball_query_f32(centres.data_ptr(), *centres.stride(), points.data_ptr(), *points.stride(),
                                                B, S, N, C, float(r2), K,
                                                i64.data_ptr() if want_idx64 else None,
-                                               i32.data_ptr() if want_idx32 else None, None, _stream(points)))
+                                               i32.data_ptr() if want_idx32 else None,
+                                               empty_flag.data_ptr() if empty_flag is not None else None, _stream(points)))
         return i64, i32
 
-    def ball_query_multi(self, centres, points, r2_list, numbers, want_idx64=False, want_idx32=True):
+    def ball_query_multi(self, centres, points, r2_list, numbers, want_idx64=False, want_idx32=True, empty_flag=None):
         """All radii of one MSG layer in one scan: -> list of (idx64 | None, idx32 | None) [B,S,K_r] per radius; every list
         is bit-identical to ball_query(centres, points, r2_list[r], numbers[r])."""
         _need_cuda("new_points", centres, torch.float32)
@@ -201,7 +203,7 @@ class Native:
         R = len(r2_list)
         dev = points.device
         if R > 3:
-            return [self.ball_query(centres, points, r2, K, want_idx64, want_idx32) for r2, K in zip(r2_list, numbers)]
+            return [self.ball_query(centres, points, r2, K, want_idx64, want_idx32, empty_flag) for r2, K in zip(r2_list, numbers)]
         outs = [(torch.empty(B, S, int(K), dtype=torch.int64, device=dev) if want_idx64 else None,
                  torch.empty(B, S, int(K), dtype=torch.int32, device=dev) if want_idx32 else None) for K in numbers]
         r2 = (ctypes.c_float * R)(*[float(v) for v in r2_list])
@@ -211,7 +213,8 @@ class Native:
         with torch.cuda.device(dev), self._span("ball_query_multi", B=B, N=N, C=C, S=S, K=[int(K) for K in numbers]):
             _check(self.lib.pn2_ball_query_multi_f32(centres.data_ptr(), *centres.stride(), points.data_ptr(), *points.stride(),
                                                      B, S, N, C, R, r2, ks, p64 if want_idx64 else None,
-                                                     p32 if want_idx32 else None, None, _stream(points)))
+                                                     p32 if want_idx32 else None,
+                                                     empty_flag.data_ptr() if empty_flag is not None else None, _stream(points)))
         return outs
 
     # -- grouping ------------------------------------------------------------------------------------------

@@ -54,6 +54,10 @@ __global__ void group_kernel(const float *__restrict__ points, int64_t sb, int64
         const int64_t b = g / S;
         const int n = (order == PN2_ORDER_ALL) ? (int)(r % K) : idx32[r];
         float *o = out + r * W;
+        if (n < 0 || n >= N) {                   // 'no neighbour' marker of an empty ball (:85): a zero row, never an OOB read
+            for (int k = lane; k < W; k += 32) o[k] = 0.f;
+            continue;
+        }
         const float *p = points + b * sb + (int64_t)n * sn;
         for (int k = lane; k < C; k += 32) {
             float x = __ldg(p + (int64_t)k * sc);
@@ -72,7 +76,7 @@ __global__ void group_kernel(const float *__restrict__ points, int64_t sb, int64
 // (gather + centre subtraction into shared memory), and writes the 32 * C floats as contiguous 128-byte lines.
 __global__ void __launch_bounds__(256) group_rows_small_kernel(const float *__restrict__ points, int64_t sb, int64_t sn, int64_t sc,
                                                                const int32_t *__restrict__ idx32, const float *__restrict__ centres,
-                                                               int S, int K, int C, int order, int64_t rows, float *__restrict__ out)
+                                                               int N, int S, int K, int C, int order, int64_t rows, float *__restrict__ out)
 {
     __shared__ float s_rows[8][32 * 16];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -85,11 +89,12 @@ __global__ void __launch_bounds__(256) group_rows_small_kernel(const float *__re
             const int64_t g = r / K;
             const int64_t b = g / S;
             const int n = (order == PN2_ORDER_ALL) ? (int)(r % K) : idx32[r];
-            const float *p = points + b * sb + (int64_t)n * sn;
+            const bool ok = n >= 0 && n < N;      // n == N: empty ball (:85) -> zero row
+            const float *p = points + b * sb + (int64_t)(ok ? n : 0) * sn;
             for (int k = 0; k < C; ++k) {
                 float x = __ldg(p + (int64_t)k * sc);
                 if (order != PN2_ORDER_ALL) x = __fsub_rn(x, __ldg(centres + g * C + k));
-                sr[lane * C + k] = x;
+                sr[lane * C + k] = ok ? x : 0.f;
             }
         }
         __syncwarp();
@@ -109,7 +114,7 @@ int launch_group(const float *points, int64_t sb, int64_t sn, int64_t sc,
     if (D == 0 && C <= 16) {
         int64_t blocks = (rows + 255) / 256;
         if (blocks > 148 * 16) blocks = 148 * 16;
-        group_rows_small_kernel<<<(unsigned)blocks, 256, 0, st>>>(points, sb, sn, sc, idx32, centres, S, K, C, order, rows, out);
+        group_rows_small_kernel<<<(unsigned)blocks, 256, 0, st>>>(points, sb, sn, sc, idx32, centres, N, S, K, C, order, rows, out);
         return launch_status("pn2_group_f32");
     }
     int64_t blocks = (rows + 7) / 8;

@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(SA_THREADS) sa_f32_kernel(const SaF32Params p)
                             for (int j = 0; j < SA_CW; ++j) m[j] = fmaxf(m[j], __shfl_xor_sync(0xffffffffu, m[j], o));
                         if (tx % q == 0) {
                             const int64_t g = s_g[4 * tx];
-                            if (g < p.G && s_n[4 * tx] >= 0) {
+                            if (g < p.G) {            // an empty ball (no valid row) pools to 0
                                 float *o = p.out + (g / p.S) * p.ob + (g % p.S) * p.os + p.co_off + co0 + SA_CW * ty;
 #pragma unroll
                                 for (int j = 0; j < SA_CW; ++j) {
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(SA_THREADS) sa_f32_kernel(const SaF32Params p)
                             float m = 0.f; bool any = false;
                             for (int r = r_begin; r < r_begin + rows_per_group && r < R; ++r)
                                 if (s_n[r] >= 0) { m = fmaxf(m, Y[(size_t)cl * R + r]); any = true; }
-                            if (!any) continue;
+                            (void)any;                                // an empty ball pools to 0
                             float *o = p.out + (g / p.S) * p.ob + (g % p.S) * p.os + p.co_off + co0 + cl;
                             if (p.gpt) *o = m;
                             else atomicMax(reinterpret_cast<int *>(o), __float_as_int(m));

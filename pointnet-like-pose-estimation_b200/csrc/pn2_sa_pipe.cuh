@@ -151,8 +151,8 @@ struct PoolOut {
     // group finished: max over its rows -> + bias -> ReLU -> [B,S,Ctot]; then step to the next group
     __device__ __forceinline__ void emit(float m)
     {
-        if (c_ok && gg < G && (all_valid || m > -INFINITY)) {
-            const float y = fmaxf(m + bv, 0.f);
+        if (c_ok && gg < G) {
+            const float y = fmaxf(m + bv, 0.f);       // an empty ball (every row masked to -inf) pools to 0, never to stale memory
             int64_t off;
             if (contig) off = (int64_t)gg * os;
             else { const int b = (int)((unsigned)gg / (unsigned)S); off = (int64_t)b * ob + (int64_t)(gg - b * S) * os; }

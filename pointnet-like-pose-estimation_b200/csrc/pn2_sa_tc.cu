@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
                             const int cl = (lane & (p.Kl - 1)) * nf;
                             if (p.direct) {
                                 const int64_t g = s_g[row];
-                                if (g < p.G && row_valid) {
+                                if (g < p.G) {          // an empty ball (-inf in every row) pools to relu(-inf) = 0
                                     float *o_ptr = p.out + (g / p.S) * p.ob + (g % p.S) * p.os + p.co_off + c0 + cl;
                                     const float *bs = bias_s + ly.b_off + c0 + cl;
 #pragma unroll
@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
                             else m = fmaxf(fmaxf(pool_s[c], pool_s[p.pool_cols + c]), fmaxf(pool_s[2 * p.pool_cols + c], pool_s[3 * p.pool_cols + c]));
                             const int r0 = gl * (TC_ROWS / p.gpt);
                             const int64_t g = s_g[r0];
-                            if (g >= p.G || s_n[r0] < 0 || col_base + c >= ly.Cout) continue;
+                            if (g >= p.G || col_base + c >= ly.Cout) continue;          // empty ball: m = -inf -> 0 below
                             m = fmaxf(m + bias_s[ly.b_off + col_base + c], 0.f);
                             float *o_ptr = p.out + (g / p.S) * p.ob + (g % p.S) * p.os + p.co_off + col_base + c;
                             if (p.use_atomic) atomicMax(reinterpret_cast<int *>(o_ptr), __float_as_int(m));
@@ -595,6 +595,11 @@ int launch_sa_bf16(const SaArgs &a, cudaStream_t st)
         if (rc != -100) return rc;
     }
     PN2_REQUIRE(a.D == 0 || a.feat, "pn2_sa_fused(bf16): this configuration needs the fp32 feature rows (bf16-only features are gathered by the pipelined kernels)");
+    // the streaming kernel has no bf16 side output: a caller that was promised one by pn2_sa_bf16_side_io (which cannot see the
+    // batch size or PN2_TC_RING_ONLY) must not receive an unwritten tensor
+    PN2_REQUIRE(a.out_bf16 == nullptr || !sa_bf16_pipelined_covers(a.K, a.C, a.D, a.order, a.L, a.dims),
+                "pn2_sa_fused(bf16): B*S*K = %lld rows (or PN2_TC_RING_ONLY) exceed the pipelined kernel that writes out_bf16; pass out_bf16 = NULL or split the batch",
+                (long long)a.B * a.S * a.K);
     TcPlan pl;
     PN2_REQUIRE(tc_plan(a.K, a.L, a.dims, &pl), "pn2_sa_fused(bf16): layer widths do not fit shared memory");
     TcParams p;

@@ -32,7 +32,8 @@ from _pn2_native import ORDER_ALL, ORDER_MSG, ORDER_SSG, PREC_BF16, PREC_F32
 
 __all__ = ["square_distance", "index_points", "farthest_point_sample", "query_ball_point", "sample_and_group",
            "sample_and_group_all", "PointNetSetAbstraction", "PointNetSetAbstractionMsg",
-           "set_precision", "get_precision", "set_reference_strides", "fps_start_source"]
+           "set_precision", "get_precision", "set_reference_strides", "fps_start_source",
+           "invalidate_caches", "empty_ball_seen"]
 
 _native = None              # created on first use; tests may monkeypatch this attribute
 _precision = os.environ.get("PN2_PRECISION", "fp32")
@@ -40,6 +41,8 @@ _reference_strides = False
 _factorise_first_layer = os.environ.get("PN2_FACTORISE", "1") != "0"     # see _FactorisedFirstLayer
 _train_fused = os.environ.get("PN2_TRAIN_FUSED", "1") != "0"            # see _shared_mlp_train_rows
 _start_source = None        # optional callable (B, N) -> int64 CPU tensor [B]; default = torch.randint
+_cache_generation = 0       # part of every derived-weight cache key, see invalidate_caches()
+_empty_flags = {}           # device -> int32 [1]: set by the ball queries of the modules when a centre has no neighbour
 
 
 def _backend():
@@ -91,6 +94,42 @@ def _draw_start(B: int, N: int, device) -> torch.Tensor:
     return start.to(device, non_blocking=start.is_pinned())     # pinned sources (pn2_graph.py) must not synchronise
 
 
+def invalidate_caches() -> None:
+    """Drop every derived weight cache (BN-folded / bf16-packed weights) so that the next forward repacks.
+
+    The caches follow parameter updates through ``tensor._version`` (optimizer steps, ``load_state_dict``, in-place ops on
+    the parameter).  Writes through ``param.data`` (``p.data.copy_()``, ``m.weight.data.normal_()``, EMA code) bump a
+    different version counter and are NOT seen: call this after such an update.  CUDA graphs captured by
+    ``pn2_graph.GraphedForward`` notice the new generation and re-capture."""
+    global _cache_generation
+    _cache_generation += 1
+
+
+def _empty_flag(device) -> torch.Tensor:
+    key = (device.type, device.index if (device.index is not None or device.type != "cuda") else torch.cuda.current_device())
+    t = _empty_flags.get(key)
+    if t is None:
+        t = _empty_flags[key] = torch.zeros(1, dtype=torch.int32, device=device)
+    return t
+
+
+def empty_ball_seen(device=None, reset: bool = True) -> bool:
+    """True if, since the last reset, a set-abstraction module on `device` met a centre with NO point inside its radius.
+
+    The reference writes index N for such a centre and crashes in the next ``index_points`` (:85-89, :44); that cannot
+    happen when the centres are FPS picks of the same cloud unless the expanded-form distance d(s,s) rounds above r**2
+    (un-normalised, large-magnitude clouds).  The modules here neither crash nor read out of bounds: the group's rows
+    are zeros (training) / its pooled feature is 0 (eval), and this flag records it without a device synchronisation on
+    the forward path.  Reading it synchronises.  The stand-alone ``sample_and_group`` raises IndexError like the reference."""
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    flag = _empty_flag(torch.device(device))
+    seen = bool(flag.item())
+    if seen and reset:
+        flag.zero_()
+    return seen
+
+
 def _radius_sq(radius) -> float:
     # Python squares in double (0.2**2 = 0.04000000000000001), ATen then compares in fp32 (:85)
     return float(np.float32(float(radius) ** 2))
@@ -129,7 +168,10 @@ def sample_and_group(points, feature, point_number, sample_number, radius, retur
     B, N, C = points.shape
     start = _draw_start(B, N, points.device)
     fps_idx, _, new_points = be.fps(points, start, point_number, want_idx64=True, want_new_points=True)
-    _, idx32 = be.ball_query(new_points, points, _radius_sq(radius), sample_number, want_idx64=False, want_idx32=True)
+    flag = torch.zeros(1, dtype=torch.int32, device=points.device)
+    _, idx32 = be.ball_query(new_points, points, _radius_sq(radius), sample_number, want_idx64=False, want_idx32=True, empty_flag=flag)
+    if int(flag.item()):        # the reference indexes with N here and fails in index_points (:109 -> :44)
+        raise IndexError(f"sample_and_group: a centre has no point within radius {radius} (index {N} is out of bounds for dimension 1 with size {N})")
     new_feature = be.group(points, feature, idx32, new_points, ORDER_SSG)
     if returnfps:
         grouped = be.index_points(feature if feature is not None else points, idx32.long(), check=False)
@@ -167,7 +209,7 @@ class _FoldedMLP:
         for conv, bn in zip(convs, bns):
             tensors += [conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var]
         prec = _prec_code()
-        key = (prec, C, order, tuple((t.data_ptr(), t._version) for t in tensors))
+        key = (_cache_generation, prec, C, order, tuple((t.data_ptr(), t._version) for t in tensors))
         if key != self.key:
             layers = [(conv.weight.detach().reshape(conv.out_channels, conv.in_channels), conv.bias.detach(),
                        bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var)
@@ -199,7 +241,7 @@ class _FactorisedFirstLayer:
         tensors = []
         for conv, bn in zip(convs, bns):
             tensors += [conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var]
-        key = (C, D, tuple((t.data_ptr(), t._version) for t in tensors))
+        key = (_cache_generation, C, D, tuple((t.data_ptr(), t._version) for t in tensors))
         if key != self.key:
             conv0, bn0 = convs[0], bns[0]
             n0 = conv0.out_channels
@@ -392,7 +434,8 @@ class PointNetSetAbstraction(nn.Module):
             S, K = self.point_number, self.sample_number
             start = _draw_start(B, N, pts.device)
             _, _, new_points = be.fps(pts, start, S, want_idx64=False, want_new_points=True)
-            _, idx32 = be.ball_query(new_points, pts, _radius_sq(self.radius), K, want_idx64=False, want_idx32=True)
+            _, idx32 = be.ball_query(new_points, pts, _radius_sq(self.radius), K, want_idx64=False, want_idx32=True,
+                                     empty_flag=_empty_flag(pts.device))
         alloc = torch.zeros if be.sa_needs_zero(S, K, dims, prec) else torch.empty
         pooled = alloc(B, S, dims[-1], dtype=torch.float32, device=pts.device)
         side = be.sa_bf16_side_io(K, C, order, dims, prec)
@@ -403,8 +446,9 @@ class PointNetSetAbstraction(nn.Module):
         return _finish(new_points, pooled, twin_out)
 
     def _forward_train(self, pts, feat):
-        # Training mode (batch-statistics BatchNorm + autograd): sampling and grouping run on our kernels,
-        # the MLP on cuDNN/ATen so that gradients flow.  Fused training kernels are the next scope row.
+        # Training mode (batch-statistics BatchNorm + autograd): sampling and grouping run on our kernels, the shared MLP
+        # layer by layer on the grouped rows (_shared_mlp_train_rows: GEMM + the fused BatchNorm / ReLU / max-pool kernels
+        # of csrc/pn2_bn_train.cu, forward and backward).
         be = _backend()
         B, N, C = pts.shape
         if self.group_all:
@@ -416,7 +460,8 @@ class PointNetSetAbstraction(nn.Module):
             S, K = self.point_number, self.sample_number
             start = _draw_start(B, N, pts.device)
             _, _, new_points = be.fps(pts.detach(), start, S, want_idx64=False, want_new_points=True)
-            _, idx32 = be.ball_query(new_points, pts.detach(), _radius_sq(self.radius), K, want_idx64=False, want_idx32=True)
+            _, idx32 = be.ball_query(new_points, pts.detach(), _radius_sq(self.radius), K, want_idx64=False, want_idx32=True,
+                                     empty_flag=_empty_flag(pts.device))
             rows = be.group(pts.detach(), None, idx32, new_points, ORDER_SSG)
             if feat is not None:
                 rows = torch.cat([rows, _gather_rows(feat, idx32)], dim=-1)
@@ -496,7 +541,8 @@ class PointNetSetAbstractionMsg(nn.Module):
         co = 0
         feat_bf16 = None
         # one scan of the cloud serves every radius of the layer (the distances do not depend on it)
-        groups = be.ball_query_multi(new_points, pts, [_radius_sq(r) for r in self.radius_list], self.sample_number_list)
+        groups = be.ball_query_multi(new_points, pts, [_radius_sq(r) for r in self.radius_list], self.sample_number_list,
+                                     empty_flag=_empty_flag(pts.device))
         for (_, idx32), K, (packed, dims, prec), wf in zip(groups, self.sample_number_list, plans, fact):
             if wf is not None:
                 # first layer factorised: P = feat (s Wf)^T once per point, gathered in place of the feature rows
@@ -516,7 +562,8 @@ class PointNetSetAbstractionMsg(nn.Module):
         S = self.point_number
         _, _, new_points = be.fps(pts.detach(), start, S, want_idx64=False, want_new_points=True)
         outs = []
-        groups = be.ball_query_multi(new_points, pts.detach(), [_radius_sq(r) for r in self.radius_list], self.sample_number_list)
+        groups = be.ball_query_multi(new_points, pts.detach(), [_radius_sq(r) for r in self.radius_list], self.sample_number_list,
+                                     empty_flag=_empty_flag(pts.device))
         for i, (_, idx32) in enumerate(groups):
             rows = be.group(pts.detach(), None, idx32, new_points, ORDER_MSG)            # [B,S,K,C] xyz - centre
             convs, bns = self.conv_blocks[i], self.bn_blocks[i]

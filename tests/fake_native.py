@@ -23,10 +23,10 @@ class OracleNative:
         return (idx if want_idx64 else None, idx.int() if want_idx32 else None,
                 orc.index_points(points, idx).contiguous() if want_new_points else None)
 
-    def ball_query_multi(self, centres, points, r2_list, numbers, want_idx64=False, want_idx32=True):
+    def ball_query_multi(self, centres, points, r2_list, numbers, want_idx64=False, want_idx32=True, empty_flag=None):
         self.calls.append("ball_query_multi")
         n = len(self.calls)
-        outs = [self.ball_query(centres, points, r2, K, want_idx64, want_idx32) for r2, K in zip(r2_list, numbers)]
+        outs = [self.ball_query(centres, points, r2, K, want_idx64, want_idx32, empty_flag) for r2, K in zip(r2_list, numbers)]
         del self.calls[n:]
         return outs
 
@@ -81,7 +81,7 @@ class OracleNative:
         self.calls.append("square_distance")
         return orc.square_distance(src, dst)
 
-    def ball_query(self, centres, points, r2, number, want_idx64=True, want_idx32=False):
+    def ball_query(self, centres, points, r2, number, want_idx64=True, want_idx32=False, empty_flag=None):
         self.calls.append("ball_query")
         B, N, C = points.shape
         S = centres.shape[1]
@@ -90,6 +90,8 @@ class OracleNative:
         cen = centres.contiguous()
         rc = orc.lib().pn2o_ball_query(cen.data_ptr(), points.data_ptr(), sb, sn, sc, B, S, N, C, r2, number, out.data_ptr())
         assert rc >= 0
+        if empty_flag is not None and bool((out == N).any()):
+            empty_flag.fill_(1)
         return (out if want_idx64 else None, out.int() if want_idx32 else None)
 
     def group(self, points, feature, idx32, centres, order):

@@ -281,3 +281,91 @@ def test_full_size_properties_of_the_bench_workload(pu):
     assert torch.isfinite(whole).all() and torch.equal(whole, again)
     # the set-abstraction path is per cloud; the FC head behind it is a library GEMM whose blocking depends on the batch size
     assert torch.allclose(part, whole[:160], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_graphed_forward_recaptures_after_a_weight_update(pu):
+    """the graph bakes in the packed-weight pointers.  After a parameter update, a load_state_dict, a precision
+    switch or invalidate_caches() (the hook for `.data` writes) the replay must equal the eager forward of the NEW weights."""
+    import pn2_graph
+    import pn2_models
+    torch.manual_seed(0)
+    model = pn2_models.get_model("pointnet2_cls_ssg", 7)
+    pn2_models.randomize_bn_(model)
+    model = model.eval().to(DEV)
+    x = cloudgen.channels_first(cloudgen.uniform_cloud(8, 1024, 5)).to(DEV)
+    pu.set_precision("bf16")
+    g = pn2_graph.GraphedForward(model, x)
+
+    def both():
+        torch.manual_seed(3)
+        a = g(x)[0].clone()
+        torch.manual_seed(3)
+        with torch.no_grad():
+            b = model(x)[0].clone()
+        return a, b
+
+    a0, b0 = both()
+    assert torch.equal(a0, b0) and g.captures == 1
+    with torch.no_grad():
+        model.sa2.mlp_convs[1].weight.mul_(1.5)                 # what an optimizer step does: in-place, version bump
+    a1, b1 = both()
+    assert torch.equal(a1, b1) and not torch.equal(a1, a0) and g.captures == 2
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    sd["sa1.mlp_bns.0.running_mean"] += 0.25
+    model.load_state_dict(sd)
+    a2, b2 = both()
+    assert torch.equal(a2, b2) and not torch.equal(a2, a1) and g.captures == 3
+    model.sa3.mlp_convs[0].weight.data.mul_(0.5)                # `.data` write: invisible to the version counters ...
+    pu.invalidate_caches()                                      # ... so the documented hook is called
+    a3, b3 = both()
+    assert torch.equal(a3, b3) and not torch.equal(a3, a2) and g.captures == 4
+    pu.set_precision("fp32")
+    a4, b4 = both()
+    assert torch.equal(a4, b4) and g.captures == 5
+    a5, _ = both()
+    assert torch.equal(a5, a4) and g.captures == 5              # nothing changed: plain replay
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_empty_balls_pool_to_zero_and_are_flagged(pu, prec):
+    """a centre with no point in radius (the reference writes index N and crashes in index_points, :85-89 / :44).
+    Here: no out-of-bounds read, the group's pooled feature is 0 (never uninitialised memory), empty_ball_seen() reports it,
+    training-mode rows are zeros, and the stand-alone sample_and_group raises IndexError like the reference."""
+    pu.set_precision(prec)
+    be = pu._backend()
+    B, N, S, K = 3, 256, 16, 8
+    x = cloudgen.uniform_cloud(B, N, 12).to(DEV)
+    cen = x[:, :S].clone().contiguous()
+    cen[1, 3] = 40.0                                            # far away from every point: empty ball
+    cen[2, S - 1] = -55.0
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    _, idx32 = be.ball_query(cen, x, pu._radius_sq(0.3), K, want_idx64=False, want_idx32=True, empty_flag=flag)
+    assert int(flag.item()) == 1 and bool((idx32[1, 3] == N).all()) and bool((idx32[2, S - 1] == N).all())
+    rows = be.group(x, None, idx32, cen, 0)
+    assert not rows[1, 3].any() and not rows[2, S - 1].any() and torch.isfinite(rows).all()
+    f = torch.randn(B, N, 24, generator=torch.Generator().manual_seed(1)).to(DEV)
+    rows = be.group(x, f, idx32, cen, 1)
+    assert not rows[1, 3].any() and torch.isfinite(rows).all()
+    import test_gpu_kernels as tk
+    for dims, feat in (([3, 32, 64], None), ([27, 64, 128], f), ([27, 16, 24], f)):
+        layers = [tuple(t.to(DEV) for t in l) for l in tk.rand_layers(dims, 5)]
+        code = 0 if prec == "fp32" else 1
+        packed, _ = be.pack(layers, 1e-5, code, 3, 0)
+        out = torch.full((B, S, dims[-1]), float("nan"), device=DEV)
+        if be.sa_needs_zero(S, K, dims, code):
+            out.zero_()
+        be.sa_fused(x, feat, cen, idx32, 0, dims, packed, code, out, 0)
+        assert torch.isfinite(out).all()
+        assert not out[1, 3].any() and not out[2, S - 1].any() and bool(out[0].any())
+    # module level: flag without a synchronisation on the forward path
+    pu.empty_ball_seen(DEV)
+    sa = pu.PointNetSetAbstraction(S, K, 1e-4, 3, [16, 32], False).to(DEV).eval()
+    big = (x * 4000.0 + 9000.0).permute(0, 2, 1).contiguous()  # d(s,s) of the expanded form rounds far above r^2
+    with torch.no_grad():
+        _, feat_out = sa(big, None)
+    assert torch.isfinite(feat_out).all()
+    assert pu.empty_ball_seen(DEV) and not pu.empty_ball_seen(DEV)
+    with pytest.raises(IndexError):
+        pu.sample_and_group(big.permute(0, 2, 1), None, S, K, 1e-4)
