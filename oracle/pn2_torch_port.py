@@ -151,3 +151,23 @@ class PointNetSetAbstractionMsg(nn.Module):
                 rows = torch.cat([take_rows(feat, nbr), rows], dim=-1)        # [feat, xyz_norm]  (:208-209)
             outs.append(_mlp_pool(rows, convs, bns))
         return centres.permute(0, 2, 1), torch.cat(outs, dim=1)
+
+
+def v1_forward(model, x, mean=None):
+    """The PointNet-v1-like pose heads (model/width.py:32-44, rotation.py:34-50, translation.py:37-51, sign.py:31-43) as the
+    reference runs them on the CPU: Conv1d(k=1) + BatchNorm1d + ReLU x 5 over all points, global max, FC stack.  `model`
+    only supplies the parameters (a pn2_v1.PointNetV1Head: same attribute names as the reference files); timing baseline
+    of configs[3]'s width head."""
+    if model.kind == "trans" and model.mean_mlp == "True":
+        mean = model.fc2(F.relu(model.bn1(model.fc1(mean))))
+    for conv, bn in zip(model.conv, model.bn_conv):
+        x = F.relu(bn(conv(x)))
+    x = torch.max(x, 2, keepdim=True)[0].view(-1, model.pooled_width)
+    for i in range(len(model.fc)):
+        x = F.relu(model.dropout(model.bn_fc[i](model.fc[i](x)))) if i < len(model.fc) - 1 else model.fc[i](x)
+    if model.kind == "trans":
+        return x + mean
+    if model.kind == "sign":
+        x = torch.sigmoid(x)
+        return x, torch.sign(x - 0.5)
+    return x

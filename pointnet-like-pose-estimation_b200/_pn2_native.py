@@ -283,9 +283,10 @@ class Native:
         return bool(rc)
 
     def sa_fused(self, points, feature, centres, idx32, order, dims, packed, prec, out, co_off=0,
-                 feature_bf16=None, out_bf16=None):
+                 feature_bf16=None, out_bf16=None, algo_dims=None):
         """Fused gather -> MLP -> max.  out [B,S,Ctot] (channels-last) receives channels [co_off, co_off+dims[-1]).
-        feature_bf16 [B,N,D] / out_bf16 [B,S,Ctot]: optional bf16 side tensors (see include/pn2.h)."""
+        feature_bf16 [B,N,D] / out_bf16 [B,S,Ctot]: optional bf16 side tensors (see include/pn2.h).
+        algo_dims: trace metadata only -- the layer widths of the module when `dims` describes a factorised first layer."""
         _need_cuda("points", points, torch.float32)
         _need_cuda("out", out, torch.float32)
         B, N, C = points.shape
@@ -315,7 +316,8 @@ class Native:
             _need_cuda("out_bf16", out_bf16, torch.bfloat16)
             assert out_bf16.shape == out.shape and out_bf16.stride() == out.stride()
         d = _dims_array(dims)
-        with torch.cuda.device(points.device), self._span("sa_fused", B=B, N=N, S=S, K=K, C=C, D=D, dims=tuple(dims), prec=prec):
+        with torch.cuda.device(points.device), self._span("sa_fused", B=B, N=N, S=S, K=K, C=C, D=D, dims=tuple(dims), prec=prec,
+                                                             algo_dims=tuple(algo_dims) if algo_dims else None):
             _check(self.lib.pn2_sa_fused(points.data_ptr(), *points.stride(), fptr, *fstr, cptr, iptr,
                                          B, N, S, K, C, D, order, len(dims) - 1, d.ctypes.data, packed.data_ptr(), prec,
                                          out.data_ptr(), out.stride(0), out.stride(1), int(co_off),

@@ -5,8 +5,8 @@ body: ``Conv1d(k=1) + BatchNorm1d + ReLU`` x 5 (10|13 -> 64 -> 64 -> 64 -> 128 -
 over the points, then ``relu(dropout(bn(fc)))`` x 2 and a last ``fc``.  The point-wise stack followed by the max is
 exactly the fused kernel's ``group_all`` mode without any grouping: the [B, C, N] input is the "coordinate" operand
 (C <= 16), there are no features, one group per cloud holds all N rows, and the [B, N, 1024] activations never reach HBM.
-In eval mode on a CUDA tensor ``PointNetV1Head`` runs that; in training mode (batch-statistics BatchNorm, autograd) it
-runs the reference's op sequence on ATen.
+In eval mode ``PointNetV1Head`` runs that (CUDA tensors only: there is no CPU implementation); in training mode
+(batch-statistics BatchNorm, autograd) it runs the reference's op sequence on ATen.
 
 Attribute names (``conv, bn_conv, fc, bn_fc, dropout``, rotation's ``ftnet``, translation's ``fc1, fc2, bn1``) and the
 construction order follow the reference files, so seeded construction and ``state_dict``s are interchangeable
@@ -112,9 +112,9 @@ class PointNetV1Head(nn.Module):
         self.pooled_width = mlp_list[-1]
 
     def _encode(self, x):
-        if not self.training and x.is_cuda:
+        if not self.training:                                  # eval: the fused kernel; a CPU tensor raises (no CPU path)
             return pointwise_mlp_max(x, self.conv, self.bn_conv, self._folded)
-        for i in range(len(self.conv)):                        # the reference's op sequence (training / CPU)
+        for i in range(len(self.conv)):                        # training mode: the reference's op sequence under autograd
             x = F.relu(self.bn_conv[i](self.conv[i](x)))
             if self.kind == "rot" and i == 1 and self.training:
                 self.ftnet(x)                                  # computed and discarded (rotation.py:37)

@@ -543,14 +543,15 @@ class PointNetSetAbstractionMsg(nn.Module):
         # one scan of the cloud serves every radius of the layer (the distances do not depend on it)
         groups = be.ball_query_multi(new_points, pts, [_radius_sq(r) for r in self.radius_list], self.sample_number_list,
                                      empty_flag=_empty_flag(pts.device))
-        for (_, idx32), K, (packed, dims, prec), wf in zip(groups, self.sample_number_list, plans, fact):
+        for i, ((_, idx32), K, (packed, dims, prec), wf) in enumerate(zip(groups, self.sample_number_list, plans, fact)):
             if wf is not None:
                 # first layer factorised: P = feat (s Wf)^T once per point, gathered in place of the feature rows
                 if feat_bf16 is None:
                     feat_bf16 = twin_in if twin_in is not None else feat.to(torch.bfloat16).contiguous()
                 p_rows = torch.matmul(feat_bf16, wf.t())                       # [B,N,N0] bf16, fp32 accumulation (cuBLAS)
                 be.sa_fused(pts, None, new_points, idx32, ORDER_MSG, dims, packed, prec, pooled, co,
-                            feature_bf16=p_rows, out_bf16=twin_out)
+                            feature_bf16=p_rows, out_bf16=twin_out,
+                            algo_dims=[D + C] + [c.out_channels for c in self.conv_blocks[i]])
             else:
                 be.sa_fused(pts, feat, new_points, idx32, ORDER_MSG, dims, packed, prec, pooled, co,   # branch concat (:222) is the channel offset
                             feature_bf16=twin_in, out_bf16=twin_out)

@@ -110,7 +110,7 @@ class OracleNative:
         return False
 
     def sa_fused(self, points, feature, centres, idx32, order, dims, packed, prec, out, co_off=0,
-                 feature_bf16=None, out_bf16=None):
+                 feature_bf16=None, out_bf16=None, algo_dims=None):
         self.calls.append("sa_fused")
         layers, eps = packed
         rows = orc.group(points, feature, None if idx32 is None else idx32.long(), centres, order)

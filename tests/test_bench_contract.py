@@ -26,13 +26,21 @@ def test_reference_arm_line():
     cpu = line["cpu_baseline"]
     assert cpu["kind"] == "port" and cpu["cores"] >= 1 and cpu["value"] == line["value"] and "24 clouds" in cpu["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    # same workload description as the product arm; the bounded sample is stated next to it
+    # the SAME config object as the product arm (the driver compares them); the bounded sample is named inside it and
+    # described in cpu_baseline.sample
     sys.path.insert(0, ROOT)
     import bench
-    ours = bench.workload_config(2048, 1, "fp32")
-    for k, v in ours.items():
-        assert line["config"][k] == v
-    assert "sample" in line["config"]
+    assert line["config"] == bench.workload_config(0, 2048, 1)
+    assert "24-cloud" in line["config"]["reference_arm_sample"]
+
+
+def test_reference_arm_of_the_microbenchmark_config():
+    line = _bench("--config", "2", "--impl", "reference", "--steps", "1", "--warmup", "0")
+    assert line["impl"] == "reference" and line["unit"] == "us" and line["higher_is_better"] is False
+    assert line["value"] == line["cpu_fps_us"] + line["cpu_ball_query_us"] > 0
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["config"] == bench.cfg2_config(1)
 
 
 def test_product_arm_fails_loudly_without_a_gpu():

@@ -369,3 +369,73 @@ def test_empty_balls_pool_to_zero_and_are_flagged(pu, prec):
     assert pu.empty_ball_seen(DEV) and not pu.empty_ball_seen(DEV)
     with pytest.raises(IndexError):
         pu.sample_and_group(big.permute(0, 2, 1), None, S, K, 1e-4)
+
+
+@pytest.mark.gpu
+def test_pose_pipeline_modes_agree_and_match_the_golden_heads(pu):
+    """configs[3]: pn2_pipeline.PosePipeline.  (1) On the golden inputs every PointNet++ head of the pipeline -- eager, graphed,
+    and graphed on one stream per head -- reproduces the live-reference golden output of that model (FPS starts seeded with 42
+    per head, like the golden generator).  (2) On a 48-cloud batch with device-side input preparation the three schedules are
+    bit-identical under the same draws."""
+    import pn2_pipeline
+    import pn2_shard
+    cases = golden_io.model_cases()
+    names = [n for n in pn2_pipeline.HEADS if n in cases]
+    assert len(names) == 6
+    pu.set_precision("fp32")
+    torch.manual_seed(0)
+    heads = {}
+    import pn2_models
+    for n in names:
+        torch.manual_seed(0)
+        m = pn2_models.get_model(n, 7)
+        pn2_models.randomize_bn_(m, 7)
+        heads[n] = m.eval().to(DEV)
+    d = cases[names[0]]
+    xyz = torch.from_numpy(d["xyz"])
+    x = cloudgen.channels_first(cloudgen.with_category(xyz)).to(DEV)
+    mean = torch.from_numpy(cases["translation_ssg"]["mean"]).to(DEV)
+    B = x.shape[0]
+
+    class SeededPerHead:
+        """Every head's first draw restarts the generator at 42 (the golden generator seeds before each model)."""
+        def __init__(self):
+            self.g = torch.Generator()
+        def __call__(self, B_, N_):
+            if N_ == 1024:
+                self.g.manual_seed(42)
+            return torch.randint(0, N_, (B_,), generator=self.g, dtype=torch.long)
+
+    for mode in ("eager", "graphs", "streams"):
+        pipe = pn2_pipeline.PosePipeline(heads, mode=mode, start_source=SeededPerHead())
+        for rep in range(2):
+            outs = pipe.forward_prepared(x, mean, None)
+            torch.cuda.synchronize()
+            for n in names:
+                c = cases[n]
+                if abs(float(sum(v.double().abs().sum() for v in heads[n].state_dict().values())) - float(c["sd_checksum"][0])) > 1e-6 * float(c["sd_checksum"][0]):
+                    pytest.skip("seeded initialisation differs from the build container's torch")
+                assert rel_err(outs[n][0].cpu(), torch.from_numpy(c["out0"])) <= 5e-5, (mode, n, rep)
+    # (2) schedules agree bit for bit on a larger batch, raw inputs through the device-side preparation
+    pu.set_precision("bf16")
+    heads = pn2_pipeline.build_heads(DEV)
+    g = torch.Generator().manual_seed(3)
+    raw = (torch.rand(48, 1024, 3, generator=g) * 2 - 1 + torch.randn(48, 1, 3, generator=g)).to(DEV)
+    nrm = torch.randn(48, 1024, 3, generator=g).to(DEV)
+    cat = (torch.arange(48) % 7).to(DEV)
+    ref = None
+    for mode in ("eager", "graphs", "streams"):
+        pipe = pn2_pipeline.PosePipeline(heads, mode=mode, start_source=pn2_shard.GlobalStarts(48, 1, 0, seed=5))
+        got = []
+        for rep in range(2):
+            outs = pipe(raw, nrm, cat)
+            torch.cuda.synchronize()
+            got.append({n: [t.clone() for t in o] for n, o in outs.items()})
+        if ref is None:
+            ref = got
+            assert set(ref[0]) == set(pn2_pipeline.HEADS)
+            assert not torch.equal(ref[0]["rotation_ssg"][0], ref[1]["rotation_ssg"][0])      # fresh draws every pass
+        else:
+            for a, b in zip(ref, got):
+                for n in a:
+                    assert all(torch.equal(u, v) for u, v in zip(a[n], b[n])), (mode, n)

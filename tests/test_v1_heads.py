@@ -47,7 +47,7 @@ def test_fused_entry_point_matches_the_op_sequence_on_the_oracle(fake_native, na
 
 @pytest.mark.reference
 @pytest.mark.parametrize("name", sorted(pn2_v1.V1_ARCH))
-def test_state_dicts_and_outputs_interchange_with_the_reference_files(name):
+def test_state_dicts_and_outputs_interchange_with_the_reference_files(fake_native, name):
     sys.path.append(REFERENCE_MODEL_DIR)
     try:
         for m in (name, "pointnet_utils"):
