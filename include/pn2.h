@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PN2_ABI_VERSION 10
+#define PN2_ABI_VERSION 11
 #define PN2_MAX_COORD 16 /* exact summation-order rules are verified against ATen for C <= 16 */
 #define PN2_MAX_LAYERS 8
 
@@ -165,6 +165,28 @@ int pn2_bn_relu_train_fwd_f32(const float *y, int64_t M, int C, int K, const flo
                               float *running_mean, float *running_var, const float *conv_bias, float factor, void *stream);
 int pn2_bn_relu_train_bwd_f32(const float *dz, const float *y, const int32_t *arg, int64_t M, int C, int K,
                               const float *stats, void *ws, float *sums, float *dy, void *stream);
+
+/* Fused FC head, eval mode -- the tail of every model after the last set abstraction: pointnet2_cls_ssg.py:31-38
+ * (fc1/bn1/relu/drop -> fc2/bn2/relu/drop -> fc3 -> log_softmax, argmax), rotation_ssg.py:32-38, translation_ssg.py:31-33,39-44
+ * (+ mean, optionally through mean_fc1/mean_bn1/relu/mean_fc2), sign_ssg.py:29-36 (sigmoid, sign(. - 0.5)); the PointNet-v1
+ * heads (width.py:39-44 ...) have the same shape.  One launch instead of ~14 library launches.
+ *   x [B,K0] fp32 with row stride x_stride (the pooled features of the last set abstraction), K0 -> H1 -> H2 -> OUT.
+ *   BatchNorm1d is folded by the caller: w1p / w2p = the folded weights W' [H][K] packed as [K/4][H][4] floats, b1 / b2 the
+ *   folded biases; w3 [OUT][H2] row-major, b3 [OUT].  kind = PN2_HEAD_*:
+ *     PLAIN  out [B,OUT] = fc3(.)                         CLS   out = log_softmax, aux = int64 [B] argmax (may be NULL)
+ *     TRANS  out = fc3(.) + m, m = mean [B,3] (row stride mean_stride) or, when mean_mlp != NULL, W2 relu(W1' mean + b1') + b2
+ *            with mean_mlp = 45 floats {W1' [6][3], b1' [6], W2 [3][6], b2 [3]} (BatchNorm1d(6) folded into W1', b1')
+ *     SIGN   out = sigmoid(fc3(.)), aux = float [B,OUT] sign(out - 0.5) (may be NULL)
+ *   Widths: H1, H2 = 8 x a divisor of 256; K0 >= 256; OUT <= 16 (the reference: 1024 -> 512 -> 256 -> 7 | 3 | 1). */
+#define PN2_HEAD_PLAIN 0
+#define PN2_HEAD_CLS 1
+#define PN2_HEAD_TRANS 2
+#define PN2_HEAD_SIGN 3
+int pn2_fc_head_f32(const float *x, int64_t x_stride, int B, int K0, int H1, int H2, int OUT,
+                    const float *w1p, const float *b1, const float *w2p, const float *b2,
+                    const float *w3, const float *b3, int kind,
+                    const float *mean, int64_t mean_stride, const float *mean_mlp,
+                    float *out, void *aux, void *stream);
 
 /* Device self-test of the tcgen05 building blocks (one 128xN tile against a scalar loop in the same
  * launch).  Returns 0 and writes max|err| to *max_err (device float). */

@@ -22,7 +22,8 @@ LIB_PATH = os.path.join(_HERE, LIB_NAME)
 ORDER_SSG, ORDER_MSG, ORDER_ALL = 0, 1, 2
 PREC_F32, PREC_BF16 = 0, 1
 MAX_COORD = 16
-ABI_VERSION = 10
+ABI_VERSION = 11
+HEAD_PLAIN, HEAD_CLS, HEAD_TRANS, HEAD_SIGN = 0, 1, 2, 3
 
 _i64, _i32, _f32, _vp = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p
 
@@ -52,6 +53,7 @@ _SIGNATURES = {
     "pn2_bn_train_ws_bytes": ([_i32], _i64),
     "pn2_bn_relu_train_fwd_f32": ([_vp, _i64, _i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp], _i32),
     "pn2_bn_relu_train_bwd_f32": ([_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp], _i32),
+    "pn2_fc_head_f32": ([_vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp], _i32),
     "pn2_selftest_umma": ([_i32, _i32, _i32, _vp, _vp, _vp], _i32),
     "pn2_debug_trace": ([_vp], _i32),
     "pn2_selftest_tma_gather": ([_vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp], _i32),
@@ -404,6 +406,31 @@ class Native:
             _check(self.lib.pn2_bn_relu_train_bwd_f32(dz.data_ptr(), y.data_ptr(), arg.data_ptr() if K else None, M, C, int(K),
                                                       stats.data_ptr(), ws.data_ptr(), sums.data_ptr(), dy.data_ptr(), _stream(y)))
         return dy, sums
+
+    def fc_head(self, x, w1p, b1, w2p, b2, w3, b3, kind, mean=None, mean_mlp=None):
+        """Fused FC head (include/pn2.h: pn2_fc_head_f32): x [B,K0] -> (out [B,OUT], aux | None); folded / packed weights
+        from pointnet2_utils._FoldedHead."""
+        _need_cuda("x", x, torch.float32)
+        B, K0 = x.shape
+        H1, H2, OUT = b1.numel(), b2.numel(), b3.numel()
+        assert x.stride(1) == 1
+        out = torch.empty(B, OUT, dtype=torch.float32, device=x.device)
+        aux = None
+        if kind == HEAD_CLS:
+            aux = torch.empty(B, dtype=torch.int64, device=x.device)
+        elif kind == HEAD_SIGN:
+            aux = torch.empty(B, OUT, dtype=torch.float32, device=x.device)
+        mptr, mstr = None, 0
+        if kind == HEAD_TRANS:
+            _need_cuda("mean", mean, torch.float32)
+            assert mean.shape == (B, 3) and mean.stride(1) == 1
+            mptr, mstr = mean.data_ptr(), mean.stride(0)
+        with torch.cuda.device(x.device), self._span("fc_head", B=B, K0=K0, H1=H1, H2=H2, OUT=OUT):
+            _check(self.lib.pn2_fc_head_f32(x.data_ptr(), x.stride(0), B, K0, H1, H2, OUT, w1p.data_ptr(), b1.data_ptr(),
+                                            w2p.data_ptr(), b2.data_ptr(), w3.data_ptr(), b3.data_ptr(), int(kind), mptr, mstr,
+                                            mean_mlp.data_ptr() if mean_mlp is not None else None, out.data_ptr(),
+                                            aux.data_ptr() if aux is not None else None, _stream(x)))
+        return out, aux
 
     def selftest_umma(self, n_cols, k_dim, variant, device="cuda:0", dump=False):
         err = torch.full((1,), -1.0, dtype=torch.float32, device=device)

@@ -57,8 +57,9 @@ def _derived_buffers(model: torch.nn.Module):
     for m in model.modules():
         for v in vars(m).values():
             for c in (v if isinstance(v, (list, tuple)) else (v,)):
-                if isinstance(c, (_pu._FoldedMLP, _pu._FactorisedFirstLayer)):
-                    keep += [t for t in (c.packed, getattr(c, "wf", None)) if isinstance(t, torch.Tensor)]
+                if isinstance(c, (_pu._FoldedMLP, _pu._FactorisedFirstLayer, _pu._FoldedHead)):
+                    for t in vars(c).values():
+                        keep += [u for u in (t if isinstance(t, (list, tuple)) else (t,)) if isinstance(u, torch.Tensor)]
     return keep
 
 

@@ -59,6 +59,8 @@ class PointNet2Head(nn.Module):
         CUDA-backed pointnet2_utils; the CPU baseline legs of bench.py and the tests pass other providers)."""
         super().__init__()
         sa_impl = sa_impl or _default_sa
+        self._sa_impl = sa_impl
+        self._head_cache = None
         backbone, pose, out_width, self.kind = ARCH[name]
         self.arch = name
         c = 3 + num_category if pose else 3
@@ -83,13 +85,17 @@ class PointNet2Head(nn.Module):
 
     def forward(self, points, mean=None):
         B = points.shape[0]
-        if self.kind == "trans" and self.mean_mlp == "True":  # translation_ssg.py:31-33
+        fused = (not self.training and hasattr(self._sa_impl, "fc_head")
+                 and self._sa_impl._FoldedHead.supported((self.fc1, self.fc2, self.fc3)))
+        if self.kind == "trans" and self.mean_mlp == "True" and not fused:  # translation_ssg.py:31-33 (fused: inside the head kernel)
             mean = self.mean_fc2(F.relu(self.mean_bn1(self.mean_fc1(mean))))
         xyz, feat = points, None
         for i in range(1, self.n_sa + 1):
             xyz, feat = getattr(self, f"sa{i}")(xyz, feat)
         global_feature = feat
         x = global_feature.view(B, 1024)
+        if fused:
+            return self._head_fused(x, global_feature, mean)
         x = self.drop(F.relu(self.bn1(self.fc1(x))))
         x = self.drop(F.relu(self.bn2(self.fc2(x))))
         x = self.fc3(x)
@@ -102,6 +108,23 @@ class PointNet2Head(nn.Module):
             x = torch.sigmoid(x)
             return x, torch.sign(x - 0.5)
         return x                                               # rotation_ssg.py:38
+
+
+    def _head_fused(self, x, global_feature, mean):
+        """Eval mode: fc1/bn1/relu -> fc2/bn2/relu -> fc3 -> epilogue (and the translation heads' mean MLP) in one launch
+        (pn2_fc_head_f32) instead of ~14 library launches; dropout is the identity in eval mode."""
+        from _pn2_native import HEAD_CLS, HEAD_PLAIN, HEAD_SIGN, HEAD_TRANS
+        if self._head_cache is None:
+            self._head_cache = self._sa_impl._FoldedHead()
+        kind = {"cls": HEAD_CLS, "trans": HEAD_TRANS, "sign": HEAD_SIGN, "reg": HEAD_PLAIN}[self.kind]
+        mm = (self.mean_fc1, self.mean_bn1, self.mean_fc2) if (self.kind == "trans" and self.mean_mlp == "True") else None
+        out, aux = self._sa_impl.fc_head(x, (self.fc1, self.fc2, self.fc3), (self.bn1, self.bn2), kind, self._head_cache,
+                                         mean=mean if self.kind == "trans" else None, mean_mlp=mm)
+        if self.kind == "cls":
+            return out, global_feature, aux
+        if self.kind == "sign":
+            return out, aux
+        return out
 
 
 def get_model(name: str, num_category: int = 7, **kw) -> PointNet2Head:

@@ -109,6 +109,7 @@ class PointNetV1Head(nn.Module):
             self.bn1 = nn.BatchNorm1d(6)
         self.dropout = nn.Dropout(p=0.4)
         self._folded = _pu._FoldedMLP()
+        self._folded_head = _pu._FoldedHead()
         self.pooled_width = mlp_list[-1]
 
     def _encode(self, x):
@@ -121,9 +122,17 @@ class PointNetV1Head(nn.Module):
         return torch.max(x, 2, keepdim=True)[0].view(-1, self.pooled_width)
 
     def forward(self, x, mean=None):
-        if self.kind == "trans" and self.mean_mlp == "True":
+        fused = not self.training and len(self.fc) == 3 and _pu._FoldedHead.supported(tuple(self.fc))
+        if self.kind == "trans" and self.mean_mlp == "True" and not fused:
             mean = self.fc2(F.relu(self.bn1(self.fc1(mean))))
         x = self._encode(x)
+        if fused:      # eval: fc/bn/relu x 2 -> fc -> epilogue in one launch (dropout is the identity)
+            from _pn2_native import HEAD_PLAIN, HEAD_SIGN, HEAD_TRANS
+            kind = {"trans": HEAD_TRANS, "sign": HEAD_SIGN}.get(self.kind, HEAD_PLAIN)
+            mm = (self.fc1, self.bn1, self.fc2) if (self.kind == "trans" and self.mean_mlp == "True") else None
+            out, aux = _pu.fc_head(x, tuple(self.fc), (self.bn_fc[0], self.bn_fc[1]), kind, self._folded_head,
+                                   mean=mean if self.kind == "trans" else None, mean_mlp=mm)
+            return (out, aux) if self.kind == "sign" else out
         for i in range(len(self.fc)):
             if i < len(self.fc) - 1:
                 x = F.relu(self.dropout(self.bn_fc[i](self.fc[i](x))))       # dropout BEFORE relu, as in the reference

@@ -262,6 +262,60 @@ class _FactorisedFirstLayer:
         return self.packed, self.dims, self.wf
 
 
+class _FoldedHead:
+    """Derived cache of the FC head behind the last set abstraction (fc1/bn1 -> fc2/bn2 -> fc3, pointnet2_cls_ssg.py:31-38 and
+    the same tail in every pose head): eval-mode BatchNorm1d folded into the Linear weights, packed [K/4][H][4] for
+    pn2_fc_head_f32 (include/pn2.h).  Same invalidation rule as _FoldedMLP."""
+
+    def __init__(self):
+        self.key = None
+        self.tensors = None          # (w1p, b1, w2p, b2, w3, b3, mean_mlp | None)
+
+    @staticmethod
+    def supported(fcs) -> bool:
+        def ok(K, H):
+            if H % 8 or H // 8 > 256 or 256 % (H // 8):
+                return False
+            return K % (4 * (256 // (H // 8))) == 0
+        k0, h1, h2, out = fcs[0].in_features, fcs[0].out_features, fcs[1].out_features, fcs[2].out_features
+        return len(fcs) == 3 and 256 <= k0 <= 2048 and h1 <= 1024 and h2 <= 1024 and out <= 16 and ok(k0, h1) and ok(h1, h2)
+
+    @staticmethod
+    def _fold(fc, bn):
+        s = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
+        return fc.weight.detach() * s[:, None], (fc.bias.detach() - bn.running_mean) * s + bn.bias.detach()
+
+    @staticmethod
+    def _pack(w):                    # [H, K] -> [K/4][H][4]
+        H, K = w.shape
+        return w.reshape(H, K // 4, 4).permute(1, 0, 2).contiguous()
+
+    def get(self, fcs, bns, mean_mlp=None):
+        """fcs = (fc1, fc2, fc3), bns = (bn1, bn2); mean_mlp = (mean_fc1, mean_bn1, mean_fc2) of the translation heads or None."""
+        mods = list(fcs) + list(bns) + (list(mean_mlp) if mean_mlp else [])
+        ts = [t for m in mods for t in list(m.parameters()) + list(m.buffers())]
+        key = (_cache_generation, tuple((t.data_ptr(), t._version) for t in ts))
+        if key != self.key:
+            with torch.no_grad():
+                w1, b1 = self._fold(fcs[0], bns[0])
+                w2, b2 = self._fold(fcs[1], bns[1])
+                mm = None
+                if mean_mlp:
+                    f1, bn, f2 = mean_mlp
+                    mw1, mb1 = self._fold(f1, bn)
+                    mm = torch.cat([mw1.reshape(-1), mb1, f2.weight.detach().reshape(-1), f2.bias.detach()]).float().contiguous()
+                self.tensors = (self._pack(w1.float()), b1.float().contiguous(), self._pack(w2.float()), b2.float().contiguous(),
+                                fcs[2].weight.detach().float().contiguous(), fcs[2].bias.detach().float().contiguous(), mm)
+            self.key = key
+        return self.tensors
+
+
+def fc_head(x, fcs, bns, kind, cache, mean=None, mean_mlp=None):
+    """Eval-mode FC head in ONE launch: x [B,K0] (CUDA fp32) -> (out [B,OUT], aux): see _pn2_native.Native.fc_head."""
+    w1p, b1, w2p, b2, w3, b3, mm = cache.get(fcs, bns, mean_mlp)
+    return _backend().fc_head(x, w1p, b1, w2p, b2, w3, b3, kind, mean=mean, mean_mlp=mm)
+
+
 def _finish(new_points_bsc, pooled_bsc, pooled_bf16=None):
     new_points = new_points_bsc.permute(0, 2, 1)       # view of contiguous [B,S,C], like the reference (:173)
     new_feature = pooled_bsc.permute(0, 2, 1)

@@ -103,6 +103,25 @@ class OracleNative:
         dims = [int(layers[0][0].shape[1])] + [int(l[0].shape[0]) for l in layers]
         return ([tuple(t.detach().clone() for t in tup) for tup in layers], eps), dims
 
+    def fc_head(self, x, w1p, b1, w2p, b2, w3, b3, kind, mean=None, mean_mlp=None):
+        self.calls.append("fc_head")
+        unpack = lambda wp: wp.permute(1, 0, 2).reshape(wp.shape[1], -1)          # [K/4][H][4] -> [H, K]
+        h = torch.relu(x @ unpack(w1p).t() + b1)
+        h = torch.relu(h @ unpack(w2p).t() + b2)
+        y = h @ w3.t() + b3
+        if kind == 1:
+            y = torch.log_softmax(y, -1)
+            return y, y.max(1)[1]
+        if kind == 2:
+            if mean_mlp is not None:
+                q = mean_mlp
+                mean = torch.relu(mean @ q[:18].view(6, 3).t() + q[18:24]) @ q[24:42].view(3, 6).t() + q[42:45]
+            return y + mean, None
+        if kind == 3:
+            y = torch.sigmoid(y)
+            return y, torch.sign(y - 0.5)
+        return y, None
+
     def sa_needs_zero(self, S, K, dims, prec):
         return False
 

@@ -385,3 +385,80 @@ def test_fps_cluster_variants_keep_parity(variant):
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_kernels.py"), "-m", "gpu", "-q", "-x",
                         "-k", "test_fps_vs_oracle and (4096 or 8192 or 6000 or 4128 or 5000)"], env=e, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
+
+
+# ---- fused FC head ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("B", [1, 24, 70, 2048])
+@pytest.mark.parametrize("kind,out_w,mean_mlp", [("cls", 7, False), ("reg", 3, False), ("trans", 3, True), ("trans", 3, False), ("sign", 1, False)])
+def test_fc_head_vs_torch_fp32(nat, B, kind, out_w, mean_mlp):
+    """pn2_fc_head_f32 (one launch: fc1/bn1/relu -> fc2/bn2/relu -> fc3 -> log_softmax+argmax | +mean(MLP) | sigmoid+sign)
+    against the reference's op sequence in plain PyTorch fp32 on the CPU (pointnet2_cls_ssg.py:31-38, translation_ssg.py:31-33,
+    39-44, sign_ssg.py:29-36), eval mode, non-trivial BatchNorm statistics."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    import pointnet2_utils as pu
+    import pn2_models
+    from _pn2_native import HEAD_CLS, HEAD_PLAIN, HEAD_SIGN, HEAD_TRANS
+    torch.manual_seed(3)
+    fc1, fc2, fc3 = nn.Linear(1024, 512), nn.Linear(512, 256), nn.Linear(256, out_w)
+    bn1, bn2 = nn.BatchNorm1d(512), nn.BatchNorm1d(256)
+    mfc1, mbn, mfc2 = nn.Linear(3, 6), nn.BatchNorm1d(6), nn.Linear(6, 3)
+    holder = nn.ModuleList([fc1, fc2, fc3, bn1, bn2, mfc1, mbn, mfc2]).eval()
+    pn2_models.randomize_bn_(holder, 5)
+    g = torch.Generator().manual_seed(B)
+    x = torch.relu(torch.randn(B, 1024, generator=g))                       # pooled features are post-ReLU maxima
+    mean = torch.randn(B, 3, generator=g)
+    with torch.no_grad():
+        h = F.relu(bn1(fc1(x)))
+        h = F.relu(bn2(fc2(h)))
+        y = fc3(h)
+        if kind == "cls":
+            exp, exp_aux = F.log_softmax(y, -1), None
+            exp_aux = exp.max(1)[1]
+        elif kind == "trans":
+            m = mfc2(F.relu(mbn(mfc1(mean)))) if mean_mlp else mean
+            exp, exp_aux = y + m, None
+        elif kind == "sign":
+            exp = torch.sigmoid(y)
+            exp_aux = torch.sign(exp - 0.5)
+        else:
+            exp, exp_aux = y, None
+    holder.to("cuda:0")
+    cache = pu._FoldedHead()
+    code = {"cls": HEAD_CLS, "reg": HEAD_PLAIN, "trans": HEAD_TRANS, "sign": HEAD_SIGN}[kind]
+    # x as the models hand it over: the [B,1024] view of the pooled [B,1,1024] buffer
+    xd = x.to("cuda:0").view(B, 1, 1024).permute(0, 2, 1).view(B, 1024)
+    out, aux = pu.fc_head(xd, (fc1, fc2, fc3), (bn1, bn2), code, cache, mean=mean.to("cuda:0") if kind == "trans" else None,
+                          mean_mlp=(mfc1, mbn, mfc2) if (kind == "trans" and mean_mlp) else None)
+    assert out.shape == exp.shape
+    assert rel_err(out.cpu(), exp) <= TOL_F32
+    if kind == "cls":
+        # argmax: equal wherever the two largest log-probabilities are not within rounding of each other
+        top2 = exp.topk(2, dim=1).values
+        clear = (top2[:, 0] - top2[:, 1]) > 1e-4
+        assert aux.dtype == torch.int64 and torch.equal(aux.cpu()[clear], exp_aux[clear])
+        assert torch.equal(aux.cpu(), out.cpu().max(1)[1])
+    if kind == "sign":
+        clear = (exp - 0.5).abs() > 1e-5
+        assert torch.equal(aux.cpu()[clear], exp_aux[clear])
+    # a weight update is followed (derived cache keyed on the parameter versions)
+    with torch.no_grad():
+        fc3.bias.add_(1.0)
+    out2, _ = pu.fc_head(xd, (fc1, fc2, fc3), (bn1, bn2), code, cache, mean=mean.to("cuda:0") if kind == "trans" else None,
+                         mean_mlp=(mfc1, mbn, mfc2) if (kind == "trans" and mean_mlp) else None)
+    if kind in ("reg", "trans"):
+        assert torch.allclose(out2, out + 1.0, atol=1e-5)
+
+
+def test_fc_head_propagates_nan_and_rejects_bad_widths(nat):
+    import pointnet2_utils as pu
+    x = torch.zeros(3, 1024, device="cuda:0")
+    x[1, 5] = float("nan")
+    w1p = torch.randn(256, 512, 4, device="cuda:0")
+    w2p = torch.randn(128, 256, 4, device="cuda:0")
+    b1, b2 = torch.zeros(512, device="cuda:0"), torch.zeros(256, device="cuda:0")
+    w3, b3 = torch.randn(3, 256, device="cuda:0"), torch.zeros(3, device="cuda:0")
+    out, _ = nat.fc_head(x, w1p, b1, w2p, b2, w3, b3, 0)
+    assert torch.isnan(out[1]).all() and torch.isfinite(out[0]).all() and torch.isfinite(out[2]).all()
+    with pytest.raises(RuntimeError):
+        nat.fc_head(x, w1p, b1, w2p, torch.zeros(100, device="cuda:0"), torch.randn(3, 100, device="cuda:0"), b3, 0)
