@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PN2_ABI_VERSION 11
+#define PN2_ABI_VERSION 12
 #define PN2_MAX_COORD 16 /* exact summation-order rules are verified against ATen for C <= 16 */
 #define PN2_MAX_LAYERS 8
 
@@ -187,6 +187,19 @@ int pn2_fc_head_f32(const float *x, int64_t x_stride, int B, int K0, int H1, int
                     const float *w3, const float *b3, int kind,
                     const float *mean, int64_t mean_stride, const float *mean_mlp,
                     float *out, void *aux, void *stream);
+
+/* Row GEMM on the tensor cores: C[M,N] = A[M,K] . W[N,K]^T for tall operands (M = point or grouped rows) -- the 1x1
+ * convolutions of the path where they are not fused into pn2_sa_fused: the per-point product of an MSG branch's factorised
+ * first layer (pointnet2_utils.py:208-217 evaluated once per point) and the training-mode convolutions / input gradients
+ * (pointnet2_utils.py:168-170, :214-217 under train_rotation.py:121-124).
+ *   A [M,K] row stride lda, W [N,K] row stride ldw, C [M,N] row stride ldc (all in elements), dtypes PN2_DT_*.
+ *   w_dtype = BF16: bf16 x bf16 -> fp32 accumulate (fp32 A rows are converted on load); K % 8 == 0.
+ *   w_dtype = F32 : TF32 product of fp32 operands (the precision policy of the reference's cuDNN convolutions); K % 4 == 0.
+ *   Rows of A, W and C must start on 16-byte boundaries.  N is arbitrary (<= 256 output columns per CTA, tiled beyond). */
+#define PN2_DT_F32 0
+#define PN2_DT_BF16 1
+int pn2_rows_gemm(const void *A, int64_t lda, int a_dtype, const void *W, int64_t ldw, int w_dtype,
+                  void *C, int64_t ldc, int c_dtype, int64_t M, int N, int K, void *stream);
 
 /* Device self-test of the tcgen05 building blocks (one 128xN tile against a scalar loop in the same
  * launch).  Returns 0 and writes max|err| to *max_err (device float). */

@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(_HERE, LIB_NAME)
 ORDER_SSG, ORDER_MSG, ORDER_ALL = 0, 1, 2
 PREC_F32, PREC_BF16 = 0, 1
 MAX_COORD = 16
-ABI_VERSION = 11
+ABI_VERSION = 12
 HEAD_PLAIN, HEAD_CLS, HEAD_TRANS, HEAD_SIGN = 0, 1, 2, 3
 
 _i64, _i32, _f32, _vp = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p
@@ -54,6 +54,7 @@ _SIGNATURES = {
     "pn2_bn_relu_train_fwd_f32": ([_vp, _i64, _i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp], _i32),
     "pn2_bn_relu_train_bwd_f32": ([_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp], _i32),
     "pn2_fc_head_f32": ([_vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp], _i32),
+    "pn2_rows_gemm": ([_vp, _i64, _i32, _vp, _i64, _i32, _vp, _i64, _i32, _i64, _i32, _i32, _vp], _i32),
     "pn2_selftest_umma": ([_i32, _i32, _i32, _vp, _vp, _vp], _i32),
     "pn2_debug_trace": ([_vp], _i32),
     "pn2_selftest_tma_gather": ([_vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp], _i32),
@@ -431,6 +432,26 @@ class Native:
                                             mean_mlp.data_ptr() if mean_mlp is not None else None, out.data_ptr(),
                                             aux.data_ptr() if aux is not None else None, _stream(x)))
         return out, aux
+
+    def rows_gemm(self, a, w, out_dtype=None, out=None):
+        """C [M,N] = a [M,K] @ w [N,K]^T on the tensor cores (include/pn2.h: pn2_rows_gemm).  w bf16: bf16 product (fp32 rows of
+        `a` converted on load); w fp32: TF32 product.  Rows of a / w may be strided views (unit stride along K)."""
+        dt = {torch.float32: 0, torch.bfloat16: 1}
+        if a.dtype not in dt or w.dtype not in dt:
+            raise RuntimeError(f"pn2: rows_gemm takes fp32 / bf16 operands (got {a.dtype}, {w.dtype})")
+        _need_cuda("a", a, a.dtype)
+        _need_cuda("w", w, w.dtype)
+        M, K = a.shape
+        N = w.shape[0]
+        assert w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1
+        out_dtype = out_dtype or (torch.bfloat16 if w.dtype == torch.bfloat16 else torch.float32)
+        if out is None:
+            out = torch.empty(M, N, dtype=out_dtype, device=a.device)
+        assert out.shape == (M, N) and out.stride(1) == 1 and out.dtype in dt
+        with torch.cuda.device(a.device), self._span("rows_gemm", M=M, N=N, K=K, tf32=w.dtype == torch.float32):
+            _check(self.lib.pn2_rows_gemm(a.data_ptr(), a.stride(0), dt[a.dtype], w.data_ptr(), w.stride(0), dt[w.dtype],
+                                          out.data_ptr(), out.stride(0), dt[out.dtype], M, N, K, _stream(a)))
+        return out
 
     def selftest_umma(self, n_cols, k_dim, variant, device="cuda:0", dump=False):
         err = torch.full((1,), -1.0, dtype=torch.float32, device=device)

@@ -40,6 +40,7 @@ _precision = os.environ.get("PN2_PRECISION", "fp32")
 _reference_strides = False
 _factorise_first_layer = os.environ.get("PN2_FACTORISE", "1") != "0"     # see _FactorisedFirstLayer
 _train_fused = os.environ.get("PN2_TRAIN_FUSED", "1") != "0"            # see _shared_mlp_train_rows
+_train_own_gemm = os.environ.get("PN2_TRAIN_OWN_GEMM", "1") != "0"       # training convolutions on pn2_rows_gemm (else cuBLAS)
 _start_source = None        # optional callable (B, N) -> int64 CPU tensor [B]; default = torch.randint
 _cache_generation = 0       # part of every derived-weight cache key, see invalidate_caches()
 _empty_flags = {}           # device -> int32 [1]: set by the ball queries of the modules when a centre has no neighbour
@@ -359,12 +360,21 @@ class _gemm_precision_of_the_reference_convs:
         torch.backends.cuda.matmul.allow_tf32 = self.prev
 
 
+def _own_gemm(rows, w) -> bool:
+    """The training GEMMs run on pn2_rows_gemm (TF32 tensor-core product) whenever the reference's own convolutions would run
+    in TF32 (torch.backends.cudnn.allow_tf32, default True); with TF32 switched off they stay full-fp32 library GEMMs."""
+    return (_train_own_gemm and rows.is_cuda and bool(torch.backends.cudnn.allow_tf32) and rows.dtype == torch.float32
+            and rows.is_contiguous() and rows.shape[1] % 4 == 0 and w.shape[0] % 4 == 0 and w.shape[1] % 4 == 0)
+
+
 class _RowsLinear(torch.autograd.Function):
     """y [M, Cout] = x [M, Cin] @ w[Cout, Cin]^T: a 1x1 convolution on channels-last rows, bias left to the BatchNorm."""
 
     @staticmethod
     def forward(ctx, x, w):
         ctx.save_for_backward(x, w)
+        if _own_gemm(x, w):                                        # TF32 tcgen05 product, fp32 rows out
+            return _backend().rows_gemm(x, w if (w.stride(1) == 1 and w.stride(0) % 4 == 0) else w.contiguous())
         with _gemm_precision_of_the_reference_convs():
             return torch.mm(x, w.t())
 
@@ -372,9 +382,10 @@ class _RowsLinear(torch.autograd.Function):
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
         dx = dw = None
+        dy = dy.contiguous()
         with _gemm_precision_of_the_reference_convs():
             if ctx.needs_input_grad[0]:
-                dx = torch.mm(dy, w)
+                dx = _backend().rows_gemm(dy, w.t().contiguous()) if _own_gemm(dy, w) else torch.mm(dy, w)
             if ctx.needs_input_grad[1]:
                 dw = _rows_outer(dy, x)
         return dx, dw
@@ -600,9 +611,10 @@ class PointNetSetAbstractionMsg(nn.Module):
         for i, ((_, idx32), K, (packed, dims, prec), wf) in enumerate(zip(groups, self.sample_number_list, plans, fact)):
             if wf is not None:
                 # first layer factorised: P = feat (s Wf)^T once per point, gathered in place of the feature rows
-                if feat_bf16 is None:
-                    feat_bf16 = twin_in if twin_in is not None else feat.to(torch.bfloat16).contiguous()
-                p_rows = torch.matmul(feat_bf16, wf.t())                       # [B,N,N0] bf16, fp32 accumulation (cuBLAS)
+                if feat_bf16 is None:       # bf16 twin of the previous layer if present, else the fp32 rows (converted on load)
+                    feat_bf16 = twin_in if twin_in is not None else (feat if feat.is_contiguous() else feat.contiguous())
+                # [B,N,N0] bf16 rows, fp32 accumulation: pn2_rows_gemm (tcgen05), one launch per branch
+                p_rows = be.rows_gemm(feat_bf16.view(B * N, D), wf, torch.bfloat16).view(B, N, -1)
                 be.sa_fused(pts, None, new_points, idx32, ORDER_MSG, dims, packed, prec, pooled, co,
                             feature_bf16=p_rows, out_bf16=twin_out,
                             algo_dims=[D + C] + [c.out_channels for c in self.conv_blocks[i]])

@@ -122,6 +122,11 @@ class OracleNative:
             return y, torch.sign(y - 0.5)
         return y, None
 
+    def rows_gemm(self, a, w, out_dtype=None, out=None):
+        self.calls.append("rows_gemm")
+        y = a.float() @ w.float().t()
+        return y.to(out_dtype or (torch.bfloat16 if w.dtype == torch.bfloat16 else torch.float32))
+
     def sa_needs_zero(self, S, K, dims, prec):
         return False
 

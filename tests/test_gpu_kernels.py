@@ -462,3 +462,38 @@ def test_fc_head_propagates_nan_and_rejects_bad_widths(nat):
     assert torch.isnan(out[1]).all() and torch.isfinite(out[0]).all() and torch.isfinite(out[2]).all()
     with pytest.raises(RuntimeError):
         nat.fc_head(x, w1p, b1, w2p, torch.zeros(100, device="cuda:0"), torch.randn(3, 100, device="cuda:0"), b3, 0)
+
+
+# ---- row GEMM on the tensor cores (MSG factorised first layer, training convolutions) ------------------------------------------
+@pytest.mark.parametrize("M,K,N", [(128, 64, 64), (1000, 320, 128), (5000, 320, 64), (70001, 128, 256), (4096, 512, 1024), (333, 16, 96),
+                                   (20000, 332, 40), (257, 1024, 512)])
+@pytest.mark.parametrize("mode", ["bf16", "bf16_from_f32", "tf32"])
+def test_rows_gemm_vs_torch(nat, M, K, N, mode):
+    """pn2_rows_gemm against fp64 products of the SAME rounded operands (bf16 modes) / of the fp32 operands (TF32 mode)."""
+    g = torch.Generator().manual_seed(M + K + N)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    if mode == "tf32":
+        if K % 4:
+            pytest.skip("TF32 rows are multiples of 16 bytes")
+        got = nat.rows_gemm(a.cuda(), w.cuda())
+        assert got.dtype == torch.float32
+        exp = a.double() @ w.double().t()
+        assert rel_err(got.cpu(), exp) <= 2e-3                      # 10-bit mantissas
+        # strided rows (a column slice of a wider buffer) and a preallocated strided output
+        wide = torch.zeros(M, K + 8).cuda()
+        wide[:, 4:4 + K] = a.cuda()
+        out = torch.full((M, N + 4), -3.0).cuda()
+        nat.rows_gemm(wide[:, 4:4 + K], w.cuda(), out=out[:, :N])
+        assert torch.equal(out[:, :N], got) and bool((out[:, N:] == -3.0).all())
+        return
+    if K % 8:
+        pytest.skip("bf16 rows are multiples of 16 bytes")
+    wb = w.bfloat16()
+    ab = a.bfloat16()
+    got = nat.rows_gemm(ab.cuda() if mode == "bf16" else a.cuda(), wb.cuda(), torch.bfloat16)
+    assert got.dtype == torch.bfloat16
+    exp = (ab.double() @ wb.double().t())
+    assert rel_err(got.float().cpu(), exp) <= 2.0 ** -8             # one bf16 rounding of the fp32-accumulated result
+    got32 = nat.rows_gemm(ab.cuda(), wb.cuda(), torch.float32)
+    assert rel_err(got32.cpu(), exp) <= 1e-5

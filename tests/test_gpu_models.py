@@ -391,11 +391,11 @@ def test_pose_pipeline_modes_agree_and_match_the_golden_heads(pu):
         m = pn2_models.get_model(n, 7)
         pn2_models.randomize_bn_(m, 7)
         heads[n] = m.eval().to(DEV)
-    d = cases[names[0]]
-    xyz = torch.from_numpy(d["xyz"])
-    x = cloudgen.channels_first(cloudgen.with_category(xyz)).to(DEV)
-    mean = torch.from_numpy(cases["translation_ssg"]["mean"]).to(DEV)
-    B = x.shape[0]
+    inputs = {}
+    for n in names:                       # every golden case has its own cloud (and mean)
+        xyz = torch.from_numpy(cases[n]["xyz"])
+        inputs[n] = (cloudgen.channels_first(cloudgen.with_category(xyz)).to(DEV),
+                     torch.from_numpy(cases[n]["mean"]).to(DEV) if "mean" in cases[n] else xyz[:, :3, :].mean(1).to(DEV))
 
     class SeededPerHead:
         """Every head's first draw restarts the generator at 42 (the golden generator seeds before each model)."""
@@ -409,9 +409,9 @@ def test_pose_pipeline_modes_agree_and_match_the_golden_heads(pu):
     for mode in ("eager", "graphs", "streams"):
         pipe = pn2_pipeline.PosePipeline(heads, mode=mode, start_source=SeededPerHead())
         for rep in range(2):
-            outs = pipe.forward_prepared(x, mean, None)
-            torch.cuda.synchronize()
-            for n in names:
+            for n in names:               # the whole pipeline on head n's golden cloud; head n's output is the pinned one
+                outs = pipe.forward_prepared(*inputs[n], None)
+                torch.cuda.synchronize()
                 c = cases[n]
                 if abs(float(sum(v.double().abs().sum() for v in heads[n].state_dict().values())) - float(c["sd_checksum"][0])) > 1e-6 * float(c["sd_checksum"][0]):
                     pytest.skip("seeded initialisation differs from the build container's torch")
