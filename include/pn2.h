@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PN2_ABI_VERSION 12
+#define PN2_ABI_VERSION 13
 #define PN2_MAX_COORD 16 /* exact summation-order rules are verified against ATen for C <= 16 */
 #define PN2_MAX_LAYERS 8
 
@@ -200,6 +200,14 @@ int pn2_fc_head_f32(const float *x, int64_t x_stride, int B, int K0, int H1, int
 #define PN2_DT_BF16 1
 int pn2_rows_gemm(const void *A, int64_t lda, int a_dtype, const void *W, int64_t ldw, int w_dtype,
                   void *C, int64_t ldc, int c_dtype, int64_t M, int N, int K, void *stream);
+
+/* Weight gradient of a 1x1 convolution on rows (training mode, backward of pointnet2_utils.py:170 / :217):
+ *   dW[Cout,Cin] = dy[M,Cout]^T . x[M,Cin], TF32 product, fp32 accumulation in TMEM per row range, partials added in a fixed
+ *   order (deterministic).  dy / x rows (strides ldy / ldx elements) start on 16-byte boundaries; Cout, Cin multiples of 4.
+ *   ws = pn2_rows_wgrad_ws_bytes(M, Cout, Cin) bytes of scratch; dW [Cout][Cin] contiguous. */
+int64_t pn2_rows_wgrad_ws_bytes(int64_t M, int Cout, int Cin);
+int pn2_rows_wgrad_tf32(const float *dy, int64_t ldy, const float *x, int64_t ldx, int64_t M, int Cout, int Cin,
+                        void *ws, float *dW, void *stream);
 
 /* Device self-test of the tcgen05 building blocks (one 128xN tile against a scalar loop in the same
  * launch).  Returns 0 and writes max|err| to *max_err (device float). */

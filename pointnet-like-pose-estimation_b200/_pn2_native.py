@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(_HERE, LIB_NAME)
 ORDER_SSG, ORDER_MSG, ORDER_ALL = 0, 1, 2
 PREC_F32, PREC_BF16 = 0, 1
 MAX_COORD = 16
-ABI_VERSION = 12
+ABI_VERSION = 13
 HEAD_PLAIN, HEAD_CLS, HEAD_TRANS, HEAD_SIGN = 0, 1, 2, 3
 
 _i64, _i32, _f32, _vp = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p
@@ -55,6 +55,8 @@ _SIGNATURES = {
     "pn2_bn_relu_train_bwd_f32": ([_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp], _i32),
     "pn2_fc_head_f32": ([_vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp], _i32),
     "pn2_rows_gemm": ([_vp, _i64, _i32, _vp, _i64, _i32, _vp, _i64, _i32, _i64, _i32, _i32, _vp], _i32),
+    "pn2_rows_wgrad_ws_bytes": ([_i64, _i32, _i32], _i64),
+    "pn2_rows_wgrad_tf32": ([_vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp], _i32),
     "pn2_selftest_umma": ([_i32, _i32, _i32, _vp, _vp, _vp], _i32),
     "pn2_debug_trace": ([_vp], _i32),
     "pn2_selftest_tma_gather": ([_vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp], _i32),
@@ -452,6 +454,20 @@ class Native:
             _check(self.lib.pn2_rows_gemm(a.data_ptr(), a.stride(0), dt[a.dtype], w.data_ptr(), w.stride(0), dt[w.dtype],
                                           out.data_ptr(), out.stride(0), dt[out.dtype], M, N, K, _stream(a)))
         return out
+
+    def rows_wgrad(self, dy, x):
+        """dW [Cout,Cin] = dy [M,Cout]^T @ x [M,Cin] (TF32 tensor-core product, deterministic): include/pn2.h pn2_rows_wgrad_tf32."""
+        _need_cuda("dy", dy, torch.float32)
+        _need_cuda("x", x, torch.float32)
+        M, Cout = dy.shape
+        Cin = x.shape[1]
+        assert x.shape[0] == M and dy.stride(1) == 1 and x.stride(1) == 1
+        ws = torch.empty(max(1, self.lib.pn2_rows_wgrad_ws_bytes(M, Cout, Cin)), dtype=torch.uint8, device=dy.device)
+        dw = torch.empty(Cout, Cin, dtype=torch.float32, device=dy.device)
+        with torch.cuda.device(dy.device), self._span("rows_wgrad", M=M, Cout=Cout, Cin=Cin):
+            _check(self.lib.pn2_rows_wgrad_tf32(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), M, Cout, Cin,
+                                                ws.data_ptr(), dw.data_ptr(), _stream(dy)))
+        return dw
 
     def selftest_umma(self, n_cols, k_dim, variant, device="cuda:0", dump=False):
         err = torch.full((1,), -1.0, dtype=torch.float32, device=device)

@@ -7,10 +7,14 @@
 //     under train_rotation.py:121-124): fp32 operands, kind::tf32 (the reference's cuDNN policy), fp32 out.
 // These products are HBM-bound (2 K N / (K + N) flops per byte moved is far below the tensor roof), so the kernel is built
 // around the streams, not the MMA: a persistent CTA keeps its slice of W (<= 256 output columns) resident in shared memory as
-// 128-byte-swizzled K-major blocks, 8 loader warps stream 128-row blocks of A through a 4-stage ring (coalesced 16-byte
-// loads -> optional conversion -> swizzled st.shared -> fence -> mbarrier), one warp issues tcgen05.mma into one of two
-// TMEM accumulators, and four epilogue warps drain the other one (tcgen05.ld -> convert -> 16-byte global stores) -- the
-// loads of tile t+1, the MMAs of tile t and the stores of tile t-1 overlap.
+// 128-byte-swizzled K-major blocks; 128-row blocks of A arrive through a 4-stage ring by TMA (cp.async.bulk.tensor, 128-byte
+// swizzle = the MMA operand image, rows / columns outside the tensor zero-filled by the copy engine; fp32 rows that must
+// become bf16 go through 8 loader warps instead: coalesced 16-byte loads -> convert -> swizzled st.shared -> fence); one
+// warp issues tcgen05.mma into one of two TMEM accumulators, and four epilogue warps drain the other one: tcgen05.ld ->
+// convert -> a swizzled 16 KB staging tile -> TMA store (whole 128-byte lines, clipped at the tensor edge).  The loads of
+// tile t+1, the MMAs of tile t and the stores of tile t-1 overlap.
+#include <cuda.h>
+#include <string.h>
 #include "pn2_tc.cuh"
 
 namespace pn2 {
@@ -38,7 +42,24 @@ struct GemmParams {
     int nkb;            // K blocks of 128 bytes (64 bf16 / 32 tf32 elements)
     int64_t tiles_m;
     int tmem_cols;
+    alignas(64) CUtensorMap tmA;      // A as [M][K], box 128 bytes x 128 rows (unused by the converting loaders)
+    alignas(64) CUtensorMap tmC;      // C as [M][N], box 128 bytes x 128 rows
 };
+
+__device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int c0, int c1, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const void *tmap, int c0, int c1, const void *src)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(src)) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 3, 128;" ::: "memory"); }
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
@@ -87,14 +108,16 @@ __device__ __forceinline__ uint4 load_chunk(const void *row, int k0, int K)
 }
 
 template <bool A_F32, bool TF32>
-__global__ void __launch_bounds__(GM_THREADS, 1) rows_gemm_kernel(const GemmParams p)
+__global__ void __launch_bounds__(GM_THREADS, 1) rows_gemm_kernel(const __grid_constant__ GemmParams p)
 {
+    constexpr bool TMA_A = !(A_F32 && !TF32);       // plain copies go through the copy engine; fp32 -> bf16 through registers
     extern __shared__ __align__(1024) unsigned char gsm_raw[];
     unsigned char *gsm = gsm_raw + ((1024u - (smem_u32(gsm_raw) & 1023u)) & 1023u);
     const int w_block = p.Nt * 128;
-    unsigned char *Wsm = gsm;                                           // [nkb][Nt rows x 128 B], 128-byte swizzle
-    unsigned char *Asm = gsm + (size_t)p.nkb * w_block;                 // [GM_STAGES][128 rows x 128 B]
-    uint64_t *full = reinterpret_cast<uint64_t *>(Asm + GM_STAGES * GM_BLOCK);
+    unsigned char *Asm = gsm;                                           // [GM_STAGES][128 rows x 128 B]
+    unsigned char *Csm = Asm + GM_STAGES * GM_BLOCK;                    // [2][128 rows x 128 B] output staging
+    unsigned char *Wsm = Csm + 2 * GM_BLOCK;                            // [nkb][Nt rows x 128 B], 128-byte swizzle
+    uint64_t *full = reinterpret_cast<uint64_t *>(Wsm + (size_t)p.nkb * w_block);
     uint64_t *empty = full + GM_STAGES;
     uint64_t *acc_full = empty + GM_STAGES;
     uint64_t *acc_empty = acc_full + 2;
@@ -108,7 +131,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) rows_gemm_kernel(const GemmPara
     const int ncols = min(p.Nt, p.N - n0);
 
     if (tid == 0) {
-        for (int s = 0; s < GM_STAGES; ++s) { mbar_init(full + s, GM_LOAD_WARPS); mbar_init(empty + s, 1); }
+        for (int s = 0; s < GM_STAGES; ++s) { mbar_init(full + s, TMA_A ? 1 : GM_LOAD_WARPS); mbar_init(empty + s, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, GM_EPI_WARPS); }
         fence_mbar_init();
     }
@@ -133,6 +156,17 @@ __global__ void __launch_bounds__(GM_THREADS, 1) rows_gemm_kernel(const GemmPara
         // ================================ loaders: A blocks -> ring ==========================================================
         const int lt = tid - GM_LOAD_WARP0 * 32;            // 0 .. 255
         uint32_t q = 0;
+        if constexpr (TMA_A) {
+            if (lt == 0) {
+                for (int64_t t = blockIdx.x; t < p.tiles_m; t += gridDim.x)
+                    for (int kb = 0; kb < p.nkb; ++kb, ++q) {
+                        const int s = q % GM_STAGES;
+                        mbar_wait(empty + s, ((q / GM_STAGES) & 1u) ^ 1u);
+                        mbar_expect_tx(full + s, (uint32_t)GM_BLOCK);
+                        tma_load_2d(Asm + (size_t)s * GM_BLOCK, &p.tmA, kb * KPB, (int)(t * TC_ROWS), full + s);
+                    }
+            }
+        } else
         for (int64_t t = blockIdx.x; t < p.tiles_m; t += gridDim.x) {
             const int64_t m0 = t * TC_ROWS;
             for (int kb = 0; kb < p.nkb; ++kb, ++q) {
@@ -190,53 +224,245 @@ __global__ void __launch_bounds__(GM_THREADS, 1) rows_gemm_kernel(const GemmPara
             }
         }
     } else {
-        // ================================ epilogue: TMEM -> global =========================================================
+        // ================================ epilogue: TMEM -> staging tile -> TMA store ========================================
         const int qd = warp;                                        // TMEM lane quarter
-        uint32_t tl = 0;
+        const int row = qd * 32 + lane;
+        const uint32_t row_off = (uint32_t)(row * 128);
+        const int cps = p.c_bf16 ? 64 : 32;                         // output columns per 128-byte staging row
+        uint32_t tl = 0, sq = 0;                                    // sq: staging tiles written so far (buffer = sq & 1)
         for (int64_t t = blockIdx.x; t < p.tiles_m; t += gridDim.x, ++tl) {
             const uint32_t buf = tl & 1u;
             mbar_wait(acc_full + buf, (tl >> 1) & 1u);
             tc_fence_after();
-            const int64_t m = t * TC_ROWS + qd * 32 + lane;
             const uint32_t trow = tmem_base + buf * (uint32_t)p.Nt + ((uint32_t)(qd * 32) << 16);
-            for (int c0 = 0; c0 < p.Nt; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld16(trow + (uint32_t)c0, r);
-                tmem_ld_wait();
-                if (m >= p.M || c0 >= ncols) continue;
-                const int nv = min(16, ncols - c0);
-                if (p.c_bf16) {
-                    __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(p.C) + m * p.ldc + n0 + c0;
-                    if (nv == 16) {
-                        uint4 *o4 = reinterpret_cast<uint4 *>(o);
-                        o4[0] = make_uint4(pack_bf16x2(__uint_as_float(r[0]), __uint_as_float(r[1])), pack_bf16x2(__uint_as_float(r[2]), __uint_as_float(r[3])),
-                                           pack_bf16x2(__uint_as_float(r[4]), __uint_as_float(r[5])), pack_bf16x2(__uint_as_float(r[6]), __uint_as_float(r[7])));
-                        o4[1] = make_uint4(pack_bf16x2(__uint_as_float(r[8]), __uint_as_float(r[9])), pack_bf16x2(__uint_as_float(r[10]), __uint_as_float(r[11])),
-                                           pack_bf16x2(__uint_as_float(r[12]), __uint_as_float(r[13])), pack_bf16x2(__uint_as_float(r[14]), __uint_as_float(r[15])));
+            for (int c0 = 0; c0 < ncols; c0 += cps, ++sq) {
+                unsigned char *stg = Csm + (size_t)(sq & 1u) * GM_BLOCK;
+                if (tid == 0) tma_store_wait_read<1>();             // the store that read this buffer two tiles ago is done with it
+                epi_bar();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (h == 1 && !p.c_bf16) break;
+                    const int cc = c0 + 32 * h;                     // 32 accumulator columns -> 8 (fp32) or 4 (bf16) chunks
+                    uint32_t r[32];
+                    if (cc < p.Nt) {
+                        if (cc + 32 <= p.Nt) tmem_ld32_nowait(trow + (uint32_t)cc, r);
+                        else {
+                            uint32_t r16[16];
+                            tmem_ld16(trow + (uint32_t)cc, r16);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) { r[i] = r16[i]; r[16 + i] = 0u; }
+                        }
+                        tmem_ld_wait();
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) if (i < nv) o[i] = __float2bfloat16_rn(__uint_as_float(r[i]));
+                        for (int i = 0; i < 32; ++i) r[i] = 0u;
                     }
-                } else {
-                    float *o = reinterpret_cast<float *>(p.C) + m * p.ldc + n0 + c0;
-                    if (nv == 16) {
-                        uint4 *o4 = reinterpret_cast<uint4 *>(o);
+                    if (p.c_bf16) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) o4[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+                        for (int i = 0; i < 4; ++i) {
+                            const int j = 4 * h + i;
+                            *reinterpret_cast<uint4 *>(stg + row_off + ((j ^ (row & 7)) << 4)) =
+                                make_uint4(pack_bf16x2(__uint_as_float(r[8 * i + 0]), __uint_as_float(r[8 * i + 1])),
+                                           pack_bf16x2(__uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3])),
+                                           pack_bf16x2(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5])),
+                                           pack_bf16x2(__uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7])));
+                        }
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) if (i < nv) o[i] = __uint_as_float(r[i]);
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<uint4 *>(stg + row_off + ((j ^ (row & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
                     }
+                }
+                fence_proxy_async();
+                epi_bar();
+                if (tid == 0) {
+                    tma_store_2d(&p.tmC, n0 + c0, (int)(t * TC_ROWS), stg);
+                    tma_store_commit();
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + buf);
         }
+        if (tid == 0) tma_store_wait_read<0>();
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Weight gradient of a 1x1 convolution on rows:  dW[Cout,Cin] = dy[M,Cout]^T . x[M,Cin]  (M = grouped rows, in the millions;
+// the output a few thousand elements).  The reduction runs over the ROW index, so both operands are "MN-major" for the
+// tensor core: a block of 32 rows x 32 channels (128 bytes per row) copied as it lies in HBM IS the canonical MN-major
+// SWIZZLE_128B operand (channels contiguous, 8-row swizzle atoms), which TMA delivers without touching a register.  A CTA
+// owns a contiguous range of rows and one (128 output channels) x (<= 256 input channels) tile of dW, accumulates it in TMEM
+// over its whole range (one tf32 MMA per 8 rows), and writes an fp32 partial; a second small kernel adds the partials in a
+// fixed order (deterministic).
+constexpr int WG_KT = 32;                         // rows per ring stage
+constexpr int WG_STAGES = 4;
+constexpr int WG_THREADS = 6 * 32;                // 4 epilogue warps, MMA warp, TMA warp
+constexpr int WG_MNBLOCK = WG_KT * 128;           // 32 rows x 128 bytes: one 32-channel block of a stage
+
+struct WgradParams {
+    int64_t M, rows_per_cta;
+    int Cout, Cin, nt, nbb;       // nt: input channels per tile (multiple of 16, <= 256); nbb = ceil(nt / 32)
+    int n_ci_tiles, tmem_cols;
+    float *ws;                    // [gridDim.x][Cout][Cin] partials
+    alignas(64) CUtensorMap tmY;  // dy as [M][Cout], box 32 channels x 32 rows
+    alignas(64) CUtensorMap tmX;  // x as [M][Cin],  box 32 channels x 32 rows
+};
+
+// MN-major SWIZZLE_128B descriptor: LBO = bytes between 32-channel blocks, SBO = bytes between 8-row groups
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((1024u >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) rows_wgrad_kernel(const __grid_constant__ WgradParams p)
+{
+    extern __shared__ __align__(1024) unsigned char wsm_raw[];
+    unsigned char *sm = wsm_raw + ((1024u - (smem_u32(wsm_raw) & 1023u)) & 1023u);
+    const int stage_bytes = (4 + p.nbb) * WG_MNBLOCK;
+    uint64_t *full = reinterpret_cast<uint64_t *>(sm + (size_t)WG_STAGES * stage_bytes);
+    uint64_t *empty = full + WG_STAGES;
+    uint64_t *acc_full = empty + WG_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int co0 = (blockIdx.y / p.n_ci_tiles) * TC_ROWS, ci0 = (blockIdx.y % p.n_ci_tiles) * p.nt;
+    const int64_t r_begin = (int64_t)blockIdx.x * p.rows_per_cta;
+    int64_t r_end = r_begin + p.rows_per_cta;
+    if (r_end > p.M) r_end = p.M;
+    const int n_st = r_end > r_begin ? (int)((r_end - r_begin + WG_KT - 1) / WG_KT) : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < WG_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 5) {
+        if (lane == 0) {
+            for (int i = 0; i < n_st; ++i) {
+                const int s = i % WG_STAGES;
+                mbar_wait(empty + s, ((i / WG_STAGES) & 1u) ^ 1u);
+                mbar_expect_tx(full + s, (uint32_t)stage_bytes);
+                unsigned char *dst = sm + (size_t)s * stage_bytes;
+                // rows past the CTA's range would double-count: the last stage of a range is clipped by r_end through the
+                // tensor map only at the end of the tensor, so ranges are multiples of WG_KT rows (host) except the last one
+                const int row = (int)(r_begin + (int64_t)i * WG_KT);
+                for (int b = 0; b < 4; ++b) tma_load_2d(dst + b * WG_MNBLOCK, &p.tmY, co0 + 32 * b, row, full + s);
+                for (int b = 0; b < p.nbb; ++b) tma_load_2d(dst + (4 + b) * WG_MNBLOCK, &p.tmX, ci0 + 32 * b, row, full + s);
+            }
+        }
+    } else if (warp == 4) {
+        // D[co][ci] += dy^T (A: M = 128 output channels, MN-major) x (B: N = nt input channels, MN-major), K = 8 rows per MMA
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.nt >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+        for (int i = 0; i < n_st; ++i) {
+            const int s = i % WG_STAGES;
+            mbar_wait(full + s, (i / WG_STAGES) & 1u);
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(sm) + (uint32_t)(s * stage_bytes);
+            const uint32_t b0 = a0 + 4u * WG_MNBLOCK;
+            if (elect_one()) {
+#pragma unroll
+                for (int j = 0; j < WG_KT / 8; ++j)
+                    umma_tf32(tmem_base, smem_desc_mn_sw128(a0 + (uint32_t)(j * 1024), WG_MNBLOCK), smem_desc_mn_sw128(b0 + (uint32_t)(j * 1024), WG_MNBLOCK),
+                              idesc, (i | j) ? 1u : 0u);
+                umma_commit(empty + s);
+                if (i == n_st - 1) umma_commit(acc_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        // partial tile -> workspace (zeros when this CTA's row range is empty)
+        if (n_st > 0) { mbar_wait(acc_full, 0); tc_fence_after(); }
+        const int co = co0 + warp * 32 + lane;
+        float *dst = p.ws + ((int64_t)blockIdx.x * p.Cout + co) * p.Cin + ci0;
+        const int nci = min(p.nt, p.Cin - ci0);
+        for (int c0 = 0; c0 < p.nt; c0 += 16) {
+            uint32_t r[16];
+            if (n_st > 0) { tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r); tmem_ld_wait(); }
+            else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) r[i] = 0u;
+            }
+            if (co < p.Cout) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) if (c0 + i < nci) dst[c0 + i] = __uint_as_float(r[i]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+__global__ void rows_wgrad_reduce_kernel(const float *__restrict__ ws, int n_part, int64_t n, float *__restrict__ dW)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float a = 0.f;
+    for (int q = 0; q < n_part; ++q) a += ws[(int64_t)q * n + i];
+    dW[i] = a;
+}
+
+static void wgrad_plan(int64_t M, int Cout, int Cin, int *gx, int *nt, int *n_ci, int *n_co, int64_t *rows_per_cta)
+{
+    const int cin_pad = rup(Cin, 16);
+    *n_ci = (cin_pad + 255) / 256;
+    *nt = rup((cin_pad + *n_ci - 1) / *n_ci, 16);
+    *n_co = (Cout + TC_ROWS - 1) / TC_ROWS;
+    int g = 148 / (*n_ci * *n_co);
+    if (g < 1) g = 1;
+    const int64_t units = (M + WG_KT - 1) / WG_KT;
+    if (g > units) g = (int)units;
+    if (g < 1) g = 1;
+    *rows_per_cta = (units + g - 1) / g * WG_KT;
+    *gx = (int)((M + *rows_per_cta - 1) / *rows_per_cta);
+    if (*gx < 1) *gx = 1;
+}
+
+int64_t rows_wgrad_ws_bytes(int64_t M, int Cout, int Cin)
+{
+    int gx, nt, n_ci, n_co; int64_t rpc;
+    wgrad_plan(M, Cout, Cin, &gx, &nt, &n_ci, &n_co, &rpc);
+    return (int64_t)gx * Cout * Cin * 4;
+}
+
+int launch_rows_wgrad(const float *dy, int64_t ldy, const float *x, int64_t ldx, int64_t M, int Cout, int Cin, float *ws, float *dW, cudaStream_t st)
+{
+    PN2_REQUIRE(ldy % 4 == 0 && ldx % 4 == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)x & 15) == 0,
+                "pn2_rows_wgrad_tf32: operand rows must start on 16-byte boundaries");
+    PN2_REQUIRE(M >= 1 && M < (1ll << 31), "pn2_rows_wgrad_tf32: M = %lld outside [1, 2^31)", (long long)M);
+    WgradParams p;
+    int gx, n_co;
+    wgrad_plan(M, Cout, Cin, &gx, &p.nt, &p.n_ci_tiles, &n_co, &p.rows_per_cta);
+    p.M = M; p.Cout = Cout; p.Cin = Cin; p.nbb = (p.nt + 31) / 32; p.ws = ws;
+    int tc = 32;
+    while (tc < p.nt) tc <<= 1;
+    p.tmem_cols = tc;
+    int rc = make_tile_map(dy, 4, M, Cout, ldy * 4, WG_KT, &p.tmY);
+    if (rc) return rc;
+    rc = make_tile_map(x, 4, M, Cin, ldx * 4, WG_KT, &p.tmX);
+    if (rc) return rc;
+    const size_t smem = 1024 + (size_t)WG_STAGES * (4 + p.nbb) * WG_MNBLOCK + 256;
+    cudaError_t e = cudaFuncSetAttribute(rows_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("rows_wgrad: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return (int)e; }
+    rows_wgrad_kernel<<<dim3((unsigned)gx, (unsigned)(n_co * p.n_ci_tiles)), WG_THREADS, smem, st>>>(p);
+    rc = launch_status("pn2_rows_wgrad_tf32");
+    if (rc) return rc;
+    const int64_t n = (int64_t)Cout * Cin;
+    rows_wgrad_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws, gx, n, dW);
+    return launch_status("pn2_rows_wgrad_tf32(reduce)");
 }
 
 }  // namespace
@@ -258,7 +484,7 @@ int launch_rows_gemm(const void *A, int64_t lda, int a_f32, const void *W, int64
     const int kpb = tf32 ? 32 : 64;
     p.nkb = (K + kpb - 1) / kpb;
     // columns per CTA: W slice resident next to the A ring
-    const int budget = TC_SMEM_LIMIT - GM_STAGES * GM_BLOCK - 2048;
+    const int budget = TC_SMEM_LIMIT - (GM_STAGES + 2) * GM_BLOCK - 2048;
     int nt_max = budget / (p.nkb * 128) / 16 * 16;
     if (nt_max > 256) nt_max = 256;
     PN2_REQUIRE(nt_max >= 16, "pn2_rows_gemm: K = %d too large for a resident weight slice", K);
@@ -268,7 +494,16 @@ int launch_rows_gemm(const void *A, int64_t lda, int a_f32, const void *W, int64
     int tc = 32;
     while (tc < 2 * p.Nt) tc <<= 1;
     p.tmem_cols = tc;
-    const size_t smem = 1024 + (size_t)p.nkb * p.Nt * 128 + (size_t)GM_STAGES * GM_BLOCK + 256;
+    const size_t smem = 1024 + (size_t)p.nkb * p.Nt * 128 + (size_t)(GM_STAGES + 2) * GM_BLOCK + 256;
+    const bool tma_a = !(a_f32 && !tf32);
+    if (tma_a) {
+        const int rc = make_tile_map(A, a_f32 ? 4 : 2, M, K, lda * (a_f32 ? 4 : 2), TC_ROWS, &p.tmA);
+        if (rc) return rc;
+    } else memset(&p.tmA, 0, sizeof(p.tmA));
+    {
+        const int rc = make_tile_map(C, c_bf16 ? 2 : 4, M, N, ldc * (c_bf16 ? 2 : 4), TC_ROWS, &p.tmC);
+        if (rc) return rc;
+    }
     int64_t gx = 148 / n_tiles;
     if (gx < 1) gx = 1;
     if (gx > p.tiles_m) gx = p.tiles_m;
@@ -297,4 +532,18 @@ extern "C" int pn2_rows_gemm(const void *A, int64_t lda, int a_dtype, const void
     PN2_REQUIRE(M < (1ll << 40), "pn2_rows_gemm: M too large");
     return launch_rows_gemm(A, lda, a_dtype == PN2_DT_F32, W, ldw, w_dtype == PN2_DT_F32, C, ldc, c_dtype == PN2_DT_BF16, M, N, K,
                             (cudaStream_t)stream);
+}
+
+extern "C" int64_t pn2_rows_wgrad_ws_bytes(int64_t M, int Cout, int Cin)
+{
+    if (M < 1 || Cout < 1 || Cin < 1) return 0;
+    return rows_wgrad_ws_bytes(M, Cout, Cin);
+}
+
+extern "C" int pn2_rows_wgrad_tf32(const float *dy, int64_t ldy, const float *x, int64_t ldx, int64_t M, int Cout, int Cin,
+                                   void *ws, float *dW, void *stream)
+{
+    PN2_REQUIRE(dy && x && ws && dW, "pn2_rows_wgrad_tf32: null pointer");
+    PN2_REQUIRE(Cout >= 1 && Cin >= 1 && Cout % 4 == 0 && Cin % 4 == 0, "pn2_rows_wgrad_tf32: channel counts must be multiples of 4 (16-byte rows)");
+    return launch_rows_wgrad(dy, ldy, x, ldx, M, Cout, Cin, (float *)ws, dW, (cudaStream_t)stream);
 }

@@ -40,6 +40,29 @@ int make_row_gather_map(const void *base, int64_t rows, int cols, void *out_map 
     return 0;
 }
 
+// 2-D row-major tensor [rows][cols] of bf16 (elem_bytes 2) or fp32 (4) elements with a row pitch of `pitch_bytes` (multiple of
+// 16); box = 128 bytes of columns x box_rows rows, 128-byte swizzle: the shared-memory image is the K-major SWIZZLE_128B MMA
+// operand block (loads) / the staging tile of the GEMM epilogue (stores).  Elements outside the tensor read as zero and are
+// not written.
+int make_tile_map(const void *base, int elem_bytes, int64_t rows, int64_t cols, int64_t pitch_bytes, int box_rows, void *out_map)
+{
+    PFN_cuTensorMapEncodeTiled enc = get_encode();
+    if (!enc) { set_error("tensor map: cuTensorMapEncodeTiled entry point not available"); return -2; }
+    if ((elem_bytes != 2 && elem_bytes != 4) || pitch_bytes % 16 != 0 || ((uintptr_t)base & 15) || box_rows < 1 || box_rows > 256) {
+        set_error("tensor map: rows must be 16-byte aligned with a pitch that is a multiple of 16 bytes");
+        return -1;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)pitch_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc((CUtensorMap *)out_map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                           const_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("tensor map: cuTensorMapEncodeTiled failed (%d)", (int)r); return -3; }
+    return 0;
+}
+
 __global__ void __launch_bounds__(32, 1) tma_gather_selftest_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *rows4, int n_inst,
                                                                    int col0, unsigned char *out)
 {

@@ -387,7 +387,8 @@ class _RowsLinear(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 dx = _backend().rows_gemm(dy, w.t().contiguous()) if _own_gemm(dy, w) else torch.mm(dy, w)
             if ctx.needs_input_grad[1]:
-                dw = _rows_outer(dy, x)
+                own = _own_gemm(dy, w) and x.is_contiguous() and 0 < x.shape[0] < 2 ** 31
+                dw = _backend().rows_wgrad(dy, x) if own else _rows_outer(dy, x)
         return dx, dw
 
 

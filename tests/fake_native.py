@@ -127,6 +127,10 @@ class OracleNative:
         y = a.float() @ w.float().t()
         return y.to(out_dtype or (torch.bfloat16 if w.dtype == torch.bfloat16 else torch.float32))
 
+    def rows_wgrad(self, dy, x):
+        self.calls.append("rows_wgrad")
+        return dy.t() @ x
+
     def sa_needs_zero(self, S, K, dims, prec):
         return False
 

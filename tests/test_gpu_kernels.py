@@ -497,3 +497,19 @@ def test_rows_gemm_vs_torch(nat, M, K, N, mode):
     assert rel_err(got.float().cpu(), exp) <= 2.0 ** -8             # one bf16 rounding of the fp32-accumulated result
     got32 = nat.rows_gemm(ab.cuda(), wb.cuda(), torch.float32)
     assert rel_err(got32.cpu(), exp) <= 1e-5
+
+
+@pytest.mark.parametrize("M,Cout,Cin", [(4096, 64, 32), (100000, 96, 64), (33, 32, 12), (70001, 128, 128), (5000, 256, 128), (3000, 1024, 512),
+                                        (20000, 128, 332), (257, 64, 16), (1, 32, 4)])
+def test_rows_wgrad_vs_torch(nat, M, Cout, Cin):
+    """pn2_rows_wgrad_tf32 (dy^T x, MN-major tcgen05 operands straight from TMA) against the fp64 product; run twice: bitwise
+    repeatable (partials are added in a fixed order)."""
+    g = torch.Generator().manual_seed(M + Cout + Cin)
+    dy = torch.randn(M, Cout, generator=g)
+    x = torch.randn(M, Cin, generator=g)
+    exp = dy.double().t() @ x.double()
+    got = nat.rows_wgrad(dy.cuda(), x.cuda())
+    assert got.shape == (Cout, Cin)
+    scale = float(exp.abs().max()) + M ** 0.5
+    assert float((got.cpu().double() - exp).abs().max()) <= 2e-3 * scale
+    assert torch.equal(got, nat.rows_wgrad(dy.cuda(), x.cuda()))
