@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PN2_ABI_VERSION 13
+#define PN2_ABI_VERSION 14
 #define PN2_MAX_COORD 16 /* exact summation-order rules are verified against ATen for C <= 16 */
 #define PN2_MAX_LAYERS 8
 
@@ -80,6 +80,14 @@ int pn2_group_f32(const float *points, int64_t sb, int64_t sn, int64_t sc,
                   const float *feat, int64_t fb, int64_t fn, int64_t fc,
                   const int32_t *idx32, const float *centres,
                   int B, int N, int S, int K, int C, int D, int order, float *out, void *stream);
+
+/* Differentiable feature gather of training mode -- index_points(feature, idx) of pointnet2_utils.py:112 / :208 and its
+ * backward.  feat [B,N,D] with element strides (fb, fn, 1); idx32 [B,M] (M = S*K); out [B,M,D] contiguous.
+ * pn2_scatter_add_rows_f32 adds grad [B,M,D] into grad_feat [B,N,D] (contiguous, zero-filled by the caller) with fp32
+ * reductions; an index outside [0,N) (the empty-ball marker N) gathers a zero row and scatters nothing. */
+int pn2_gather_rows_f32(const float *feat, int64_t fb, int64_t fn, int64_t fc, const int32_t *idx32, int B, int N, int64_t M, int D,
+                        float *out, void *stream);
+int pn2_scatter_add_rows_f32(const float *grad, const int32_t *idx32, int B, int N, int64_t M, int D, float *grad_feat, void *stream);
 
 /* Fold eval-mode BatchNorm into the 1x1 convolutions and lay the weights out for the fused kernels
  * (pointnet2_utils.py:154-155, :168-170).  L layers; dims[L+1] = {Cin, C1..CL}.  For layer l the six

@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(_HERE, LIB_NAME)
 ORDER_SSG, ORDER_MSG, ORDER_ALL = 0, 1, 2
 PREC_F32, PREC_BF16 = 0, 1
 MAX_COORD = 16
-ABI_VERSION = 13
+ABI_VERSION = 14
 HEAD_PLAIN, HEAD_CLS, HEAD_TRANS, HEAD_SIGN = 0, 1, 2, 3
 
 _i64, _i32, _f32, _vp = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p
@@ -57,6 +57,8 @@ _SIGNATURES = {
     "pn2_rows_gemm": ([_vp, _i64, _i32, _vp, _i64, _i32, _vp, _i64, _i32, _i64, _i32, _i32, _vp], _i32),
     "pn2_rows_wgrad_ws_bytes": ([_i64, _i32, _i32], _i64),
     "pn2_rows_wgrad_tf32": ([_vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp], _i32),
+    "pn2_gather_rows_f32": ([_vp, _i64, _i64, _i64, _vp, _i32, _i32, _i64, _i32, _vp, _vp], _i32),
+    "pn2_scatter_add_rows_f32": ([_vp, _vp, _i32, _i32, _i64, _i32, _vp, _vp], _i32),
     "pn2_selftest_umma": ([_i32, _i32, _i32, _vp, _vp, _vp], _i32),
     "pn2_debug_trace": ([_vp], _i32),
     "pn2_selftest_tma_gather": ([_vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp], _i32),
@@ -454,6 +456,33 @@ class Native:
             _check(self.lib.pn2_rows_gemm(a.data_ptr(), a.stride(0), dt[a.dtype], w.data_ptr(), w.stride(0), dt[w.dtype],
                                           out.data_ptr(), out.stride(0), dt[out.dtype], M, N, K, _stream(a)))
         return out
+
+    def gather_rows(self, feat, idx32):
+        """feat [B,N,D] (unit channel stride), idx32 [B,S,K] -> [B,S,K,D] (training mode's feature gather)."""
+        _need_cuda("feature", feat, torch.float32)
+        _need_cuda("idx", idx32, torch.int32)
+        B, N, D = feat.shape
+        if feat.stride(2) != 1:
+            feat = feat.contiguous()
+        idx32 = idx32.contiguous()
+        M = idx32.numel() // max(B, 1)
+        out = torch.empty(*idx32.shape, D, dtype=torch.float32, device=feat.device)
+        with torch.cuda.device(feat.device), self._span("gather_rows", B=B, N=N, M=M, D=D):
+            _check(self.lib.pn2_gather_rows_f32(feat.data_ptr(), feat.stride(0), feat.stride(1), 1, idx32.data_ptr(), B, N, M, D,
+                                                out.data_ptr(), _stream(feat)))
+        return out
+
+    def scatter_add_rows(self, grad, idx32, N):
+        """Backward of gather_rows: grad [B,S,K,D] -> grad_feat [B,N,D]."""
+        _need_cuda("grad", grad, torch.float32)
+        grad = grad.contiguous()
+        idx32 = idx32.contiguous()
+        B, D = grad.shape[0], grad.shape[-1]
+        M = idx32.numel() // max(B, 1)
+        gfeat = torch.zeros(B, N, D, dtype=torch.float32, device=grad.device)
+        with torch.cuda.device(grad.device), self._span("scatter_add_rows", B=B, N=N, M=M, D=D):
+            _check(self.lib.pn2_scatter_add_rows_f32(grad.data_ptr(), idx32.data_ptr(), B, N, M, D, gfeat.data_ptr(), _stream(grad)))
+        return gfeat
 
     def rows_wgrad(self, dy, x):
         """dW [Cout,Cin] = dy [M,Cout]^T @ x [M,Cin] (TF32 tensor-core product, deterministic): include/pn2.h pn2_rows_wgrad_tf32."""

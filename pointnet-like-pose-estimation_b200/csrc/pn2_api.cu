@@ -235,4 +235,19 @@ int pn2_selftest_umma(int n_cols, int k_dim, int variant, float *max_err, float 
     return launch_selftest_umma(n_cols, k_dim, variant, max_err, dump, (cudaStream_t)stream);
 }
 
+
+int pn2_gather_rows_f32(const float *feat, int64_t fb, int64_t fn, int64_t fc, const int32_t *idx32, int B, int N, int64_t M, int D,
+                        float *out, void *stream)
+{
+    PN2_REQUIRE(feat && idx32 && out, "pn2_gather_rows_f32: null pointer");
+    PN2_REQUIRE(B >= 0 && N >= 1 && M >= 0 && D >= 0 && fc == 1, "pn2_gather_rows_f32: bad sizes / rows must have unit channel stride");
+    return launch_gather_rows(feat, fb, fn, idx32, B, N, M, D, out, (cudaStream_t)stream);
+}
+
+int pn2_scatter_add_rows_f32(const float *grad, const int32_t *idx32, int B, int N, int64_t M, int D, float *grad_feat, void *stream)
+{
+    PN2_REQUIRE(grad && idx32 && grad_feat, "pn2_scatter_add_rows_f32: null pointer");
+    PN2_REQUIRE(B >= 0 && N >= 1 && M >= 0 && D >= 0, "pn2_scatter_add_rows_f32: bad sizes");
+    return launch_scatter_add_rows(grad, idx32, B, N, M, D, grad_feat, (cudaStream_t)stream);
+}
 }  // extern "C"

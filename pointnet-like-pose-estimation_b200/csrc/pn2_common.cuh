@@ -177,6 +177,8 @@ int launch_ball_query(const float *centres, int64_t csb, int64_t csn, int64_t cs
                       const float *points, int64_t sb, int64_t sn, int64_t sc,
                       int B, int S, int N, int C, float r2, int K,
                       int64_t *idx64, int32_t *idx32, int32_t *empty_flag, cudaStream_t st);
+int launch_gather_rows(const float *feat, int64_t fb, int64_t fn, const int32_t *idx32, int B, int N, int64_t M, int D, float *out, cudaStream_t st);
+int launch_scatter_add_rows(const float *grad, const int32_t *idx32, int B, int N, int64_t M, int D, float *gfeat, cudaStream_t st);
 int launch_group(const float *points, int64_t sb, int64_t sn, int64_t sc,
                  const float *feat, int64_t fb, int64_t fn, int64_t fc,
                  const int32_t *idx32, const float *centres,
@@ -222,7 +224,7 @@ int launch_bn_bwd(const float *dz, const float *y, const int32_t *arg, int64_t M
 int launch_normalize_splice(const float *xyz, int64_t sb, int64_t sn, int64_t sc, int B, int N,
                             const int64_t *category, int num_category, float *out, cudaStream_t st);
 int make_row_gather_map(const void *base, int64_t rows, int cols, void *out_map);
-int make_tile_map(const void *base, int elem_bytes, int64_t rows, int64_t cols, int64_t pitch_bytes, int box_rows, void *out_map);
+int make_tile_map(const void *base, int elem_bytes, int64_t rows, int64_t cols, int64_t pitch_bytes, int box_rows, void *out_map, int atom32 = 0);
 int launch_selftest_tma_gather(const void *src_bf16, int64_t rows, int cols, const int32_t *rows4, int n_inst, int col0, void *out, cudaStream_t st);
 int launch_selftest_umma(int n_cols, int k_dim, int variant, float *max_err, float *dump, cudaStream_t st);
 

@@ -296,7 +296,8 @@ __global__ void __launch_bounds__(GM_THREADS, 1) rows_gemm_kernel(const __grid_c
 // Weight gradient of a 1x1 convolution on rows:  dW[Cout,Cin] = dy[M,Cout]^T . x[M,Cin]  (M = grouped rows, in the millions;
 // the output a few thousand elements).  The reduction runs over the ROW index, so both operands are "MN-major" for the
 // tensor core: a block of 32 rows x 32 channels (128 bytes per row) copied as it lies in HBM IS the canonical MN-major
-// SWIZZLE_128B operand (channels contiguous, 8-row swizzle atoms), which TMA delivers without touching a register.  A CTA
+// operand (channels contiguous; SWIZZLE_128B_BASE32B, the 32-byte-atom swizzle TMA applies as CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B),
+// delivered without touching a register.  A CTA
 // owns a contiguous range of rows and one (128 output channels) x (<= 256 input channels) tile of dW, accumulates it in TMEM
 // over its whole range (one tf32 MMA per 8 rows), and writes an fp32 partial; a second small kernel adds the partials in a
 // fixed order (deterministic).
@@ -314,11 +315,13 @@ struct WgradParams {
     alignas(64) CUtensorMap tmX;  // x as [M][Cin],  box 32 channels x 32 rows
 };
 
-// MN-major SWIZZLE_128B descriptor: LBO = bytes between 32-channel blocks, SBO = bytes between 8-row groups
+// MN-major descriptor for 32-bit operands: SWIZZLE_128B_BASE32B (layout type 1; the only layout the tensor core takes for
+// MN-major tf32): rows of 128 bytes = 32 channels, atoms of 4 rows with 32-byte chunk c of row r at position c ^ (r & 3);
+// LBO = bytes between 32-channel blocks, SBO = bytes between 4-row atoms (512: rows are consecutive)
 __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes)
 {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((1024u >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+           ((uint64_t)((512u >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (1ull << 61);
 }
 
 __global__ void __launch_bounds__(WG_THREADS, 1) rows_wgrad_kernel(const __grid_constant__ WgradParams p)
@@ -450,9 +453,9 @@ int launch_rows_wgrad(const float *dy, int64_t ldy, const float *x, int64_t ldx,
     int tc = 32;
     while (tc < p.nt) tc <<= 1;
     p.tmem_cols = tc;
-    int rc = make_tile_map(dy, 4, M, Cout, ldy * 4, WG_KT, &p.tmY);
+    int rc = make_tile_map(dy, 4, M, Cout, ldy * 4, WG_KT, &p.tmY, 1);
     if (rc) return rc;
-    rc = make_tile_map(x, 4, M, Cin, ldx * 4, WG_KT, &p.tmX);
+    rc = make_tile_map(x, 4, M, Cin, ldx * 4, WG_KT, &p.tmX, 1);
     if (rc) return rc;
     const size_t smem = 1024 + (size_t)WG_STAGES * (4 + p.nbb) * WG_MNBLOCK + 256;
     cudaError_t e = cudaFuncSetAttribute(rows_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -179,4 +179,76 @@ int launch_normalize_splice(const float *xyz, int64_t sb, int64_t sn, int64_t sc
     return launch_status("pn2_normalize_splice_f32");
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Differentiable feature gather of training mode: index_points(feature, idx) of pointnet2_utils.py:112 / :208 and its
+// backward (a scatter-add into the feature gradient).  One warp per gathered row, 16-byte accesses when the rows allow it;
+// the 'no neighbour' index (n == N, empty ball) gathers zeros and scatters nothing.
+template <bool VEC>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float *__restrict__ feat, int64_t fb, int64_t fn, const int32_t *__restrict__ idx32,
+                                                          int N, int64_t M, int D, int64_t rows, float *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < rows; r += nwarps) {
+        const int n = idx32[r];
+        const bool ok = n >= 0 && n < N;
+        const float *f = feat + (r / M) * fb + (int64_t)(ok ? n : 0) * fn;
+        float *o = out + r * D;
+        if (VEC) {
+            for (int k = lane * 4; k < D; k += 128) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok) v = __ldg(reinterpret_cast<const float4 *>(f + k));
+                *reinterpret_cast<float4 *>(o + k) = v;
+            }
+        } else {
+            for (int k = lane; k < D; k += 32) o[k] = ok ? __ldg(f + k) : 0.f;
+        }
+    }
+}
+template <bool VEC>
+__global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float *__restrict__ grad, const int32_t *__restrict__ idx32, int N, int64_t M,
+                                                               int D, int64_t rows, float *__restrict__ gfeat)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < rows; r += nwarps) {
+        const int n = idx32[r];
+        if (n < 0 || n >= N) continue;
+        const float *g = grad + r * D;
+        float *o = gfeat + ((r / M) * N + n) * (int64_t)D;
+        if (VEC) {
+            for (int k = lane * 4; k < D; k += 128) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(g + k));
+                atomicAdd(reinterpret_cast<float4 *>(o + k), v);        // one 16-byte reduction (sm_90+)
+            }
+        } else {
+            for (int k = lane; k < D; k += 32) atomicAdd(o + k, __ldg(g + k));
+        }
+    }
+}
+int launch_gather_rows(const float *feat, int64_t fb, int64_t fn, const int32_t *idx32, int B, int N, int64_t M, int D, float *out, cudaStream_t st)
+{
+    const int64_t rows = (int64_t)B * M;
+    if (rows == 0 || D == 0) return 0;
+    int64_t blocks = (rows + 7) / 8;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    const bool vec = D % 4 == 0 && fb % 4 == 0 && fn % 4 == 0 && ((uintptr_t)feat & 15) == 0 && ((uintptr_t)out & 15) == 0;
+    if (vec) gather_rows_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(feat, fb, fn, idx32, N, M, D, rows, out);
+    else gather_rows_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(feat, fb, fn, idx32, N, M, D, rows, out);
+    return launch_status("pn2_gather_rows_f32");
+}
+int launch_scatter_add_rows(const float *grad, const int32_t *idx32, int B, int N, int64_t M, int D, float *gfeat, cudaStream_t st)
+{
+    const int64_t rows = (int64_t)B * M;
+    if (rows == 0 || D == 0) return 0;
+    int64_t blocks = (rows + 7) / 8;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    const bool vec = D % 4 == 0 && ((uintptr_t)grad & 15) == 0 && ((uintptr_t)gfeat & 15) == 0;
+    if (vec) scatter_add_rows_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(grad, idx32, N, M, D, rows, gfeat);
+    else scatter_add_rows_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(grad, idx32, N, M, D, rows, gfeat);
+    return launch_status("pn2_scatter_add_rows_f32");
+}
+
 }  // namespace pn2

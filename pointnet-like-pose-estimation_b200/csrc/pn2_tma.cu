@@ -43,8 +43,9 @@ int make_row_gather_map(const void *base, int64_t rows, int cols, void *out_map 
 // 2-D row-major tensor [rows][cols] of bf16 (elem_bytes 2) or fp32 (4) elements with a row pitch of `pitch_bytes` (multiple of
 // 16); box = 128 bytes of columns x box_rows rows, 128-byte swizzle: the shared-memory image is the K-major SWIZZLE_128B MMA
 // operand block (loads) / the staging tile of the GEMM epilogue (stores).  Elements outside the tensor read as zero and are
-// not written.
-int make_tile_map(const void *base, int elem_bytes, int64_t rows, int64_t cols, int64_t pitch_bytes, int box_rows, void *out_map)
+// not written.  atom32: the 128-byte swizzle with 32-byte atoms (32-byte chunk c of row r at position c ^ (r & 3)) -- the only
+// layout the tensor core accepts for MN-major 32-bit operands (UMMA SWIZZLE_128B_BASE32B).
+int make_tile_map(const void *base, int elem_bytes, int64_t rows, int64_t cols, int64_t pitch_bytes, int box_rows, void *out_map, int atom32)
 {
     PFN_cuTensorMapEncodeTiled enc = get_encode();
     if (!enc) { set_error("tensor map: cuTensorMapEncodeTiled entry point not available"); return -2; }
@@ -57,7 +58,8 @@ int make_tile_map(const void *base, int elem_bytes, int64_t rows, int64_t cols, 
     const cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = enc((CUtensorMap *)out_map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
-                           const_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           const_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("tensor map: cuTensorMapEncodeTiled failed (%d)", (int)r); return -3; }
     return 0;

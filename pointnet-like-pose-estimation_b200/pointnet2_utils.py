@@ -538,12 +538,24 @@ class PointNetSetAbstraction(nn.Module):
         return new_points.permute(0, 2, 1), pooled
 
 
+class _GatherRows(torch.autograd.Function):
+    """index_points(feature, idx) of training mode (:112 / :208) on the product kernels: gather forward, scatter-add backward."""
+
+    @staticmethod
+    def forward(ctx, feat, idx32):
+        ctx.save_for_backward(idx32)
+        ctx.N = feat.shape[1]
+        return _backend().gather_rows(feat, idx32)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (idx32,) = ctx.saved_tensors
+        return _backend().scatter_add_rows(grad, idx32, ctx.N), None
+
+
 def _gather_rows(feat, idx32):
-    """Differentiable feature gather [B,N,D], [B,S,K] -> [B,S,K,D] (autograd scatter-add in backward)."""
-    B, S, K = idx32.shape
-    D = feat.shape[-1]
-    flat = idx32.reshape(B, S * K, 1).long().expand(-1, -1, D)
-    return torch.gather(feat, 1, flat).view(B, S, K, D)
+    """Differentiable feature gather [B,N,D], [B,S,K] -> [B,S,K,D] (scatter-add in backward)."""
+    return _GatherRows.apply(feat, idx32)
 
 
 class PointNetSetAbstractionMsg(nn.Module):

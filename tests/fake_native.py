@@ -127,6 +127,20 @@ class OracleNative:
         y = a.float() @ w.float().t()
         return y.to(out_dtype or (torch.bfloat16 if w.dtype == torch.bfloat16 else torch.float32))
 
+    def gather_rows(self, feat, idx32):
+        self.calls.append("gather_rows")
+        B, N, D = feat.shape
+        flat = idx32.reshape(B, -1, 1).long().clamp(0, N - 1).expand(-1, -1, D)
+        out = torch.gather(feat, 1, flat).view(*idx32.shape, D)
+        return out * ((idx32 >= 0) & (idx32 < N)).unsqueeze(-1)
+
+    def scatter_add_rows(self, grad, idx32, N):
+        self.calls.append("scatter_add_rows")
+        B, D = grad.shape[0], grad.shape[-1]
+        ok = ((idx32 >= 0) & (idx32 < N)).reshape(B, -1, 1)
+        flat = idx32.reshape(B, -1, 1).long().clamp(0, N - 1).expand(-1, -1, D)
+        return torch.zeros(B, N, D).scatter_add_(1, flat, grad.reshape(B, -1, D) * ok)
+
     def rows_wgrad(self, dy, x):
         self.calls.append("rows_wgrad")
         return dy.t() @ x

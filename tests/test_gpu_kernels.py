@@ -513,3 +513,26 @@ def test_rows_wgrad_vs_torch(nat, M, Cout, Cin):
     scale = float(exp.abs().max()) + M ** 0.5
     assert float((got.cpu().double() - exp).abs().max()) <= 2e-3 * scale
     assert torch.equal(got, nat.rows_wgrad(dy.cuda(), x.cuda()))
+
+
+@pytest.mark.parametrize("B,N,D,S,K", [(3, 512, 128, 64, 16), (2, 300, 7, 41, 5), (4, 1024, 320, 128, 32), (1, 64, 64, 64, 64)])
+def test_gather_and_scatter_add_rows_vs_torch(nat, B, N, D, S, K):
+    """Training mode's feature gather (index_points(feature, idx), :112 / :208) and its backward against torch.gather /
+    scatter_add_ in fp32 on the CPU; the empty-ball index N gathers zeros and scatters nothing."""
+    g = torch.Generator().manual_seed(B + N + D)
+    feat = torch.randn(B, N, D, generator=g)
+    idx = torch.randint(0, N, (B, S, K), generator=g, dtype=torch.int32)
+    idx[0, 0, :] = N                                             # an empty ball
+    ok = (idx < N).unsqueeze(-1)
+    flat = idx.reshape(B, -1, 1).long().clamp(0, N - 1).expand(-1, -1, D)
+    exp = torch.gather(feat, 1, flat).view(B, S, K, D) * ok
+    got = nat.gather_rows(feat.cuda(), idx.cuda())
+    assert torch.equal(got.cpu(), exp)
+    # strided feature rows (a channel slice of a wider tensor)
+    wide = torch.randn(B, N, D + 8, generator=g)
+    got2 = nat.gather_rows(wide.cuda()[:, :, 4:4 + D], idx.cuda())
+    assert torch.equal(got2.cpu(), torch.gather(wide[:, :, 4:4 + D], 1, flat).view(B, S, K, D) * ok)
+    grad = torch.randn(B, S, K, D, generator=g)
+    exp_g = torch.zeros(B, N, D).scatter_add_(1, flat, (grad * ok).reshape(B, -1, D))
+    got_g = nat.scatter_add_rows(grad.cuda(), idx.cuda(), N)
+    assert rel_err(got_g.cpu(), exp_g) <= 1e-5                   # fp32 reductions in a different order
