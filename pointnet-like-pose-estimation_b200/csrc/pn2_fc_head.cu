@@ -47,17 +47,32 @@ __device__ __forceinline__ void hidden_layer(cg::cluster_group &cluster, const f
     for (int t = 0; t < TB; ++t) acc[t] = 0.f;
     const float4 *w4 = reinterpret_cast<const float4 *>(wp) + (size_t)(kq * kspan / 4) * H + rank * OPC + o;
     const float *xin = in + kq * kspan;
-#pragma unroll 2
-    for (int k = 0; k < kspan; k += 4) {
-        const float4 w = __ldg(w4);
-        w4 += H;
+    // weights come from L2 (~600+ cycles): four 16-byte loads in flight per thread ahead of the FMAs that use them
+    // (kspan is a multiple of 16 for every supported width)
+    float4 wq[4];
 #pragma unroll
-        for (int t = 0; t < TB; ++t) {
-            const float4 v = *reinterpret_cast<const float4 *>(xin + t * K + k);
-            acc[t] = fmaf(v.x, w.x, acc[t]);
-            acc[t] = fmaf(v.y, w.y, acc[t]);
-            acc[t] = fmaf(v.z, w.z, acc[t]);
-            acc[t] = fmaf(v.w, w.w, acc[t]);
+    for (int i = 0; i < 4; ++i) wq[i] = __ldg(w4 + (size_t)i * H);
+#pragma unroll 1
+    for (int k = 0; k < kspan; k += 16) {
+        float4 wc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) wc[i] = wq[i];
+        w4 += (size_t)4 * H;
+        if (k + 16 < kspan) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) wq[i] = __ldg(w4 + (size_t)i * H);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 w = wc[i];
+#pragma unroll
+            for (int t = 0; t < TB; ++t) {
+                const float4 v = *reinterpret_cast<const float4 *>(xin + t * K + k + 4 * i);
+                acc[t] = fmaf(v.x, w.x, acc[t]);
+                acc[t] = fmaf(v.y, w.y, acc[t]);
+                acc[t] = fmaf(v.z, w.z, acc[t]);
+                acc[t] = fmaf(v.w, w.w, acc[t]);
+            }
         }
     }
     // scratch may alias `in` of the FIRST layer (the staged inputs): everyone is done reading before anyone writes
@@ -204,10 +219,10 @@ extern "C" int pn2_fc_head_f32(const float *x, int64_t x_stride, int B, int K0, 
         const int opc = H / FC_CS;
         if (opc < 1 || opc > FC_THREADS || FC_THREADS % opc) return false;
         const int ks = FC_THREADS / opc;
-        return K % (4 * ks) == 0;
+        return K % (16 * ks) == 0;
     };
     PN2_REQUIRE(K0 >= 4 && K0 <= 2048 && layer_ok(K0, H1) && layer_ok(H1, H2) && H1 <= 1024 && H2 <= 1024,
-                "pn2_fc_head_f32: unsupported widths %d -> %d -> %d (hidden widths must be 8 * a divisor of 256, K a multiple of 4 * the K split)", K0, H1, H2);
+                "pn2_fc_head_f32: unsupported widths %d -> %d -> %d (hidden widths must be 8 * a divisor of 256, K a multiple of 16 * the K split)", K0, H1, H2);
     PN2_REQUIRE(K0 >= FC_THREADS, "pn2_fc_head_f32: K0 = %d < %d (the K-split scratch reuses the staged input tile)", K0, FC_THREADS);
     PN2_REQUIRE(x_stride % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)w1p & 15) == 0 && ((uintptr_t)w2p & 15) == 0,
                 "pn2_fc_head_f32: x / packed weights must be 16-byte aligned with a row stride that is a multiple of 4");

@@ -277,7 +277,7 @@ class _FoldedHead:
         def ok(K, H):
             if H % 8 or H // 8 > 256 or 256 % (H // 8):
                 return False
-            return K % (4 * (256 // (H // 8))) == 0
+            return K % (16 * (256 // (H // 8))) == 0
         k0, h1, h2, out = fcs[0].in_features, fcs[0].out_features, fcs[1].out_features, fcs[2].out_features
         return len(fcs) == 3 and 256 <= k0 <= 2048 and h1 <= 1024 and h2 <= 1024 and out <= 16 and ok(k0, h1) and ok(h1, h2)
 
