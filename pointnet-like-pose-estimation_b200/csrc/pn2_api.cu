@@ -113,8 +113,8 @@ int pn2_pack_weights(int L, const int *dims, const void *const *ptrs, float eps,
     PN2_REQUIRE(valid_dims(L, dims), "pn2_pack_weights: bad layer list");
     PN2_REQUIRE(ptrs && packed, "pn2_pack_weights: null pointer");
     for (int i = 0; i < 6 * L; ++i) PN2_REQUIRE(ptrs[i], "pn2_pack_weights: null parameter pointer %d", i);
-    if (prec == PN2_PREC_F32) return launch_pack_f32(L, dims, ptrs, eps, packed, (cudaStream_t)stream);
     PN2_REQUIRE(C >= 1 && C <= dims[0] && order >= 0 && order <= 2, "pn2_pack_weights: bad C=%d / order=%d", C, order);
+    if (prec == PN2_PREC_F32) return launch_pack_f32(L, dims, ptrs, eps, C, order, packed, (cudaStream_t)stream);
     if (prec == PN2_PREC_BF16) return launch_pack_bf16(L, dims, ptrs, eps, C, order, packed, (cudaStream_t)stream);
     PN2_REQUIRE(false, "pn2_pack_weights: unknown precision %d", prec);
 }

@@ -20,14 +20,20 @@ constexpr int F32_COUT_ALIGN = 256;   // a pass covers up to 256 output channels
 static inline int rup(int x, int a) { return (x + a - 1) / a * a; }
 
 // packed layout (floats): for each layer  Wt[CinPad][CoutPad] (BN scale folded, zero padded) then bias[CoutPad]
-int64_t packed_bytes_f32(int L, const int *dims)
+static int64_t ffma_image_bytes(int L, const int *dims)
 {
     int64_t n = 0;
     for (int l = 0; l < L; ++l) {
         const int64_t cip = rup(dims[l], F32_CIN_ALIGN), cop = rup(dims[l + 1], F32_COUT_ALIGN);
         n += cip * cop + cop;
     }
-    return n * (int64_t)sizeof(float);
+    return (n * (int64_t)sizeof(float) + 255) / 256 * 256;
+}
+// fp32 mode carries two images of the folded weights: the FFMA kernel's (this file) and, behind it, the split (bf16 hi, fp16 lo)
+// image of the tensor-core kernel (pn2_sa_tcs.cu); the launcher picks the kernel per configuration
+int64_t packed_bytes_f32(int L, const int *dims)
+{
+    return ffma_image_bytes(L, dims) + packed_bytes_f32_split(L, dims);
 }
 
 struct PackArgs {
@@ -62,8 +68,12 @@ __global__ void pack_f32_kernel(PackArgs a, float *__restrict__ packed)
     }
 }
 
-int launch_pack_f32(int L, const int *dims, const void *const *ptrs, float eps, void *packed, cudaStream_t st)
+int launch_pack_f32(int L, const int *dims, const void *const *ptrs, float eps, int C, int order, void *packed, cudaStream_t st)
 {
+    {
+        const int rc = launch_pack_bf16(L, dims, ptrs, eps, C, order, (unsigned char *)packed + ffma_image_bytes(L, dims), st, true);
+        if (rc) return rc;
+    }
     PackArgs a;
     a.L = L; a.eps = eps;
     for (int l = 0; l <= L; ++l) a.dims[l] = dims[l];
@@ -343,6 +353,8 @@ static void f32_plan(int S, int K, int L, const int *dims, int *R_out, int bufc[
 
 int sa_f32_needs_zero(int S, int K, int L, const int *dims)
 {
+    const int tr = sa_f32_split_tile_rows(K, L, dims);
+    if (tr) return K > tr;
     int R, bufc[2]; size_t smem;
     f32_plan(S, K, L, dims, &R, bufc, &smem);
     return K > R;
@@ -350,6 +362,10 @@ int sa_f32_needs_zero(int S, int K, int L, const int *dims)
 
 int launch_sa_f32(const SaArgs &a, cudaStream_t st)
 {
+    {   // tensor-core kernel on split operands where it covers the configuration
+        const int rc = launch_sa_f32_split(a, (const unsigned char *)a.packed + ffma_image_bytes(a.L, a.dims), st);
+        if (rc != -100) return rc;
+    }
     SaF32Params p;
     p.points = a.points; p.sb = a.sb; p.sn = a.sn; p.sc = a.sc;
     p.feat = a.feat; p.fb = a.fb; p.fn = a.fn; p.fc = a.fc;

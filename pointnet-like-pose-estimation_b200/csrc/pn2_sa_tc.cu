@@ -53,7 +53,7 @@ __global__ void pack_bf16_kernel(TcPackArgs a, unsigned char *__restrict__ packe
                 float v = 0.f;
                 if (n < y.Cout) v = __fadd_rn(__fmul_rn(__fsub_rn(a.b[l][n], a.mu[l][n]), s), a.be[l][n]);
                 bias_out[y.b_off + n] = v;
-                if (l < a.lay.L - 1) {          // bias slice (see pn2_tc.cuh): hi and lo bf16 parts in k = 0, 1
+                if (l < a.lay.L - 1 && !a.lay.split) {          // bias slice (see pn2_tc.cuh): hi and lo bf16 parts in k = 0, 1
                     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
                     const __nv_bfloat16 lo = __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(hi)));
                     __nv_bfloat16 *sl = reinterpret_cast<__nv_bfloat16 *>(packed + y.bs_off);
@@ -74,17 +74,21 @@ __global__ void pack_bf16_kernel(TcPackArgs a, unsigned char *__restrict__ packe
             if (n < y.Cout && src >= 0) v = __fmul_rn(a.w[l][(int64_t)n * cin + src], s);
             // chunk (slab, kb) then canonical no-swizzle K-major inside the chunk
             const int slab = n / y.NS, nl = n % y.NS, kb = k / KBLK, kl = k % KBLK;
-            int64_t off = y.w_off + (int64_t)slab * y.NS * y.K * 2 + (int64_t)kb * y.NS * KBLK * 2;
+            const int sp = a.lay.split ? 2 : 1;
+            int64_t off = y.w_off + sp * ((int64_t)slab * y.NS * y.K * 2 + (int64_t)kb * y.NS * KBLK * 2);
             off += (int64_t)(kl / 8) * (y.NS * 16) + nl * 16 + (kl % 8) * 2;
-            *reinterpret_cast<__nv_bfloat16 *>(packed + off) = __float2bfloat16_rn(v);
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            *reinterpret_cast<__nv_bfloat16 *>(packed + off) = hi;
+            if (a.lay.split)        // fp32 mode: the fp16 remainder in the second image of the chunk (pn2_sa_tcs.cu)
+                *reinterpret_cast<__half *>(packed + off + tc_chunk_bytes(y, kb)) = __float2half_rn(__fsub_rn(v, __bfloat162float(hi)));
         }
     }
 }
 
-int launch_pack_bf16(int L, const int *dims, const void *const *ptrs, float eps, int C, int order, void *packed, cudaStream_t st)
+int launch_pack_bf16(int L, const int *dims, const void *const *ptrs, float eps, int C, int order, void *packed, cudaStream_t st, bool split)
 {
     TcPackArgs a;
-    a.lay = tc_layout(L, dims);
+    a.lay = tc_layout(L, dims, split);
     a.eps = eps; a.C = C; a.D = dims[0] - C; a.order = order;
     for (int l = 0; l <= L; ++l) a.dims[l] = dims[l];
     for (int l = 0; l < L; ++l) {

@@ -2,6 +2,7 @@
 // tcgen05 / mbarrier / bulk-copy PTX wrappers.  Not part of the ABI.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "pn2_common.cuh"
 
 namespace pn2 {
@@ -39,6 +40,7 @@ struct TcLayout {
     int max_chunk;     // bytes of the largest chunk
     int n_chunks;
     int total_bytes;   // weights + fp32 biases + bias slices
+    int split;         // fp32 mode on the tensor cores (pn2_sa_tcs.cu): every chunk is [bf16 hi image | fp16 lo image], twice the bytes
 };
 // Bias slice of a hidden layer (used by the pipelined kernels, pn2_sa_tc2.cu): one extra K = 16 slice of the weight
 // operand, [Npad] rows in the canonical K-major no-swizzle layout (k-groups at Npad*16 bytes), holding
@@ -52,9 +54,11 @@ static __host__ __device__ inline int tc_chunk_bytes(const TcLayer &ly, int kb)
     return ly.NS * kw * 2;
 }
 
-static inline TcLayout tc_layout(int L, const int *dims)
+static inline TcLayout tc_layout(int L, const int *dims, bool split = false)
 {
     TcLayout t;
+    const int sp = split ? 2 : 1;
+    t.split = split ? 1 : 0;
     t.L = L; t.w_bytes = 0; t.bias_floats = 0; t.max_chunk = 0; t.n_chunks = 0;
     int K = rup(dims[0], 16);
     // wide stacks (group_all heads) stream their weights through a small ring next to a large activation
@@ -74,16 +78,16 @@ static inline TcLayout tc_layout(int L, const int *dims)
         y.nslab = y.Npad / y.NS;
         y.nkb = (K + KBLK - 1) / KBLK;
         y.w_off = t.w_bytes; y.b_off = t.bias_floats;
-        t.w_bytes += y.Npad * K * 2;
+        t.w_bytes += y.Npad * K * 2 * sp;
         t.bias_floats += y.Npad;
-        for (int kb = 0; kb < y.nkb; ++kb) { const int c = tc_chunk_bytes(y, kb); if (c > t.max_chunk) t.max_chunk = c; }
+        for (int kb = 0; kb < y.nkb; ++kb) { const int c = sp * tc_chunk_bytes(y, kb); if (c > t.max_chunk) t.max_chunk = c; }
         t.n_chunks += y.nslab * y.nkb;
         K = y.Npad;
     }
     t.total_bytes = t.w_bytes + t.bias_floats * 4;
     for (int l = 0; l < L; ++l) {
         t.ly[l].bs_off = t.total_bytes;
-        if (l < L - 1) t.total_bytes += t.ly[l].Npad * BIAS_SLICE_K * 2;
+        if (l < L - 1 && !split) t.total_bytes += t.ly[l].Npad * BIAS_SLICE_K * 2;
     }
     return t;
 }

@@ -536,3 +536,16 @@ def test_gather_and_scatter_add_rows_vs_torch(nat, B, N, D, S, K):
     exp_g = torch.zeros(B, N, D).scatter_add_(1, flat, (grad * ok).reshape(B, -1, D))
     got_g = nat.scatter_add_rows(grad.cuda(), idx.cuda(), N)
     assert rel_err(got_g.cpu(), exp_g) <= 1e-5                   # fp32 reductions in a different order
+
+
+@pytest.mark.parametrize("env", [{"PN2_F32_FFMA": "1"}, {"PN2_F32_PASSES": "3"}, {"PN2_F32_CLUSTER": "1"}, {"PN2_F32_CLUSTER": "4"}])
+def test_fp32_mode_variants_keep_parity(env):
+    """fp32 mode runs on the tensor cores with split (bf16 hi + fp16 lo) operands, four passes per K step (pn2_sa_tcs.cu).  The
+    process-wide switches select the FFMA kernel instead (PN2_F32_FFMA), three passes, and the cluster size of the weight
+    multicast; every variant must stay within the fp32 tolerance on the fp32 parity cases."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ, **env)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_kernels.py"), os.path.join(root, "tests", "test_gpu_models.py"),
+                        "-m", "gpu", "-q", "-x", "-k", "fp32 and not variants"], env=e, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
