@@ -29,7 +29,7 @@ static int64_t ffma_image_bytes(int L, const int *dims)
     }
     return (n * (int64_t)sizeof(float) + 255) / 256 * 256;
 }
-// fp32 mode carries two images of the folded weights: the FFMA kernel's (this file) and, behind it, the split (bf16 hi, fp16 lo)
+// fp32 mode carries two images of the folded weights: the FFMA kernel's (this file) and, behind it, the split (bf16 hi, bf16 lo)
 // image of the tensor-core kernel (pn2_sa_tcs.cu); the launcher picks the kernel per configuration
 int64_t packed_bytes_f32(int L, const int *dims)
 {

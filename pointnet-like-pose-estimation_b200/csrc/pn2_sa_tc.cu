@@ -79,8 +79,8 @@ __global__ void pack_bf16_kernel(TcPackArgs a, unsigned char *__restrict__ packe
             off += (int64_t)(kl / 8) * (y.NS * 16) + nl * 16 + (kl % 8) * 2;
             const __nv_bfloat16 hi = __float2bfloat16_rn(v);
             *reinterpret_cast<__nv_bfloat16 *>(packed + off) = hi;
-            if (a.lay.split)        // fp32 mode: the fp16 remainder in the second image of the chunk (pn2_sa_tcs.cu)
-                *reinterpret_cast<__half *>(packed + off + tc_chunk_bytes(y, kb)) = __float2half_rn(__fsub_rn(v, __bfloat162float(hi)));
+            if (a.lay.split)        // fp32 mode: the bf16 remainder in the second image of the chunk (pn2_sa_tcs.cu)
+                *reinterpret_cast<__nv_bfloat16 *>(packed + off + tc_chunk_bytes(y, kb)) = __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(hi)));
         }
     }
 }

@@ -3,13 +3,13 @@
 // (reference: model/pointnet2_utils.py:166-172 and :204-218 at the reference's own precision; BatchNorm folded by pn2_pack_weights).
 //
 // Precision.  Every fp32 value v (activation or folded weight) is carried as v = hi + lo + d with hi = bf16(v) and
-// lo = fp16(v - hi): |v - hi| <= 2^-9 |v| and fp16 keeps 11 bits of it, so |d| <= 2^-20 |v| (or 2^-25 absolute once lo falls into
-// fp16's subnormals, far below the 1e-5 of max|y| this mode promises).  A product x w is the sum of the four exact
-// tensor-core products xh wh + xh wl + xl wh + xl wl accumulated in fp32 in TMEM (kind::f16 takes bf16 and fp16 operands in
-// any combination: the two formats are fields of the instruction descriptor), leaving only the d terms: ~2^-19 relative per
-// product, random in sign -- measured 3e-7 .. 7e-7 of max|y| through three layers against 1e-7 .. 3e-7 for fp32 FFMA sums in
-// another order (tests/test_gpu_kernels.py::test_sa_fused_vs_oracle, fp32 cases).  With PN2_F32_PASSES=3 the xl wl pass is
-// dropped (2^-18 per product, ~3e-6).
+// lo = bf16(v - hi): |v - hi| <= 2^-9 |v| and the second rounding keeps 8 more bits, so |d| <= 2^-18 |v| -- both parts have fp32's
+// exponent range, so nothing can overflow or flush that would not in fp32.  A product x w is the sum of the four exact
+// tensor-core products xh wh + xh wl + xl wh + xl wl accumulated in fp32 in TMEM, leaving only the d terms: <= 2^-17 relative
+// per product, random in sign over the K terms of a sum -- measured ~3e-6 of max|y| through three layers (the tolerance of this
+// mode is 1e-5; fp32 FFMA sums in another order differ by 1e-7 .. 3e-7).  With PN2_F32_PASSES=3 the xl wl pass is dropped
+// (another 2^-18 per product, ~5e-6).  (bf16 hi + fp16 lo would reach 5e-7, but kind::f16 rejects operands of different
+// formats in one instruction: illegal instruction on sm_100a.)
 //
 // Shape.  Same tile / TMEM / epilogue structure as the streaming bf16 kernel (pn2_sa_tc.cu): 128 grouped rows = the 128 TMEM
 // lanes, one row per epilogue thread, weights either resident or streamed through an mbarrier ring by a producer warp (one
@@ -18,7 +18,6 @@
 // gather and the three epilogues.  Operand bytes double (hi + lo), so wide stacks (-> 512 hidden channels) use 64-row
 // tiles: the A descriptor still spans 128 rows (rows 64..127 alias the next k-group: garbage accumulator lanes nobody
 // reads), the activations of a tile then fit beside the weight ring.
-#include <cuda_fp16.h>
 #include <stdlib.h>
 #include "pn2_tc.cuh"
 
@@ -31,7 +30,7 @@ struct TcsParams {
     const float *feat;   int64_t fb, fn, fc;
     const float *centres; const int32_t *idx32;
     int N, S, K, C, D, order;
-    TcLayout lay;                    // split layout: every chunk = [bf16 hi image | fp16 lo image]
+    TcLayout lay;                    // split layout: every chunk = [bf16 hi image | bf16 lo image]
     const unsigned char *packed;
     float *out; int64_t ob, os; int co_off;
     int64_t G, tiles, n_iter;
@@ -44,23 +43,17 @@ struct TcsParams {
     int pool_cols, passes;
 };
 
-// bf16 hi parts (packed pair) and fp16 lo parts of two fp32 values
+// bf16 hi parts and bf16 lo parts (packed pairs) of two fp32 values
 __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo)
 {
     hi = pack_bf16x2(a, b);
     const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xffff0000u);
-    const __half2 l = __floats2half2_rn(a - ah, b - bh);        // a - ah is exact in fp32
-    lo = *reinterpret_cast<const uint32_t *>(&l);
+    lo = pack_bf16x2(a - ah, b - bh);                            // a - ah is exact in fp32
 }
 __device__ __forceinline__ void split8(float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7, uint4 &hi, uint4 &lo)
 {
     split2(v0, v1, hi.x, lo.x); split2(v2, v3, hi.y, lo.y);
     split2(v4, v5, hi.z, lo.z); split2(v6, v7, hi.w, lo.w);
-}
-// instruction descriptor: D = f32, M = 128, N = n, K-major operands; formats 1 = bf16, 0 = fp16
-__device__ __forceinline__ uint32_t instr_desc_fmt(int n, uint32_t a_fmt, uint32_t b_fmt)
-{
-    return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 2) sa_tcs_kernel(const TcsParams p)
@@ -235,7 +228,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tcs_kernel(const TcsParams p
                         const __nv_bfloat16 h = __float2bfloat16_rn(x);
                         unsigned char *dst = A0 + (size_t)(k / 8) * a_lbo + r * 16 + (k % 8) * 2;
                         *reinterpret_cast<__nv_bfloat16 *>(dst) = h;
-                        *reinterpret_cast<__half *>(dst + lo_off) = __float2half_rn(x - __bfloat162float(h));
+                        *reinterpret_cast<__nv_bfloat16 *>(dst + lo_off) = __float2bfloat16_rn(x - __bfloat162float(h));
                     }
                 }
             }
@@ -252,8 +245,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tcs_kernel(const TcsParams p
                 unsigned char *a_out = smem + out_off;
                 const uint32_t out_lo = (uint32_t)p.a_lo[a1_off ? (ib ^ 1) : 0];
                 const int slabs_per_round = p.tmem_cols / ly.NS;
-                const uint32_t id_bb = instr_desc_fmt(ly.NS, 1u, 1u), id_bh = instr_desc_fmt(ly.NS, 1u, 0u),
-                               id_hb = instr_desc_fmt(ly.NS, 0u, 1u), id_hh = instr_desc_fmt(ly.NS, 0u, 0u);
+                const uint32_t idesc = instr_desc_bf16(ly.NS);
                 for (int sl0 = 0; sl0 < ly.nslab; sl0 += slabs_per_round) {
                     const int sl1 = min(ly.nslab, sl0 + slabs_per_round);
                     tc_fence_before();
@@ -285,10 +277,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tcs_kernel(const TcsParams p
                                     for (int j = 0; j < kw / 16; ++j) {
                                         const uint64_t dah = mk_desc64(ah + (uint32_t)j * a_step, DESC_HI_NS), dal = mk_desc64(al + (uint32_t)j * a_step, DESC_HI_NS);
                                         const uint64_t dbh = mk_desc64(bh + (uint32_t)j * b_step, DESC_HI_NS), dbl = mk_desc64(bl + (uint32_t)j * b_step, DESC_HI_NS);
-                                        umma_bf16(d_tmem, dah, dbh, id_bb, (kb | j) ? 1u : 0u);
-                                        umma_bf16(d_tmem, dah, dbl, id_bh, 1u);
-                                        umma_bf16(d_tmem, dal, dbh, id_hb, 1u);
-                                        if (p.passes > 3) umma_bf16(d_tmem, dal, dbl, id_hh, 1u);
+                                        umma_bf16(d_tmem, dah, dbh, idesc, (kb | j) ? 1u : 0u);
+                                        umma_bf16(d_tmem, dah, dbl, idesc, 1u);
+                                        umma_bf16(d_tmem, dal, dbh, idesc, 1u);
+                                        if (p.passes > 3) umma_bf16(d_tmem, dal, dbl, idesc, 1u);
                                     }
                                     if (!p.resident) umma_commit(empty_bar + s);
                                 }

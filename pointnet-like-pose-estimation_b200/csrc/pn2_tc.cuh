@@ -2,7 +2,6 @@
 // tcgen05 / mbarrier / bulk-copy PTX wrappers.  Not part of the ABI.
 #pragma once
 #include <cuda_bf16.h>
-#include <cuda_fp16.h>
 #include "pn2_common.cuh"
 
 namespace pn2 {
@@ -40,7 +39,7 @@ struct TcLayout {
     int max_chunk;     // bytes of the largest chunk
     int n_chunks;
     int total_bytes;   // weights + fp32 biases + bias slices
-    int split;         // fp32 mode on the tensor cores (pn2_sa_tcs.cu): every chunk is [bf16 hi image | fp16 lo image], twice the bytes
+    int split;         // fp32 mode on the tensor cores (pn2_sa_tcs.cu): every chunk is [bf16 hi image | bf16 lo image], twice the bytes
 };
 // Bias slice of a hidden layer (used by the pipelined kernels, pn2_sa_tc2.cu): one extra K = 16 slice of the weight
 // operand, [Npad] rows in the canonical K-major no-swizzle layout (k-groups at Npad*16 bytes), holding
