@@ -174,19 +174,35 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tcs_kernel(const TcsParams p
                 const int K0 = lay.ly[0].K;
                 if (p.feat_fast) {
                     const int cpr = D / 8;
-                    for (int i = tid; i < TR * cpr; i += TC_CTHREADS) {
-                        const int r = i % TR, kg = i / TR;
-                        const int n = s_n[r];
-                        uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
-                        if (n >= 0) {
-                            const float *f = p.feat + (int64_t)(s_g[r] / p.S) * p.fb + (int64_t)n * p.fn + kg * 8;
-                            const float4 x = __ldg(reinterpret_cast<const float4 *>(f));
-                            const float4 y = __ldg(reinterpret_cast<const float4 *>(f) + 1);
-                            split8(x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w, hi, lo);
+                    // four 32-byte segments per thread in flight before the first store (the loads are L2 / HBM latency)
+                    for (int i0 = tid; i0 < TR * cpr; i0 += 4 * TC_CTHREADS) {
+                        float4 x[4], y[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = i0 + u * TC_CTHREADS;
+                            x[u] = y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (i < TR * cpr) {
+                                const int r = i % TR, kg = i / TR;
+                                const int n = s_n[r];
+                                if (n >= 0) {
+                                    const float *f = p.feat + (int64_t)(s_g[r] / p.S) * p.fb + (int64_t)n * p.fn + kg * 8;
+                                    x[u] = __ldg(reinterpret_cast<const float4 *>(f));
+                                    y[u] = __ldg(reinterpret_cast<const float4 *>(f) + 1);
+                                }
+                            }
                         }
-                        unsigned char *dst = A0 + (size_t)kg * a_lbo + r * 16;
-                        *reinterpret_cast<uint4 *>(dst) = hi;
-                        *reinterpret_cast<uint4 *>(dst + lo_off) = lo;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = i0 + u * TC_CTHREADS;
+                            if (i < TR * cpr) {
+                                const int r = i % TR, kg = i / TR;
+                                uint4 hi, lo;
+                                split8(x[u].x, x[u].y, x[u].z, x[u].w, y[u].x, y[u].y, y[u].z, y[u].w, hi, lo);
+                                unsigned char *dst = A0 + (size_t)kg * a_lbo + r * 16;
+                                *reinterpret_cast<uint4 *>(dst) = hi;
+                                *reinterpret_cast<uint4 *>(dst + lo_off) = lo;
+                            }
+                        }
                     }
                     if (tid < TR) {
                         const int r = tid, n = s_n[r];
@@ -429,9 +445,13 @@ bool tcs_plan(int K, int L, const int *dims, TcsPlan *pl)
         };
         TcsPlan c;
         const bool two_ok = max_ns <= 256;
+        // two CTAs per SM first (one CTA's gather / epilogue under the other's MMAs: the schedule inside a CTA is lock-step),
+        // with ping-pong activation buffers or, when those do not fit twice, one buffer overwritten in place
         if (two_ok && eval(256, 2, true, false, &c)) { *pl = c; return true; }
+        if (two_ok && eval(256, 2, true, true, &c)) { *pl = c; return true; }
         if (eval(512, 1, true, false, &c)) { *pl = c; return true; }
         if (two_ok && eval(256, 2, false, false, &c)) { *pl = c; return true; }
+        if (two_ok && eval(256, 2, false, true, &c)) { *pl = c; return true; }
         if (eval(512, 1, false, false, &c)) { *pl = c; return true; }
         if (eval(512, 1, true, true, &c)) { *pl = c; return true; }
         if (eval(512, 1, false, true, &c)) { *pl = c; return true; }
