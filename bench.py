@@ -81,26 +81,6 @@ def peaks():
     return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
-def measure_tf32_peak(dev):
-    """TF32 tensor peak measured the way MEASURED_PEAKS.json measures bf16: torch.matmul 8192^3, best of 10 (burst)."""
-    prev = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = True
-    try:
-        a = torch.randn(8192, 8192, device=dev)
-        b = torch.randn(8192, 8192, device=dev)
-        best = 1e9
-        for _ in range(12):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            torch.matmul(a, b)
-            e1.record()
-            torch.cuda.synchronize(dev)
-            best = min(best, e0.elapsed_time(e1))
-        return 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = prev
-
-
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed regions run."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -247,7 +227,7 @@ def summarise_trace(trace, steps):
     return table, top_key, per[top_key]
 
 
-def roofline_of(top_key, top, prec, pk, region_s, clk, tf32_peak=None):
+def roofline_of(top_key, top, prec, pk, region_s, clk, fp32_tc=False):
     m = top["meta"]
     dur_s = 1e-3 * top["ms"] / top["launches"]
     if top["name"] == "sa_fused":
@@ -259,10 +239,11 @@ def roofline_of(top_key, top, prec, pk, region_s, clk, tf32_peak=None):
             peak, src = pick_peak(pk, region_s, clk)
             roof.update(peak=peak, frac=ach / peak, peak_source=src,
                         frac_vs_burst=ach / pk["bf16_burst"], frac_vs_sustained=ach / pk["bf16_sustained"])
-        elif tf32_peak:
-            roof.update(peak=tf32_peak, frac=ach / tf32_peak,
-                        peak_source="TF32 tensor peak measured in this run (torch.matmul 8192^3, allow_tf32, best of 12); the fp32 mode "
-                                    "issues 3 TF32 MMAs per algorithmic MMA, so its ceiling is a third of this")
+        elif fp32_tc:
+            peak, src = pick_peak(pk, region_s, clk)
+            roof.update(peak=peak / 4, frac=ach / (peak / 4), frac_vs_burst=ach / (pk["bf16_burst"] / 4), frac_vs_sustained=ach / (pk["bf16_sustained"] / 4),
+                        peak_source=src + " / 4: fp32 mode runs every algorithmic MMA as four bf16 tensor-core passes on split (hi, lo) operands "
+                                          "(pn2_sa_tcs.cu), so its ceiling is a quarter of the bf16 peak")
         else:
             sm = (clk or {}).get("sm_mhz") or 1965.0
             peak = 148 * 128 * 2 * sm * 1e6 / 1e12
@@ -471,7 +452,6 @@ def run_forward(cfg_id, args, R):
                                                    "cuda_graph_clouds_per_s": cb * 20 / (1e-3 * ev0.elapsed_time(ev1))}
         if cfg_id == 0:
             extra.update(micro_cfg2(dev, be))
-    tf32_peak = measure_tf32_peak(dev) if (R.rank == 0 and not args.quick) else None
     clk = clocks.stop() if clocks else None
     if R.rank != 0:
         R.finish()
@@ -485,16 +465,15 @@ def run_forward(cfg_id, args, R):
                "e2e": {"value": B * R.world * K / (1e-3 * m["ms_e2e"]), "unit": "clouds/s", "h2d_bytes_per_step": B * 3 * npts * 4,
                        "d2h_bytes_per_step": B * 7 * 4 + B * 8},
                "gpu_launches": m["launches"],
-               "roofline": roofline_of(top_key, top, prec, pk, 1e-3 * m["ms"], clk, tf32_peak if prec == "fp32" and fp32_on_tensor_cores(kernels) else None),
+               "roofline": roofline_of(top_key, top, prec, pk, 1e-3 * m["ms"], clk, prec == "fp32" and fp32_on_tensor_cores()),
                "model_tflops": value * flops / 1e12, "kernels": kernels}
         if prec == "bf16":
             peak, _ = pick_peak(pk, 1e-3 * m["ms"], clk)
             rec["model_tensor_frac"] = value / R.world * flops / 1e12 / peak
         return rec
 
-    def fp32_on_tensor_cores(kernels):
-        import _pn2_native
-        return bool(getattr(_pn2_native, "FP32_ON_TENSOR_CORES", False))
+    def fp32_on_tensor_cores():
+        return os.environ.get("PN2_F32_FFMA") is None
 
     cpu = None
     if R.world == 1 and not args.no_cpu_baseline and not args.quick:
@@ -516,7 +495,6 @@ def run_forward(cfg_id, args, R):
             "cpu_baseline": cpu}
     if second is not None:
         line[f"{other}_mode"] = record(second, other)
-        line[f"{other}_mode"]["tf32_peak_tflops_measured"] = tf32_peak
     line.update(extra)
     print(json.dumps(line))
     R.finish()

@@ -73,14 +73,15 @@ __global__ void pack_bf16_kernel(TcPackArgs a, unsigned char *__restrict__ packe
             float v = 0.f;
             if (n < y.Cout && src >= 0) v = __fmul_rn(a.w[l][(int64_t)n * cin + src], s);
             // chunk (slab, kb) then canonical no-swizzle K-major inside the chunk
-            const int slab = n / y.NS, nl = n % y.NS, kb = k / KBLK, kl = k % KBLK;
+            const int kblk = a.lay.kblk;
+            const int slab = n / y.NS, nl = n % y.NS, kb = k / kblk, kl = k % kblk;
             const int sp = a.lay.split ? 2 : 1;
-            int64_t off = y.w_off + sp * ((int64_t)slab * y.NS * y.K * 2 + (int64_t)kb * y.NS * KBLK * 2);
+            int64_t off = y.w_off + sp * ((int64_t)slab * y.NS * y.K * 2 + (int64_t)kb * y.NS * kblk * 2);
             off += (int64_t)(kl / 8) * (y.NS * 16) + nl * 16 + (kl % 8) * 2;
             const __nv_bfloat16 hi = __float2bfloat16_rn(v);
             *reinterpret_cast<__nv_bfloat16 *>(packed + off) = hi;
             if (a.lay.split)        // fp32 mode: the bf16 remainder in the second image of the chunk (pn2_sa_tcs.cu)
-                *reinterpret_cast<__nv_bfloat16 *>(packed + off + tc_chunk_bytes(y, kb)) = __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(hi)));
+                *reinterpret_cast<__nv_bfloat16 *>(packed + off + tc_chunk_bytes(y, kb, kblk)) = __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(hi)));
         }
     }
 }

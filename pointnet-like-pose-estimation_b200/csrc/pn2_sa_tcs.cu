@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tcs_kernel(const TcsParams p
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const TcLayout &lay = p.lay;
-    const int TR = p.TR, a_lbo = p.a_lbo;
+    const int TR = p.TR, a_lbo = p.a_lbo, kblk = p.lay.kblk;
 
     if (tid == 0) {
         for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); mbar_init(slot_free + s, (uint32_t)p.cs); }
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tcs_kernel(const TcsParams p
                 for (int l = 0; l < lay.L; ++l)
                     for (int sl = 0; sl < lay.ly[l].nslab; ++sl)
                         for (int kb = 0; kb < lay.ly[l].nkb; ++kb) {
-                            const int cb = 2 * tc_chunk_bytes(lay.ly[l], kb);
+                            const int cb = 2 * tc_chunk_bytes(lay.ly[l], kb, lay.kblk);
                             bulk_g2s(Wsm + off, p.packed + off, (uint32_t)cb, full_bar);
                             off += cb;
                         }
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tcs_kernel(const TcsParams p
                     for (int l = 0; l < lay.L; ++l)
                         for (int sl = 0; sl < lay.ly[l].nslab; ++sl)
                             for (int kb = 0; kb < lay.ly[l].nkb; ++kb, ++q) {
-                                const int cb = 2 * tc_chunk_bytes(lay.ly[l], kb);
+                                const int cb = 2 * tc_chunk_bytes(lay.ly[l], kb, lay.kblk);
                                 const int s = q % p.nstage;
                                 const uint32_t ph = (q / p.nstage) & 1u;
                                 mbar_wait(empty_bar + s, ph ^ 1u);
@@ -271,11 +271,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tcs_kernel(const TcsParams p
                         for (int sl = sl0; sl < sl1; ++sl) {
                             const uint32_t d_tmem = tmem_base + (uint32_t)((sl - sl0) * ly.NS);
                             for (int kb = 0; kb < ly.nkb; ++kb) {
-                                const int cb = tc_chunk_bytes(ly, kb);         // bytes of one (hi or lo) image of the chunk
+                                const int cb = tc_chunk_bytes(ly, kb, kblk);   // bytes of one (hi or lo) image of the chunk
                                 uint32_t w_addr;
                                 int s = 0;
                                 if (p.resident) {
-                                    w_addr = smem_u32(Wsm) + (uint32_t)(ly.w_off + 2 * (sl * ly.NS * ly.K * 2 + kb * ly.NS * KBLK * 2));
+                                    w_addr = smem_u32(Wsm) + (uint32_t)(ly.w_off + 2 * (sl * ly.NS * ly.K * 2 + kb * ly.NS * kblk * 2));
                                 } else {
                                     s = wq % p.nstage;
                                     mbar_wait(full_bar + s, (wq / p.nstage) & 1u);
@@ -283,9 +283,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tcs_kernel(const TcsParams p
                                     w_addr = smem_u32(Wsm) + (uint32_t)(s * p.stage_bytes);
                                     ++wq;
                                 }
-                                const int kw = min(KBLK, ly.K - kb * KBLK);
-                                const uint32_t ah = desc_lo_ns(a_in + (uint32_t)(kb * 8 * a_lbo), (uint32_t)a_lbo);
-                                const uint32_t al = desc_lo_ns(a_in_lo + (uint32_t)(kb * 8 * a_lbo), (uint32_t)a_lbo);
+                                const int kw = min(kblk, ly.K - kb * kblk);
+                                const uint32_t ah = desc_lo_ns(a_in + (uint32_t)(kb * (kblk / 8) * a_lbo), (uint32_t)a_lbo);
+                                const uint32_t al = desc_lo_ns(a_in_lo + (uint32_t)(kb * (kblk / 8) * a_lbo), (uint32_t)a_lbo);
                                 const uint32_t bh = desc_lo_ns(w_addr, (uint32_t)(ly.NS * 16));
                                 const uint32_t bl = desc_lo_ns(w_addr + (uint32_t)cb, (uint32_t)(ly.NS * 16));
                                 const uint32_t a_step = (uint32_t)(2 * a_lbo / 16), b_step = (uint32_t)(2 * ly.NS);

@@ -39,6 +39,7 @@ struct TcLayout {
     int max_chunk;     // bytes of the largest chunk
     int n_chunks;
     int total_bytes;   // weights + fp32 biases + bias slices
+    int kblk;          // k extent of a weight chunk: KBLK, or 32 in the split layout (16 KB hi + lo chunks at NS = 128)
     int split;         // fp32 mode on the tensor cores (pn2_sa_tcs.cu): every chunk is [bf16 hi image | bf16 lo image], twice the bytes
 };
 // Bias slice of a hidden layer (used by the pipelined kernels, pn2_sa_tc2.cu): one extra K = 16 slice of the weight
@@ -47,9 +48,9 @@ struct TcLayout {
 // are 1.0 it adds the folded bias inside the MMA (to ~2^-17 relative), so the epilogue is ReLU + convert only.
 constexpr int BIAS_SLICE_K = 16;
 
-static __host__ __device__ inline int tc_chunk_bytes(const TcLayer &ly, int kb)
+static __host__ __device__ inline int tc_chunk_bytes(const TcLayer &ly, int kb, int kblk = KBLK)
 {
-    const int kw = (ly.K - kb * KBLK) < KBLK ? (ly.K - kb * KBLK) : KBLK;
+    const int kw = (ly.K - kb * kblk) < kblk ? (ly.K - kb * kblk) : kblk;
     return ly.NS * kw * 2;
 }
 
@@ -57,12 +58,14 @@ static inline TcLayout tc_layout(int L, const int *dims, bool split = false)
 {
     TcLayout t;
     const int sp = split ? 2 : 1;
+    const int kblk = split ? 32 : KBLK;
     t.split = split ? 1 : 0;
+    t.kblk = kblk;
     t.L = L; t.w_bytes = 0; t.bias_floats = 0; t.max_chunk = 0; t.n_chunks = 0;
     int K = rup(dims[0], 16);
     // wide stacks (group_all heads) stream their weights through a small ring next to a large activation
     // buffer: keep the chunks at 16 KB there
-    int ns_cap = 256;
+    int ns_cap = split ? 128 : 256;
     for (int l = 0; l < L; ++l) if (rup(dims[l], 16) > 256) ns_cap = 128;
     for (int l = 0; l < L; ++l) {
         TcLayer &y = t.ly[l];
@@ -75,11 +78,11 @@ static inline TcLayout tc_layout(int L, const int *dims, bool split = false)
         if (y.Npad <= ns_cap) y.NS = y.Npad;
         else for (int ns = ns_cap; ns >= 32; ns >>= 1) if (y.Npad % ns == 0) { y.NS = ns; break; }
         y.nslab = y.Npad / y.NS;
-        y.nkb = (K + KBLK - 1) / KBLK;
+        y.nkb = (K + kblk - 1) / kblk;
         y.w_off = t.w_bytes; y.b_off = t.bias_floats;
         t.w_bytes += y.Npad * K * 2 * sp;
         t.bias_floats += y.Npad;
-        for (int kb = 0; kb < y.nkb; ++kb) { const int c = sp * tc_chunk_bytes(y, kb); if (c > t.max_chunk) t.max_chunk = c; }
+        for (int kb = 0; kb < y.nkb; ++kb) { const int c = sp * tc_chunk_bytes(y, kb, kblk); if (c > t.max_chunk) t.max_chunk = c; }
         t.n_chunks += y.nslab * y.nkb;
         K = y.Npad;
     }
