@@ -58,7 +58,11 @@ static inline TcLayout tc_layout(int L, const int *dims, bool split = false)
 {
     TcLayout t;
     const int sp = split ? 2 : 1;
-    const int kblk = split ? 32 : KBLK;
+    // split layout: 32-wide chunks (16 KB of hi + lo at NS = 128) so that an sa2-sized stack keeps two CTAs per SM beside its
+    // ring (16.2 -> 10.7 ms); wide stacks stream megabytes per tile with one CTA per SM and want the larger chunks (3.2 vs 4.5 ms)
+    bool wide = false;
+    for (int l = 0; l <= L; ++l) if (rup(dims[l], 16) > 256) wide = true;
+    const int kblk = (split && !wide) ? 32 : KBLK;
     t.split = split ? 1 : 0;
     t.kblk = kblk;
     t.L = L; t.w_bytes = 0; t.bias_floats = 0; t.max_chunk = 0; t.n_chunks = 0;
