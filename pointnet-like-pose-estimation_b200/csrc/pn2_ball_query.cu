@@ -468,6 +468,269 @@ __global__ void ball_query_generic_kernel(const float *__restrict__ centres, int
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Ball query with an exact spatial cull (small radii): the points of the cloud are bucketed into a uniform grid over their
+// bounding box whose cells are at least R_c = 1.01 * sqrt(r^2 + e) wide, e an upper bound of the rounding error of the
+// reference's expanded-form distance (so a point the fp32 formula puts inside the ball is geometrically within R_c of the
+// centre and therefore in one of the 27 cells around the centre's cell; the 1 % slack absorbs the rounding of the cell index
+// itself).  A warp evaluates one centre against the points of those cells only -- with the SAME distance arithmetic as the
+// scan kernel -- and sets a bit per hit in a per-warp N-bit mask; the first K set bits in index order are the reference's
+// "first K in ascending index order" (:86-89).  The cull only decides WHICH pairs are evaluated, never the result of a pair:
+// bit-identical rows.  Clouds with non-finite coordinates, and centres far outside the cloud, take every point as candidate.
+constexpr int BQC_WARPS = 16;
+constexpr int BQC_THREADS = BQC_WARPS * 32;
+constexpr int BQC_GMAX = 16;
+constexpr int BQC_CELLS = BQC_GMAX * BQC_GMAX * BQC_GMAX;
+
+struct BqGrid {
+    float lo[3], inv_w[3];
+    int G[3];
+    int full;            // every point is a candidate (non-finite cloud)
+    float m2cap;         // 4 * max |p|^2: centres beyond it scan everything
+};
+
+template <int C>
+__global__ void __launch_bounds__(BQC_THREADS)
+ball_query_cell_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, int64_t csc,
+                       const float *__restrict__ points, int64_t sb, int64_t sn, int64_t sc,
+                       int S, int N, int cpc /*centres per CTA*/, float r2, int K,
+                       int64_t *__restrict__ idx64, int32_t *__restrict__ idx32, int32_t *__restrict__ empty_flag)
+{
+    extern __shared__ float smem[];
+    const int NW = (N + 31) >> 5;                       // words of a hit mask
+    float *sp = smem;                                   // [C][N]
+    float *sp2 = sp + (size_t)C * N;                    // [N]
+    int *order = reinterpret_cast<int *>(sp2 + N);      // [N] point indices sorted by cell
+    int *cstart = order + N;                            // [BQC_CELLS + 1]
+    unsigned *words = reinterpret_cast<unsigned *>(cstart + BQC_CELLS + 1);    // [BQC_WARPS][NW]
+    int *stage = reinterpret_cast<int *>(words + (size_t)BQC_WARPS * NW);       // [BQC_WARPS][K]
+    int *rs = stage + (size_t)BQC_WARPS * K;                                     // [BQC_WARPS][20]: 9 x (start, exclusive prefix)
+    __shared__ float red[BQC_WARPS][8];
+    __shared__ BqGrid grid;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    const float *P = points + (int64_t)b * sb;
+    const bool pcontig = (sc == 1);
+
+    // ---- stage the cloud (same arithmetic as ball_query_kernel), bounding box, largest norm, finiteness ---------------------
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY}, m2 = 0.f;
+    bool fin = true;
+    for (int n = tid; n < N; n += BQC_THREADS) {
+        float v[C];
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            v[k] = __ldg(P + (int64_t)n * sn + (int64_t)k * sc);
+            sp[k * N + n] = v[k];
+            fin = fin && fabsf(v[k]) <= 3.0e38f;
+        }
+        const float q = sqnorm<C>(v, pcontig, n >= (N & ~31));
+        sp2[n] = q;
+        m2 = fmaxf(m2, q);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { mn[k] = fminf(mn[k], v[k]); mx[k] = fmaxf(mx[k], v[k]); }
+    }
+    for (int i = tid; i < BQC_WARPS * NW; i += BQC_THREADS) words[i] = 0u;
+    for (int i = tid; i <= BQC_CELLS; i += BQC_THREADS) cstart[i] = 0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+            mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+        }
+        m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+    }
+    const bool all_fin = __syncthreads_and(fin ? 1 : 0) != 0;
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { red[warp][k] = mn[k]; red[warp][3 + k] = mx[k]; }
+        red[warp][6] = m2;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float lo[3], hi[3], M2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { lo[k] = INFINITY; hi[k] = -INFINITY; }
+        for (int w = 0; w < BQC_WARPS; ++w) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], red[w][k]); hi[k] = fmaxf(hi[k], red[w][3 + k]); }
+            M2 = fmaxf(M2, red[w][6]);
+        }
+        const bool ok = all_fin && M2 <= 1.0e30f && r2 >= 0.f && r2 <= 1.0e30f;
+        grid.full = ok ? 0 : 1;
+        grid.m2cap = 4.0f * M2;
+        // |d_fp32 - |s - p|^2| <= u (4C + 8) max(|s|^2, |p|^2) with u = 2^-24; centres are admitted up to |s|^2 = 4 max|p|^2
+        // and the bound is doubled once more
+        const float err = 1.1920929e-7f * (4 * C + 8) * 4.0f * M2;
+        const float h = 1.01f * sqrtf(r2 + err) + 1.0e-30f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float ext = ok ? hi[k] - lo[k] : 0.f;
+            float g = floorf(fminf(ext / h, (float)BQC_GMAX));
+            if (!(g >= 1.f)) g = 1.f;
+            grid.G[k] = (int)g;
+            grid.lo[k] = ok ? lo[k] : 0.f;
+            grid.inv_w[k] = (ok && ext > 0.f) ? g / ext : 0.f;
+        }
+    }
+    __syncthreads();
+    const BqGrid gr = grid;
+    const int G0 = gr.G[0], G1 = gr.G[1], G2 = gr.G[2];
+    auto cell_coord = [&](float x, int k, int Gk) -> int {       // unclamped cell coordinate, limited to [-2, Gk + 1]
+        float c = floorf((x - gr.lo[k]) * gr.inv_w[k]);
+        c = fminf(fmaxf(c, -2.f), (float)(Gk + 1));
+        return (int)c;
+    };
+    auto point_cell = [&](int n) -> int {
+        const int cx = min(G0 - 1, max(0, cell_coord(sp[n], 0, G0)));
+        const int cy = min(G1 - 1, max(0, cell_coord(sp[N + n], 1, G1)));
+        const int cz = min(G2 - 1, max(0, cell_coord(sp[2 * N + n], 2, G2)));
+        return (cz * G1 + cy) * G0 + cx;
+    };
+    // ---- counting sort of the point indices by cell ---------------------------------------------------------------------------
+    const int ncell = G0 * G1 * G2;
+    if (!gr.full) {
+        for (int n = tid; n < N; n += BQC_THREADS) atomicAdd(&cstart[point_cell(n)], 1);
+        __syncthreads();
+        // exclusive scan of the counts (ncell <= 4096 = 512 threads x 8)
+        int loc[8], sum = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const int c = tid * 8 + i; loc[i] = c < ncell ? cstart[c] : 0; sum += loc[i]; }
+        int inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        __shared__ int wsum[BQC_WARPS];
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        int base = 0;
+        for (int w = 0; w < warp; ++w) base += wsum[w];
+        int run = base + inc - sum;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const int c = tid * 8 + i; if (c < ncell) cstart[c] = run; run += loc[i]; }
+        __syncthreads();
+        // scatter: the running cursor of cell c ends at the start of cell c + 1
+        for (int n = tid; n < N; n += BQC_THREADS) order[atomicAdd(&cstart[point_cell(n)], 1)] = n;
+        __syncthreads();
+    }
+    // start of cell c = (c ? cstart[c - 1] : 0); end of cell c = cstart[c]
+    auto cell_begin = [&](int c) -> int { return c ? cstart[c - 1] : 0; };
+
+    // ---- centres: one warp per centre -----------------------------------------------------------------------------------------
+    unsigned *wm = words + (size_t)warp * NW;
+    int *stg = stage + (size_t)warp * K;
+    int *wr = rs + warp * 20;
+    const int s_begin = blockIdx.x * cpc;
+    const int s_end = min(S, s_begin + cpc);
+    const int WPL = (NW + 31) >> 5;                     // mask words per lane at emission
+    for (int sidx = s_begin + warp; sidx < s_end; sidx += BQC_WARPS) {
+        float sc_[C];
+#pragma unroll
+        for (int k = 0; k < C; ++k) sc_[k] = __ldg(centres + (int64_t)b * csb + (int64_t)sidx * csn + (int64_t)k * csc);
+        const float s2 = sqnorm<C>(sc_, csc == 1, sidx >= (S & ~31));
+        const bool full = gr.full || !(s2 <= gr.m2cap);            // NaN / far centres: every point is a candidate
+        int T = N;
+        if (!full) {
+            const int cx = cell_coord(sc_[0], 0, G0), cy = cell_coord(sc_[1], 1, G1), cz = cell_coord(sc_[2], 2, G2);
+            int start = 0, len = 0;
+            if (lane < 9) {
+                const int y = cy + (lane % 3) - 1, z = cz + (lane / 3) - 1;
+                const int x0 = max(cx - 1, 0), x1 = min(cx + 1, G0 - 1);
+                if (y >= 0 && y < G1 && z >= 0 && z < G2 && x0 <= x1) {
+                    const int c0 = (z * G1 + y) * G0 + x0, c1 = (z * G1 + y) * G0 + x1;
+                    start = cell_begin(c0);
+                    len = cstart[c1] - start;
+                }
+            }
+            int inc = len;
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            if (lane < 9) { wr[2 * lane] = start; wr[2 * lane + 1] = inc - len; }
+            T = __shfl_sync(0xffffffffu, inc, 8);
+            __syncwarp();
+        }
+        for (int i0 = 0; i0 < T; i0 += 32) {
+            const int i = i0 + lane;
+            if (i < T) {
+                int n = i;
+                if (!full) {
+                    int j = 0;
+#pragma unroll
+                    for (int t = 1; t < 9; ++t) j += (i >= wr[2 * t + 1]) ? 1 : 0;      // exclusive prefixes are non-decreasing
+                    n = order[wr[2 * j] + (i - wr[2 * j + 1])];
+                }
+                float dot = __fmul_rn(sc_[0], sp[n]);
+#pragma unroll
+                for (int k = 1; k < C; ++k) dot = __fmaf_rn(sc_[k], sp[k * N + n], dot);
+                float d = __fmaf_rn(-2.0f, dot, s2);        // fl(-2 dot + |s|^2): -2 dot is exact, one rounding either way
+                d = __fadd_rn(d, sp2[n]);
+                if (!(d > r2)) atomicOr(&wm[n >> 5], 1u << (n & 31));
+            }
+        }
+        __syncwarp();
+        // ---- the first K set bits in index order ------------------------------------------------------------------------------
+        int cnt = 0;
+        for (int w = 0; w < WPL; ++w) { const int wi = lane * WPL + w; if (wi < NW) cnt += __popc(wm[wi]); }
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        const int total = __shfl_sync(0xffffffffu, inc, 31);
+        int pos = inc - cnt;
+        for (int w = 0; w < WPL; ++w) {
+            const int wi = lane * WPL + w;
+            if (wi < NW) {
+                unsigned m = wm[wi];
+                wm[wi] = 0u;
+                while (m && pos < K) { const int bit = __ffs(m) - 1; stg[pos++] = (wi << 5) + bit; m &= m - 1; }
+            }
+        }
+        __syncwarp();
+        const int cc = total > K ? K : total;
+        const int frst = cc ? stg[0] : N;
+        if (cc == 0 && lane == 0 && empty_flag) atomicOr(empty_flag, 1);
+        const int64_t o = ((int64_t)b * S + sidx) * K;
+        for (int j = lane; j < K; j += 32) {
+            const int v = (j < cc) ? stg[j] : frst;
+            if (idx64) idx64[o + j] = v;
+            if (idx32) idx32[o + j] = v;
+        }
+        __syncwarp();
+    }
+}
+
+static size_t bq_cell_smem(int C, int N, int K)
+{
+    const int NW = (N + 31) >> 5;
+    return sizeof(float) * (size_t)(C + 1) * N + sizeof(int) * ((size_t)N + BQC_CELLS + 1 + (size_t)BQC_WARPS * NW + (size_t)BQC_WARPS * K + BQC_WARPS * 20);
+}
+
+// returns -100 when the culled kernel does not apply (the caller scans)
+template <int C>
+static int launch_bq_cells(const float *centres, int64_t csb, int64_t csn, int64_t csc,
+                           const float *points, int64_t sb, int64_t sn, int64_t sc,
+                           int B, int S, int N, float r2, int K,
+                           int64_t *idx64, int32_t *idx32, int32_t *empty_flag, cudaStream_t st)
+{
+    // PN2_BQ_CELLS: 0 = never, 1 = always (where it fits), unset = radii up to 0.26 -- for clouds normalised to the unit sphere
+    // (provider.normalization, the reference's convention) that is a grid of >= 7^3 cells; wider balls cover most of the 27
+    // cells' points anyway and the four-centres-per-pass scan is faster
+    static const int env = getenv("PN2_BQ_CELLS") ? atoi(getenv("PN2_BQ_CELLS")) : -1;
+    if (env == 0 || (env < 0 && !(r2 <= 0.0676f))) return -100;
+    const size_t smem = bq_cell_smem(C, N, K);
+    if (smem > 200 * 1024 || N < 64) return -100;
+    auto kern = ball_query_cell_kernel<C>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("ball_query(cells): smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    // one CTA per cloud when there are enough clouds; otherwise tiles of >= 64 centres, each rebuilding the grid (O(N))
+    int tiles = 1;
+    if (B < 296) { tiles = (296 + B - 1) / B; const int tmax = (S + 63) / 64; if (tiles > tmax) tiles = tmax; if (tiles < 1) tiles = 1; }
+    const int cpc = ((S + tiles - 1) / tiles + BQC_WARPS - 1) / BQC_WARPS * BQC_WARPS;
+    dim3 g((S + cpc - 1) / cpc, B);
+    kern<<<g, BQC_THREADS, smem, st>>>(centres, csb, csn, csc, points, sb, sn, sc, S, N, cpc, r2, K, idx64, idx32, empty_flag);
+    return launch_status("pn2_ball_query_f32(cells)");
+}
+
 template <int C, int BQ_WARPS>
 static int launch_bq_w(const float *centres, int64_t csb, int64_t csn, int64_t csc,
                        const float *points, int64_t sb, int64_t sn, int64_t sc,
@@ -510,6 +773,10 @@ static int launch_bq_c(const float *centres, int64_t csb, int64_t csn, int64_t c
 {
     // a staged cloud of more than ~100 KB leaves room for one CTA per SM: give it 32 warps instead of 8 (C <= 4 only: the
     // C = 10 kernel needs more than the 64 registers a 1024-thread CTA can have)
+    {
+        const int rc = launch_bq_cells<C>(centres, csb, csn, csc, points, sb, sn, sc, B, S, N, r2, K, idx64, idx32, empty_flag, st);
+        if (rc != -100) return rc;
+    }
     const size_t cloud = (size_t)(C + 1) * ((N + 63) & ~63) * sizeof(float);
     if (C <= 4 && cloud > 100 * 1024 && cloud + sizeof(int) * (size_t)BQ_WARPS_BIG * BQ_CPB<C>::value * K <= 200 * 1024)
         return launch_bq_w<C, BQ_WARPS_BIG>(centres, csb, csn, csc, points, sb, sn, sc, B, S, N, r2, K, idx64, idx32, empty_flag, st);

@@ -305,3 +305,49 @@ def test_public_sample_and_group_on_cuda(pu, oracle, B, N, C, D, S, K, r, layout
     z, rows = pu.sample_and_group_all(x.to(DEV), None if f is None else f.to(DEV))
     assert z.shape == (B, 1, C) and not z.any()
     assert rows.shape == (B, 1, N, C + D) and torch.equal(rows.cpu(), oracle.group(x, f, None, None, 2))
+
+
+@pytest.mark.parametrize("cells", ["0", "1"])
+def test_ball_query_grid_cull_variants_keep_parity(cells):
+    """PN2_BQ_CELLS (read once per process): 1 forces the exact spatial cull (grid of cells >= the radius, 27-cell
+    neighbourhood, hit bit mask) for every radius and cloud -- non-normalised, duplicate-heavy, C = 10, few cells included --
+    0 forces the scan kernel; both must return the oracle's rows on every ball-query case of the suite."""
+    e = dict(os.environ, PN2_BQ_CELLS=cells)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_kernels.py"),
+                        os.path.join(ROOT, "tests", "test_gpu_bench_shapes.py"), "-m", "gpu", "-q", "-x",
+                        "-k", "test_ball_query_vs_oracle or test_golden_fps_ball_sqdist or test_ball_query_batched_launch_shapes or "
+                              "test_config2 or test_ball_query_empty or test_ball_query_odd_clouds or test_bench_workload_indices"],
+                       env=e, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
+
+
+@pytest.mark.parametrize("kind", ["scaled", "shifted", "nan_point", "nan_centre", "far_centre", "flat", "inf_point"])
+def test_ball_query_odd_clouds_vs_oracle(pu, oracle, kind):
+    """Clouds the grid cull must not get wrong: un-normalised coordinates (x1000, +5000: the fp32 rounding of the expanded form
+    grows with |p|^2), a NaN / Inf point (NaN distances count as in radius, :85), NaN and far-away centres, a degenerate
+    (planar) bounding box."""
+    B, N, S, K, r = 3, 700, 90, 24, 0.2
+    x = cloudgen.uniform_cloud(B, N, 321)
+    start = torch.randint(0, N, (B,), generator=torch.Generator().manual_seed(8), dtype=torch.long)
+    scale = 1.0
+    if kind == "scaled":
+        x, scale = x * 1000.0, 1000.0
+    elif kind == "shifted":
+        x = x + 5000.0
+    elif kind == "flat":
+        x[..., 2] = 0.25
+    cen = oracle.index_points(x, oracle.farthest_point_sample(x, S, start)).contiguous()
+    if kind == "nan_point":
+        x[1, 17, 1] = float("nan")
+    elif kind == "inf_point":
+        x[2, 5, 0] = float("inf")
+    elif kind == "nan_centre":
+        cen[0, 3, 2] = float("nan")
+    elif kind == "far_centre":
+        cen[1, 7] = torch.tensor([30.0, -40.0, 5.0])
+    be = pu._backend()
+    for rr in (r * scale, 0.05 * scale):
+        exp = oracle.query_ball_point(rr, K, x, cen)
+        i64, i32 = be.ball_query(cen.to(DEV), x.to(DEV), oracle.radius_sq_f32(rr), K, want_idx64=True, want_idx32=True)
+        assert torch.equal(i64.cpu(), exp), (kind, rr)
+        assert torch.equal(i32.cpu().long(), exp)
