@@ -710,11 +710,13 @@ static int launch_bq_cells(const float *centres, int64_t csb, int64_t csn, int64
                            int B, int S, int N, float r2, int K,
                            int64_t *idx64, int32_t *idx32, int32_t *empty_flag, cudaStream_t st)
 {
-    // PN2_BQ_CELLS: 0 = never, 1 = always (where it fits), unset = radii up to 0.26 -- for clouds normalised to the unit sphere
-    // (provider.normalization, the reference's convention) that is a grid of >= 7^3 cells; wider balls cover most of the 27
-    // cells' points anyway and the four-centres-per-pass scan is faster
-    static const int env = getenv("PN2_BQ_CELLS") ? atoi(getenv("PN2_BQ_CELLS")) : -1;
-    if (env == 0 || (env < 0 && !(r2 <= 0.0676f))) return -100;
+    // PN2_BQ_CELLS=1 selects this kernel (where it fits); OFF by default.  Measured on B200 (profiles/r02_bq_cells.txt): the
+    // reference's clouds are normalised to the unit sphere, where a radius of 0.2 leaves a 5^3 grid and the 27 cells around a
+    // centre still hold ~22 % of the cloud; one centre per warp on those candidates costs as much as the scan kernel, which
+    // tests four centres against 64 points per trip: 665 vs 666 us (B = 2048, N = 1024), 212 vs 180 us (B = 512), 62 vs 70 us
+    // (B = 16, N = 4096), 234 vs 131 us (configs[2], N = 8192: one CTA per SM, grid rebuilt by every tile of centres).
+    static const int env = getenv("PN2_BQ_CELLS") ? atoi(getenv("PN2_BQ_CELLS")) : 0;
+    if (env <= 0) return -100;
     const size_t smem = bq_cell_smem(C, N, K);
     if (smem > 200 * 1024 || N < 64) return -100;
     auto kern = ball_query_cell_kernel<C>;

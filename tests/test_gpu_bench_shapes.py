@@ -347,7 +347,7 @@ def test_ball_query_odd_clouds_vs_oracle(pu, oracle, kind):
         cen[1, 7] = torch.tensor([30.0, -40.0, 5.0])
     be = pu._backend()
     for rr in (r * scale, 0.05 * scale):
-        exp = oracle.query_ball_point(rr, K, x, cen)
+        exp = oracle.query_ball_point(rr, K, x, cen, allow_empty=True)         # a far centre has no neighbour: row of N
         i64, i32 = be.ball_query(cen.to(DEV), x.to(DEV), oracle.radius_sq_f32(rr), K, want_idx64=True, want_idx32=True)
         assert torch.equal(i64.cpu(), exp), (kind, rr)
         assert torch.equal(i32.cpu().long(), exp)
