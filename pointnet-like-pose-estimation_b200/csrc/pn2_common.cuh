@@ -202,6 +202,7 @@ int launch_pack_bf16(int L, const int *dims, const void *const *ptrs, float eps,
 int64_t packed_bytes_f32_split(int L, const int *dims);
 int sa_f32_split_tile_rows(int K, int L, const int *dims);
 int launch_sa_f32_split(const SaArgs &a, const void *packed_split, cudaStream_t st);   // -100: configuration not covered
+int launch_sa_f32_split_units(const SaArgs &a, const void *packed_split, cudaStream_t st);   // -100: not covered (stacks with feature channels, ...)
 int sa_f32_needs_zero(int S, int K, int L, const int *dims);
 int sa_bf16_needs_zero(int S, int K, int L, const int *dims);
 int launch_sa_f32(const SaArgs &a, cudaStream_t st);

@@ -19,6 +19,8 @@ struct Tc2Layer {
     uint32_t w_step;      // descriptor increment per K = 16 step
     uint32_t bs_lo_rel;   // hidden layers: the bias slice, same encoding
     uint32_t idesc;       // instruction descriptor (N = layer width; last layer: M = 128 channels, N = 128 rows)
+    uint32_t s_cbf16, s_cbl16;   // split layout (fp32 mode): bytes >> 4 of one image (hi or lo) of a full / of the last weight chunk
+    int s_spc;            // split layout: K = 16 steps per weight chunk (kblk / 16)
     int nks;              // K = 16 steps over the swizzled activation blocks (layer 0: the D feature channels)
     int nb32;             // hidden layers: Npad / 32
     int n_mh;             // last layer: Npad / 128
@@ -41,6 +43,8 @@ struct Tc2Params {
     unsigned long long *trace;   // debug timeline (pn2_debug_trace), CTA 0 only; nullptr = off
     int use_tma, feat_rows;      // bf16 features gathered by TMA (tile::gather4) through `tmap` = [feat_rows = B*N][D]
     int static_sched;            // pn2_sa_tc4.cu: 1 = fixed (layer, unit) schedule, 0 = units polled dynamically
+    int split;                   // fp32 mode: every operand as (bf16 hi, bf16 lo), four MMAs per K step (sa_tc2_kernel<0, ., true>)
+    uint32_t a_lo_off;           // split: bytes from a unit's hi operand image to its lo image
     alignas(64) CUtensorMap tmap;
 };
 
@@ -304,6 +308,81 @@ __device__ __forceinline__ void issue_layer_mmas(const Tc2Params &p, int l, uint
     }
 }
 
+// Split operands (fp32 mode, pn2_sa_tcs.cu explains the arithmetic): the same layer with every K = 16 step issued four times,
+// (hi, hi), (hi, lo), (lo, hi), (lo, lo).  Weight chunks are [hi image | lo image] of s_spc steps each; `a_lo16` = distance
+// (>> 4) from a unit's hi activation image to its lo image (swizzled blocks and coordinate block alike).
+__device__ __forceinline__ void issue_layer_mmas_split(const Tc2Params &p, int l, uint32_t wsm16, uint32_t a_sw, uint32_t a_xyz, uint32_t ones,
+                                                       uint32_t d_tm, uint32_t a_lo16)
+{
+    const Tc2Layer &y = p.ly[l];
+    const int nks = y.nks;
+    const int nst = nks + (l == 0 ? 1 : 0);             // layer 0: the coordinate block is the last K step
+    const uint32_t idesc = y.idesc, w_step = y.w_step;
+    const bool hidden = l < p.L - 1;
+    const int n_mh = hidden ? 1 : y.n_mh;
+    for (int mh = 0; mh < n_mh; ++mh) {
+        const uint32_t wb = wsm16 + y.w_lo_rel + (uint32_t)(mh * TC_ROWS);
+        const uint32_t d = d_tm + (uint32_t)(mh * TC_ROWS);
+        uint32_t acc = 0;
+        for (int t = 0; t < nst; ++t) {
+            const int c = t / y.s_spc, r = t - c * y.s_spc;
+            const bool last_chunk = (c + 1) * y.s_spc >= nst;
+            const uint32_t wh = wb + (uint32_t)c * 2u * y.s_cbf16 + (uint32_t)r * w_step;
+            const uint32_t wl = wh + (last_chunk ? y.s_cbl16 : y.s_cbf16);
+            uint64_t ah, al;
+            if (t < nks) {
+                const uint32_t a = a_sw + (uint32_t)(((t >> 2) << 10) + ((t & 3) << 1));
+                ah = mk_desc64(a, DESC_HI_SW128); al = mk_desc64(a + a_lo16, DESC_HI_SW128);
+            } else {
+                ah = mk_desc64(a_xyz, DESC_HI); al = mk_desc64(a_xyz + a_lo16, DESC_HI);
+            }
+            const uint64_t dwh = mk_desc64(wh, DESC_HI), dwl = mk_desc64(wl, DESC_HI);
+            if (hidden) {
+                umma_bf16(d, ah, dwh, idesc, acc);
+                umma_bf16(d, ah, dwl, idesc, 1u);
+                umma_bf16(d, al, dwh, idesc, 1u);
+                umma_bf16(d, al, dwl, idesc, 1u);
+            } else {                                    // transposed: weights are the M operand
+                umma_bf16(d, dwh, ah, idesc, acc);
+                umma_bf16(d, dwl, ah, idesc, 1u);
+                umma_bf16(d, dwh, al, idesc, 1u);
+                umma_bf16(d, dwl, al, idesc, 1u);
+            }
+            acc = 1u;
+        }
+        if (hidden) umma_bf16(d, mk_desc64(ones, DESC_HI), mk_desc64(wsm16 + y.bs_lo_rel, DESC_HI), idesc, 1u);
+    }
+}
+// hidden-layer epilogue on split operands: accumulator (three-part bias included) -> ReLU in fp32 -> (bf16 hi, bf16 lo) ->
+// the hi and lo images of the next layer's operand (same swizzled addressing as epi_store32)
+__device__ __forceinline__ void split_pair(uint32_t a, uint32_t b, uint32_t &hi, uint32_t &lo)
+{
+    float x = __uint_as_float(a), y = __uint_as_float(b);
+    x = x > 0.f ? x : (x != x ? x : 0.f);
+    y = y > 0.f ? y : (y != y ? y : 0.f);
+    hi = pack_bf16x2(x, y);
+    lo = pack_bf16x2(x - __uint_as_float(hi << 16), y - __uint_as_float(hi & 0xffff0000u));
+}
+__device__ __forceinline__ void epi_hidden_split(int nb32, uint32_t tmem_row, uint32_t a_rowx, uint32_t a_lo_off)
+{
+#pragma unroll 1
+    for (int b = 0; b < nb32; ++b) {
+        uint32_t r[32];
+        tmem_ld32_nowait(tmem_row + (uint32_t)(32 * b), r);
+        tmem_ld_wait();
+        const uint32_t base = (a_rowx ^ (uint32_t)((b & 1) << 6)) + (uint32_t)((b >> 1) * SW128_BLOCK);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) split_pair(r[8 * i + 2 * j], r[8 * i + 2 * j + 1], h[j], l[j]);
+            const uint32_t addr = base ^ (uint32_t)(i << 4);
+            sts128(addr, h[0], h[1], h[2], h[3]);
+            sts128(addr + a_lo_off, l[0], l[1], l[2], l[3]);
+        }
+    }
+}
+
 // shared-memory carve-up, identical in both kernels
 struct Tc2Smem {
     unsigned char *A_base, *ones, *Wsm;
@@ -349,9 +428,9 @@ __device__ __forceinline__ void cta_prologue(const Tc2Smem &s, const Tc2Params &
             bulk_g2s(s.Wsm + off, p.packed + off, (uint32_t)nb, s.w_bar);
         }
     }
-    // constant slice: k-group 0 = {1, 1, 0, ...} per row, k-group 1 = 0
+    // constant slice: k-group 0 = {1, 1, 0, ...} per row ({1, 1, 1, 0, ...} for split operands: three bias parts), k-group 1 = 0
     for (int i = tid; i < 2 * TC_ROWS; i += (int)blockDim.x)
-        *reinterpret_cast<uint4 *>(s.ones + i * 16) = make_uint4(i < TC_ROWS ? 0x3F803F80u : 0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4 *>(s.ones + i * 16) = make_uint4(i < TC_ROWS ? 0x3F803F80u : 0u, (i < TC_ROWS && p.split) ? 0x00003F80u : 0u, 0u, 0u);
     fence_proxy_async();
 }
 

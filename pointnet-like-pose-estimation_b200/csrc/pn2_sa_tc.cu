@@ -53,12 +53,14 @@ __global__ void pack_bf16_kernel(TcPackArgs a, unsigned char *__restrict__ packe
                 float v = 0.f;
                 if (n < y.Cout) v = __fadd_rn(__fmul_rn(__fsub_rn(a.b[l][n], a.mu[l][n]), s), a.be[l][n]);
                 bias_out[y.b_off + n] = v;
-                if (l < a.lay.L - 1 && !a.lay.split) {          // bias slice (see pn2_tc.cuh): hi and lo bf16 parts in k = 0, 1
+                if (l < a.lay.L - 1) {          // bias slice (see pn2_tc.cuh): three bf16 parts in k = 0, 1, 2
                     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-                    const __nv_bfloat16 lo = __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(hi)));
+                    const float r1 = __fsub_rn(v, __bfloat162float(hi));
+                    const __nv_bfloat16 lo = __float2bfloat16_rn(r1);
+                    const __nv_bfloat16 lo2 = __float2bfloat16_rn(__fsub_rn(r1, __bfloat162float(lo)));
                     __nv_bfloat16 *sl = reinterpret_cast<__nv_bfloat16 *>(packed + y.bs_off);
                     for (int k2 = 0; k2 < BIAS_SLICE_K; ++k2)
-                        sl[(k2 / 8) * (y.Npad * 8) + n * 8 + (k2 % 8)] = k2 == 0 ? hi : (k2 == 1 ? lo : __float2bfloat16_rn(0.f));
+                        sl[(k2 / 8) * (y.Npad * 8) + n * 8 + (k2 % 8)] = k2 == 0 ? hi : (k2 == 1 ? lo : (k2 == 2 ? lo2 : __float2bfloat16_rn(0.f)));
                 }
                 continue;
             }

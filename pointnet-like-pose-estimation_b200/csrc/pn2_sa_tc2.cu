@@ -32,6 +32,7 @@
 //                  issues every MMA; the MMAs of one tile always run underneath the CUDA-core phase of the other.
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 #include "pn2_sa_pipe.cuh"
 
 namespace pn2 {
@@ -40,9 +41,10 @@ namespace pn2 {
 // (bf16 rows by cp.async, fp32 rows through registers, strided fp32).  PRE_XYZ: C <= 4, coordinates prefetched one
 // tile ahead.  Separate instantiations keep the register allocation of the common cases free of spills (a spilled
 // prefetch register turns the prefetch into a blocking load).
-template <int FMODE, bool PRE_XYZ>
+template <int FMODE, bool PRE_XYZ, bool SPLIT = false>
 __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const __grid_constant__ Tc2Params p)
 {
+    static_assert(!SPLIT || FMODE == 0, "split operands (fp32 mode): stacks without feature channels only");
     extern __shared__ __align__(128) unsigned char smem[];
     const Tc2Smem sm = carve(smem, p);
     const int U = p.U;
@@ -184,7 +186,8 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const __grid_
                 if (!w_ready) { mbar_wait(sm.w_bar, 0); w_ready = true; }
                 tc_fence_after();
                 if (elect_one()) {
-                    issue_layer_mmas(p, l, wsm16, a_sw, a_xyz, ones_lo, d_tm);
+                    if constexpr (SPLIT) issue_layer_mmas_split(p, l, wsm16, a_sw, a_xyz, ones_lo, d_tm, p.a_lo_off >> 4);
+                    else issue_layer_mmas(p, l, wsm16, a_sw, a_xyz, ones_lo, d_tm);
                     umma_commit(my_acc_ready);
                 }
                 __syncwarp();
@@ -222,9 +225,16 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const __grid_
                 }
             }
             if (pre_xyz) {
-                *reinterpret_cast<uint4 *>(X_row) = make_uint4(pack_bf16x2(__fsub_rn(px[0], pc[0]), __fsub_rn(px[1], pc[1])),
-                                                               pack_bf16x2(__fsub_rn(px[2], pc[2]), __fsub_rn(px[3], pc[3])), 0u, 0u);
+                const float d0 = __fsub_rn(px[0], pc[0]), d1 = __fsub_rn(px[1], pc[1]), d2 = __fsub_rn(px[2], pc[2]), d3 = __fsub_rn(px[3], pc[3]);
+                const uint32_t h0 = pack_bf16x2(d0, d1), h1 = pack_bf16x2(d2, d3);
+                *reinterpret_cast<uint4 *>(X_row) = make_uint4(h0, h1, 0u, 0u);
                 *reinterpret_cast<uint4 *>(X_row + A_LBO) = make_uint4(0u, 0u, 0u, 0u);
+                if constexpr (SPLIT) {      // the bf16 remainders: second operand image
+                    *reinterpret_cast<uint4 *>(X_row + p.a_lo_off) =
+                        make_uint4(pack_bf16x2(d0 - __uint_as_float(h0 << 16), d1 - __uint_as_float(h0 & 0xffff0000u)),
+                                   pack_bf16x2(d2 - __uint_as_float(h1 << 16), d3 - __uint_as_float(h1 & 0xffff0000u)), 0u, 0u);
+                    *reinterpret_cast<uint4 *>(X_row + p.a_lo_off + A_LBO) = make_uint4(0u, 0u, 0u, 0u);
+                }
             } else {
                 const float *pp = p.points + (int64_t)b * p.sb + (int64_t)n * p.sn;
                 const float *cc = p.centres + (int64_t)g * C;
@@ -236,8 +246,19 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const __grid_
                     pp += p.sc;
                     x[i] = __fsub_rn(a0, a1);
                 }
-                *reinterpret_cast<uint4 *>(X_row) = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
-                *reinterpret_cast<uint4 *>(X_row + A_LBO) = make_uint4(pack_bf16x2(x[8], x[9]), pack_bf16x2(x[10], x[11]), pack_bf16x2(x[12], x[13]), pack_bf16x2(x[14], x[15]));
+                uint32_t h[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) h[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
+                *reinterpret_cast<uint4 *>(X_row) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4 *>(X_row + A_LBO) = make_uint4(h[4], h[5], h[6], h[7]);
+                if constexpr (SPLIT) {
+                    uint32_t lw[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        lw[i] = pack_bf16x2(x[2 * i] - __uint_as_float(h[i] << 16), x[2 * i + 1] - __uint_as_float(h[i] & 0xffff0000u));
+                    *reinterpret_cast<uint4 *>(X_row + p.a_lo_off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                    *reinterpret_cast<uint4 *>(X_row + p.a_lo_off + A_LBO) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+                }
             }
             if constexpr (FMODE == 1) { mbar_wait(my_feat_ready, feat_phase); feat_phase ^= 1u; }
             if constexpr (FMODE == 2) { if (twin) asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -257,7 +278,8 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) sa_tc2_kernel(const __grid_
                 tr.mark(0x400 + l);
                 if (l < L - 1) {
                     // ---- hidden layer: accumulator (bias included) -> ReLU -> bf16 -> the next layer's A operand (in place) --
-                    epi_hidden_any(p.ly[l].nb32, tmem_row, a_rowx);
+                    if constexpr (SPLIT) epi_hidden_split(p.ly[l].nb32, tmem_row, a_rowx, p.a_lo_off);
+                    else epi_hidden_any(p.ly[l].nb32, tmem_row, a_rowx);
                     tc_fence_before();           // TMEM reads ordered before the next MMA's write to this region
                     fence_proxy_async();
                     tr.mark(0x500 + l);
@@ -561,7 +583,7 @@ static int pow2_at_least(int x) { int p = 32; while (p < x) p <<= 1; return p; }
 
 struct Tc2Plan { int U, cols_per_unit, tmem_cols, a_unit_bytes, xyz_off; size_t smem; };
 
-static bool tc2_plan(int K, int C, int D, int order, const TcLayout &t, Tc2Plan *pl)
+static bool tc2_plan(int K, int C, int D, int order, const TcLayout &t, Tc2Plan *pl, bool split = false)
 {
     // features fill whole K = 16 slices of the swizzled blocks, the (<= 16) coordinate channels their own slice
     if (D % 16 != 0 || C < 1 || C > 16 || t.ly[0].K != D + 16) return false;
@@ -577,7 +599,7 @@ static bool tc2_plan(int K, int C, int D, int order, const TcLayout &t, Tc2Plan 
     }
     pl->cols_per_unit = pow2_at_least(nmax);
     pl->xyz_off = (kmax + 63) / 64 * SW128_BLOCK;                   // swizzled 64-channel blocks, then [2][128][16 B] coordinates
-    pl->a_unit_bytes = pl->xyz_off + 2 * A_LBO;
+    pl->a_unit_bytes = (pl->xyz_off + 2 * A_LBO) * (split ? 2 : 1);      // split operands: hi image, then lo image
     for (int U = T2_MAX_UNITS; U >= 1; U >>= 1) {
         if (U * pl->cols_per_unit > 512) continue;
         const size_t smem = tc2_smem_bytes(U, pl->a_unit_bytes, t.total_bytes);
@@ -637,6 +659,7 @@ int launch_sa_bf16_pipelined(const SaArgs &a, cudaStream_t st)
     p.out_bf16 = (__nv_bfloat16 *)a.out_bf16;
     p.trace = g_trace;
     p.use_tma = 0; p.feat_rows = a.B * a.N; p.static_sched = 1;
+    p.split = 0; p.a_lo_off = 0;
     static const bool no_tma = getenv("PN2_NO_TMA_GATHER") != nullptr;
     if (p.feat_bf16 && a.D % 64 == 0 && (int64_t)a.B * a.N < (1ll << 31) - 1 && !no_tma) {
         if (make_row_gather_map(p.feat_bf16, (int64_t)a.B * a.N, a.D, &p.tmap) == 0) p.use_tma = 1;
@@ -670,6 +693,65 @@ int launch_sa_bf16_pipelined(const SaArgs &a, cudaStream_t st)
     if (fmode == 0) return pre ? run(sa_tc2_kernel<0, true>) : run(sa_tc2_kernel<0, false>);
     if (fmode == 1) return pre ? run(sa_tc2_kernel<1, true>) : run(sa_tc2_kernel<1, false>);
     return pre ? run(sa_tc2_kernel<2, true>) : run(sa_tc2_kernel<2, false>);
+}
+
+// fp32 mode (split operands, see pn2_sa_tcs.cu) on the four-unit schedule above: stacks WITHOUT feature channels (sa1 of every
+// model: D = 0) whose split weights fit shared memory next to four units.  `packed_split` = the split image of
+// pn2_pack_weights(PN2_PREC_F32).  Returns -100 when the configuration is not covered (the caller uses pn2_sa_tcs.cu).
+int launch_sa_f32_split_units(const SaArgs &a, const void *packed_split, cudaStream_t st)
+{
+    static const bool off = getenv("PN2_F32_UNITS") != nullptr && atoi(getenv("PN2_F32_UNITS")) == 0;
+    if (off || a.D != 0) return -100;
+    const TcLayout lay = tc_layout(a.L, a.dims, true);
+    Tc2Plan pl;
+    if (!tc2_plan(a.K, a.C, a.D, a.order, lay, &pl, true) || pl.U < 2) return -100;
+    Tc2Params p;
+    p.points = a.points; p.sb = a.sb; p.sn = a.sn; p.sc = a.sc;
+    p.feat = nullptr; p.fb = p.fn = p.fc = 0;
+    p.centres = a.centres; p.idx32 = a.idx32;
+    p.N = a.N; p.S = a.S; p.K = a.K; p.C = a.C; p.D = 0; p.order = a.order;
+    p.L = lay.L;
+    const int spc = lay.kblk / 16;
+    for (int l = 0; l < lay.L; ++l) {
+        const TcLayer &y = lay.ly[l];
+        const bool last = (l == lay.L - 1);
+        Tc2Layer &t = p.ly[l];
+        const uint32_t lbo = (uint32_t)(last ? y.Npad : y.NS) * 16u;
+        t.w_lo_rel = ((uint32_t)y.w_off >> 4) | ((lbo >> 4) << 16);
+        t.w_step = (2u * lbo) >> 4;
+        t.bs_lo_rel = ((uint32_t)y.bs_off >> 4) | ((lbo >> 4) << 16);
+        t.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((last ? TC_ROWS : y.NS) >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+        t.nks = (l == 0 ? 0 : y.K) / 16;
+        t.nb32 = y.Npad / 32;
+        t.n_mh = y.Npad / TC_ROWS;
+        t.Cout = y.Cout; t.b_off = y.b_off;
+        t.s_spc = spc;
+        t.s_cbf16 = (uint32_t)tc_chunk_bytes(y, 0, lay.kblk) >> 4;
+        t.s_cbl16 = (uint32_t)tc_chunk_bytes(y, y.nkb - 1, lay.kblk) >> 4;
+    }
+    p.img_bytes = lay.total_bytes; p.bias_off = lay.w_bytes;
+    p.packed = (const unsigned char *)packed_split;
+    p.out = a.out; p.ob = a.ob; p.os = a.os; p.co_off = a.co_off;
+    p.G = (int64_t)a.B * a.S;
+    p.rows = p.G * a.K;
+    p.tiles = (p.rows + TC_ROWS - 1) / TC_ROWS;
+    if (p.rows >= (1ll << 31) - TC_ROWS) return -100;
+    p.U = pl.U; p.cols_per_unit = pl.cols_per_unit; p.tmem_cols = pl.tmem_cols;
+    p.a_unit_bytes = pl.a_unit_bytes; p.xyz_off = pl.xyz_off;
+    p.feat_fast = 1; p.feat_bf16 = nullptr; p.out_bf16 = nullptr;
+    p.trace = nullptr; p.use_tma = 0; p.feat_rows = a.B * a.N; p.static_sched = 1;
+    p.split = 1; p.a_lo_off = (uint32_t)(pl.a_unit_bytes / 2);
+    memset(&p.tmap, 0, sizeof(p.tmap));
+    if (p.tiles == 0) return 0;
+    int64_t grid = (p.tiles + pl.U - 1) / pl.U;
+    if (grid > 148) grid = 148;
+    auto run = [&](auto kern) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+        if (e != cudaSuccess) { set_error("sa_tc2(split): smem attribute (%zu B): %s", pl.smem, cudaGetErrorString(e)); return (int)e; }
+        kern<<<(unsigned)grid, 4 * pl.U * 32, pl.smem, st>>>(p);
+        return launch_status("pn2_sa_fused(f32, split units)");
+    };
+    return a.C <= 4 ? run(sa_tc2_kernel<0, true, true>) : run(sa_tc2_kernel<0, false, true>);
 }
 
 }  // namespace pn2

@@ -481,6 +481,10 @@ int launch_sa_f32_split(const SaArgs &a, const void *packed_split, cudaStream_t 
 {
     static const bool off = getenv("PN2_F32_FFMA") != nullptr;
     if (off) return -100;
+    {   // stacks without feature channels (sa1 of every model): the four-unit schedule of pn2_sa_tc2.cu with split operands
+        const int rc = launch_sa_f32_split_units(a, packed_split, st);
+        if (rc != -100) return rc;
+    }
     TcsPlan pl;
     if (!tcs_plan(a.K, a.L, a.dims, &pl)) return -100;
     TcsParams p;

@@ -44,8 +44,9 @@ struct TcLayout {
 };
 // Bias slice of a hidden layer (used by the pipelined kernels, pn2_sa_tc2.cu): one extra K = 16 slice of the weight
 // operand, [Npad] rows in the canonical K-major no-swizzle layout (k-groups at Npad*16 bytes), holding
-// k = 0: bf16(b), k = 1: bf16(b - bf16(b)), zeros elsewhere.  Multiplied by an activation slice whose channels 0 and 1
-// are 1.0 it adds the folded bias inside the MMA (to ~2^-17 relative), so the epilogue is ReLU + convert only.
+// k = 0: bf16(b), k = 1: bf16(b - bf16(b)), k = 2: the bf16 of what is left, zeros elsewhere.  Multiplied by an activation
+// slice whose channels 0 and 1 are 1.0 it adds the folded bias inside the MMA (to ~2^-17 relative), so the epilogue is
+// ReLU + convert only; the split (fp32 mode) kernels set channel 2 to 1.0 as well: three parts = the fp32 bias to ~2^-25.
 constexpr int BIAS_SLICE_K = 16;
 
 static __host__ __device__ inline int tc_chunk_bytes(const TcLayer &ly, int kb, int kblk = KBLK)
@@ -93,7 +94,7 @@ static inline TcLayout tc_layout(int L, const int *dims, bool split = false)
     t.total_bytes = t.w_bytes + t.bias_floats * 4;
     for (int l = 0; l < L; ++l) {
         t.ly[l].bs_off = t.total_bytes;
-        if (l < L - 1 && !split) t.total_bytes += t.ly[l].Npad * BIAS_SLICE_K * 2;
+        if (l < L - 1) t.total_bytes += t.ly[l].Npad * BIAS_SLICE_K * 2;
     }
     return t;
 }
