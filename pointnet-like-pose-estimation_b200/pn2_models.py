@@ -5,7 +5,7 @@ run unchanged on top of this directory's ``pointnet2_utils``.  The GPU box that 
 ``-m gpu`` tests has no reference checkout, so the same eight architectures are restated here from one spec
 table: same attribute names (``sa1..sa3, fc1..fc3, bn1, bn2, drop, mean_fc1, mean_fc2, mean_bn1``), same
 construction order (so a seeded construction draws identical initial weights) and therefore interchangeable
-``state_dict``s -- tests/test_models_reference.py checks exactly that against the live reference.
+``state_dict``s -- tests/test_reference_live.py checks exactly that against the live reference.
 """
 from __future__ import annotations
 

@@ -12,10 +12,12 @@ collective per step:
     call on the compute stream right after backward -- 1.74 M elements = 6.97 MB for rotation_msg, i.e. launch-latency
     sized for NVSwitch; splitting it into per-layer buckets would only add launches.
 
-Sampling and grouping (FPS, ball query, neighbour gather) run on the hand-written kernels in every mode; in training
-mode the shared MLP + BatchNorm run on ATen so that autograd provides the backward (fused training kernels are the next
-scope row, DESIGN.md).  The FPS start indices are drawn on the CPU generator once per layer like the reference (:59);
-``pn2_shard.GlobalStarts`` makes every rank slice one global draw.
+Sampling and grouping (FPS, ball query, neighbour gather / scatter-add) run on the hand-written kernels in every mode; in
+training mode the shared MLP runs layer by layer on the grouped rows: the 1x1 convolutions, their input and weight gradients
+on our tcgen05 row GEMMs (TF32, the policy of the reference's cuDNN convolutions; csrc/pn2_gemm.cu), batch-statistics
+BatchNorm + ReLU + max-pool forward and backward on the fused kernels of csrc/pn2_bn_train.cu, wired into autograd by
+``torch.autograd.Function``s in pointnet2_utils.py.  The FPS start indices are drawn on the CPU generator once per layer like
+the reference (:59); ``pn2_shard.GlobalStarts`` makes every rank slice one global draw.
 """
 from __future__ import annotations
 

@@ -99,11 +99,17 @@ def run(args, R):
                 ar_ms += e2.elapsed_time(e3) / 3
     # kernel shares of one step (torch profiler, outside the timed regions)
     shares = None
-    if R.rank == 0 and not args.quick:
-        from torch.profiler import ProfilerActivity, profile
-        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    if not args.quick:
+        # every rank takes the step (it contains the all-reduce); only rank 0 records it
+        if R.rank == 0:
+            from torch.profiler import ProfilerActivity, profile
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                step(False)
+                torch.cuda.synchronize(dev)
+        else:
             step(False)
             torch.cuda.synchronize(dev)
+    if R.rank == 0 and not args.quick:
         rows = sorted(((e.key, e.device_time_total / 1e3) for e in prof.key_averages() if e.device_time_total > 0), key=lambda r: -r[1])
         tot = sum(r[1] for r in rows) or 1.0
         shares = {"kernel_ms_total": round(tot, 3), "top": [{"name": k[:80], "ms": round(v, 3), "share": round(v / tot, 3)} for k, v in rows[:12]],
