@@ -196,3 +196,62 @@ def test_training_mode_factorised_msg_branch_matches_the_direct_form(fake_native
     scale = max(float(b.abs().max()) for b in grads[1])     # a convolution bias in front of BatchNorm has zero gradient: noise only
     for a, b in zip(*grads):
         assert float((a - b).abs().max()) / scale < 1e-5
+
+
+def test_data_writes_need_invalidate_caches(fake_native):
+    """the derived-weight caches key on tensor._version, which a write through `.data` does not bump -- the
+    documented hook `invalidate_caches()` makes the next forward repack."""
+    pu = fake_native
+    m = pu.PointNetSetAbstraction(8, 4, 0.8, 3, [8, 8], False).eval()
+    pts = cloudgen.channels_first(cloudgen.uniform_cloud(2, 64, 3))
+    with torch.no_grad():
+        torch.manual_seed(1)
+        a = m(pts, None)[1].clone()
+        m.mlp_convs[0].weight.data.mul_(3.0)           # invisible to the version counter
+        torch.manual_seed(1)
+        b = m(pts, None)[1].clone()
+        pu.invalidate_caches()
+        torch.manual_seed(1)
+        c = m(pts, None)[1].clone()
+    assert torch.equal(a, b) and not torch.equal(a, c)
+
+
+def test_fused_head_is_used_in_eval_and_matches_the_op_sequence(fake_native):
+    """Eval-mode models hand the FC head to ONE fc_head call (BatchNorm1d folded, weights packed [K/4][H][4]); the result equals
+    the reference's op sequence; training mode keeps the ATen sequence (autograd)."""
+    import pn2_models
+    import torch.nn.functional as F
+    pu = fake_native
+    for name in ("pointnet2_cls_ssg", "translation_ssg", "sign_ssg", "rotation_ssg"):
+        torch.manual_seed(0)
+        model = pn2_models.get_model(name, 7)
+        pn2_models.randomize_bn_(model)
+        model.eval()
+        xyz = cloudgen.uniform_cloud(2, 1024, 5)
+        pose = not name.startswith("pointnet2_cls")
+        x = cloudgen.channels_first(cloudgen.with_category(xyz) if pose else xyz)
+        mean = xyz[:, :3, :].mean(1)
+        args = (x, mean) if name.startswith("translation") else (x,)
+        pu._native.calls.clear()
+        with torch.no_grad():
+            torch.manual_seed(4)
+            out = model(*args)
+            assert pu._native.calls.count("fc_head") == 1
+            # the same forward with the head computed by the reference's op sequence
+            torch.manual_seed(4)
+            feat, pts = None, x
+            for i in range(1, model.n_sa + 1):
+                pts, feat = getattr(model, f"sa{i}")(pts, feat)
+            h = F.relu(model.bn1(model.fc1(feat.view(2, 1024))))
+            h = F.relu(model.bn2(model.fc2(h)))
+            y = model.fc3(h)
+            if name.startswith("pointnet2_cls"):
+                exp = F.log_softmax(y, -1)
+            elif name.startswith("translation"):
+                exp = y + model.mean_fc2(F.relu(model.mean_bn1(model.mean_fc1(mean))))
+            elif name.startswith("sign"):
+                exp = torch.sigmoid(y)
+            else:
+                exp = y
+        got = out[0] if isinstance(out, tuple) else out
+        assert torch.allclose(got, exp, rtol=1e-5, atol=1e-6), name
