@@ -21,6 +21,7 @@ from __future__ import annotations
 import contextlib
 import math
 import os
+import threading
 
 import numpy as np
 import torch
@@ -85,14 +86,47 @@ def fps_start_source(fn):
         _start_source = prev
 
 
+class _PinnedDraws:
+    """A small ring of pinned [B] int64 buffers per batch size for the FPS start draw: `torch.randint(..., out=pinned)` makes
+    exactly the draw of the reference (same generator, same values) but the upload that follows is a true asynchronous copy
+    -- the pageable `.to(device)` of the plain form stages through the driver and stalls the enqueueing thread once per
+    sampling layer.  A buffer is reused only after the copy that read it has completed (one event per buffer)."""
+    SLOTS = 8
+
+    def __init__(self):
+        self.rings = {}
+
+    def draw(self, B, N, device):
+        key = (B, device.index if device.index is not None else torch.cuda.current_device(), threading.get_ident())
+        ring = self.rings.get(key)
+        if ring is None:
+            ring = self.rings[key] = {"bufs": [torch.empty(B, dtype=torch.long).pin_memory() for _ in range(self.SLOTS)],
+                                      "evs": [torch.cuda.Event() for _ in range(self.SLOTS)], "i": 0, "used": [False] * self.SLOTS}
+        i = ring["i"]
+        ring["i"] = (i + 1) % self.SLOTS
+        if ring["used"][i]:
+            ring["evs"][i].synchronize()
+        buf = ring["bufs"][i]
+        torch.randint(0, N, (B,), dtype=torch.long, out=buf)
+        dev_t = buf.to(device, non_blocking=True)
+        ring["evs"][i].record(torch.cuda.current_stream(device))
+        ring["used"][i] = True
+        return dev_t
+
+
+_pinned_draws = _PinnedDraws()
+
+
 def _draw_start(B: int, N: int, device) -> torch.Tensor:
     # The reference draws on the CPU default generator even when the model is on the GPU (:59); keep that,
     # one draw per farthest_point_sample call, so seeded runs choose the same centroids.
     if _start_source is not None:
         start = _start_source(B, N)
-    else:
-        start = torch.randint(0, N, (B,), dtype=torch.long)
-    return start.to(device, non_blocking=start.is_pinned())     # pinned sources (pn2_graph.py) must not synchronise
+        return start.to(device, non_blocking=start.is_pinned())     # pinned sources (pn2_graph.py) must not synchronise
+    device = torch.device(device)
+    if device.type == "cuda" and not torch.cuda.is_current_stream_capturing():
+        return _pinned_draws.draw(B, N, device)
+    return torch.randint(0, N, (B,), dtype=torch.long).to(device)
 
 
 def invalidate_caches() -> None:
