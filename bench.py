@@ -261,8 +261,8 @@ def roofline_of(top_key, top, prec, pk, region_s, clk, fp32_tc=False):
     traffic_file = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(traffic_file):
         with open(traffic_file) as f:
-            t = json.load(f).get(top_key)
-        if t and t.get("batch") == m["B"] and t.get("precision", "bf16") == prec:
+            t = json.load(f).get(top_key if prec == "bf16" else f"{top_key}|{prec}")
+        if t and t.get("batch") == m["B"]:
             roof["traffic"] = t["dram_bytes_per_launch"]
     return roof
 
