@@ -513,16 +513,18 @@ int launch_sa_f32_split(const SaArgs &a, const void *packed_split, cudaStream_t 
     const int64_t cap = (int64_t)148 * pl.ctas_per_sm;
     if (grid > cap) grid = cap;
     // streamed weights with one CTA per SM: the CTAs of a cluster share every chunk through one TMA multicast (the four-pass
-    // MMAs of a chunk take long enough to hide the cluster round trip); wide stacks re-stream megabytes per tile: 4 CTAs
+    // MMAs of a chunk take long enough to hide the cluster round trip).  Measured (cls_ssg, B = 2048): sa3 2.80 ms with pairs,
+    // 3.17 ms with clusters of four; with two CTAs per SM (sa2: a two-stage ring each) the lock-step handshake of a cluster
+    // costs far more than the L2 traffic it saves: 10.7 ms alone, 20.3 / 22.9 ms in clusters of 2 / 4 (PN2_F32_CLUSTER forces it)
     static const int cs_env = getenv("PN2_F32_CLUSTER") ? atoi(getenv("PN2_F32_CLUSTER")) : 0;
     p.cs = 1;
-    if (!pl.resident && pl.ctas_per_sm == 1) {
-        int cs = cs_env > 0 ? cs_env : (pl.lay.w_bytes > (1 << 20) ? 4 : 2);
+    if (!pl.resident && (pl.ctas_per_sm == 1 || cs_env > 1)) {
+        int cs = cs_env > 0 ? cs_env : 2;
         if (cs > 8) cs = 8;
         while (cs > 1 && (cs & (cs - 1))) --cs;
         while (cs > 1 && p.tiles < 2 * cs) cs >>= 1;
         p.cs = cs;
-        if (cs > 1) { const int64_t ncl = (p.tiles + cs - 1) / cs; grid = (ncl < 148 / cs ? ncl : 148 / cs) * cs; }
+        if (cs > 1) { const int64_t ncl = (p.tiles + cs - 1) / cs, cap_cl = (int64_t)148 * pl.ctas_per_sm / cs; grid = (ncl < cap_cl ? ncl : cap_cl) * cs; }
     }
     if (p.cs == 1) {
         p.n_iter = (p.tiles + grid - 1) / grid;
