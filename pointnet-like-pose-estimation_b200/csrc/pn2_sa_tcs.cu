@@ -41,6 +41,7 @@ struct TcsParams {
     int a_bytes[2];                  // activation buffers (hi + lo); a_bytes[1] == 0: one buffer, overwritten in place
     int a_lo[2];                     // offset of the lo copy inside each buffer
     int pool_cols, passes;
+    int U;                           // tiles in flight per CTA: 1, or 2 teams of 8 compute warps sharing every streamed weight chunk
 };
 
 // bf16 hi parts and bf16 lo parts (packed pairs) of two fp32 values
@@ -56,48 +57,73 @@ __device__ __forceinline__ void split8(float v0, float v1, float v2, float v3, f
     split2(v4, v5, hi.z, lo.z); split2(v6, v7, hi.w, lo.w);
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 2) sa_tcs_kernel(const TcsParams p)
+// U = 1: one tile per CTA at a time (two CTAs per SM overlap each other).  U = 2: TWO TEAMS of eight compute warps, each with
+// its own tile (activation buffers, TMEM half, pooling scratch), walk the layers in lock step and share every streamed weight
+// chunk: team 0's first warp issues the chunk's MMAs for both tiles before the ring slot is released -- half the weight
+// traffic per tile, a ring deep enough to hide the L2 latency (the activations of two CTAs per SM leave room for two 16 KB
+// stages each: every chunk then waits ~2000 cycles for ~500 cycles of MMAs), and the fixed latencies of a layer (barriers,
+// commit, TMEM loads) amortised over two tiles.
+template <int U>
+__global__ void __launch_bounds__((U * TC_CWARPS + 1) * 32, U == 1 ? 2 : 1) sa_tcs_kernel(const TcsParams p)
 {
-    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int NCT = U * TC_CTHREADS;                     // compute threads
+    constexpr int NTHREADS = NCT + 32;
+    extern __shared__ __align__(128) unsigned char smem_all[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp_all = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int team = (U == 2 && warp_all >= TC_CWARPS && warp_all < 2 * TC_CWARPS) ? 1 : 0;
+    const int warp = warp_all - team * TC_CWARPS;            // warp inside the team (the producer warp reads as TC_CWARPS of team 0 ... U*TC_CWARPS)
+    const int ttid = tid - team * TC_CTHREADS;               // thread inside the team
+    const int a_team = p.a_bytes[0] + p.a_bytes[1];
+    unsigned char *smem = smem_all + (size_t)team * a_team;  // this team's activation buffers
     const uint32_t a1_off = p.a_bytes[1] ? (uint32_t)p.a_bytes[0] : 0u;
-    unsigned char *Wsm = smem + p.a_bytes[0] + p.a_bytes[1];
+    unsigned char *Wsm = smem_all + (size_t)U * a_team;
     const int w_region = p.resident ? p.lay.w_bytes : p.nstage * p.stage_bytes;
     float *bias_s = reinterpret_cast<float *>(Wsm + w_region);
-    float *pool_s = bias_s + p.lay.bias_floats;                 // [4][pool_cols]
-    int *s_n = reinterpret_cast<int *>(pool_s + 4 * p.pool_cols);
+    float *pool_s = bias_s + p.lay.bias_floats + (size_t)team * 4 * p.pool_cols;      // [4][pool_cols] per team
+    int *s_n = reinterpret_cast<int *>(bias_s + p.lay.bias_floats + (size_t)U * 4 * p.pool_cols) + team * 2 * TC_ROWS;
     int *s_g = s_n + TC_ROWS;
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(s_g + TC_ROWS);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(reinterpret_cast<int *>(bias_s + p.lay.bias_floats + (size_t)U * 4 * p.pool_cols) + U * 2 * TC_ROWS);
     uint64_t *empty_bar = full_bar + TC_MAX_STAGES;
     uint64_t *acc_bar = empty_bar + TC_MAX_STAGES;
     uint64_t *slot_free = acc_bar + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(slot_free + TC_MAX_STAGES);
 
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const TcLayout &lay = p.lay;
     const int TR = p.TR, a_lbo = p.a_lbo, kblk = p.lay.kblk;
+    const bool is_producer = warp_all == U * TC_CWARPS;
+    // barriers: 1 + team = the team's eight warps; 3 = every compute warp of the CTA
+    auto team_sync = [&]() {
+        if (U == 1) cbar_sync();
+        else asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "n"(TC_CTHREADS) : "memory");
+    };
+    auto all_sync = [&]() {
+        if (U == 1) cbar_sync();
+        else asm volatile("bar.sync 3, %0;" ::"n"(NCT) : "memory");
+    };
 
     if (tid == 0) {
         for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); mbar_init(slot_free + s, (uint32_t)p.cs); }
         mbar_init(acc_bar, 1);
         fence_mbar_init();
     }
-    if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    if (warp_all == 0) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     {
         const float *bsrc = reinterpret_cast<const float *>(p.packed + lay.w_bytes);
-        for (int i = tid; i < lay.bias_floats; i += TC_THREADS) bias_s[i] = __ldg(bsrc + i);
+        for (int i = tid; i < lay.bias_floats; i += NTHREADS) bias_s[i] = __ldg(bsrc + i);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_all = *tmem_slot;
+    const uint32_t tmem_base = tmem_all + (uint32_t)(team * (p.tmem_cols / U));       // this team's accumulator columns
     uint32_t cta_rank = 0;
     if (p.cs > 1) {
         asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
         asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     }
 
-    if (warp == TC_CWARPS) {
+    if (is_producer) {
         // ================================ producer warp: weight chunks (hi | lo) -> shared memory ==============================
         if (lane == 0) {
             if (p.resident) {
@@ -149,13 +175,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tcs_kernel(const TcsParams p
         const bool row_in_tile = row < TR;
         const int K = p.K, C = p.C, D = p.D;
         uint32_t acc_phase = 0, wq = 0;
-        if (p.resident && warp == 0) mbar_wait(full_bar, 0);
+        if (p.resident && warp_all == 0) mbar_wait(full_bar, 0);
 
         for (int64_t it = 0; it < p.n_iter; ++it) {
-            const int64_t tile = it * gridDim.x + blockIdx.x;
-            cbar_sync();
-            if (tid < TC_ROWS) {
-                const int r = tid;
+            const int64_t tile = (it * gridDim.x + blockIdx.x) * U + team;
+            team_sync();
+            if (ttid < TC_ROWS) {
+                const int r = ttid;
                 int64_t g = p.G; int j = 0;
                 if (r < TR && tile < p.tiles) {
                     if (p.cpg == 1) { g = tile * p.gpt + r / K; j = r % K; if (r >= p.gpt * K) g = p.G; }
@@ -166,7 +192,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tcs_kernel(const TcsParams p
                 if (n >= p.N) n = -1;            // 'no neighbour' marker of an empty ball (pointnet2_utils.py:85)
                 s_n[r] = n; s_g[r] = (int)g;
             }
-            cbar_sync();
+            team_sync();
             // ---- gather: layer-0 A operand (hi, lo), internal channel order [feat(D), xyz(C), zero pad] --------------------------
             {
                 unsigned char *A0 = smem;
@@ -175,7 +201,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tcs_kernel(const TcsParams p
                 if (p.feat_fast) {
                     const int cpr = D / 8;
                     // four 32-byte segments per thread in flight before the first store (the loads are L2 / HBM latency)
-                    for (int i0 = tid; i0 < TR * cpr; i0 += 4 * TC_CTHREADS) {
+                    for (int i0 = ttid; i0 < TR * cpr; i0 += 4 * TC_CTHREADS) {
                         float4 x[4], y[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
@@ -204,8 +230,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tcs_kernel(const TcsParams p
                             }
                         }
                     }
-                    if (tid < TR) {
-                        const int r = tid, n = s_n[r];
+                    if (ttid < TR) {
+                        const int r = ttid, n = s_n[r];
                         const int64_t g = s_g[r];
                         for (int kg = D / 8; kg < K0 / 8; ++kg) {
                             float v[8];
@@ -227,7 +253,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tcs_kernel(const TcsParams p
                         }
                     }
                 } else {
-                    for (int i = tid; i < TR * K0; i += TC_CTHREADS) {
+                    for (int i = ttid; i < TR * K0; i += TC_CTHREADS) {
                         const int r = i % TR, k = i / TR;
                         const int n = s_n[r];
                         float x = 0.f;
@@ -260,16 +286,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tcs_kernel(const TcsParams p
                 const uint32_t a_in_lo = a_in + (uint32_t)p.a_lo[a1_off ? ib : 0];
                 unsigned char *a_out = smem + out_off;
                 const uint32_t out_lo = (uint32_t)p.a_lo[a1_off ? (ib ^ 1) : 0];
-                const int slabs_per_round = p.tmem_cols / ly.NS;
+                const int slabs_per_round = (p.tmem_cols / U) / ly.NS;
                 const uint32_t idesc = instr_desc_bf16(ly.NS);
                 for (int sl0 = 0; sl0 < ly.nslab; sl0 += slabs_per_round) {
                     const int sl1 = min(ly.nslab, sl0 + slabs_per_round);
                     tc_fence_before();
-                    cbar_sync();
-                    if (warp == 0) {
+                    all_sync();            // the A operands of every team are complete / the previous round's TMEM reads and pool scratch drained
+                    if (warp_all == 0) {
                         tc_fence_after();
                         for (int sl = sl0; sl < sl1; ++sl) {
-                            const uint32_t d_tmem = tmem_base + (uint32_t)((sl - sl0) * ly.NS);
+                            const uint32_t d_tmem = tmem_all + (uint32_t)((sl - sl0) * ly.NS);
                             for (int kb = 0; kb < ly.nkb; ++kb) {
                                 const int cb = tc_chunk_bytes(ly, kb, kblk);   // bytes of one (hi or lo) image of the chunk
                                 uint32_t w_addr;
@@ -284,19 +310,26 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tcs_kernel(const TcsParams p
                                     ++wq;
                                 }
                                 const int kw = min(kblk, ly.K - kb * kblk);
+                                // team 0's addresses; team u's operands and accumulator lie u * a_team bytes / tmem_cols / U columns further
                                 const uint32_t ah = desc_lo_ns(a_in + (uint32_t)(kb * (kblk / 8) * a_lbo), (uint32_t)a_lbo);
                                 const uint32_t al = desc_lo_ns(a_in_lo + (uint32_t)(kb * (kblk / 8) * a_lbo), (uint32_t)a_lbo);
+                                const uint32_t u_a16 = (uint32_t)(a_team >> 4), u_cols = (uint32_t)(p.tmem_cols / U);
                                 const uint32_t bh = desc_lo_ns(w_addr, (uint32_t)(ly.NS * 16));
                                 const uint32_t bl = desc_lo_ns(w_addr + (uint32_t)cb, (uint32_t)(ly.NS * 16));
                                 const uint32_t a_step = (uint32_t)(2 * a_lbo / 16), b_step = (uint32_t)(2 * ly.NS);
                                 if (elect_one()) {
-                                    for (int j = 0; j < kw / 16; ++j) {
-                                        const uint64_t dah = mk_desc64(ah + (uint32_t)j * a_step, DESC_HI_NS), dal = mk_desc64(al + (uint32_t)j * a_step, DESC_HI_NS);
-                                        const uint64_t dbh = mk_desc64(bh + (uint32_t)j * b_step, DESC_HI_NS), dbl = mk_desc64(bl + (uint32_t)j * b_step, DESC_HI_NS);
-                                        umma_bf16(d_tmem, dah, dbh, idesc, (kb | j) ? 1u : 0u);
-                                        umma_bf16(d_tmem, dah, dbl, idesc, 1u);
-                                        umma_bf16(d_tmem, dal, dbh, idesc, 1u);
-                                        if (p.passes > 3) umma_bf16(d_tmem, dal, dbl, idesc, 1u);
+#pragma unroll
+                                    for (int u = 0; u < U; ++u) {
+                                        const uint32_t dt = d_tmem + (uint32_t)u * u_cols;
+                                        for (int j = 0; j < kw / 16; ++j) {
+                                            const uint64_t dah = mk_desc64(ah + (uint32_t)u * u_a16 + (uint32_t)j * a_step, DESC_HI_NS);
+                                            const uint64_t dal = mk_desc64(al + (uint32_t)u * u_a16 + (uint32_t)j * a_step, DESC_HI_NS);
+                                            const uint64_t dbh = mk_desc64(bh + (uint32_t)j * b_step, DESC_HI_NS), dbl = mk_desc64(bl + (uint32_t)j * b_step, DESC_HI_NS);
+                                            umma_bf16(dt, dah, dbh, idesc, (kb | j) ? 1u : 0u);
+                                            umma_bf16(dt, dah, dbl, idesc, 1u);
+                                            umma_bf16(dt, dal, dbh, idesc, 1u);
+                                            if (p.passes > 3) umma_bf16(dt, dal, dbl, idesc, 1u);
+                                        }
                                     }
                                     if (!p.resident) umma_commit(empty_bar + s);
                                 }
@@ -359,8 +392,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tcs_kernel(const TcsParams p
                         }
                     }
                     if (last && !p.direct) {
-                        cbar_sync();
-                        for (int i = tid; i < ncols * p.gpt; i += TC_CTHREADS) {
+                        team_sync();
+                        for (int i = ttid; i < ncols * p.gpt; i += TC_CTHREADS) {
                             const int c = i % ncols, gl = i / ncols;
                             float m;
                             if (p.gpt == 2) m = fmaxf(pool_s[(2 * gl) * p.pool_cols + c], pool_s[(2 * gl + 1) * p.pool_cols + c]);
@@ -379,15 +412,15 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tcs_kernel(const TcsParams p
             }
         }
         tc_fence_before();
-        cbar_sync();
-        if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+        all_sync();
+        if (warp_all == 0) tmem_dealloc(tmem_all, (uint32_t)p.tmem_cols);
     }
     if (p.cs > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 struct TcsPlan {
     TcLayout lay;
-    int TR, a_bytes[2], a_lo[2], pool_cols, tmem_cols, resident, nstage, stage_bytes, ctas_per_sm;
+    int TR, a_bytes[2], a_lo[2], pool_cols, tmem_cols, resident, nstage, stage_bytes, ctas_per_sm, U;
     size_t smem;
     int gpt, cpg, Kl, direct, use_atomic;
 };
@@ -419,18 +452,20 @@ bool tcs_plan(int K, int L, const int *dims, TcsPlan *pl)
             if (ab > pp[l & 1]) pp[l & 1] = ab;
         }
         if (pp[1] == 0) pp[1] = 16;
-        auto eval = [&](int tmem_cols, int ctas, bool want_resident, bool inplace, TcsPlan *o) -> bool {
+        auto eval = [&](int tmem_cols, int ctas, bool want_resident, bool inplace, TcsPlan *o, int U = 1) -> bool {
             *o = *pl;
-            o->TR = TR;
-            if (inplace && max_mid > tmem_cols) return false;
+            o->TR = TR; o->U = U;
+            const int cols_team = tmem_cols / U;              // accumulator columns of one tile
+            if (inplace && max_mid > cols_team) return false;
+            if (max_ns > cols_team) return false;
             const int b0 = inplace ? (pp[0] > pp[1] ? pp[0] : pp[1]) : pp[0];
             const int b1 = inplace ? 0 : pp[1];
             o->a_bytes[0] = 2 * b0; o->a_bytes[1] = 2 * b1;
             o->a_lo[0] = b0; o->a_lo[1] = b1;
-            const size_t fixed = (size_t)o->a_bytes[0] + o->a_bytes[1] + misc;
+            const size_t fixed = (size_t)U * (o->a_bytes[0] + o->a_bytes[1]) + misc + (size_t)(U - 1) * 2 * TC_ROWS * 4;
             o->tmem_cols = tmem_cols; o->ctas_per_sm = ctas;
-            o->pool_cols = o->direct ? 0 : (last_npad < tmem_cols ? last_npad : tmem_cols);
-            const size_t base = fixed + (size_t)4 * o->pool_cols * 4;
+            o->pool_cols = o->direct ? 0 : (last_npad < cols_team ? last_npad : cols_team);
+            const size_t base = fixed + (size_t)U * 4 * o->pool_cols * 4;
             const size_t budget = (size_t)TC_SMEM_LIMIT / ctas - (ctas > 1 ? 1024 : 0);
             if (want_resident) {
                 if (base + t.w_bytes > budget) return false;
@@ -450,6 +485,11 @@ bool tcs_plan(int K, int L, const int *dims, TcsPlan *pl)
         if (two_ok && eval(256, 2, true, false, &c)) { *pl = c; return true; }
         if (two_ok && eval(256, 2, true, true, &c)) { *pl = c; return true; }
         if (eval(512, 1, true, false, &c)) { *pl = c; return true; }
+        // streamed weights: two tiles per CTA sharing every chunk (one CTA per SM, a deep ring) before two CTAs with their own
+        // shallow rings (sa2: see the kernel comment); PN2_F32_U2=0 switches the two-team form off
+        static const bool u2 = !(getenv("PN2_F32_U2") && atoi(getenv("PN2_F32_U2")) == 0);
+        if (u2 && two_ok && eval(512, 1, false, false, &c, 2) && c.nstage >= 4) { *pl = c; return true; }
+        if (u2 && two_ok && eval(512, 1, false, true, &c, 2) && c.nstage >= 4) { *pl = c; return true; }
         if (two_ok && eval(256, 2, false, false, &c)) { *pl = c; return true; }
         if (two_ok && eval(256, 2, false, true, &c)) { *pl = c; return true; }
         if (eval(512, 1, false, false, &c)) { *pl = c; return true; }
@@ -503,13 +543,15 @@ int launch_sa_f32_split(const SaArgs &a, const void *packed_split, cudaStream_t 
     p.feat_fast = (a.D == 0) || (a.fc == 1 && a.D % 8 == 0 && a.fn % 4 == 0 && a.fb % 4 == 0 && ((uintptr_t)a.feat & 15) == 0);
     p.tmem_cols = pl.tmem_cols; p.resident = pl.resident; p.nstage = pl.nstage; p.stage_bytes = pl.stage_bytes;
     p.a_bytes[0] = pl.a_bytes[0]; p.a_bytes[1] = pl.a_bytes[1]; p.a_lo[0] = pl.a_lo[0]; p.a_lo[1] = pl.a_lo[1];
-    p.pool_cols = pl.pool_cols;
+    p.pool_cols = pl.pool_cols; p.U = pl.U;
     static const int passes_env = getenv("PN2_F32_PASSES") ? atoi(getenv("PN2_F32_PASSES")) : 4;
     p.passes = passes_env == 3 ? 3 : 4;
     if (p.tiles == 0) return 0;
-    cudaError_t e = cudaFuncSetAttribute(sa_tcs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    auto kern = pl.U == 2 ? sa_tcs_kernel<2> : sa_tcs_kernel<1>;
+    const unsigned nthreads = (unsigned)((pl.U * TC_CWARPS + 1) * 32);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) { set_error("sa_tcs: smem attribute (%zu B): %s", pl.smem, cudaGetErrorString(e)); return (int)e; }
-    int64_t grid = p.tiles;
+    int64_t grid = (p.tiles + pl.U - 1) / pl.U;
     const int64_t cap = (int64_t)148 * pl.ctas_per_sm;
     if (grid > cap) grid = cap;
     // streamed weights with one CTA per SM: the CTAs of a cluster share every chunk through one TMA multicast (the four-pass
@@ -522,27 +564,27 @@ int launch_sa_f32_split(const SaArgs &a, const void *packed_split, cudaStream_t 
         int cs = cs_env > 0 ? cs_env : 2;
         if (cs > 8) cs = 8;
         while (cs > 1 && (cs & (cs - 1))) --cs;
-        while (cs > 1 && p.tiles < 2 * cs) cs >>= 1;
+        while (cs > 1 && p.tiles < 2 * cs * pl.U) cs >>= 1;
         p.cs = cs;
-        if (cs > 1) { const int64_t ncl = (p.tiles + cs - 1) / cs, cap_cl = (int64_t)148 * pl.ctas_per_sm / cs; grid = (ncl < cap_cl ? ncl : cap_cl) * cs; }
+        if (cs > 1) { const int64_t ncl = ((p.tiles + pl.U - 1) / pl.U + cs - 1) / cs, cap_cl = (int64_t)148 * pl.ctas_per_sm / cs; grid = (ncl < cap_cl ? ncl : cap_cl) * cs; }
     }
     if (p.cs == 1) {
-        p.n_iter = (p.tiles + grid - 1) / grid;
-        sa_tcs_kernel<<<(unsigned)grid, TC_THREADS, pl.smem, st>>>(p);
+        p.n_iter = (p.tiles + grid * pl.U - 1) / (grid * pl.U);
+        kern<<<(unsigned)grid, nthreads, pl.smem, st>>>(p);
     } else {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(nthreads); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = (unsigned)p.cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         int max_clusters = 0;
-        e = cudaOccupancyMaxActiveClusters(&max_clusters, sa_tcs_kernel, &cfg);
+        e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
         if (e != cudaSuccess || max_clusters < 1) { set_error("sa_tcs: cluster occupancy (cs=%d): %s", p.cs, cudaGetErrorString(e)); return e ? (int)e : -1; }
         if (grid / p.cs > max_clusters) grid = (int64_t)max_clusters * p.cs;
         cfg.gridDim = dim3((unsigned)grid);
-        p.n_iter = (p.tiles + grid - 1) / grid;
-        e = cudaLaunchKernelEx(&cfg, sa_tcs_kernel, p);
+        p.n_iter = (p.tiles + grid * pl.U - 1) / (grid * pl.U);
+        e = cudaLaunchKernelEx(&cfg, kern, p);
         if (e != cudaSuccess) { set_error("sa_tcs: cluster launch (cs=%d): %s", p.cs, cudaGetErrorString(e)); return (int)e; }
     }
     return launch_status("pn2_sa_fused(f32, split tensor-core)");
