@@ -57,12 +57,10 @@ __device__ __forceinline__ void split8(float v0, float v1, float v2, float v3, f
     split2(v4, v5, hi.z, lo.z); split2(v6, v7, hi.w, lo.w);
 }
 
-// U = 1: one tile per CTA at a time (two CTAs per SM overlap each other).  U = 2: TWO TEAMS of eight compute warps, each with
-// its own tile (activation buffers, TMEM half, pooling scratch), walk the layers in lock step and share every streamed weight
-// chunk: team 0's first warp issues the chunk's MMAs for both tiles before the ring slot is released -- half the weight
-// traffic per tile, a ring deep enough to hide the L2 latency (the activations of two CTAs per SM leave room for two 16 KB
-// stages each: every chunk then waits ~2000 cycles for ~500 cycles of MMAs), and the fixed latencies of a layer (barriers,
-// commit, TMEM loads) amortised over two tiles.
+// U = 1 (default): one tile per CTA at a time (two CTAs per SM overlap each other).  U = 2 (opt-in, measured slower, see
+// tcs_plan): TWO TEAMS of eight compute warps, each with its own tile (activation buffers, TMEM half, pooling scratch), walk
+// the layers in lock step and share every streamed weight chunk: team 0's first warp issues the chunk's MMAs for both tiles
+// before the ring slot is released -- half the weight traffic per tile and a deeper ring.
 template <int U>
 __global__ void __launch_bounds__((U * TC_CWARPS + 1) * 32, U == 1 ? 2 : 1) sa_tcs_kernel(const TcsParams p)
 {
@@ -485,9 +483,10 @@ bool tcs_plan(int K, int L, const int *dims, TcsPlan *pl)
         if (two_ok && eval(256, 2, true, false, &c)) { *pl = c; return true; }
         if (two_ok && eval(256, 2, true, true, &c)) { *pl = c; return true; }
         if (eval(512, 1, true, false, &c)) { *pl = c; return true; }
-        // streamed weights: two tiles per CTA sharing every chunk (one CTA per SM, a deep ring) before two CTAs with their own
-        // shallow rings (sa2: see the kernel comment); PN2_F32_U2=0 switches the two-team form off
-        static const bool u2 = !(getenv("PN2_F32_U2") && atoi(getenv("PN2_F32_U2")) == 0);
+        // streamed weights: two tiles per CTA sharing every chunk (one CTA per SM, a four-stage ring) is OPT-IN (PN2_F32_U2=1):
+        // measured on sa2 (cls_ssg, B = 2048) it takes 13.4 ms against 10.7 ms for two independent CTAs per SM with two-stage
+        // rings -- the lock-step barrier over 16 warps and the single issuing warp cost more than the shared chunks save
+        static const bool u2 = getenv("PN2_F32_U2") && atoi(getenv("PN2_F32_U2")) == 1;
         if (u2 && two_ok && eval(512, 1, false, false, &c, 2) && c.nstage >= 4) { *pl = c; return true; }
         if (u2 && two_ok && eval(512, 1, false, true, &c, 2) && c.nstage >= 4) { *pl = c; return true; }
         if (two_ok && eval(256, 2, false, false, &c)) { *pl = c; return true; }

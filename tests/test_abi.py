@@ -79,7 +79,7 @@ def test_tensor_core_kernels_do_not_spill():
     out = subprocess.run(["cuobjdump", "--dump-resource-usage", _pn2_native.LIB_PATH], capture_output=True, text=True, timeout=120).stdout
     seen = 0
     for fn, usage in re.findall(r"Function (\S+):\n\s*(REG:.*)", out):
-        if re.search(r"sa_tc[s\d]?_kernel", fn):
+        if re.search(r"sa_tc\d?_kernel", fn):
             seen += 1
             stack, local = int(re.search(r"STACK:(\d+)", usage).group(1)), int(re.search(r"LOCAL:(\d+)", usage).group(1))
             assert stack == 0 and local == 0, (fn, usage)

@@ -538,7 +538,7 @@ def test_gather_and_scatter_add_rows_vs_torch(nat, B, N, D, S, K):
     assert rel_err(got_g.cpu(), exp_g) <= 1e-5                   # fp32 reductions in a different order
 
 
-@pytest.mark.parametrize("env", [{"PN2_F32_FFMA": "1"}, {"PN2_F32_PASSES": "3"}, {"PN2_F32_CLUSTER": "1"}, {"PN2_F32_CLUSTER": "4"}, {"PN2_F32_UNITS": "0"}])
+@pytest.mark.parametrize("env", [{"PN2_F32_FFMA": "1"}, {"PN2_F32_PASSES": "3"}, {"PN2_F32_CLUSTER": "1"}, {"PN2_F32_CLUSTER": "4"}, {"PN2_F32_UNITS": "0"}, {"PN2_F32_U2": "1"}])
 def test_fp32_mode_variants_keep_parity(env):
     """fp32 mode runs on the tensor cores with split (bf16 hi + bf16 lo) operands, four passes per K step (pn2_sa_tcs.cu).  The
     process-wide switches select the FFMA kernel instead (PN2_F32_FFMA), three passes, and the cluster size of the weight
