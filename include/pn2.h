@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PN2_ABI_VERSION 14
+#define PN2_ABI_VERSION 15
 #define PN2_MAX_COORD 16 /* exact summation-order rules are verified against ATen for C <= 16 */
 #define PN2_MAX_LAYERS 8
 
@@ -88,6 +88,13 @@ int pn2_group_f32(const float *points, int64_t sb, int64_t sn, int64_t sc,
 int pn2_gather_rows_f32(const float *feat, int64_t fb, int64_t fn, int64_t fc, const int32_t *idx32, int B, int N, int64_t M, int D,
                         float *out, void *stream);
 int pn2_scatter_add_rows_f32(const float *grad, const int32_t *idx32, int B, int N, int64_t M, int D, float *grad_feat, void *stream);
+
+/* Upload of the FPS start indices (the torch.randint draw of pointnet2_utils.py:59, made on the host like the reference's):
+ * `host_mapped` = n int64 in PINNED, device-mapped host memory (cudaHostAlloc under unified addressing: the host pointer is
+ * valid on the device); a kernel on `stream` copies them to dst (device).  Unlike a cudaMemcpyAsync this does not queue on the
+ * host-to-device copy engine behind a large input upload of the same process, and unlike a pageable copy it does not stall the
+ * enqueueing thread.  The caller keeps the host buffer unchanged until the stream has passed this launch. */
+int pn2_upload_i64(const int64_t *host_mapped, int64_t *dst, int64_t n, void *stream);
 
 /* Fold eval-mode BatchNorm into the 1x1 convolutions and lay the weights out for the fused kernels
  * (pointnet2_utils.py:154-155, :168-170).  L layers; dims[L+1] = {Cin, C1..CL}.  For layer l the six

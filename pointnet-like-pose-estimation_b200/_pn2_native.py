@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(_HERE, LIB_NAME)
 ORDER_SSG, ORDER_MSG, ORDER_ALL = 0, 1, 2
 PREC_F32, PREC_BF16 = 0, 1
 MAX_COORD = 16
-ABI_VERSION = 14
+ABI_VERSION = 15
 HEAD_PLAIN, HEAD_CLS, HEAD_TRANS, HEAD_SIGN = 0, 1, 2, 3
 
 _i64, _i32, _f32, _vp = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p
@@ -59,6 +59,7 @@ _SIGNATURES = {
     "pn2_rows_wgrad_tf32": ([_vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp], _i32),
     "pn2_gather_rows_f32": ([_vp, _i64, _i64, _i64, _vp, _i32, _i32, _i64, _i32, _vp, _vp], _i32),
     "pn2_scatter_add_rows_f32": ([_vp, _vp, _i32, _i32, _i64, _i32, _vp, _vp], _i32),
+    "pn2_upload_i64": ([_vp, _vp, _i64, _vp], _i32),
     "pn2_selftest_umma": ([_i32, _i32, _i32, _vp, _vp, _vp], _i32),
     "pn2_debug_trace": ([_vp], _i32),
     "pn2_selftest_tma_gather": ([_vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp], _i32),
@@ -153,6 +154,14 @@ class Native:
                                         i32.data_ptr() if want_idx32 else None,
                                         npts.data_ptr() if want_new_points else None, _stream(points)))
         return i64, i32, npts
+
+    def upload_i64(self, pinned, device):
+        """pinned int64 CPU tensor (page-locked) -> device tensor, copied by a kernel on the current stream (pn2_upload_i64)."""
+        assert pinned.dtype == torch.int64 and pinned.is_pinned() and pinned.is_contiguous()
+        out = torch.empty(pinned.shape, dtype=torch.int64, device=device)
+        with torch.cuda.device(device):
+            _check(self.lib.pn2_upload_i64(pinned.data_ptr(), out.data_ptr(), pinned.numel(), _stream(out)))
+        return out
 
     def index_points(self, src, idx, check=True):
         """src [B,N,C] strided, idx [B,...] int64 -> [B,...,C] contiguous."""

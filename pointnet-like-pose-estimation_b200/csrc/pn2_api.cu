@@ -250,4 +250,18 @@ int pn2_scatter_add_rows_f32(const float *grad, const int32_t *idx32, int B, int
     PN2_REQUIRE(B >= 0 && N >= 1 && M >= 0 && D >= 0, "pn2_scatter_add_rows_f32: bad sizes");
     return launch_scatter_add_rows(grad, idx32, B, N, M, D, grad_feat, (cudaStream_t)stream);
 }
+
+// see include/pn2.h
+__global__ void upload_i64_kernel(const int64_t *__restrict__ src, int64_t *__restrict__ dst, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+int pn2_upload_i64(const int64_t *host_mapped, int64_t *dst, int64_t n, void *stream)
+{
+    PN2_REQUIRE(host_mapped && dst && n >= 0, "pn2_upload_i64: bad arguments");
+    if (n == 0) return 0;
+    upload_i64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(host_mapped, dst, n);
+    return launch_status("pn2_upload_i64");
+}
 }  // extern "C"
