@@ -226,11 +226,12 @@ ball_query_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, i
                     if (!(ci + c < cpw && sidx < S)) continue;
                     const int *stg = stage + c * K;
                     const int cc = cn[c] > K ? K : cn[c];
-                    const int frst = cc ? stg[0] : N;                                               // hits are staged in index order
-                    if (cc == 0 && lane == 0 && empty_flag) atomicOr(empty_flag, 1);
+                    // hits are staged in index order; a NaN centre also "hits" the padding slots (indices >= N, always last)
+                    const int frst = (cc && stg[0] < N) ? stg[0] : N;
+                    if (frst == N && lane == 0 && empty_flag) atomicOr(empty_flag, 1);
                     const int64_t o = ((int64_t)b * S + sidx) * K;
                     for (int j = lane; j < K; j += 32) {
-                        const int v = (j < cc) ? stg[j] : frst;
+                        const int v = (j < cc && stg[j] < N) ? stg[j] : frst;
                         if (idx64) idx64[o + j] = v;
                         if (idx32) idx32[o + j] = v;
                     }
@@ -260,6 +261,158 @@ ball_query_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, i
             if (idx64) idx64[o + j] = v;
             if (idx32) idx32[o + j] = v;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Ball query with DEFERRED hit bookkeeping (C <= 4, cloud staged whole; the default for those shapes).
+//
+// The scan kernel above is issue-bound and a third of what it issues is bookkeeping: per (trip, centre) with a hit it computes
+// two prefix popcounts, two slot addresses and two predicated stores (~19 instructions, three trips in four at N = 1024,
+// r = 0.2), on top of 13 for the distances and ballots.  Here a trip only RECORDS: a trip covers 128 points, four per lane
+// (one LDS.128 per channel), staged so that component j of lane l is point 128 t + 32 j + l -- ballot j of trip t is then the
+// hit mask of the 32 CONSECUTIVE points of word 4 t + j, and it is parked in lane 4 t + j (one predicated move).  After 8 trips
+// = 1024 points every lane holds one word of the 1024-bit hit mask of each of the four centres in flight, in index order, and
+// the lists are resolved once: prefix sum of the popcounts over the lanes, then every lane emits its own set bits at its base
+// slot.  "First K in ascending index order" (:86-89) is unchanged -- the same pairs get the same distance arithmetic, only the
+// place where a hit's slot is computed moves.  Early exit: after every trip the per-centre totals (one REDUX over the parked
+// words) are compared with K.  Per 1024 points x 4 centres: ~1050 instructions against ~1800.
+template <int C, int BQ_WARPS>
+__global__ void __launch_bounds__(BQ_WARPS * 32, BQ_WARPS == BQ_WARPS_BIG ? 1 : 4)
+ball_query_masks_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, int64_t csc,
+                        const float *__restrict__ points, int64_t sb, int64_t sn, int64_t sc,
+                        int S, int N, int NCH /* multiple of 128 */, int cpw, float r2, int K,
+                        int64_t *__restrict__ idx64, int32_t *__restrict__ idx32, int32_t *__restrict__ empty_flag)
+{
+    static_assert(C <= 4, "one float4 of points per channel per lane");
+    constexpr int BQ_THREADS = BQ_WARPS * 32;
+    constexpr int CPB = 4;
+    extern __shared__ float smem[];
+    float *sp = smem;                       // [C][NCH], permuted inside every block of 128 points (see above)
+    float *sp2 = smem + (size_t)C * NCH;    // [NCH]
+    int *stage = (int *)(sp2 + NCH) + (threadIdx.x >> 5) * (CPB * K);      // [CPB][K] per warp
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    const int s_begin = (blockIdx.x * BQ_WARPS + warp) * cpw;
+    const float *P = points + (int64_t)b * sb;
+    const bool pcontig = (sc == 1);
+
+    // ---- stage the cloud: same arithmetic as ball_query_kernel; point n of a 128-block goes to slot 4 (n % 32) + n / 32 -----
+#pragma unroll(BQ_WARPS == BQ_WARPS_BIG ? 4 : 1)
+    for (int n = tid; n < N; n += BQ_THREADS) {
+        float v[C];
+        const int pos = (n & ~127) | ((n & 31) << 2) | ((n >> 5) & 3);
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            v[k] = __ldg(P + (int64_t)n * sn + (int64_t)k * sc);
+            sp[k * NCH + pos] = v[k];
+        }
+        sp2[pos] = sqnorm<C>(v, pcontig, n >= (N & ~31));
+    }
+    // padding up to NCH: zero coordinates and |p|^2 = +inf (d = +inf: never in radius; a NaN centre's hits beyond N are
+    // masked off when the lists are resolved)
+    for (int n = N + tid; n < NCH; n += BQ_THREADS) {
+        const int pos = (n & ~127) | ((n & 31) << 2) | ((n >> 5) & 3);
+#pragma unroll
+        for (int k = 0; k < C; ++k) sp[k * NCH + pos] = 0.f;
+        sp2[pos] = INFINITY;
+    }
+    __syncthreads();
+
+    const f32x2 m2v = pk2(-2.0f, -2.0f);
+    const bool odd = (lane & 1) != 0, upper = (lane & 2) != 0;
+    for (int ci = 0; ci < cpw; ci += CPB) {
+        if (s_begin + ci >= S) break;                                   // warp-uniform
+        f32x2 sv[CPB][C], s2v[CPB];
+        int cn[CPB];                                                    // hits resolved so far (warp-uniform)
+        unsigned hm[CPB];                                               // this lane's word of the current 1024-point window
+#pragma unroll
+        for (int c = 0; c < CPB; ++c) {
+            const int sidx = s_begin + ci + c;
+            const bool act = ci + c < cpw && sidx < S;
+            float sc_[C];
+#pragma unroll
+            for (int k = 0; k < C; ++k) sc_[k] = act ? __ldg(centres + (int64_t)b * csb + (int64_t)sidx * csn + (int64_t)k * csc) : 0.f;
+            const float q2 = sqnorm<C>(sc_, csc == 1, sidx >= (S & ~31));
+#pragma unroll
+            for (int k = 0; k < C; ++k) sv[c][k] = pk2(sc_[k], sc_[k]);
+            s2v[c] = pk2(q2, q2);
+            cn[c] = act ? 0 : K;                                        // an inactive slot counts as finished
+        }
+        for (int w0 = 0; w0 < NCH; w0 += 1024) {                        // windows of 1024 points = 32 mask words
+            const int trips = min(8, (NCH - w0) >> 7);
+#pragma unroll
+            for (int c = 0; c < CPB; ++c) hm[c] = 0u;
+            const float *prow = sp + w0 + 4 * lane;
+            for (int t = 0; t < trips; ++t, prow += 128) {
+                float4 pv[C];
+#pragma unroll
+                for (int k = 0; k < C; ++k) pv[k] = *reinterpret_cast<const float4 *>(prow + k * NCH);
+                const float4 p2 = *reinterpret_cast<const float4 *>(prow + C * NCH);
+                const f32x2 p2a = pk2(p2.x, p2.y), p2b = pk2(p2.z, p2.w);
+                const bool mine = (lane >> 2) == t;                     // lanes 4 t .. 4 t + 3 park the four ballots of this trip
+#pragma unroll
+                for (int c = 0; c < CPB; ++c) {
+                    f32x2 da = mul2(sv[c][0], pk2(pv[0].x, pv[0].y));
+                    f32x2 db = mul2(sv[c][0], pk2(pv[0].z, pv[0].w));
+#pragma unroll
+                    for (int k = 1; k < C; ++k) {
+                        da = fma2(sv[c][k], pk2(pv[k].x, pv[k].y), da);
+                        db = fma2(sv[c][k], pk2(pv[k].z, pv[k].w), db);
+                    }
+                    const float2 d01 = unpk2(add2(fma2(m2v, da, s2v[c]), p2a));     // fl(-2 dot + |s|^2): -2 dot is exact, one rounding either way
+                    const float2 d23 = unpk2(add2(fma2(m2v, db, s2v[c]), p2b));
+                    const unsigned m0 = __ballot_sync(0xffffffffu, !(d01.x > r2));
+                    const unsigned m1 = __ballot_sync(0xffffffffu, !(d01.y > r2));
+                    const unsigned m2 = __ballot_sync(0xffffffffu, !(d23.x > r2));
+                    const unsigned m3 = __ballot_sync(0xffffffffu, !(d23.y > r2));
+                    const unsigned pick = odd ? (upper ? m3 : m1) : (upper ? m2 : m0);       // ballot (lane & 3): selects, no branches
+                    hm[c] = mine ? pick : hm[c];
+                }
+                bool all_done = true;
+#pragma unroll
+                for (int c = 0; c < CPB; ++c) all_done = all_done && cn[c] + (int)__reduce_add_sync(0xffffffffu, (unsigned)__popc(hm[c])) >= K;
+                if (all_done) break;
+            }
+            // ---- resolve the window: lane l owns points w0 + 32 l .. + 31 ------------------------------------------------------
+            const int nb = w0 + 32 * lane;
+            const unsigned valid = nb + 32 <= N ? 0xffffffffu : (nb >= N ? 0u : (1u << (N - nb)) - 1u);
+            bool all_full = true;
+#pragma unroll
+            for (int c = 0; c < CPB; ++c) {
+                unsigned m = hm[c] & valid;
+                const int pc = __popc(m);
+                int inc = pc;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+                const int total = __shfl_sync(0xffffffffu, inc, 31);
+                if (cn[c] < K && total) {                               // warp-uniform
+                    int pos = cn[c] + inc - pc;
+                    int *stg = stage + c * K;
+                    while (m && pos < K) { stg[pos++] = nb + __ffs(m) - 1; m &= m - 1; }
+                }
+                cn[c] = min(K, cn[c] + total);
+                all_full = all_full && cn[c] >= K;
+            }
+            if (all_full) break;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < CPB; ++c) {
+            const int sidx = s_begin + ci + c;
+            if (!(ci + c < cpw && sidx < S)) continue;
+            const int *stg = stage + c * K;
+            const int cc = cn[c];
+            const int frst = cc ? stg[0] : N;                           // hits are staged in index order
+            if (cc == 0 && lane == 0 && empty_flag) atomicOr(empty_flag, 1);
+            const int64_t o = ((int64_t)b * S + sidx) * K;
+            for (int j = lane; j < K; j += 32) {
+                const int v = (j < cc) ? stg[j] : frst;
+                if (idx64) idx64[o + j] = v;
+                if (idx32) idx32[o + j] = v;
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -413,11 +566,11 @@ ball_query_multi_kernel(const float *__restrict__ centres, int64_t csb, int64_t 
                 const int K = q.K[r];
                 const int *stg = stage + c * q.ktot + q.koff[r];
                 const int cc = cn[c][r] > K ? K : cn[c][r];
-                const int frst = cc ? stg[0] : N;
-                if (cc == 0 && lane == 0 && empty_flag) atomicOr(empty_flag, 1);
+                const int frst = (cc && stg[0] < N) ? stg[0] : N;            // padding slots (NaN centre) are never reported
+                if (frst == N && lane == 0 && empty_flag) atomicOr(empty_flag, 1);
                 const int64_t o = ((int64_t)b * S + sidx) * K;
                 for (int j = lane; j < K; j += 32) {
-                    const int v = (j < cc) ? stg[j] : frst;
+                    const int v = (j < cc && stg[j] < N) ? stg[j] : frst;
                     if (q.idx64[r]) q.idx64[r][o + j] = v;
                     if (q.idx32[r]) q.idx32[r][o + j] = v;
                 }
@@ -741,7 +894,12 @@ static int launch_bq_w(const float *centres, int64_t csb, int64_t csn, int64_t c
 {
     const size_t stage_bytes = sizeof(int) * (size_t)BQ_WARPS * BQ_CPB<C>::value * K;
     const size_t budget = 200 * 1024 - stage_bytes;
-    int NCH = (N + 63) & ~63, cpw;          // rows padded to 64 points: the packed inner loop scans 64 per trip, unguarded
+    // deferred hit bookkeeping (ball_query_masks_kernel) wherever the cloud is staged whole and C <= 4; PN2_BQ_V1=1 keeps the
+    // per-trip bookkeeping of ball_query_kernel (the round-1 kernel) for re-measurement
+    static const bool v1_env = getenv("PN2_BQ_V1") && atoi(getenv("PN2_BQ_V1")) == 1;
+    bool masks = false;
+    if constexpr (C <= 4) masks = !v1_env && (size_t)(C + 1) * ((N + 127) & ~127) * sizeof(float) <= budget;
+    int NCH = masks ? ((N + 127) & ~127) : ((N + 63) & ~63), cpw;          // rows padded to whole trips (128 / 64 points): the inner loops are unguarded
     if ((size_t)(C + 1) * NCH * sizeof(float) > budget) {
         NCH = (int)(budget / ((C + 1) * sizeof(float))) & ~31;
         cpw = 1;  // multi-chunk path keeps one centre per warp in registers
@@ -756,12 +914,24 @@ static int launch_bq_w(const float *centres, int64_t csb, int64_t csn, int64_t c
         if (cpw_env > 0) cpw = cpw_env;
     }
     const size_t smem = (size_t)(C + 1) * NCH * sizeof(float) + stage_bytes;
+    dim3 grid((S + BQ_WARPS * cpw - 1) / (BQ_WARPS * cpw), B);
+    if constexpr (C <= 4) {
+        if (masks) {
+            auto kern = ball_query_masks_kernel<C, BQ_WARPS>;
+            if (smem > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) { set_error("ball_query(masks): smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+            }
+            kern<<<grid, BQ_WARPS * 32, smem, st>>>(centres, csb, csn, csc, points, sb, sn, sc, S, N, NCH, cpw, r2, K,
+                                                    idx64, idx32, empty_flag);
+            return launch_status("pn2_ball_query_f32(masks)");
+        }
+    }
     auto kern = ball_query_kernel<C, BQ_WARPS>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("ball_query: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
     }
-    dim3 grid((S + BQ_WARPS * cpw - 1) / (BQ_WARPS * cpw), B);
     kern<<<grid, BQ_WARPS * 32, smem, st>>>(centres, csb, csn, csc, points, sb, sn, sc, S, N, NCH, cpw, r2, K,
                                             idx64, idx32, empty_flag);
     return launch_status("pn2_ball_query_f32");

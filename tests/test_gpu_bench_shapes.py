@@ -321,6 +321,39 @@ def test_ball_query_grid_cull_variants_keep_parity(cells):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
 
 
+def test_ball_query_per_trip_bookkeeping_kernel_keeps_parity():
+    """PN2_BQ_V1=1 (read once per process) selects the round-1 scan kernel (slot arithmetic inside every trip) instead of the
+    deferred-bookkeeping kernel that is the default for C <= 4 (hit masks parked in lanes, lists resolved once per 1024
+    points): the same cases must pass on both, so the switch stays usable for re-measurement."""
+    e = dict(os.environ, PN2_BQ_V1="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_kernels.py"),
+                        os.path.join(ROOT, "tests", "test_gpu_bench_shapes.py"), "-m", "gpu", "-q", "-x",
+                        "-k", "test_ball_query_vs_oracle or test_golden_fps_ball_sqdist or test_ball_query_batched_launch_shapes or "
+                              "test_config2 or test_ball_query_empty or test_ball_query_odd_clouds or test_ball_query_few_points"],
+                       env=e, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
+
+
+@pytest.mark.parametrize("N,S,K,r,kind", [(20, 8, 20, 0.5, "plain"), (20, 8, 20, 0.5, "nan_centre"), (130, 40, 130, 3.0, "plain"),
+                                          (1025, 64, 40, 0.3, "plain"), (1024, 64, 1024, 3.0, "plain"), (2049, 33, 64, 0.25, "nan_centre"),
+                                          (3000, 50, 3000, 3.0, "plain"), (1056, 40, 16, 0.02, "plain")])
+def test_ball_query_few_points_and_window_edges_vs_oracle(pu, oracle, N, S, K, r, kind):
+    """Edges of the deferred-bookkeeping kernel: lists as long as the cloud (K = N is the reference's limit, :86 slices the
+    sorted [B,S,N] tensor; the padding slots of the staged cloud must never be reported, not even for a NaN centre whose every
+    distance is NaN = in radius, :85), lists longer than one 1024-point window, clouds one point past a window / a 128-point trip, and balls that are nearly always empty."""
+    B = 3
+    x = cloudgen.uniform_cloud(B, N, 77 + N)
+    start = torch.randint(0, N, (B,), generator=torch.Generator().manual_seed(8), dtype=torch.long)
+    cen = oracle.index_points(x, oracle.farthest_point_sample(x, S, start)).contiguous()
+    if kind == "nan_centre":
+        cen[1, 2, 0] = float("nan")
+    exp = oracle.query_ball_point(r, K, x, cen, allow_empty=True)
+    be = pu._backend()
+    i64, i32 = be.ball_query(cen.to(DEV), x.to(DEV), oracle.radius_sq_f32(r), K, want_idx64=True, want_idx32=True)
+    assert torch.equal(i64.cpu(), exp)
+    assert torch.equal(i32.cpu().long(), exp)
+
+
 @pytest.mark.parametrize("kind", ["scaled", "shifted", "nan_point", "nan_centre", "far_centre", "flat", "inf_point"])
 def test_ball_query_odd_clouds_vs_oracle(pu, oracle, kind):
     """Clouds the grid cull must not get wrong: un-normalised coordinates (x1000, +5000: the fp32 rounding of the expanded form
