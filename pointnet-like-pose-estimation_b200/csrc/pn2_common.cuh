@@ -210,6 +210,7 @@ int launch_sa_bf16(const SaArgs &a, cudaStream_t st);
 int launch_sa_bf16_pipelined(const SaArgs &a, cudaStream_t st);   // -100: configuration not covered
 int sa_bf16_pipelined_covers(int K, int C, int D, int order, int L, const int *dims);
 void set_debug_trace(void *buf);
+unsigned long long *get_debug_trace();     // the buffer of pn2_debug_trace (NULL = tracing off)
 int launch_ball_query_multi(const float *centres, int64_t csb, int64_t csn, int64_t csc,
                             const float *points, int64_t sb, int64_t sn, int64_t sc,
                             int B, int S, int N, int C, int NR, const float *r2, const int *K,

@@ -17,6 +17,7 @@
 // LBO bytes.  For A, LBO = 128*16: a k-group column holds the 128 rows back to back, so a warp that writes
 // 32 consecutive rows of one k-group (gather and epilogue both do) stores 512 contiguous bytes.
 #include <stdlib.h>
+#include <type_traits>
 #include "pn2_sa_pipe.cuh"
 
 namespace pn2 {
@@ -24,7 +25,7 @@ namespace pn2 {
 int64_t packed_bytes_bf16(int L, const int *dims)
 {
     const TcLayout t = tc_layout(L, dims);
-    return (int64_t)t.total_bytes;
+    return t.replicas > 1 ? (int64_t)t.replicas * t.rep_stride : (int64_t)t.total_bytes;
 }
 
 struct TcPackArgs {
@@ -100,6 +101,10 @@ int launch_pack_bf16(int L, const int *dims, const void *const *ptrs, float eps,
         a.mu[l] = (const float *)ptrs[6 * l + 4]; a.var[l] = (const float *)ptrs[6 * l + 5];
     }
     pack_bf16_kernel<<<148, 256, 0, st>>>(a, (unsigned char *)packed);
+    for (int r = 1; r < a.lay.replicas; ++r) {
+        cudaError_t e = cudaMemcpyAsync((unsigned char *)packed + (size_t)r * a.lay.rep_stride, packed, (size_t)a.lay.total_bytes, cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) { set_error("pn2_pack_weights: replica copy: %s", cudaGetErrorString(e)); return (int)e; }
+    }
     return launch_status("pn2_pack_weights(bf16)");
 }
 
@@ -109,6 +114,7 @@ int launch_pack_bf16(int L, const int *dims, const void *const *ptrs, float eps,
 struct TcParams {
     const float *points; int64_t sb, sn, sc;
     const float *feat;   int64_t fb, fn, fc;
+    const __nv_bfloat16 *feat_bf16;      // optional bf16 copy of feat, [B,N,D] contiguous (D % 8 == 0): gathered instead of the fp32 rows
     const float *centres; const int32_t *idx32;
     int N, S, K, C, D, order;
     TcLayout lay;
@@ -130,6 +136,8 @@ struct TcParams {
     int a_bytes[2];    // activation buffers (a_bytes[1] == 0: one buffer, each layer's epilogue overwrites its own input)
     int pool_cols;     // columns of the cross-warp pooling scratch (0 if direct)
     int pipelined_last;   // last layer transposed + pipelined over 128-column TMEM buffers (needs 128-channel slabs)
+    int gather_depth;     // feature-row segments a thread keeps in flight during the gather (1 or 4)
+    unsigned long long *trace;   // pn2_debug_trace buffer (CTA 0: role 0 = compute warp 0, 1 = producer warp, 2 = pooling warp 4)
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
@@ -184,6 +192,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
     // producer warp: weights -> shared memory through the bulk-copy engine
     // =====================================================================================================
     if (warp == TC_CWARPS) {
+        Tracer tr; tr.init(p.trace, 1, blockIdx.x == 0 && lane == 0);
         if (lane == 0) {
             if (p.resident) {
                 mbar_expect_tx(full_bar, (uint32_t)lay.w_bytes);
@@ -204,6 +213,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
                 uint32_t free_remote = 0;
                 if (p.cs > 1) asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(free_remote) : "r"(smem_u32(slot_free)));
                 const uint16_t mask = (uint16_t)((1u << p.cs) - 1u);
+                // this CTA's (cluster's) copy of the weight image: same bytes, different L2 lines than its neighbours read
+                const unsigned char *wsrc = p.packed + (size_t)((blockIdx.x / (unsigned)p.cs) % (unsigned)lay.replicas) * lay.rep_stride;
                 for (int64_t it = 0; it < p.n_iter; ++it) {
                     int off = 0;
                     for (int l = 0; l < lay.L; ++l)
@@ -213,15 +224,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
                                 const int s = q % p.nstage;
                                 const uint32_t ph = (q / p.nstage) & 1u;
                                 mbar_wait(empty_bar + s, ph ^ 1u);
+                                tr.mark(0x900);
                                 mbar_expect_tx(full_bar + s, (uint32_t)cb);
                                 if (p.cs == 1) {
-                                    bulk_g2s(Wsm + (size_t)s * p.stage_bytes, p.packed + off, (uint32_t)cb, full_bar + s);
+                                    bulk_g2s(Wsm + (size_t)s * p.stage_bytes, wsrc + off, (uint32_t)cb, full_bar + s);
                                 } else {
                                     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(free_remote + (uint32_t)(s * 8)) : "memory");
                                     if (cta_rank == 0) {
                                         mbar_wait_cluster(slot_free + s, ph);
                                         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-                                                     ::"r"(smem_u32(Wsm + (size_t)s * p.stage_bytes)), "l"(p.packed + off), "r"((uint32_t)cb),
+                                                     ::"r"(smem_u32(Wsm + (size_t)s * p.stage_bytes)), "l"(wsrc + off), "r"((uint32_t)cb),
                                                        "r"(smem_u32(full_bar + s)), "h"(mask) : "memory");
                                     }
                                 }
@@ -242,10 +254,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
         const int K = p.K, C = p.C, D = p.D;
         uint32_t acc_phase = 0, wq = 0, gsl = 0;      // gsl: last-layer slabs issued / pooled so far (TMEM buffer ring position)
         if (p.resident && warp == 0) mbar_wait(full_bar, 0);
+        Tracer tr; tr.init(p.trace, warp == 4 ? 2 : 0, blockIdx.x == 0 && (warp == 0 || warp == 4) && lane == 0);
 
         for (int64_t it = 0; it < p.n_iter; ++it) {
             const int64_t tile = it * gridDim.x + blockIdx.x;     // beyond p.tiles: an all-padding tile (keeps the cluster's ring in step)
             cbar_sync();
+            tr.mark(0x100);
             // ---- row bookkeeping ------------------------------------------------------------------------
             if (tid < TC_ROWS) {
                 const int r = tid;
@@ -265,6 +279,52 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
                 const int K0 = lay.ly[0].K;
                 if (p.feat_fast) {
                     const int cpr = D / 8;                               // 16-byte chunks per row
+                    if (p.feat_bf16) {
+                        // the previous layer left a bf16 copy of its rows: 16 bytes = the 8 channels of one core-matrix row, copied by
+                        // cp.async straight into the operand (no conversion, no register held while in flight, every segment of the
+                        // tile on its way at once; half the bytes of the fp32 rows)
+                        // lane pairs take the two 16-byte halves of one 32-byte sector (k-groups 2j, 2j+1 of a row) in the same instruction
+                        for (int i = tid; i < TC_ROWS * ((cpr + 1) & ~1); i += TC_CTHREADS) {
+                            const int kg = ((i >> 1) / TC_ROWS) * 2 + (i & 1), r = (i >> 1) % TC_ROWS;
+                            const int n = s_n[r];
+                            const __nv_bfloat16 *f = p.feat_bf16 + ((int64_t)(s_g[r] / p.S) * p.N + (n < 0 ? 0 : n)) * D + kg * 8;
+                            if (kg < cpr) cp_async16_zfill(A0 + (size_t)kg * A_LBO + r * 16, n < 0 ? p.feat_bf16 : f, n >= 0);
+                        }
+                        asm volatile("cp.async.commit_group;" ::: "memory");
+                    } else if (p.gather_depth > 1) {
+                        // DEPTH 32-byte segments per thread in flight before the first store: the loads are L2 / HBM latency and
+                        // nothing else runs in this CTA during the gather (one CTA per SM for the wide stacks)
+                        auto gather_feat = [&](auto depth_tag) {
+                            constexpr int DEPTH = decltype(depth_tag)::value;
+                            for (int i0 = tid; i0 < TC_ROWS * cpr; i0 += DEPTH * TC_CTHREADS) {
+                                float4 x[DEPTH], y[DEPTH];
+#pragma unroll
+                                for (int u = 0; u < DEPTH; ++u) {
+                                    const int i = i0 + u * TC_CTHREADS;
+                                    x[u] = y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                    if (i < TC_ROWS * cpr) {
+                                        const int r = i % TC_ROWS, kg = i / TC_ROWS;
+                                        const int n = s_n[r];
+                                        if (n >= 0) {
+                                            const float *f = p.feat + (int64_t)(s_g[r] / p.S) * p.fb + (int64_t)n * p.fn + kg * 8;
+                                            x[u] = __ldg(reinterpret_cast<const float4 *>(f));
+                                            y[u] = __ldg(reinterpret_cast<const float4 *>(f) + 1);
+                                        }
+                                    }
+                                }
+#pragma unroll
+                                for (int u = 0; u < DEPTH; ++u) {
+                                    const int i = i0 + u * TC_CTHREADS;
+                                    if (i < TC_ROWS * cpr) {
+                                        const int r = i % TC_ROWS, kg = i / TC_ROWS;
+                                        *reinterpret_cast<uint4 *>(A0 + (size_t)kg * A_LBO + r * 16) =
+                                            make_uint4(pack_bf16x2(x[u].x, x[u].y), pack_bf16x2(x[u].z, x[u].w), pack_bf16x2(y[u].x, y[u].y), pack_bf16x2(y[u].z, y[u].w));
+                                    }
+                                }
+                            }
+                        };
+                        gather_feat(std::integral_constant<int, 4>{});
+                    } else
                     for (int it = tid; it < TC_ROWS * cpr; it += TC_CTHREADS) {
                         const int r = it % TC_ROWS, kg = it / TC_ROWS;
                         const int n = s_n[r];
@@ -296,6 +356,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
                                 make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
                         }
                     }
+                    if (p.feat_bf16) asm volatile("cp.async.wait_group 0;" ::: "memory");
                 } else {
                     // generic strides / D not a multiple of 8: one element at a time
                     for (int it = tid; it < TC_ROWS * K0; it += TC_CTHREADS) {
@@ -317,6 +378,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
                 }
             }
             fence_proxy_async();     // generic-proxy stores -> visible to the tensor core's async proxy
+            tr.mark(0x200);
 
             const bool row_valid = s_n[row] >= 0;   // written before the last cbar_sync
             // ---- layers ---------------------------------------------------------------------------------------
@@ -337,6 +399,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
                     const int nbuf = p.tmem_cols / TC_ROWS;
                     tc_fence_before();
                     cbar_sync();                                   // the layer's A operand is complete
+                    tr.mark(0x300 + l);
                     if (warp == 0) {
                         tc_fence_after();
                         for (int sl = 0; sl < ly.nslab; ++sl, ++gsl) {
@@ -353,6 +416,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
                                     s = wq % p.nstage;
                                     mbar_wait(full_bar + s, (wq / p.nstage) & 1u);
                                     tc_fence_after();
+                                    tr.mark(0x800);
                                     w_addr = smem_u32(Wsm) + (uint32_t)(s * p.stage_bytes);
                                     ++wq;
                                 }
@@ -369,6 +433,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
                             }
                             if (elect_one()) umma_commit(acc_full + buf);
                             __syncwarp();
+                            tr.mark(0x700 + sl);
                         }
                     } else if (warp >= 4) {
                         // valid-row ballots of the tile (rows without a neighbour pool as -inf), shared by the four pooling warps
@@ -397,6 +462,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(acc_empty + buf);
+                            tr.mark(0xA00 + sl);
                         }
                     } else {
                         gsl += (uint32_t)ly.nslab;                 // warps 1-3: keep the slab counter in step
@@ -407,6 +473,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
                     const int sl1 = min(ly.nslab, sl0 + slabs_per_round);
                     tc_fence_before();
                     cbar_sync();       // A operand complete / previous round's TMEM reads and pool scratch drained
+                    tr.mark(0x300 + l);
                     if (warp == 0) {
                         // the whole warp walks the chunk sequence (warp-uniform addresses -> uniform datapath), one
                         // elected lane issues: ~65 cycles per MMA instead of ~120 from a divergent single thread
@@ -422,6 +489,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
                                     s = wq % p.nstage;
                                     mbar_wait(full_bar + s, (wq / p.nstage) & 1u);
                                     tc_fence_after();
+                                    tr.mark(0x800);
                                     w_addr = smem_u32(Wsm) + (uint32_t)(s * p.stage_bytes);
                                     ++wq;
                                 }
@@ -440,9 +508,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
                         if (elect_one()) umma_commit(acc_bar);
                     }
                     __syncwarp();
+                    tr.mark(0x400 + l);
                     mbar_wait(acc_bar, acc_phase);
                     acc_phase ^= 1u;
                     tc_fence_after();
+                    tr.mark(0x500 + l);
 
                     // ---- epilogue of this round: columns [sl0*NS, sl1*NS) -----------------------------------------
                     const int ncols = (sl1 - sl0) * ly.NS;
@@ -506,6 +576,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
                         }
                     }
                     if (!last) fence_proxy_async();
+                    tr.mark(0x600 + l);
                 }
             }
         }
@@ -601,7 +672,9 @@ int launch_sa_bf16(const SaArgs &a, cudaStream_t st)
         const int rc = launch_sa_bf16_pipelined(a, st);
         if (rc != -100) return rc;
     }
-    PN2_REQUIRE(a.D == 0 || a.feat, "pn2_sa_fused(bf16): this configuration needs the fp32 feature rows (bf16-only features are gathered by the pipelined kernels)");
+    static const bool twin_off = getenv("PN2_TC_RING_TWIN") && atoi(getenv("PN2_TC_RING_TWIN")) == 0;
+    const bool use_twin = !twin_off && a.feat_bf16 && a.D > 0 && a.D % 8 == 0 && ((uintptr_t)a.feat_bf16 & 15) == 0;
+    PN2_REQUIRE(a.D == 0 || a.feat || use_twin, "pn2_sa_fused(bf16): this configuration needs the fp32 feature rows (or bf16 rows with D %% 8 == 0)");
     // the streaming kernel has no bf16 side output: a caller that was promised one by pn2_sa_bf16_side_io (which cannot see the
     // batch size or PN2_TC_RING_ONLY) must not receive an unwritten tensor
     PN2_REQUIRE(a.out_bf16 == nullptr || !sa_bf16_pipelined_covers(a.K, a.C, a.D, a.order, a.L, a.dims),
@@ -622,10 +695,15 @@ int launch_sa_bf16(const SaArgs &a, cudaStream_t st)
     p.gpt = pl.gpt; p.cpg = pl.cpg; p.Kl = pl.Kl; p.direct = pl.direct; p.use_atomic = pl.use_atomic;
     p.tiles = pl.cpg > 1 ? p.G * pl.cpg : (p.G + pl.gpt - 1) / pl.gpt;
     p.feat_fast = (a.D == 0) || (a.fc == 1 && a.D % 8 == 0 && a.fn % 4 == 0 && a.fb % 4 == 0 && ((uintptr_t)a.feat & 15) == 0);
+    p.feat_bf16 = use_twin ? (const __nv_bfloat16 *)a.feat_bf16 : nullptr;     // PN2_TC_RING_TWIN=0: always the fp32 rows
+    if (p.feat_bf16) p.feat_fast = 1;         // the twin is contiguous [B,N,D] whatever the strides of the fp32 rows
     p.tmem_cols = pl.tmem_cols; p.resident = pl.resident; p.nstage = pl.nstage; p.stage_bytes = pl.stage_bytes;
     p.a_bytes[0] = pl.a_bytes[0]; p.a_bytes[1] = pl.a_bytes[1]; p.pool_cols = pl.pool_cols;
     static const int pipe_env = getenv("PN2_RING_PIPELINED") ? atoi(getenv("PN2_RING_PIPELINED")) : 1;
     p.pipelined_last = (pipe_env && pl.lay.ly[a.L - 1].NS == TC_ROWS && pl.tmem_cols >= 2 * TC_ROWS && TC_ROWS / pl.gpt >= 8) ? 1 : 0;
+    static const int gather_env = getenv("PN2_TC_GATHER") ? atoi(getenv("PN2_TC_GATHER")) : 4;
+    p.gather_depth = gather_env == 1 ? 1 : 4;       // fp32 rows (no bf16 copy from the previous layer): segments in flight per thread
+    p.trace = get_debug_trace();
     if (p.tiles == 0) return 0;
     cudaError_t e = cudaFuncSetAttribute(sa_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) { set_error("sa_tc: smem attribute (%zu B): %s", pl.smem, cudaGetErrorString(e)); return (int)e; }

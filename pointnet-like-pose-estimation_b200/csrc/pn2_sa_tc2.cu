@@ -578,6 +578,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) sa_tc3_kernel(const __grid_cons
 // ------------------------------------------------------------------------------------------------------
 static unsigned long long *g_trace = nullptr;
 void set_debug_trace(void *buf) { g_trace = (unsigned long long *)buf; }
+unsigned long long *get_debug_trace() { return g_trace; }
 
 static int pow2_at_least(int x) { int p = 32; while (p < x) p <<= 1; return p; }
 

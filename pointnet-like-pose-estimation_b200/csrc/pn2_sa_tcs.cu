@@ -19,7 +19,8 @@
 // tiles: the A descriptor still spans 128 rows (rows 64..127 alias the next k-group: garbage accumulator lanes nobody
 // reads), the activations of a tile then fit beside the weight ring.
 #include <stdlib.h>
-#include "pn2_tc.cuh"
+#include <type_traits>
+#include "pn2_sa_pipe.cuh"
 
 namespace pn2 {
 
@@ -42,6 +43,8 @@ struct TcsParams {
     int a_lo[2];                     // offset of the lo copy inside each buffer
     int pool_cols, passes;
     int U;                           // tiles in flight per CTA: 1, or 2 teams of 8 compute warps sharing every streamed weight chunk
+    int gather_depth;                // gather: 0 = cp.async + in-place conversion, 4 = register-staged loads, four 32-byte segments in flight
+    unsigned long long *trace;       // pn2_debug_trace buffer (role 0 = compute warp 0, role 1 = producer warp; CTA 0 only)
 };
 
 // bf16 hi parts and bf16 lo parts (packed pairs) of two fp32 values
@@ -123,6 +126,7 @@ __global__ void __launch_bounds__((U * TC_CWARPS + 1) * 32, U == 1 ? 2 : 1) sa_t
 
     if (is_producer) {
         // ================================ producer warp: weight chunks (hi | lo) -> shared memory ==============================
+        Tracer tr; tr.init(p.trace, 1, blockIdx.x == 0 && lane == 0);
         if (lane == 0) {
             if (p.resident) {
                 mbar_expect_tx(full_bar, (uint32_t)lay.w_bytes);
@@ -139,6 +143,8 @@ __global__ void __launch_bounds__((U * TC_CWARPS + 1) * 32, U == 1 ? 2 : 1) sa_t
                 uint32_t free_remote = 0;
                 if (p.cs > 1) asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(free_remote) : "r"(smem_u32(slot_free)));
                 const uint16_t mask = (uint16_t)((1u << p.cs) - 1u);
+                // this CTA's (cluster's) copy of the weight image (tc_weight_replicas)
+                const unsigned char *wsrc = p.packed + (size_t)((blockIdx.x / (unsigned)p.cs) % (unsigned)lay.replicas) * lay.rep_stride;
                 for (int64_t it = 0; it < p.n_iter; ++it) {
                     int off = 0;
                     for (int l = 0; l < lay.L; ++l)
@@ -148,15 +154,16 @@ __global__ void __launch_bounds__((U * TC_CWARPS + 1) * 32, U == 1 ? 2 : 1) sa_t
                                 const int s = q % p.nstage;
                                 const uint32_t ph = (q / p.nstage) & 1u;
                                 mbar_wait(empty_bar + s, ph ^ 1u);
+                                tr.mark(0x900);
                                 mbar_expect_tx(full_bar + s, (uint32_t)cb);
                                 if (p.cs == 1) {
-                                    bulk_g2s(Wsm + (size_t)s * p.stage_bytes, p.packed + off, (uint32_t)cb, full_bar + s);
+                                    bulk_g2s(Wsm + (size_t)s * p.stage_bytes, wsrc + off, (uint32_t)cb, full_bar + s);
                                 } else {
                                     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(free_remote + (uint32_t)(s * 8)) : "memory");
                                     if (cta_rank == 0) {
                                         mbar_wait_cluster(slot_free + s, ph);
                                         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-                                                     ::"r"(smem_u32(Wsm + (size_t)s * p.stage_bytes)), "l"(p.packed + off), "r"((uint32_t)cb),
+                                                     ::"r"(smem_u32(Wsm + (size_t)s * p.stage_bytes)), "l"(wsrc + off), "r"((uint32_t)cb),
                                                        "r"(smem_u32(full_bar + s)), "h"(mask) : "memory");
                                     }
                                 }
@@ -174,10 +181,12 @@ __global__ void __launch_bounds__((U * TC_CWARPS + 1) * 32, U == 1 ? 2 : 1) sa_t
         const int K = p.K, C = p.C, D = p.D;
         uint32_t acc_phase = 0, wq = 0;
         if (p.resident && warp_all == 0) mbar_wait(full_bar, 0);
+        Tracer tr; tr.init(p.trace, 0, blockIdx.x == 0 && warp_all == 0 && lane == 0);
 
         for (int64_t it = 0; it < p.n_iter; ++it) {
             const int64_t tile = (it * gridDim.x + blockIdx.x) * U + team;
             team_sync();
+            tr.mark(0x100);
             if (ttid < TC_ROWS) {
                 const int r = ttid;
                 int64_t g = p.G; int j = 0;
@@ -198,36 +207,57 @@ __global__ void __launch_bounds__((U * TC_CWARPS + 1) * 32, U == 1 ? 2 : 1) sa_t
                 const int K0 = lay.ly[0].K;
                 if (p.feat_fast) {
                     const int cpr = D / 8;
-                    // four 32-byte segments per thread in flight before the first store (the loads are L2 / HBM latency)
-                    for (int i0 = ttid; i0 < TR * cpr; i0 += 4 * TC_CTHREADS) {
-                        float4 x[4], y[4];
+                    // DEPTH 32-byte segments per thread in flight before the first store: the loads are L2 / HBM latency (traced on
+                    // B200: the gather was 13 k of the 44 k cycles of an sa2 tile with four in flight)
+                    auto gather_feat = [&](auto depth_tag) {
+                        constexpr int DEPTH = decltype(depth_tag)::value;
+                        for (int i0 = ttid; i0 < TR * cpr; i0 += DEPTH * TC_CTHREADS) {
+                            float4 x[DEPTH], y[DEPTH];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int i = i0 + u * TC_CTHREADS;
-                            x[u] = y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (i < TR * cpr) {
-                                const int r = i % TR, kg = i / TR;
-                                const int n = s_n[r];
-                                if (n >= 0) {
-                                    const float *f = p.feat + (int64_t)(s_g[r] / p.S) * p.fb + (int64_t)n * p.fn + kg * 8;
-                                    x[u] = __ldg(reinterpret_cast<const float4 *>(f));
-                                    y[u] = __ldg(reinterpret_cast<const float4 *>(f) + 1);
+                            for (int u = 0; u < DEPTH; ++u) {
+                                const int i = i0 + u * TC_CTHREADS;
+                                x[u] = y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (i < TR * cpr) {
+                                    const int r = i % TR, kg = i / TR;
+                                    const int n = s_n[r];
+                                    if (n >= 0) {
+                                        const float *f = p.feat + (int64_t)(s_g[r] / p.S) * p.fb + (int64_t)n * p.fn + kg * 8;
+                                        x[u] = __ldg(reinterpret_cast<const float4 *>(f));
+                                        y[u] = __ldg(reinterpret_cast<const float4 *>(f) + 1);
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int u = 0; u < DEPTH; ++u) {
+                                const int i = i0 + u * TC_CTHREADS;
+                                if (i < TR * cpr) {
+                                    const int r = i % TR, kg = i / TR;
+                                    uint4 hi, lo;
+                                    split8(x[u].x, x[u].y, x[u].z, x[u].w, y[u].x, y[u].y, y[u].z, y[u].w, hi, lo);
+                                    unsigned char *dst = A0 + (size_t)kg * a_lbo + r * 16;
+                                    *reinterpret_cast<uint4 *>(dst) = hi;
+                                    *reinterpret_cast<uint4 *>(dst + lo_off) = lo;
                                 }
                             }
                         }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int i = i0 + u * TC_CTHREADS;
-                            if (i < TR * cpr) {
-                                const int r = i % TR, kg = i / TR;
-                                uint4 hi, lo;
-                                split8(x[u].x, x[u].y, x[u].z, x[u].w, y[u].x, y[u].y, y[u].z, y[u].w, hi, lo);
-                                unsigned char *dst = A0 + (size_t)kg * a_lbo + r * 16;
-                                *reinterpret_cast<uint4 *>(dst) = hi;
-                                *reinterpret_cast<uint4 *>(dst + lo_off) = lo;
-                            }
+                    };
+                    if (p.gather_depth == 0) {
+                        // asynchronous form: the raw fp32 segment (32 B = 8 channels of one row) is copied by cp.async straight into
+                        // the two 16-byte slots its (hi, lo) images will occupy -- no register is held while the load is in flight, so
+                        // ALL sixteen segments of a thread travel at once (one memory round trip per tile instead of four) -- and the
+                        // segment is converted in place after the wait (one thread per segment reads both slots, then rewrites them)
+                        // lane pairs cover the two 16-byte halves of one 32-byte sector in the SAME instruction (a lane that copied
+                        // both halves in two instructions made L2 send every sector twice: cp.async.cg does not allocate in L1)
+                        for (int i = ttid; i < 2 * TR * cpr; i += TC_CTHREADS) {
+                            const int half = i & 1, seg = i >> 1;
+                            const int r = seg % TR, kg = seg / TR;
+                            const int n = s_n[r];
+                            const float *f = p.feat + (int64_t)(s_g[r] / p.S) * p.fb + (int64_t)(n < 0 ? 0 : n) * p.fn + kg * 8 + half * 4;
+                            unsigned char *dst = A0 + (size_t)kg * a_lbo + r * 16 + (half ? lo_off : 0u);
+                            cp_async16_zfill(dst, n < 0 ? p.feat : f, n >= 0);
                         }
-                    }
+                        asm volatile("cp.async.commit_group;" ::: "memory");
+                    } else gather_feat(std::integral_constant<int, 4>{});
                     if (ttid < TR) {
                         const int r = ttid, n = s_n[r];
                         const int64_t g = s_g[r];
@@ -246,6 +276,19 @@ __global__ void __launch_bounds__((U * TC_CWARPS + 1) * 32, U == 1 ? 2 : 1) sa_t
                             uint4 hi, lo;
                             split8(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], hi, lo);
                             unsigned char *dst = A0 + (size_t)kg * a_lbo + r * 16;
+                            *reinterpret_cast<uint4 *>(dst) = hi;
+                            *reinterpret_cast<uint4 *>(dst + lo_off) = lo;
+                        }
+                    }
+                    if (p.gather_depth == 0) {
+                        asm volatile("cp.async.wait_group 0;" ::: "memory");
+                        team_sync();                 // the two halves of a segment were copied by two lanes
+                        for (int i = ttid; i < TR * cpr; i += TC_CTHREADS) {
+                            const int r = i % TR, kg = i / TR;
+                            unsigned char *dst = A0 + (size_t)kg * a_lbo + r * 16;
+                            const float4 x = *reinterpret_cast<const float4 *>(dst), y = *reinterpret_cast<const float4 *>(dst + lo_off);
+                            uint4 hi, lo;
+                            split8(x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w, hi, lo);
                             *reinterpret_cast<uint4 *>(dst) = hi;
                             *reinterpret_cast<uint4 *>(dst + lo_off) = lo;
                         }
@@ -273,6 +316,7 @@ __global__ void __launch_bounds__((U * TC_CWARPS + 1) * 32, U == 1 ? 2 : 1) sa_t
                 }
             }
             fence_proxy_async();
+            tr.mark(0x200);
 
             const bool row_valid = s_n[row] >= 0;
             for (int l = 0; l < lay.L; ++l) {
@@ -290,6 +334,7 @@ __global__ void __launch_bounds__((U * TC_CWARPS + 1) * 32, U == 1 ? 2 : 1) sa_t
                     const int sl1 = min(ly.nslab, sl0 + slabs_per_round);
                     tc_fence_before();
                     all_sync();            // the A operands of every team are complete / the previous round's TMEM reads and pool scratch drained
+                    tr.mark(0x300 + l);
                     if (warp_all == 0) {
                         tc_fence_after();
                         for (int sl = sl0; sl < sl1; ++sl) {
@@ -304,6 +349,7 @@ __global__ void __launch_bounds__((U * TC_CWARPS + 1) * 32, U == 1 ? 2 : 1) sa_t
                                     s = wq % p.nstage;
                                     mbar_wait(full_bar + s, (wq / p.nstage) & 1u);
                                     tc_fence_after();
+                                    tr.mark(0x800);
                                     w_addr = smem_u32(Wsm) + (uint32_t)(s * p.stage_bytes);
                                     ++wq;
                                 }
@@ -337,9 +383,11 @@ __global__ void __launch_bounds__((U * TC_CWARPS + 1) * 32, U == 1 ? 2 : 1) sa_t
                         if (elect_one()) umma_commit(acc_bar);
                     }
                     __syncwarp();
+                    tr.mark(0x400 + l);
                     mbar_wait(acc_bar, acc_phase);
                     acc_phase ^= 1u;
                     tc_fence_after();
+                    tr.mark(0x500 + l);
 
                     const int ncols = (sl1 - sl0) * ly.NS;
                     const int col_base = sl0 * ly.NS;
@@ -406,6 +454,7 @@ __global__ void __launch_bounds__((U * TC_CWARPS + 1) * 32, U == 1 ? 2 : 1) sa_t
                         }
                     }
                     if (!last) fence_proxy_async();
+                    tr.mark(0x600 + l);
                 }
             }
         }
@@ -503,7 +552,7 @@ bool tcs_plan(int K, int L, const int *dims, TcsPlan *pl)
 int64_t packed_bytes_f32_split(int L, const int *dims)
 {
     const TcLayout t = tc_layout(L, dims, true);
-    return (int64_t)t.total_bytes;
+    return t.replicas > 1 ? (int64_t)t.replicas * t.rep_stride : (int64_t)t.total_bytes;
 }
 
 // tile rows the split kernel would use for this stack (0: it does not cover it)
@@ -543,6 +592,14 @@ int launch_sa_f32_split(const SaArgs &a, const void *packed_split, cudaStream_t 
     p.tmem_cols = pl.tmem_cols; p.resident = pl.resident; p.nstage = pl.nstage; p.stage_bytes = pl.stage_bytes;
     p.a_bytes[0] = pl.a_bytes[0]; p.a_bytes[1] = pl.a_bytes[1]; p.a_lo[0] = pl.a_lo[0]; p.a_lo[1] = pl.a_lo[1];
     p.pool_cols = pl.pool_cols; p.U = pl.U;
+    p.trace = get_debug_trace();
+    // PN2_F32_GATHER: 4 (default) = register-staged loads, four 32-byte segments in flight (eight need 64 registers: under the
+    // 96-register cap of two CTAs per SM ptxas serialises them again); 0 = cp.async into the operand slots + in-place conversion.
+    // Traced on B200 (tools/ring_trace.py, sa2 of cls_ssg at B = 2048): the gather phase is 11-13 k of the 44 k cycles of a tile
+    // either way -- it is bound by the index arithmetic and the hi / lo conversion (~40 instructions per segment on 16 warps per
+    // SM) and by three dependent round trips (neighbour index -> row -> wait), not by bytes in flight: 10.9 ms against 11.1-11.3 ms
+    static const int gd_env = getenv("PN2_F32_GATHER") ? atoi(getenv("PN2_F32_GATHER")) : 4;
+    p.gather_depth = gd_env == 0 ? 0 : 4;
     static const int passes_env = getenv("PN2_F32_PASSES") ? atoi(getenv("PN2_F32_PASSES")) : 4;
     p.passes = passes_env == 3 ? 3 : 4;
     if (p.tiles == 0) return 0;

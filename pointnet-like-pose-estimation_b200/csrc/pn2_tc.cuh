@@ -1,6 +1,7 @@
 // Shared by the tensor-core translation units (pn2_sa_tc.cu, pn2_sa_tc2.cu): packed-weight layout and the
 // tcgen05 / mbarrier / bulk-copy PTX wrappers.  Not part of the ABI.
 #pragma once
+#include <stdlib.h>
 #include <cuda_bf16.h>
 #include "pn2_common.cuh"
 
@@ -40,6 +41,8 @@ struct TcLayout {
     int n_chunks;
     int total_bytes;   // weights + fp32 biases + bias slices
     int kblk;          // k extent of a weight chunk: KBLK, or 32 in the split layout (16 KB hi + lo chunks at NS = 128)
+    int replicas;      // identical copies of the packed image in global memory (streamed stacks, see tc_weight_replicas)
+    int rep_stride;    // bytes between copies
     int split;         // fp32 mode on the tensor cores (pn2_sa_tcs.cu): every chunk is [bf16 hi image | bf16 lo image], twice the bytes
 };
 // Bias slice of a hidden layer (used by the pipelined kernels, pn2_sa_tc2.cu): one extra K = 16 slice of the weight
@@ -55,6 +58,24 @@ static __host__ __device__ inline int tc_chunk_bytes(const TcLayer &ly, int kb, 
     return ly.NS * kw * 2;
 }
 
+// Streamed weight sets are kept in HBM / L2 as several identical copies, CTA i reading copy i % R (PN2_W_REPLICAS, read once):
+// every persistent CTA walks the same chunk sequence at about the same time, so with one copy all 148 SMs pull the same few
+// kilobytes -- the same few L2 slices -- at any moment.  Distinct addresses spread the same traffic over the whole L2.
+static inline int tc_weight_replicas()
+{
+    static const int r = [] {
+        const char *e = getenv("PN2_W_REPLICAS");
+        int v = e ? atoi(e) : 1;
+        return v < 1 ? 1 : (v > 16 ? 16 : v);
+    }();
+    return r;
+}
+static inline int tc_split_kblk()
+{
+    static const int k = [] { const char *e = getenv("PN2_F32_KBLK"); const int v = e ? atoi(e) : 32; return (v == 16 || v == 64) ? v : 32; }();
+    return k;
+}
+
 static inline TcLayout tc_layout(int L, const int *dims, bool split = false)
 {
     TcLayout t;
@@ -63,7 +84,7 @@ static inline TcLayout tc_layout(int L, const int *dims, bool split = false)
     // ring (16.2 -> 10.7 ms); wide stacks stream megabytes per tile with one CTA per SM and want the larger chunks (3.2 vs 4.5 ms)
     bool wide = false;
     for (int l = 0; l <= L; ++l) if (rup(dims[l], 16) > 256) wide = true;
-    const int kblk = (split && !wide) ? 32 : KBLK;
+    const int kblk = (split && !wide) ? tc_split_kblk() : KBLK;
     t.split = split ? 1 : 0;
     t.kblk = kblk;
     t.L = L; t.w_bytes = 0; t.bias_floats = 0; t.max_chunk = 0; t.n_chunks = 0;
@@ -96,6 +117,9 @@ static inline TcLayout tc_layout(int L, const int *dims, bool split = false)
         t.ly[l].bs_off = t.total_bytes;
         if (l < L - 1) t.total_bytes += t.ly[l].Npad * BIAS_SLICE_K * 2;
     }
+    // weight sets too large to stay resident in shared memory are streamed per tile: those get the replicas
+    t.replicas = t.w_bytes > 100 * 1024 ? tc_weight_replicas() : 1;
+    t.rep_stride = rup(t.total_bytes, 1024);
     return t;
 }
 

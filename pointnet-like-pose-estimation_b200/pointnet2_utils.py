@@ -541,7 +541,8 @@ class PointNetSetAbstraction(nn.Module):
         alloc = torch.zeros if be.sa_needs_zero(S, K, dims, prec) else torch.empty
         pooled = alloc(B, S, dims[-1], dtype=torch.float32, device=pts.device)
         side = be.sa_bf16_side_io(K, C, order, dims, prec)
-        twin_in = _bf16_twin(feature, B, N, feat.shape[-1]) if (side and feat is not None) else None
+        # the previous layer's bf16 rows, if it left any: every bf16 kernel gathers them instead of converting the fp32 rows
+        twin_in = _bf16_twin(feature, B, N, feat.shape[-1]) if feat is not None else None
         twin_out = torch.empty(B, S, dims[-1], dtype=torch.bfloat16, device=pts.device) if side else None
         be.sa_fused(pts, feat, new_points if not self.group_all else None, idx32, order, dims, packed, prec, pooled, 0,
                     feature_bf16=twin_in, out_bf16=twin_out)
@@ -649,7 +650,7 @@ class PointNetSetAbstractionMsg(nn.Module):
         zero = any(be.sa_needs_zero(S, K, d, prec) for K, (_, d, prec) in zip(self.sample_number_list, plans))
         pooled = (torch.zeros if zero else torch.empty)(B, S, total, dtype=torch.float32, device=pts.device)
         sides = [be.sa_bf16_side_io(K, C, ORDER_MSG, d, prec) for K, (_, d, prec) in zip(self.sample_number_list, plans)]
-        twin_in = _bf16_twin(feature, B, N, feat.shape[-1]) if (any(sides) and feat is not None) else None
+        twin_in = _bf16_twin(feature, B, N, feat.shape[-1]) if feat is not None else None
         # the bf16 twin of the concatenated output is only complete if every branch's kernel writes its slice
         twin_out = torch.empty(B, S, total, dtype=torch.bfloat16, device=pts.device) if all(sides) else None
         co = 0

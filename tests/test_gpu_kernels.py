@@ -338,6 +338,41 @@ def test_sa_fused_bf16_rows_only(nat, oracle, D, K, order, mlp):
     assert rel_err(out.cpu(), exp) <= TOL_BF16
 
 
+@pytest.mark.parametrize("name,B,N,C,D,S,K,r,order,mlp", [
+    ("ssg_sa3", 5, 128, 3, 256, 1, 128, None, 2, [256, 512, 1024]), ("trans_sa2", 3, 512, 10, 128, 1, 512, None, 2, [256, 512, 1024]),
+    ("msg_all", 2, 128, 3, 640, 1, 128, None, 2, [256, 512, 1024]), ("odd_pairs", 2, 300, 3, 24, 9, 300, 2.0, 0, [32, 64]),
+    ("one_group", 2, 200, 3, 8, 20, 150, 1.0, 0, [48, 300])])
+def test_sa_fused_streaming_kernel_takes_the_bf16_rows(nat, oracle, name, B, N, C, D, S, K, r, order, mlp):
+    """The streaming (weight-ring) bf16 kernel -- wide group_all stacks, groups beyond 128 rows -- gathers the previous layer's
+    bf16 rows with cp.async when they are given: bit-identical to converting the fp32 rows itself, also as the only feature
+    tensor, also with an odd number of 16-byte segments per row (D = 24, 8) and with absent rows (K > ball size)."""
+    x = make_cloud(B, N, C, "uni", 4100 + N)
+    f = torch.randn(B, N, D, generator=torch.Generator().manual_seed(5))
+    dims = [C + D] + mlp
+    layers = rand_layers(dims, 13)
+    if order == 2:
+        idx = cen = None
+        rows = oracle.group(x, f.bfloat16().float(), None, None, 2)
+    else:
+        start = torch.randint(0, N, (B,), generator=torch.Generator().manual_seed(8), dtype=torch.long)
+        cen = oracle.index_points(x, oracle.farthest_point_sample(x, S, start)).contiguous()
+        idx = oracle.query_ball_point(r, K, x, cen)
+        rows = oracle.group(x, f.bfloat16().float(), idx, cen, order)
+    assert not nat.sa_bf16_side_io(K, C, order, dims, 1)           # not a stack of the pipelined kernels
+    packed, _ = nat.pack([tuple(dev(t) for t in l) for l in layers], 1e-5, 1, C, order)
+    twin = dev(f).bfloat16().contiguous()
+    outs = []
+    for feat, bf in ((dev(f), None), (dev(f), twin), (None, twin)):
+        alloc = torch.zeros if nat.sa_needs_zero(S, K, dims, 1) else (lambda *a, **k: torch.full(*a, fill_value=-7.0, **k))
+        out = alloc((B, S, mlp[-1]), dtype=torch.float32, device="cuda:0")
+        nat.sa_fused(dev(x), feat, None if cen is None else dev(cen), None if idx is None else dev(idx.int()), order, dims, packed, 1,
+                     out, 0, feature_bf16=bf)
+        outs.append(out.cpu())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    exp = oracle.mlp_max(rows.reshape(B * S, K, C + D), layers).reshape(B, S, -1)
+    assert rel_err(outs[0], exp) <= TOL_BF16
+
+
 def test_tma_gather4_matches_the_swizzled_operand_layout(nat):
     """cp.async.bulk.tensor tile::gather4 + 128-byte swizzle: 4 arbitrary rows -> 4 consecutive swizzled smem rows
     (chunk j of row r at r*128 + ((j ^ (r & 7)) << 4)); rows outside the tensor read as zeros."""
