@@ -580,6 +580,168 @@ ball_query_multi_kernel(const float *__restrict__ centres, int64_t csb, int64_t 
     }
 }
 
+// Multi-radius scan with deferred hit bookkeeping (C <= 4): ball_query_masks_kernel's scheme with one parked mask word per
+// (centre, radius).  A trip evaluates the distances once, ballots against the largest radius, and only when some lane hit does
+// it ballot the next smaller one (the balls are nested); the NR lists of the four centres in flight are resolved per 1024-point
+// window.  The lists fill at very different rates (the MSG layers pair a 16-entry list at r = 0.1 with a 128-entry list at
+// r = 0.4), so the scan practically always covers the whole cloud: the all-lists-full test runs in the middle and at the end of
+// a window only.
+template <int C, int BQ_WARPS, int NR>
+__global__ void __launch_bounds__(BQ_WARPS * 32, 3)
+ball_query_multi_masks_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, int64_t csc,
+                              const float *__restrict__ points, int64_t sb, int64_t sn, int64_t sc,
+                              int S, int N, int NCH /* multiple of 128 */, int cpw, const BqMulti q, int32_t *__restrict__ empty_flag)
+{
+    static_assert(C <= 4, "one float4 of points per channel per lane");
+    constexpr int BQ_THREADS = BQ_WARPS * 32;
+    constexpr int CPB = 4;
+    extern __shared__ float smem[];
+    float *sp = smem;                       // [C][NCH], permuted inside every block of 128 points (see ball_query_masks_kernel)
+    float *sp2 = smem + (size_t)C * NCH;    // [NCH]
+    int *stage = (int *)(sp2 + NCH) + (threadIdx.x >> 5) * (CPB * q.ktot);       // [CPB][ktot] per warp
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    const int s_begin = (blockIdx.x * BQ_WARPS + warp) * cpw;
+    const float *P = points + (int64_t)b * sb;
+    const bool pcontig = (sc == 1);
+
+    for (int n = tid; n < N; n += BQ_THREADS) {
+        float v[C];
+        const int pos = (n & ~127) | ((n & 31) << 2) | ((n >> 5) & 3);
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            v[k] = __ldg(P + (int64_t)n * sn + (int64_t)k * sc);
+            sp[k * NCH + pos] = v[k];
+        }
+        sp2[pos] = sqnorm<C>(v, pcontig, n >= (N & ~31));
+    }
+    for (int n = N + tid; n < NCH; n += BQ_THREADS) {
+        const int pos = (n & ~127) | ((n & 31) << 2) | ((n >> 5) & 3);
+#pragma unroll
+        for (int k = 0; k < C; ++k) sp[k * NCH + pos] = 0.f;
+        sp2[pos] = INFINITY;
+    }
+    __syncthreads();
+
+    const f32x2 m2v = pk2(-2.0f, -2.0f);
+    const bool odd = (lane & 1) != 0, upper = (lane & 2) != 0;
+    for (int ci = 0; ci < cpw; ci += CPB) {
+        if (s_begin + ci >= S) break;                                   // warp-uniform
+        f32x2 sv[CPB][C], s2v[CPB];
+        int cn[CPB][NR];                                                // hits resolved so far (warp-uniform)
+        unsigned hm[CPB][NR];                                           // this lane's word of the current window, per radius
+#pragma unroll
+        for (int c = 0; c < CPB; ++c) {
+            const int sidx = s_begin + ci + c;
+            const bool act = ci + c < cpw && sidx < S;
+            float sc_[C];
+#pragma unroll
+            for (int k = 0; k < C; ++k) sc_[k] = act ? __ldg(centres + (int64_t)b * csb + (int64_t)sidx * csn + (int64_t)k * csc) : 0.f;
+            const float q2 = sqnorm<C>(sc_, csc == 1, sidx >= (S & ~31));
+#pragma unroll
+            for (int k = 0; k < C; ++k) sv[c][k] = pk2(sc_[k], sc_[k]);
+            s2v[c] = pk2(q2, q2);
+#pragma unroll
+            for (int r = 0; r < NR; ++r) cn[c][r] = act ? 0 : q.K[r];
+        }
+        auto all_full = [&](bool with_window) -> bool {
+            bool full = true;
+#pragma unroll
+            for (int c = 0; c < CPB; ++c)
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    int have = cn[c][r];
+                    if (with_window) have += (int)__reduce_add_sync(0xffffffffu, (unsigned)__popc(hm[c][r]));
+                    full = full && have >= q.K[r];
+                }
+            return full;
+        };
+        for (int w0 = 0; w0 < NCH; w0 += 1024) {                        // windows of 1024 points = 32 mask words
+            const int trips = min(8, (NCH - w0) >> 7);
+#pragma unroll
+            for (int c = 0; c < CPB; ++c)
+#pragma unroll
+                for (int r = 0; r < NR; ++r) hm[c][r] = 0u;
+            const float *prow = sp + w0 + 4 * lane;
+            for (int t = 0; t < trips; ++t, prow += 128) {
+                float4 pv[C];
+#pragma unroll
+                for (int k = 0; k < C; ++k) pv[k] = *reinterpret_cast<const float4 *>(prow + k * NCH);
+                const float4 p2 = *reinterpret_cast<const float4 *>(prow + C * NCH);
+                const f32x2 p2a = pk2(p2.x, p2.y), p2b = pk2(p2.z, p2.w);
+                const bool mine = (lane >> 2) == t;
+#pragma unroll
+                for (int c = 0; c < CPB; ++c) {
+                    f32x2 da = mul2(sv[c][0], pk2(pv[0].x, pv[0].y));
+                    f32x2 db = mul2(sv[c][0], pk2(pv[0].z, pv[0].w));
+#pragma unroll
+                    for (int k = 1; k < C; ++k) {
+                        da = fma2(sv[c][k], pk2(pv[k].x, pv[k].y), da);
+                        db = fma2(sv[c][k], pk2(pv[k].z, pv[k].w), db);
+                    }
+                    const float2 d01 = unpk2(add2(fma2(m2v, da, s2v[c]), p2a));
+                    const float2 d23 = unpk2(add2(fma2(m2v, db, s2v[c]), p2b));
+#pragma unroll
+                    for (int r = NR - 1; r >= 0; --r) {                 // largest ball first: the smaller ones are subsets
+                        const float rr = q.r2[r];
+                        const unsigned m0 = __ballot_sync(0xffffffffu, !(d01.x > rr));
+                        const unsigned m1 = __ballot_sync(0xffffffffu, !(d01.y > rr));
+                        const unsigned m2 = __ballot_sync(0xffffffffu, !(d23.x > rr));
+                        const unsigned m3 = __ballot_sync(0xffffffffu, !(d23.y > rr));
+                        const unsigned pick = odd ? (upper ? m3 : m1) : (upper ? m2 : m0);
+                        hm[c][r] = mine ? pick : hm[c][r];
+                        if (!(m0 | m1 | m2 | m3)) break;                // warp-uniform: nothing in this ball, nothing in the smaller ones
+                    }
+                }
+                if (t == 3 && trips > 4 && all_full(true)) break;
+            }
+            // ---- resolve the window: lane l owns points w0 + 32 l .. + 31 ------------------------------------------------------
+            const int nb = w0 + 32 * lane;
+            const unsigned valid = nb + 32 <= N ? 0xffffffffu : (nb >= N ? 0u : (1u << (N - nb)) - 1u);
+#pragma unroll
+            for (int c = 0; c < CPB; ++c)
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    const int K = q.K[r];
+                    unsigned m = hm[c][r] & valid;
+                    const int pc = __popc(m);
+                    const int total = (int)__reduce_add_sync(0xffffffffu, (unsigned)pc);
+                    if (cn[c][r] < K && total) {                        // warp-uniform
+                        int inc = pc;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+                        int pos = cn[c][r] + inc - pc;
+                        int *stg = stage + c * q.ktot + q.koff[r];
+                        while (m && pos < K) { stg[pos++] = nb + __ffs(m) - 1; m &= m - 1; }
+                    }
+                    cn[c][r] = min(K, cn[c][r] + total);
+                }
+            if (all_full(false)) break;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < CPB; ++c) {
+            const int sidx = s_begin + ci + c;
+            if (!(ci + c < cpw && sidx < S)) continue;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const int K = q.K[r];
+                const int *stg = stage + c * q.ktot + q.koff[r];
+                const int cc = cn[c][r];
+                const int frst = cc ? stg[0] : N;
+                if (cc == 0 && lane == 0 && empty_flag) atomicOr(empty_flag, 1);
+                const int64_t o = ((int64_t)b * S + sidx) * K;
+                for (int j = lane; j < K; j += 32) {
+                    const int v = (j < cc) ? stg[j] : frst;
+                    if (q.idx64[r]) q.idx64[r][o + j] = v;
+                    if (q.idx32[r]) q.idx32[r][o + j] = v;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // Run-time-C fallback (C <= PN2_MAX_COORD): one thread per centre, points streamed from global memory.
 __global__ void ball_query_generic_kernel(const float *__restrict__ centres, int64_t csb, int64_t csn, int64_t csc,
                                           const float *__restrict__ points, int64_t sb, int64_t sn, int64_t sc,
@@ -978,6 +1140,22 @@ static int launch_bq_multi(const float *centres, int64_t csb, int64_t csn, int64
     constexpr int W = BQ_WARPS_SMALL;
     int cpw = 16;
     while (cpw > BQ_CPB<C>::value && (int64_t)B * ((S + W * cpw - 1) / (W * cpw)) < 592) cpw >>= 1;      // never less than one full pass
+    if constexpr (C <= 4) {
+        // deferred hit bookkeeping (ball_query_multi_masks_kernel) unless PN2_BQ_V1=1; rows padded to whole 128-point trips
+        static const bool v1_env = getenv("PN2_BQ_V1") && atoi(getenv("PN2_BQ_V1")) == 1;
+        const int NCH2 = (N + 127) & ~127;
+        const size_t smem2 = (size_t)(C + 1) * NCH2 * sizeof(float) + sizeof(int) * (size_t)W * 4 * q.ktot;
+        if (!v1_env && smem2 <= 200 * 1024) {
+            auto kern2 = ball_query_multi_masks_kernel<C, W, NR>;
+            if (smem2 > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+                if (e != cudaSuccess) { set_error("ball_query_multi(masks): smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+            }
+            dim3 grid2((S + W * cpw - 1) / (W * cpw), B);
+            kern2<<<grid2, W * 32, smem2, st>>>(centres, csb, csn, csc, points, sb, sn, sc, S, N, NCH2, cpw, q, empty_flag);
+            return launch_status("pn2_ball_query_multi_f32(masks)");
+        }
+    }
     const size_t smem = (size_t)(C + 1) * NCH * sizeof(float) + sizeof(int) * (size_t)W * BQ_CPB<C>::value * q.ktot;
     auto kern = ball_query_multi_kernel<C, W, NR>;
     if (smem > 48 * 1024) {
