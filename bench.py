@@ -248,6 +248,9 @@ def roofline_of(top_key, top, prec, pk, region_s, clk, fp32_tc=False):
             sm = (clk or {}).get("sm_mhz") or 1965.0
             peak = 148 * 128 * 2 * sm * 1e6 / 1e12
             roof.update(bound="fp32", peak=peak, frac=ach / peak, peak_source=f"FP32 FMA pipe: 148 SMs x 128 lanes x 2 x {sm:.0f} MHz")
+    elif top["name"] not in ("fps", "ball_query", "ball_query_multi"):
+        # not a kernel of the path's roofline table (under a profiler the serialised launches can make a helper the longest span)
+        return {"kernel": top_key, "bound": None, "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None}
     else:
         if top["name"] == "fps":
             nbytes = m["B"] * (4 * m["N"] * m["C"] + 4 * m["S"] * m["C"] + 8)

@@ -1124,8 +1124,11 @@ int launch_ball_query(const float *centres, int64_t csb, int64_t csn, int64_t cs
 {
     if (B == 0 || S == 0) return 0;
     PN2_REQUIRE(B <= 65535, "pn2_ball_query_f32: B=%d exceeds gridDim.y", B);
-    if (C == 3) return launch_bq_c<3>(centres, csb, csn, csc, points, sb, sn, sc, B, S, N, r2, K, idx64, idx32, empty_flag, st);
-    if (C == 10) return launch_bq_c<10>(centres, csb, csn, csc, points, sb, sn, sc, B, S, N, r2, K, idx64, idx32, empty_flag, st);
+    // the scan kernels stage K indices per centre in flight (8 warps x 4 or 2 centres): lists beyond 1024 entries (the reference's
+    // longest is 128) take the one-thread-per-centre kernel, which needs no staging
+    const bool staged = (size_t)K * sizeof(int) * BQ_WARPS_SMALL * (C <= 4 ? 4 : 2) <= 128 * 1024;
+    if (C == 3 && staged) return launch_bq_c<3>(centres, csb, csn, csc, points, sb, sn, sc, B, S, N, r2, K, idx64, idx32, empty_flag, st);
+    if (C == 10 && staged) return launch_bq_c<10>(centres, csb, csn, csc, points, sb, sn, sc, B, S, N, r2, K, idx64, idx32, empty_flag, st);
     const int64_t G = (int64_t)B * S;
     ball_query_generic_kernel<<<(unsigned)((G + 127) / 128), 128, 0, st>>>(centres, csb, csn, csc, points, sb, sn, sc,
                                                                             B, S, N, C, r2, K, idx64, idx32, empty_flag);
