@@ -119,7 +119,8 @@ int pn2_sa_needs_zero_init(int S, int K, int L, const int *dims, int prec);
  * features over in bf16 as well -- out_bf16 (same addressing as out, element type bf16) is written next to the
  * fp32 result and a later launch may pass it as feat_bf16 ([B,N,D] contiguous, D % 8 == 0), which the gather
  * then copies straight into the MMA operand with cp.async.  Both may be NULL.  pn2_sa_bf16_side_io tells the
- * caller whether the kernel that serves this configuration reads / writes them (1) or ignores them (0). */
+ * caller whether the kernel that serves this configuration WRITES out_bf16 (1) or not (0: pass NULL); feat_bf16 is
+ * read by every bf16 kernel (the streaming kernel of the wide stacks included), so pass it whenever it exists. */
 int pn2_sa_bf16_side_io(int K, int C, int order, int L, const int *dims, int prec);
 int pn2_sa_fused(const float *points, int64_t sb, int64_t sn, int64_t sc,
                  const float *feat, int64_t fb, int64_t fn, int64_t fc,

@@ -291,7 +291,7 @@ class Native:
         return bool(rc)
 
     def sa_bf16_side_io(self, K, C, order, dims, prec) -> bool:
-        """True when the kernel serving this configuration reads `feature_bf16` / writes `out_bf16`."""
+        """True when the kernel serving this configuration writes `out_bf16` (`feature_bf16` is read by every bf16 kernel)."""
         d = _dims_array(dims)
         rc = self.lib.pn2_sa_bf16_side_io(int(K), int(C), int(order), len(dims) - 1, d.ctypes.data, prec)
         if rc < 0:

@@ -94,6 +94,7 @@ class _PinnedDraws:
     engine behind the next batch's input upload (-4 % end to end).  A buffer is reused only after the stream has passed the
     launch that read it (one event per buffer)."""
     SLOTS = 8
+    KERNEL_UPLOAD_MIN_B = 512
 
     def __init__(self):
         self.rings = {}
@@ -110,7 +111,9 @@ class _PinnedDraws:
             ring["evs"][i].synchronize()
         buf = ring["bufs"][i]
         torch.randint(0, N, (B,), dtype=torch.long, out=buf)
-        dev_t = _backend().upload_i64(buf, device)
+        # small batches are launch-bound and their input uploads short: the plain asynchronous copy costs the enqueueing thread
+        # less (B = 24 eager forward: 61 k clouds/s against 50 k through the kernel's ctypes call)
+        dev_t = _backend().upload_i64(buf, device) if B >= self.KERNEL_UPLOAD_MIN_B else buf.to(device, non_blocking=True)
         ring["evs"][i].record(torch.cuda.current_stream(device))
         ring["used"][i] = True
         return dev_t
