@@ -354,6 +354,36 @@ def test_ball_query_few_points_and_window_edges_vs_oracle(pu, oracle, N, S, K, r
     assert torch.equal(i32.cpu().long(), exp)
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_ball_query_random_shapes_vs_oracle(pu, oracle, seed):
+    """Seeded random sweep over cloud sizes, list lengths, radii, layouts and batch sizes (every launch shape: 4 / 8 / 16 centres
+    per warp, one and several 1024-point windows, ragged last trips), single- and multi-radius: rows bit-equal to the oracle's."""
+    g = torch.Generator().manual_seed(9000 + seed)
+    ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=g))
+    be = pu._backend()
+    for _ in range(7):
+        N = ri(1, 3000) if ri(0, 3) else ri(1, 200)
+        S = ri(1, min(N, 600))
+        B = [1, 2, 3, 40, 150][ri(0, 4)] if N * S < 200_000 else ri(1, 3)
+        C = 3 if ri(0, 2) else 10
+        K = ri(1, min(N, 160))
+        r = [0.05, 0.1, 0.2, 0.4, 0.8, 3.0][ri(0, 5)]
+        base = cloudgen.uniform_cloud(B, N, 100 * seed + N) if ri(0, 1) else cloudgen.surface_cloud(B, N, 100 * seed + N)
+        x = cloudgen.with_category(base) if C == 10 else base
+        x = x.permute(0, 2, 1).contiguous().permute(0, 2, 1) if ri(0, 1) else x.contiguous()
+        start = torch.randint(0, N, (B,), generator=g, dtype=torch.long)
+        cen = oracle.index_points(x, oracle.farthest_point_sample(x, S, start)).contiguous()
+        exp = oracle.query_ball_point(r, K, x, cen, allow_empty=True)
+        i64, i32 = be.ball_query(cen.to(DEV), x.to(DEV), oracle.radius_sq_f32(r), K, want_idx64=True, want_idx32=True)
+        assert torch.equal(i64.cpu(), exp), (B, N, S, C, K, r)
+        assert torch.equal(i32.cpu().long(), exp), (B, N, S, C, K, r)
+        radii = sorted([r * 0.5, r, r * 1.7][: ri(2, 3)])
+        Ks = [ri(1, min(N, 140)) for _ in radii]
+        outs = be.ball_query_multi(cen.to(DEV), x.to(DEV), [oracle.radius_sq_f32(q) for q in radii], Ks, want_idx64=True)
+        for (o64, _), q, k in zip(outs, radii, Ks):
+            assert torch.equal(o64.cpu(), oracle.query_ball_point(q, k, x, cen, allow_empty=True)), (B, N, S, C, radii, Ks, q)
+
+
 @pytest.mark.parametrize("kind", ["scaled", "shifted", "nan_point", "nan_centre", "far_centre", "flat", "inf_point"])
 def test_ball_query_odd_clouds_vs_oracle(pu, oracle, kind):
     """Clouds the grid cull must not get wrong: un-normalised coordinates (x1000, +5000: the fp32 rounding of the expanded form

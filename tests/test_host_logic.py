@@ -255,3 +255,40 @@ def test_fused_head_is_used_in_eval_and_matches_the_op_sequence(fake_native):
                 exp = y
         got = out[0] if isinstance(out, tuple) else out
         assert torch.allclose(got, exp, rtol=1e-5, atol=1e-6), name
+
+
+def test_bf16_rows_are_handed_to_every_next_layer(fake_native, monkeypatch):
+    """bf16 mode: a layer whose kernel writes the bf16 copy of its pooled rows attaches it to the tensor it returns, and the NEXT
+    layer passes it on as `feature_bf16` whether or not its own kernel writes one (the streaming kernel of the wide group_all
+    stacks reads it too); a tensor modified in between loses the copy."""
+    pu = fake_native
+    be = pu._backend()
+    seen = []
+    real = be.sa_fused
+
+    def sa_fused(points, feature, centres, idx32, order, dims, packed, prec, out, co_off=0, feature_bf16=None, out_bf16=None, algo_dims=None):
+        seen.append((order, feature_bf16, out_bf16))
+        if out_bf16 is not None:
+            real(points, feature, centres, idx32, order, dims, packed, prec, out, co_off)
+            out_bf16.copy_(out.to(out_bf16.dtype))
+            return out
+        return real(points, feature, centres, idx32, order, dims, packed, prec, out, co_off)
+
+    monkeypatch.setattr(be, "sa_fused", sa_fused)
+    monkeypatch.setattr(be, "sa_bf16_side_io", lambda K, C, order, dims, prec: order != 2)      # group_all stacks: no bf16 output
+    pu.set_precision("bf16")
+    try:
+        sa1 = pu.PointNetSetAbstraction(16, 8, 0.4, 3, [8, 16], False).eval()
+        sa2 = pu.PointNetSetAbstraction(None, None, None, 16 + 3, [16, 32], True).eval()
+        x = cloudgen.channels_first(cloudgen.uniform_cloud(2, 64, 3))
+        with torch.no_grad():
+            p1, f1 = sa1(x, None)
+            assert seen[-1][1] is None and seen[-1][2] is not None              # no features in, bf16 rows out
+            twin = seen[-1][2]
+            sa2(p1, f1)
+            assert seen[-1][0] == 2 and seen[-1][1] is twin and seen[-1][2] is None
+            f1.add_(1.0)                                                         # the copy no longer describes the tensor
+            sa2(p1, f1)
+            assert seen[-1][1] is None
+    finally:
+        pu.set_precision("fp32")
