@@ -14,6 +14,7 @@
 // are read 128 times from L2 (0.34 GB) instead of the activations making 14 round trips through HBM.
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 #include "pn2_common.cuh"
 
 namespace cg = cooperative_groups;
@@ -29,6 +30,7 @@ struct FcHeadParams {
     const float *w1p, *b1, *w2p, *b2, *w3, *b3;
     const float *mean; int64_t ms; const float *mean_mlp;
     float *out; void *aux;
+    int alias_h2;
 };
 
 // one eighth of a hidden layer for TB clouds: in [TB][K] (shared), weights wp [K/4][H][4] (global), this CTA's outputs
@@ -100,10 +102,13 @@ __global__ void __cluster_dims__(FC_CS, 1, 1) __launch_bounds__(FC_THREADS) fc_h
     const int tile = blockIdx.x / FC_CS;
     const int t0 = tile * TB;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float *xs = fsm;                            // [TB][K0]; later the K-split scratch
+    float *xs = fsm;                            // [TB][K0]; later the K-split scratch (its first TB * 256 floats)
     float *h1 = xs + TB * p.K0;                 // [TB][H1]
-    float *h2 = h1 + TB * p.H1;                 // [TB][H2]
-    float *lg = h2 + TB * p.H2;                 // [TB/CS .. ][16] logits of this CTA's clouds
+    // the second hidden layer lives in the staged-input region behind the scratch when it fits there (the inputs are dead in
+    // every CTA of the cluster once the first layer's closing cluster barrier has passed): 98 instead of 115 KB for the
+    // 1024 -> 512 -> 256 heads, i.e. two CTAs per SM
+    float *h2 = p.alias_h2 ? xs + TB * FC_THREADS : h1 + TB * p.H1;        // [TB][H2]
+    float *lg = p.alias_h2 ? h1 + TB * p.H1 : h2 + TB * p.H2;              // [TB/CS .. ][16] logits of this CTA's clouds
     // all CTAs of the cluster must have started before anyone writes into a peer's shared memory
     cluster.sync();
     const int k4n = p.K0 / 4;
@@ -179,9 +184,11 @@ __global__ void __cluster_dims__(FC_CS, 1, 1) __launch_bounds__(FC_THREADS) fc_h
 }
 
 template <int TB>
-static int launch_fc_tb(const FcHeadParams &p, cudaStream_t st)
+static int launch_fc_tb(FcHeadParams p, cudaStream_t st)
 {
-    const size_t smem = sizeof(float) * ((size_t)TB * (p.K0 + p.H1 + p.H2) + 16 * ((TB + FC_CS - 1) / FC_CS));
+    static const bool alias_off = getenv("PN2_FC_ALIAS") && atoi(getenv("PN2_FC_ALIAS")) == 0;
+    p.alias_h2 = (!alias_off && p.K0 >= FC_THREADS + p.H2) ? 1 : 0;
+    const size_t smem = sizeof(float) * ((size_t)TB * (p.K0 + p.H1 + (p.alias_h2 ? 0 : p.H2)) + 16 * ((TB + FC_CS - 1) / FC_CS));
     auto kern = fc_head_kernel<TB>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
