@@ -509,7 +509,7 @@ class Native:
 
     def selftest_umma(self, n_cols, k_dim, variant, device="cuda:0", dump=False):
         err = torch.full((1,), -1.0, dtype=torch.float32, device=device)
-        d = torch.zeros(128, n_cols, dtype=torch.float32, device=device) if dump else None
+        d = torch.zeros(256 if variant == 4 else 128, n_cols, dtype=torch.float32, device=device) if dump else None
         with torch.cuda.device(err.device):
             _check(self.lib.pn2_selftest_umma(n_cols, k_dim, variant, err.data_ptr(),
                                               d.data_ptr() if dump else None, _stream(err)))

@@ -822,6 +822,86 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(int n_cols, int k
     if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
+// variant 4: the CTA-PAIR form (tcgen05.mma.cta_group::2, M = 256).  A cluster of two CTAs; CTA r holds rows 128 r .. 128 r + 127
+// of A and columns r n/2 .. of B (n/2 rows of the K-major B image) at the SAME shared-memory offsets; CTA 0 alone issues the
+// MMAs and commits to the barrier of both CTAs; each CTA finds its 128 x n block of D in its own tensor memory.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma2_selftest_kernel(int n_cols, int k_dim, float *max_err, float *dump)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float s_err[4];
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    unsigned char *base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+    const int nh = n_cols / 2;                               // this CTA's share of the B columns
+    unsigned char *As = base;                                // [k_dim/8][128 rows][16 B]
+    unsigned char *Bs = base + (size_t)(k_dim / 8) * A_LBO;  // [k_dim/8][nh rows][16 B]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    auto a_val = [](int r, int k) { return (float)(((r * 7 + k * 3) % 13) - 6); };
+    auto b_val = [](int n, int k) { return (float)(((n * 5 + k * 11) % 9) - 4); };
+    for (int i = tid; i < TC_ROWS * k_dim; i += 128) {
+        const int r = i % TC_ROWS, k = i / TC_ROWS;
+        *reinterpret_cast<__nv_bfloat16 *>(As + (size_t)(k / 8) * A_LBO + r * 16 + (k % 8) * 2) = __float2bfloat16_rn(a_val((int)rank * TC_ROWS + r, k));
+    }
+    for (int i = tid; i < nh * k_dim; i += 128) {
+        const int n = i % nh, k = i / nh;
+        *reinterpret_cast<__nv_bfloat16 *>(Bs + (size_t)(k / 8) * (nh * 16) + n * 16 + (k % 8) * 2) = __float2bfloat16_rn(b_val((int)rank * nh + n, k));
+    }
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // both CTAs' operands written and fenced, both barriers initialised, before the leader issues
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    if (rank == 0 && tid == 0) {
+        // instruction descriptor: D = f32, A = B = bf16, K-major, N = n_cols, M = 256
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+        for (int j = 0; j < k_dim / 16; ++j) {
+            const uint64_t ad = smem_desc(smem_u32(As) + (uint32_t)(j * 2 * A_LBO), A_LBO, 128);
+            const uint64_t bd = smem_desc(smem_u32(Bs) + (uint32_t)(j * 2 * nh * 16), (uint32_t)(nh * 16), 128);
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "setp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                ::"r"(tmem_base), "l"(ad), "l"(bd), "r"(idesc), "r"(j ? 1u : 0u) : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(smem_u32(&bar)), "h"((uint16_t)3) : "memory");
+    }
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    float err = 0.f;
+    const int row = warp * 32 + lane;
+    for (int blk = 0; blk < n_cols / 32; ++blk) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(blk * 32), v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int n = blk * 32 + i;
+            float ref = 0.f;
+            for (int k = 0; k < k_dim; ++k) ref += a_val((int)rank * TC_ROWS + row, k) * b_val(n, k);
+            err = fmaxf(err, fabsf(ref - v[i]));
+            if (dump) dump[(size_t)((int)rank * TC_ROWS + row) * n_cols + n] = v[i];
+        }
+    }
+    for (int o = 16; o; o >>= 1) err = fmaxf(err, __shfl_xor_sync(0xffffffffu, err, o));
+    if (lane == 0) s_err[warp] = err;
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) atomicMax(reinterpret_cast<int *>(max_err), __float_as_int(fmaxf(fmaxf(s_err[0], s_err[1]), fmaxf(s_err[2], s_err[3]))));
+    // neither CTA may leave (and release its tensor memory / shared memory) while the pair's MMAs or the peer's commit are in flight
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+}
+
 // TMEM -> register read bandwidth probe (variant >= 10 of pn2_selftest_umma): `warps` warps of one CTA each issue
 // `reps` x tcgen05.ld.32x32b.x32 back to back (wait every `batch` loads); *max_err receives bytes per clock.
 __global__ void __launch_bounds__(512, 1) tmem_bw_probe_kernel(int reps, int batch, float *result)
@@ -937,6 +1017,13 @@ int launch_selftest_umma(int n_cols, int k_dim, int variant, float *max_err, flo
     }
     PN2_REQUIRE(n_cols >= 32 && n_cols <= 256 && n_cols % 32 == 0, "pn2_selftest_umma: n_cols must be a multiple of 32 in [32,256]");
     PN2_REQUIRE(k_dim >= 16 && k_dim <= 256 && k_dim % 16 == 0, "pn2_selftest_umma: k_dim must be a multiple of 16 in [16,256]");
+    if (variant == 4) {    // CTA pair, M = 256: max_err must be initialised to a negative value (both CTAs atomicMax into it); dump is [256][n_cols]
+        const size_t smem2 = 1024 + (size_t)(k_dim / 8) * A_LBO + (size_t)(k_dim / 8) * (n_cols / 2) * 16;
+        cudaError_t e2 = cudaFuncSetAttribute(umma2_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (e2 != cudaSuccess) { set_error("selftest(pair): smem attribute: %s", cudaGetErrorString(e2)); return (int)e2; }
+        umma2_selftest_kernel<<<2, 128, smem2, st>>>(n_cols, k_dim, max_err, dump);
+        return launch_status("pn2_selftest_umma(pair)");
+    }
     PN2_REQUIRE(variant != 3 || n_cols == TC_ROWS, "pn2_selftest_umma: variant 3 needs n_cols = 128");
     const size_t sw = (size_t)((k_dim + 63) / 64) * SW128_BLOCK;
     const size_t smem = 1024 + (variant == 2 ? sw : (size_t)(k_dim / 8) * A_LBO) + (variant == 3 ? sw : (size_t)(k_dim / 8) * n_cols * 16);

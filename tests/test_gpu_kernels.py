@@ -41,6 +41,16 @@ def test_umma_selftest(nat, n_cols, k_dim, variant):
     assert float(err.item()) == 0.0
 
 
+@pytest.mark.parametrize("n_cols,k_dim", [(64, 16), (128, 64), (256, 128), (128, 256)])
+def test_umma_pair_selftest(nat, n_cols, k_dim):
+    """tcgen05.mma.cta_group::2 (M = 256 over a CTA pair): each CTA holds its 128 rows of A and half of B's columns at the same
+    shared-memory offsets, CTA 0 issues and commits to both; every element of the 256 x N product against a scalar loop."""
+    err, d = nat.selftest_umma(n_cols, k_dim, 4, dump=True)
+    torch.cuda.synchronize()
+    assert float(err.item()) == 0.0, (float(err.item()), d[:2, :8], d[128:130, :8])
+    assert bool(d[128:].abs().sum() > 0)          # the second CTA wrote its half
+
+
 # ---- golden vectors (reference outputs) ----------------------------------------------------------------------
 @pytest.mark.parametrize("case", sorted(golden_io.index_cases()))
 def test_golden_fps_ball_sqdist(nat, case):
