@@ -137,10 +137,15 @@ struct TcParams {
     int pool_cols;     // columns of the cross-warp pooling scratch (0 if direct)
     int pipelined_last;   // last layer transposed + pipelined over 128-column TMEM buffers (needs 128-channel slabs)
     int gather_depth;     // feature-row segments a thread keeps in flight during the gather (1 or 4)
+    int pair;             // CTA-pair mode (tcgen05 cta_group::2, M = 256): the two CTAs of a cluster hold one tile each and HALF of
+                          // every streamed weight chunk; CTA 0 issues the MMAs of both -- half the L2 -> SM weight bytes per tile
     unsigned long long *trace;   // pn2_debug_trace buffer (CTA 0: role 0 = compute warp 0, 1 = producer warp, 2 = pooling warp 4)
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
+// PAIR: the CTA-pair form (tcgen05 cta_group::2).  A separate instantiation: a kernel that contains pair instructions can only be
+// launched as a cluster of two (a plain launch fails with cudaErrorInvalidClusterSize), so the default kernel must not contain them.
+template <bool PAIR>
+__global__ void __launch_bounds__(TC_THREADS, PAIR ? 1 : 2) sa_tc_kernel(const TcParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     // carve-up (all offsets multiples of 16)
@@ -159,7 +164,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
     uint64_t *slot_free = acc_bar + 1;      // in cluster rank 0: every CTA of the cluster has released ring slot s
     uint64_t *acc_full = slot_free + TC_MAX_STAGES;     // last layer, per 128-column TMEM buffer: slab's MMAs retired
     uint64_t *acc_empty = acc_full + 4;                  // ... and its pooling done (4 warp arrivals)
-    uint32_t *vm_s = reinterpret_cast<uint32_t *>(acc_empty + 4);       // valid-row ballots of the tile
+    uint64_t *peer_full = acc_empty + 4;                 // pair mode, in CTA 0: the peer's half of ring slot s has landed
+    uint64_t *peer_ready = peer_full + TC_MAX_STAGES;    // pair mode, in CTA 0: the peer's operand is written / its accumulator drained
+    uint32_t *vm_s = reinterpret_cast<uint32_t *>(peer_ready + 1);       // valid-row ballots of the tile
     uint32_t *tmem_slot = vm_s + 4;
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -170,9 +177,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
         for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); mbar_init(slot_free + s, (uint32_t)p.cs); }
         mbar_init(acc_bar, 1);
         for (int i = 0; i < 4; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+        for (int s = 0; s < TC_MAX_STAGES; ++s) mbar_init(peer_full + s, 1);
+        mbar_init(peer_ready, 1);
         fence_mbar_init();
     }
-    if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    if (warp == 0) {
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    }
     {
         const float *bsrc = reinterpret_cast<const float *>(p.packed + lay.w_bytes);
         for (int i = tid; i < lay.bias_floats; i += TC_THREADS) bias_s[i] = __ldg(bsrc + i);
@@ -182,7 +196,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     uint32_t cta_rank = 0;
-    if (p.cs > 1) {
+    if (p.cs > 1 || PAIR) {
         // barriers of every CTA initialised before any remote arrive / multicast copy can reach them
         asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
         asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -225,6 +239,17 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
                                 const uint32_t ph = (q / p.nstage) & 1u;
                                 mbar_wait(empty_bar + s, ph ^ 1u);
                                 tr.mark(0x900);
+                                if (PAIR) {
+                                    // this CTA's half of the chunk: columns rank * NS/2 .. of every k-group (NS/2 rows of 16 B = one copy)
+                                    const int half_rows = lay.ly[l].NS / 2, kgs = cb / (lay.ly[l].NS * 16);
+                                    mbar_expect_tx(full_bar + s, (uint32_t)(cb / 2));
+                                    for (int kg = 0; kg < kgs; ++kg)
+                                        bulk_g2s(Wsm + (size_t)s * p.stage_bytes + (size_t)kg * half_rows * 16,
+                                                 wsrc + off + (size_t)kg * lay.ly[l].NS * 16 + (size_t)cta_rank * half_rows * 16,
+                                                 (uint32_t)(half_rows * 16), full_bar + s);
+                                    off += cb;
+                                    continue;
+                                }
                                 mbar_expect_tx(full_bar + s, (uint32_t)cb);
                                 if (p.cs == 1) {
                                     bulk_g2s(Wsm + (size_t)s * p.stage_bytes, wsrc + off, (uint32_t)cb, full_bar + s);
@@ -253,6 +278,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
         const int row = q4 * 32 + lane;     // the tile row (= TMEM lane) this thread owns in the epilogue
         const int K = p.K, C = p.C, D = p.D;
         uint32_t acc_phase = 0, wq = 0, gsl = 0;      // gsl: last-layer slabs issued / pooled so far (TMEM buffer ring position)
+        uint32_t pair_phase = 0, peer_ready_remote = 0, peer_full_remote = 0;
+        if (PAIR) {
+            asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(peer_ready_remote) : "r"(smem_u32(peer_ready)));
+            asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(peer_full_remote) : "r"(smem_u32(peer_full)));
+        }
         if (p.resident && warp == 0) mbar_wait(full_bar, 0);
         Tracer tr; tr.init(p.trace, warp == 4 ? 2 : 0, blockIdx.x == 0 && (warp == 0 || warp == 4) && lane == 0);
 
@@ -474,7 +504,49 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
                     tc_fence_before();
                     cbar_sync();       // A operand complete / previous round's TMEM reads and pool scratch drained
                     tr.mark(0x300 + l);
-                    if (warp == 0) {
+                    if (PAIR && warp == 0) {
+                        // ---- CTA pair: one instruction stream for two tiles.  The peer reports (a) that its operand is written
+                        //      and its accumulator drained (this round's barrier above), (b) every half chunk that has landed
+                        //      in its ring; CTA 0 issues M = 256 MMAs (rows 0..127 = its own tile, 128..255 = the peer's, the
+                        //      N = NS weight columns half from each CTA's ring slot) and commits to the barriers of both ----
+                        if (cta_rank != 0) {
+                            if (lane == 0) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(peer_ready_remote) : "memory");
+                            for (int sl = sl0; sl < sl1; ++sl)
+                                for (int kb = 0; kb < ly.nkb; ++kb, ++wq) {
+                                    const int s = wq % p.nstage;
+                                    mbar_wait(full_bar + s, (wq / p.nstage) & 1u);
+                                    if (lane == 0) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(peer_full_remote + (uint32_t)(s * 8)) : "memory");
+                                    __syncwarp();
+                                }
+                        } else {
+                            mbar_wait_cluster(peer_ready, pair_phase);
+                            pair_phase ^= 1u;
+                            tc_fence_after();
+                            const uint32_t idesc2 = (idesc & ~(0x1Fu << 24)) | ((uint32_t)(256 >> 4) << 24);
+                            for (int sl = sl0; sl < sl1; ++sl) {
+                                const uint32_t d_tmem = tmem_base + (uint32_t)((sl - sl0) * ly.NS);
+                                for (int kb = 0; kb < ly.nkb; ++kb, ++wq) {
+                                    const int s = wq % p.nstage;
+                                    mbar_wait(full_bar + s, (wq / p.nstage) & 1u);
+                                    mbar_wait_cluster(peer_full + s, (wq / p.nstage) & 1u);
+                                    tc_fence_after();
+                                    tr.mark(0x800);
+                                    const uint32_t w_addr = smem_u32(Wsm) + (uint32_t)(s * p.stage_bytes);
+                                    const int kw = min(KBLK, ly.K - kb * KBLK);
+                                    const uint32_t a_lo = desc_lo_ns(a_in + (uint32_t)(kb * 8 * A_LBO), A_LBO);
+                                    const uint32_t b_lo = desc_lo_ns(w_addr, (uint32_t)(ly.NS * 8));       // k-groups of NS/2 rows
+                                    if (elect_one()) {
+                                        for (int j = 0; j < kw / 16; ++j)
+                                            umma2_bf16(d_tmem, mk_desc64(a_lo + (uint32_t)(j * 2 * A_LBO / 16), DESC_HI_NS),
+                                                       mk_desc64(b_lo + (uint32_t)(j * ly.NS), DESC_HI_NS), idesc2, (kb | j) ? 1u : 0u);
+                                        umma2_commit(empty_bar + s);      // frees the slot in BOTH rings when these MMAs retire
+                                    }
+                                    __syncwarp();
+                                }
+                            }
+                            if (elect_one()) umma2_commit(acc_bar);
+                        }
+                    } else if (warp == 0) {
                         // the whole warp walks the chunk sequence (warp-uniform addresses -> uniform datapath), one
                         // elected lane issues: ~65 cycles per MMA instead of ~120 from a divergent single thread
                         tc_fence_after();
@@ -582,10 +654,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sa_tc_kernel(const TcParams p)
         }
         tc_fence_before();
         cbar_sync();
-        if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+        if (warp == 0 && !PAIR) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }
     // no CTA of a cluster may exit while a peer can still write its shared memory or signal its barriers
-    if (p.cs > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (p.cs > 1 || PAIR) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (PAIR && warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -618,7 +691,7 @@ static bool tc_plan(int K, int L, const int *dims, TcPlan *pl)
     else if (K <= TC_ROWS)     { pl->gpt = 1; pl->cpg = 1; pl->Kl = 32; pl->direct = 0; pl->use_atomic = 0; }
     else                       { pl->gpt = 1; pl->cpg = (K + TC_ROWS - 1) / TC_ROWS; pl->Kl = 32; pl->direct = 0; pl->use_atomic = 1; }
     const int last_npad = t.ly[L - 1].Npad;
-    const size_t misc = (size_t)t.bias_floats * 4 + 2 * TC_ROWS * 4 + (3 * TC_MAX_STAGES + 1 + 8) * 8 + 16 + 16;
+    const size_t misc = (size_t)t.bias_floats * 4 + 2 * TC_ROWS * 4 + (4 * TC_MAX_STAGES + 2 + 8) * 8 + 16 + 16;
     // Candidates: two CTAs per SM with 256 TMEM columns each (one CTA's epilogue overlaps the other's MMAs),
     // or one CTA per SM with all 512 columns.  Weights stay resident in shared memory when they fit, else
     // they stream through an mbarrier ring.  Preference: resident x2, resident x1, ring x2, ring x1.
@@ -705,7 +778,8 @@ int launch_sa_bf16(const SaArgs &a, cudaStream_t st)
     p.gather_depth = gather_env == 1 ? 1 : 4;       // fp32 rows (no bf16 copy from the previous layer): segments in flight per thread
     p.trace = get_debug_trace();
     if (p.tiles == 0) return 0;
-    cudaError_t e = cudaFuncSetAttribute(sa_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    cudaError_t e = cudaFuncSetAttribute(sa_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sa_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) { set_error("sa_tc: smem attribute (%zu B): %s", pl.smem, cudaGetErrorString(e)); return (int)e; }
     int64_t grid = p.tiles;
     const int64_t cap = (int64_t)148 * pl.ctas_per_sm;
@@ -713,34 +787,54 @@ int launch_sa_bf16(const SaArgs &a, cudaStream_t st)
     // streamed weights with one CTA per SM: clusters of up to 8 CTAs share each chunk through TMA multicast
     static const int cs_env = getenv("PN2_TC_CLUSTER") ? atoi(getenv("PN2_TC_CLUSTER")) : 1;   // measured slower so far (profiles/README.md): off by default
     p.cs = 1;
-    if (!pl.resident && pl.ctas_per_sm == 1) {
+    // CTA-pair mode (PN2_TC_PAIR=1, opt-in): streamed stacks with one CTA per SM; every chunk is fetched half by each CTA of a pair
+    static const int pair_env = getenv("PN2_TC_PAIR") ? atoi(getenv("PN2_TC_PAIR")) : 0;
+    p.pair = 0;
+    if (pair_env == 1 && !pl.resident && pl.ctas_per_sm == 1 && p.tiles >= 2) {
+        p.pair = 1;
+        p.pipelined_last = 0;                       // the pair issues the plain (rows x channels) form of every layer
+        p.stage_bytes = pl.stage_bytes / 2;         // half chunks: the same ring bytes hold twice the stages
+        p.nstage = pl.nstage * 2 > TC_MAX_STAGES ? TC_MAX_STAGES : pl.nstage * 2;
+        const int64_t npairs = (p.tiles + 1) / 2;
+        grid = (npairs < 74 ? npairs : 74) * 2;
+    }
+    if (!p.pair && !pl.resident && pl.ctas_per_sm == 1) {
         int cs = cs_env < 1 ? 1 : (cs_env > 8 ? 8 : cs_env);
         while (cs > 1 && (cs & (cs - 1))) --cs;
         while (cs > 1 && p.tiles < 2 * cs) cs >>= 1;
         p.cs = cs;
         if (cs > 1) { const int64_t ncl = (p.tiles + cs - 1) / cs; grid = (ncl < 148 / cs ? ncl : 148 / cs) * cs; }
     }
-    if (p.cs == 1) {
+    const int cluster = p.pair ? 2 : p.cs;
+    if (cluster == 1) {
         p.n_iter = (p.tiles + grid - 1) / grid;
-        sa_tc_kernel<<<(unsigned)grid, TC_THREADS, pl.smem, st>>>(p);
+        sa_tc_kernel<false><<<(unsigned)grid, TC_THREADS, pl.smem, st>>>(p);
     } else {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = (unsigned)p.cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[0].val.clusterDim.x = (unsigned)cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         // persistent: no more clusters than can be resident at once (a cluster must fit inside one GPC)
         int max_clusters = 0;
-        e = cudaOccupancyMaxActiveClusters(&max_clusters, sa_tc_kernel, &cfg);
-        if (e != cudaSuccess || max_clusters < 1) { set_error("sa_tc: cluster occupancy (cs=%d): %s", p.cs, cudaGetErrorString(e)); return e ? (int)e : -1; }
-        if (grid / p.cs > max_clusters) grid = (int64_t)max_clusters * p.cs;
+        e = p.pair ? cudaOccupancyMaxActiveClusters(&max_clusters, sa_tc_kernel<true>, &cfg) : cudaOccupancyMaxActiveClusters(&max_clusters, sa_tc_kernel<false>, &cfg);
+        if (e != cudaSuccess || max_clusters < 1) { set_error("sa_tc: cluster occupancy (cs=%d): %s", cluster, cudaGetErrorString(e)); return e ? (int)e : -1; }
+        if (grid / cluster > max_clusters) grid = (int64_t)max_clusters * cluster;
         cfg.gridDim = dim3((unsigned)grid);
         p.n_iter = (p.tiles + grid - 1) / grid;
-        e = cudaLaunchKernelEx(&cfg, sa_tc_kernel, p);
-        if (e != cudaSuccess) { set_error("sa_tc: cluster launch (cs=%d): %s", p.cs, cudaGetErrorString(e)); return (int)e; }
+        e = p.pair ? cudaLaunchKernelEx(&cfg, sa_tc_kernel<true>, p) : cudaLaunchKernelEx(&cfg, sa_tc_kernel<false>, p);
+        if (e != cudaSuccess) { set_error("sa_tc: cluster launch (cs=%d): %s", cluster, cudaGetErrorString(e)); return (int)e; }
     }
-    return launch_status("pn2_sa_fused(bf16)");
+    {
+        cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess) {
+            set_error("pn2_sa_fused(bf16, streaming): %s (pair=%d cluster=%d grid=%lld tiles=%lld smem=%zu resident=%d ctas=%d nstage=%d)", cudaGetErrorString(le),
+                      p.pair, cluster, (long long)grid, (long long)p.tiles, pl.smem, pl.resident, pl.ctas_per_sm, p.nstage);
+            return (int)le;
+        }
+    }
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------------
