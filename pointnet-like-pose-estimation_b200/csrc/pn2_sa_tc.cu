@@ -80,6 +80,10 @@ __global__ void pack_bf16_kernel(TcPackArgs a, unsigned char *__restrict__ packe
             const int slab = n / y.NS, nl = n % y.NS, kb = k / kblk, kl = k % kblk;
             const int sp = a.lay.split ? 2 : 1;
             int64_t off = y.w_off + sp * ((int64_t)slab * y.NS * y.K * 2 + (int64_t)kb * y.NS * kblk * 2);
+            if (a.lay.pair_halves) {      // [half][k-group][NS/2 rows][16 B]
+                const int hr = y.NS / 2;
+                off += (int64_t)(nl / hr) * (tc_chunk_bytes(y, kb, kblk) / 2) + (int64_t)(kl / 8) * (hr * 16) + (nl % hr) * 16 + (kl % 8) * 2;
+            } else
             off += (int64_t)(kl / 8) * (y.NS * 16) + nl * 16 + (kl % 8) * 2;
             const __nv_bfloat16 hi = __float2bfloat16_rn(v);
             *reinterpret_cast<__nv_bfloat16 *>(packed + off) = hi;
@@ -243,6 +247,9 @@ __global__ void __launch_bounds__(TC_THREADS, PAIR ? 1 : 2) sa_tc_kernel(const T
                                     // this CTA's half of the chunk: columns rank * NS/2 .. of every k-group (NS/2 rows of 16 B = one copy)
                                     const int half_rows = lay.ly[l].NS / 2, kgs = cb / (lay.ly[l].NS * 16);
                                     mbar_expect_tx(full_bar + s, (uint32_t)(cb / 2));
+                                    if (lay.pair_halves)
+                                        bulk_g2s(Wsm + (size_t)s * p.stage_bytes, wsrc + off + (size_t)cta_rank * (cb / 2), (uint32_t)(cb / 2), full_bar + s);
+                                    else
                                     for (int kg = 0; kg < kgs; ++kg)
                                         bulk_g2s(Wsm + (size_t)s * p.stage_bytes + (size_t)kg * half_rows * 16,
                                                  wsrc + off + (size_t)kg * lay.ly[l].NS * 16 + (size_t)cta_rank * half_rows * 16,
@@ -515,7 +522,9 @@ __global__ void __launch_bounds__(TC_THREADS, PAIR ? 1 : 2) sa_tc_kernel(const T
                                 for (int kb = 0; kb < ly.nkb; ++kb, ++wq) {
                                     const int s = wq % p.nstage;
                                     mbar_wait(full_bar + s, (wq / p.nstage) & 1u);
-                                    if (lane == 0) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(peer_full_remote + (uint32_t)(s * 8)) : "memory");
+                                    // relaxed: the chunk was written by the bulk-copy engine and is read by the tensor core, both through the
+                                    // async proxy; a release at cluster scope here is a full fence per chunk (~1000 cycles: it WAS the chunk period)
+                                    if (lane == 0) asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(peer_full_remote + (uint32_t)(s * 8)) : "memory");
                                     __syncwarp();
                                 }
                         } else {
@@ -527,8 +536,10 @@ __global__ void __launch_bounds__(TC_THREADS, PAIR ? 1 : 2) sa_tc_kernel(const T
                                 const uint32_t d_tmem = tmem_base + (uint32_t)((sl - sl0) * ly.NS);
                                 for (int kb = 0; kb < ly.nkb; ++kb, ++wq) {
                                     const int s = wq % p.nstage;
+                                    // CTA-scope waits: what the barriers order is the issue of MMAs that read the peer's shared memory through
+                                    // the async proxy, not generic loads of this thread (a cluster-scope acquire per chunk cost ~100 cycles more)
+                                    mbar_wait(peer_full + s, (wq / p.nstage) & 1u);
                                     mbar_wait(full_bar + s, (wq / p.nstage) & 1u);
-                                    mbar_wait_cluster(peer_full + s, (wq / p.nstage) & 1u);
                                     tc_fence_after();
                                     tr.mark(0x800);
                                     const uint32_t w_addr = smem_u32(Wsm) + (uint32_t)(s * p.stage_bytes);
@@ -790,7 +801,8 @@ int launch_sa_bf16(const SaArgs &a, cudaStream_t st)
     // CTA-pair mode (PN2_TC_PAIR=1, opt-in): streamed stacks with one CTA per SM; every chunk is fetched half by each CTA of a pair
     static const int pair_env = getenv("PN2_TC_PAIR") ? atoi(getenv("PN2_TC_PAIR")) : 0;
     p.pair = 0;
-    if (pair_env == 1 && !pl.resident && pl.ctas_per_sm == 1 && p.tiles >= 2) {
+    PN2_REQUIRE(!pl.lay.pair_halves || !pl.resident, "pn2_sa_fused(bf16): pair-packed weights cannot be resident");
+    if (pl.lay.pair_halves || (pair_env == 1 && !pl.resident && pl.ctas_per_sm == 1 && p.tiles >= 2)) {
         p.pair = 1;
         p.pipelined_last = 0;                       // the pair issues the plain (rows x channels) form of every layer
         p.stage_bytes = pl.stage_bytes / 2;         // half chunks: the same ring bytes hold twice the stages

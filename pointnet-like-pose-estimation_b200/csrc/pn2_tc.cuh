@@ -41,6 +41,7 @@ struct TcLayout {
     int n_chunks;
     int total_bytes;   // weights + fp32 biases + bias slices
     int kblk;          // k extent of a weight chunk: KBLK, or 32 in the split layout (16 KB hi + lo chunks at NS = 128)
+    int pair_halves;   // chunks packed as two contiguous column halves (CTA-pair kernel, see tc_pair_env)
     int replicas;      // identical copies of the packed image in global memory (streamed stacks, see tc_weight_replicas)
     int rep_stride;    // bytes between copies
     int split;         // fp32 mode on the tensor cores (pn2_sa_tcs.cu): every chunk is [bf16 hi image | bf16 lo image], twice the bytes
@@ -69,6 +70,13 @@ static inline int tc_weight_replicas()
         return v < 1 ? 1 : (v > 16 ? 16 : v);
     }();
     return r;
+}
+// PN2_TC_PAIR=1 (read once): weight sets that can never be resident (> 227 KB) are packed for the CTA-pair kernel -- inside every
+// chunk the columns [0, NS/2) of all k-groups first, then [NS/2, NS): each CTA's half of a chunk is one contiguous block
+static inline bool tc_pair_env()
+{
+    static const bool v = [] { const char *e = getenv("PN2_TC_PAIR"); return e && atoi(e) == 1; }();
+    return v;
 }
 static inline int tc_split_kblk()
 {
@@ -119,6 +127,7 @@ static inline TcLayout tc_layout(int L, const int *dims, bool split = false)
     }
     // weight sets too large to stay resident in shared memory are streamed per tile: those get the replicas
     t.replicas = t.w_bytes > 100 * 1024 ? tc_weight_replicas() : 1;
+    t.pair_halves = (!split && tc_pair_env() && t.w_bytes > TC_SMEM_LIMIT) ? 1 : 0;
     t.rep_stride = rup(t.total_bytes, 1024);
     return t;
 }
