@@ -2,14 +2,21 @@
 // stand-alone square_distance kernel.
 //
 // One CTA handles one cloud x a tile of centres.  The cloud (SoA coordinates + |p|^2, computed once per CTA
-// in the layout-dependent summation order) is staged in shared memory; one warp owns one centre at a time
-// and scans the points in index order, 32 per step: ballot + popc give each in-radius lane its output slot,
-// so the "first K in ascending index order" semantics of the reference's sort (:86) falls out without any
-// sort, and the scan stops as soon as K neighbours are found.  The [B,S,N] distance matrix and the
-// [B,S,N] int64 index tensor of the reference never exist.
+// in the layout-dependent summation order) is staged in shared memory; a warp owns four centres at a time (two for
+// C > 4) and scans the points in index order.  The "first K in ascending index order" semantics of the reference's
+// sort (:86) falls out of ballots without any sort, and the scan stops as soon as every list in flight holds K
+// neighbours.  The [B,S,N] distance matrix and the [B,S,N] int64 index tensor of the reference never exist.
+//
+// Kernels of this file:
+//   ball_query_masks_kernel / ball_query_multi_masks_kernel  (C <= 4, cloud staged whole: the default)  -- a trip of 128
+//       points only parks its four ballots in lanes; the lists are resolved once per 1024 points (deferred bookkeeping);
+//   ball_query_kernel / ball_query_multi_kernel  (C = 10; clouds beyond shared memory; PN2_BQ_V1=1)  -- 64 points per
+//       trip, ballot + popc give each in-radius lane its output slot inside the trip;
+//   ball_query_cell_kernel  (PN2_BQ_CELLS=1)  -- exact grid cull, measured not faster at the reference's densities;
+//   ball_query_generic_kernel  -- any C <= 16, lists beyond 1024 entries: one thread per centre, no staging.
 //
 // Exactness contract: dot = fl(s0*p0), dot = fma(s_k, p_k, dot) ascending k (MKL sgemm, :23);
-// d = fl(fl(-2*dot + |s|^2) + |p|^2); in radius <=> !(d > r2).
+// d = fl(fl(-2*dot + |s|^2) + |p|^2); in radius <=> !(d > r2).  Every kernel evaluates a pair with exactly this chain.
 #include <stdlib.h>
 #include <type_traits>
 #include "pn2_common.cuh"
