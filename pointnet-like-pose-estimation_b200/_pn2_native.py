@@ -90,8 +90,34 @@ def load_library(path: str = LIB_PATH):
     return _lib
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream(t: torch.Tensor) -> int:
+    """cudaStream_t of torch's current stream on t's device (the raw-handle query: the Stream object costs ~8 us per call)."""
+    if _raw_stream is not None:
+        idx = t.device.index
+        return _raw_stream(idx if idx is not None else torch.cuda.current_device())
     return torch.cuda.current_stream(t.device).cuda_stream
+
+
+class _NoCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_CTX = _NoCtx()
+
+
+def _on(device):
+    """Context that makes `device` current for a launch; nothing when it already is (the common case: ~6 us saved per call)."""
+    idx = device.index if isinstance(device, torch.device) else torch.device(device).index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NO_CTX
+    return torch.cuda.device(idx)
 
 
 def _need_cuda(name: str, t: torch.Tensor, dtype) -> None:
@@ -121,6 +147,7 @@ class Native:
         self.lib = load_library()
         self.launches = 0      # kernels launched through the C ABI (bench.py reports it as gpu_launches)
         self.trace = None      # set to a list to record (name, meta, start_event, end_event) per launch
+        self._memo = {}        # results of the pure plan queries (pn2_sa_needs_zero_init, pn2_sa_bf16_side_io)
 
     @contextlib.contextmanager
     def _span(self, name, **meta):
@@ -148,7 +175,7 @@ class Native:
         i32 = torch.empty(B, S, dtype=torch.int32, device=dev) if want_idx32 else None
         npts = torch.empty(B, S, C, dtype=torch.float32, device=dev) if want_new_points else None
         start = start.contiguous()
-        with torch.cuda.device(dev), self._span("fps", B=B, N=N, C=C, S=S):
+        with _on(dev), self._span("fps", B=B, N=N, C=C, S=S):
             _check(self.lib.pn2_fps_f32(points.data_ptr(), *points.stride(), B, N, C, start.data_ptr(), S,
                                         i64.data_ptr() if want_idx64 else None,
                                         i32.data_ptr() if want_idx32 else None,
@@ -159,7 +186,7 @@ class Native:
         """pinned int64 CPU tensor (page-locked) -> device tensor, copied by a kernel on the current stream (pn2_upload_i64)."""
         assert pinned.dtype == torch.int64 and pinned.is_pinned() and pinned.is_contiguous()
         out = torch.empty(pinned.shape, dtype=torch.int64, device=device)
-        with torch.cuda.device(device):
+        with _on(device):
             _check(self.lib.pn2_upload_i64(pinned.data_ptr(), out.data_ptr(), pinned.numel(), _stream(out)))
         return out
 
@@ -172,7 +199,7 @@ class Native:
         M = idx_c.numel() // max(B, 1)
         out = torch.empty(*idx.shape, C, dtype=torch.float32, device=src.device)
         flag = torch.zeros(1, dtype=torch.int32, device=src.device) if check else None
-        with torch.cuda.device(src.device), self._span("index_points", B=B, N=N, C=C, M=M):
+        with _on(src.device), self._span("index_points", B=B, N=N, C=C, M=M):
             _check(self.lib.pn2_index_points_f32(src.data_ptr(), *src.stride(), B, N, C, idx_c.data_ptr(), M,
                                                  out.data_ptr(), flag.data_ptr() if check else None, _stream(src)))
         if check and int(flag.item()) != 0:
@@ -185,7 +212,7 @@ class Native:
         B, S, C = src.shape
         N = dst.shape[1]
         out = torch.empty(B, S, N, dtype=torch.float32, device=src.device)
-        with torch.cuda.device(src.device), self._span("square_distance", B=B, S=S, N=N, C=C):
+        with _on(src.device), self._span("square_distance", B=B, S=S, N=N, C=C):
             _check(self.lib.pn2_square_distance_f32(src.data_ptr(), *src.stride(), dst.data_ptr(), *dst.stride(),
                                                     B, S, N, C, out.data_ptr(), _stream(src)))
         return out
@@ -201,7 +228,7 @@ class Native:
         dev = points.device
         i64 = torch.empty(B, S, K, dtype=torch.int64, device=dev) if want_idx64 else None
         i32 = torch.empty(B, S, K, dtype=torch.int32, device=dev) if want_idx32 else None
-        with torch.cuda.device(dev), self._span("ball_query", B=B, N=N, C=C, S=S, K=K, i64=bool(want_idx64)):
+        with _on(dev), self._span("ball_query", B=B, N=N, C=C, S=S, K=K, i64=bool(want_idx64)):
             _check(self.lib.pn2_ball_query_f32(centres.data_ptr(), *centres.stride(), points.data_ptr(), *points.stride(),
                                                B, S, N, C, float(r2), K,
                                                i64.data_ptr() if want_idx64 else None,
@@ -226,7 +253,7 @@ class Native:
         ks = (ctypes.c_int * R)(*[int(K) for K in numbers])
         p64 = (ctypes.c_void_p * R)(*[o[0].data_ptr() if o[0] is not None else None for o in outs])
         p32 = (ctypes.c_void_p * R)(*[o[1].data_ptr() if o[1] is not None else None for o in outs])
-        with torch.cuda.device(dev), self._span("ball_query_multi", B=B, N=N, C=C, S=S, K=[int(K) for K in numbers]):
+        with _on(dev), self._span("ball_query_multi", B=B, N=N, C=C, S=S, K=[int(K) for K in numbers]):
             _check(self.lib.pn2_ball_query_multi_f32(centres.data_ptr(), *centres.stride(), points.data_ptr(), *points.stride(),
                                                      B, S, N, C, R, r2, ks, p64 if want_idx64 else None,
                                                      p32 if want_idx32 else None,
@@ -255,7 +282,7 @@ class Native:
             _, S, K = idx32.shape
             iptr, cptr = idx32.data_ptr(), centres.data_ptr()
         out = torch.empty(B, S, K, C + D, dtype=torch.float32, device=points.device)
-        with torch.cuda.device(points.device), self._span("group", B=B, N=N, S=S, K=K, C=C, D=D):
+        with _on(points.device), self._span("group", B=B, N=N, S=S, K=K, C=C, D=D):
             _check(self.lib.pn2_group_f32(points.data_ptr(), *points.stride(), fptr, *fstr, iptr, cptr,
                                           B, N, S, K, C, D, order, out.data_ptr(), _stream(points)))
         return out
@@ -278,24 +305,34 @@ class Native:
             _check(-1)
         packed = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
         parr = (ctypes.c_void_p * len(ptrs))(*ptrs)
-        with torch.cuda.device(dev), self._span("pack", dims=tuple(dims)):
+        with _on(dev), self._span("pack", dims=tuple(dims)):
             _check(self.lib.pn2_pack_weights(len(layers), d.ctypes.data, ctypes.cast(parr, _vp), float(eps), prec,
                                              int(C), int(order), packed.data_ptr(), _stream(packed)))
         return packed, dims
 
     def sa_needs_zero(self, S, K, dims, prec) -> bool:
+        key = ("z", int(S), int(K), tuple(dims), prec)
+        hit = self._memo.get(key)
+        if hit is not None:
+            return hit
         d = _dims_array(dims)
         rc = self.lib.pn2_sa_needs_zero_init(int(S), int(K), len(dims) - 1, d.ctypes.data, prec)
         if rc < 0:
             _check(rc)
+        self._memo[key] = bool(rc)
         return bool(rc)
 
     def sa_bf16_side_io(self, K, C, order, dims, prec) -> bool:
         """True when the kernel serving this configuration writes `out_bf16` (`feature_bf16` is read by every bf16 kernel)."""
+        key = ("s", int(K), int(C), int(order), tuple(dims), prec)
+        hit = self._memo.get(key)
+        if hit is not None:
+            return hit
         d = _dims_array(dims)
         rc = self.lib.pn2_sa_bf16_side_io(int(K), int(C), int(order), len(dims) - 1, d.ctypes.data, prec)
         if rc < 0:
             _check(rc)
+        self._memo[key] = bool(rc)
         return bool(rc)
 
     def sa_fused(self, points, feature, centres, idx32, order, dims, packed, prec, out, co_off=0,
@@ -332,7 +369,7 @@ class Native:
             _need_cuda("out_bf16", out_bf16, torch.bfloat16)
             assert out_bf16.shape == out.shape and out_bf16.stride() == out.stride()
         d = _dims_array(dims)
-        with torch.cuda.device(points.device), self._span("sa_fused", B=B, N=N, S=S, K=K, C=C, D=D, dims=tuple(dims), prec=prec,
+        with _on(points.device), self._span("sa_fused", B=B, N=N, S=S, K=K, C=C, D=D, dims=tuple(dims), prec=prec,
                                                              algo_dims=tuple(algo_dims) if algo_dims else None):
             _check(self.lib.pn2_sa_fused(points.data_ptr(), *points.stride(), fptr, *fstr, cptr, iptr,
                                          B, N, S, K, C, D, order, len(dims) - 1, d.ctypes.data, packed.data_ptr(), prec,
@@ -353,7 +390,7 @@ class Native:
             assert category.shape == (B,) and category.is_contiguous()
             cptr = category.data_ptr()
         out = torch.empty(B, 3 + num_category, N, dtype=torch.float32, device=xyz.device)
-        with torch.cuda.device(xyz.device), self._span("normalize_splice", B=B, N=N):
+        with _on(xyz.device), self._span("normalize_splice", B=B, N=N):
             _check(self.lib.pn2_normalize_splice_f32(xyz.data_ptr(), *xyz.stride(), B, N, cptr, int(num_category),
                                                      out.data_ptr(), _stream(xyz)))
         return out
@@ -373,7 +410,7 @@ class Native:
         nbytes = self.lib.pn2_fps_xyz_scratch_bytes(B, N, points.element_size())
         scratch = torch.empty(nbytes, dtype=torch.uint8, device=points.device) if nbytes > 0 else None
         fn = self.lib.pn2_fps_xyz_f64 if points.dtype == torch.float64 else self.lib.pn2_fps_xyz_f32
-        with torch.cuda.device(points.device), self._span("fps_xyz", B=B, N=N, S=S):
+        with _on(points.device), self._span("fps_xyz", B=B, N=N, S=S):
             _check(fn(points.data_ptr(), *points.stride(), B, N, start.data_ptr(), int(S), idx.data_ptr(),
                       scratch.data_ptr() if scratch is not None else None, _stream(points)))
         return idx
@@ -401,7 +438,7 @@ class Native:
                 _need_cuda(name, t, torch.float32)
                 assert t.is_contiguous() and t.numel() == C
             rm, rv, cb = rm_t.data_ptr(), rv_t.data_ptr(), (cb_t.data_ptr() if cb_t is not None else None)
-        with torch.cuda.device(y.device), self._span("bn_relu_train_fwd", M=M, C=C, K=K):
+        with _on(y.device), self._span("bn_relu_train_fwd", M=M, C=C, K=K):
             _check(self.lib.pn2_bn_relu_train_fwd_f32(y.data_ptr(), M, C, int(K), gamma.data_ptr(), beta.data_ptr(), float(eps),
                                                       ws.data_ptr(), stats.data_ptr(), z.data_ptr(),
                                                       arg.data_ptr() if K else None, rm, rv, cb, float(factor), _stream(y)))
@@ -416,7 +453,7 @@ class Native:
         ws = torch.empty(self.lib.pn2_bn_train_ws_bytes(C), dtype=torch.uint8, device=y.device)
         sums = torch.empty(2, C, dtype=torch.float32, device=y.device)
         dy = torch.empty_like(y)
-        with torch.cuda.device(y.device), self._span("bn_relu_train_bwd", M=M, C=C, K=K):
+        with _on(y.device), self._span("bn_relu_train_bwd", M=M, C=C, K=K):
             _check(self.lib.pn2_bn_relu_train_bwd_f32(dz.data_ptr(), y.data_ptr(), arg.data_ptr() if K else None, M, C, int(K),
                                                       stats.data_ptr(), ws.data_ptr(), sums.data_ptr(), dy.data_ptr(), _stream(y)))
         return dy, sums
@@ -439,7 +476,7 @@ class Native:
             _need_cuda("mean", mean, torch.float32)
             assert mean.shape == (B, 3) and mean.stride(1) == 1
             mptr, mstr = mean.data_ptr(), mean.stride(0)
-        with torch.cuda.device(x.device), self._span("fc_head", B=B, K0=K0, H1=H1, H2=H2, OUT=OUT):
+        with _on(x.device), self._span("fc_head", B=B, K0=K0, H1=H1, H2=H2, OUT=OUT):
             _check(self.lib.pn2_fc_head_f32(x.data_ptr(), x.stride(0), B, K0, H1, H2, OUT, w1p.data_ptr(), b1.data_ptr(),
                                             w2p.data_ptr(), b2.data_ptr(), w3.data_ptr(), b3.data_ptr(), int(kind), mptr, mstr,
                                             mean_mlp.data_ptr() if mean_mlp is not None else None, out.data_ptr(),
@@ -461,7 +498,7 @@ class Native:
         if out is None:
             out = torch.empty(M, N, dtype=out_dtype, device=a.device)
         assert out.shape == (M, N) and out.stride(1) == 1 and out.dtype in dt
-        with torch.cuda.device(a.device), self._span("rows_gemm", M=M, N=N, K=K, tf32=w.dtype == torch.float32):
+        with _on(a.device), self._span("rows_gemm", M=M, N=N, K=K, tf32=w.dtype == torch.float32):
             _check(self.lib.pn2_rows_gemm(a.data_ptr(), a.stride(0), dt[a.dtype], w.data_ptr(), w.stride(0), dt[w.dtype],
                                           out.data_ptr(), out.stride(0), dt[out.dtype], M, N, K, _stream(a)))
         return out
@@ -476,7 +513,7 @@ class Native:
         idx32 = idx32.contiguous()
         M = idx32.numel() // max(B, 1)
         out = torch.empty(*idx32.shape, D, dtype=torch.float32, device=feat.device)
-        with torch.cuda.device(feat.device), self._span("gather_rows", B=B, N=N, M=M, D=D):
+        with _on(feat.device), self._span("gather_rows", B=B, N=N, M=M, D=D):
             _check(self.lib.pn2_gather_rows_f32(feat.data_ptr(), feat.stride(0), feat.stride(1), 1, idx32.data_ptr(), B, N, M, D,
                                                 out.data_ptr(), _stream(feat)))
         return out
@@ -489,7 +526,7 @@ class Native:
         B, D = grad.shape[0], grad.shape[-1]
         M = idx32.numel() // max(B, 1)
         gfeat = torch.zeros(B, N, D, dtype=torch.float32, device=grad.device)
-        with torch.cuda.device(grad.device), self._span("scatter_add_rows", B=B, N=N, M=M, D=D):
+        with _on(grad.device), self._span("scatter_add_rows", B=B, N=N, M=M, D=D):
             _check(self.lib.pn2_scatter_add_rows_f32(grad.data_ptr(), idx32.data_ptr(), B, N, M, D, gfeat.data_ptr(), _stream(grad)))
         return gfeat
 
@@ -502,7 +539,7 @@ class Native:
         assert x.shape[0] == M and dy.stride(1) == 1 and x.stride(1) == 1
         ws = torch.empty(max(1, self.lib.pn2_rows_wgrad_ws_bytes(M, Cout, Cin)), dtype=torch.uint8, device=dy.device)
         dw = torch.empty(Cout, Cin, dtype=torch.float32, device=dy.device)
-        with torch.cuda.device(dy.device), self._span("rows_wgrad", M=M, Cout=Cout, Cin=Cin):
+        with _on(dy.device), self._span("rows_wgrad", M=M, Cout=Cout, Cin=Cin):
             _check(self.lib.pn2_rows_wgrad_tf32(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), M, Cout, Cin,
                                                 ws.data_ptr(), dw.data_ptr(), _stream(dy)))
         return dw
@@ -510,7 +547,7 @@ class Native:
     def selftest_umma(self, n_cols, k_dim, variant, device="cuda:0", dump=False):
         err = torch.full((1,), -1.0, dtype=torch.float32, device=device)
         d = torch.zeros(256 if variant == 4 else 128, n_cols, dtype=torch.float32, device=device) if dump else None
-        with torch.cuda.device(err.device):
+        with _on(err.device):
             _check(self.lib.pn2_selftest_umma(n_cols, k_dim, variant, err.data_ptr(),
                                               d.data_ptr() if dump else None, _stream(err)))
         return err, d

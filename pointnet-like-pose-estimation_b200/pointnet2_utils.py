@@ -233,6 +233,21 @@ def _prec_code() -> int:
     return PREC_BF16 if _precision == "bf16" else PREC_F32
 
 
+def _stack_tensors(convs, bns):
+    """The tensors a folded (conv, bn) stack depends on, read straight from the modules' registries (this runs on every forward
+    to validate the caches: nn.Module.__getattr__ and parameters() cost several microseconds per tensor)."""
+    out = []
+    for conv, bn in zip(convs, bns):
+        cp, bp, bb = conv._parameters, bn._parameters, bn._buffers
+        out += [cp["weight"], cp["bias"], bp["weight"], bp["bias"], bb["running_mean"], bb["running_var"]]
+    return out
+
+
+def _leaf_tensors(m):
+    """parameters() + buffers() of a leaf module, without the generator machinery."""
+    return [t for t in m._parameters.values() if t is not None] + [t for t in m._buffers.values() if t is not None]
+
+
 class _FoldedMLP:
     """Derived cache: BN-folded, kernel-layout weights of one (Conv2d, BatchNorm2d) stack.
 
@@ -245,9 +260,7 @@ class _FoldedMLP:
         self.dims = None
 
     def get(self, convs, bns, C, order):
-        tensors = []
-        for conv, bn in zip(convs, bns):
-            tensors += [conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        tensors = _stack_tensors(convs, bns)
         prec = _prec_code()
         key = (_cache_generation, prec, C, order, tuple((t.data_ptr(), t._version) for t in tensors))
         if key != self.key:
@@ -278,9 +291,7 @@ class _FactorisedFirstLayer:
         self.packed = self.dims = self.wf = None
 
     def get(self, convs, bns, C, D):
-        tensors = []
-        for conv, bn in zip(convs, bns):
-            tensors += [conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        tensors = _stack_tensors(convs, bns)
         key = (_cache_generation, C, D, tuple((t.data_ptr(), t._version) for t in tensors))
         if key != self.key:
             conv0, bn0 = convs[0], bns[0]
@@ -333,7 +344,7 @@ class _FoldedHead:
     def get(self, fcs, bns, mean_mlp=None):
         """fcs = (fc1, fc2, fc3), bns = (bn1, bn2); mean_mlp = (mean_fc1, mean_bn1, mean_fc2) of the translation heads or None."""
         mods = list(fcs) + list(bns) + (list(mean_mlp) if mean_mlp else [])
-        ts = [t for m in mods for t in list(m.parameters()) + list(m.buffers())]
+        ts = [t for m in mods for t in _leaf_tensors(m)]
         key = (_cache_generation, tuple((t.data_ptr(), t._version) for t in ts))
         if key != self.key:
             with torch.no_grad():
